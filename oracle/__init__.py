@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the CPU oracle (oracle/h2aes_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this package.  The product package (halo2_aes_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_DIR, "libh2aes_oracle.so")
+
+KIND_AES = 0
+KIND_KEYSCHED = 1
+
+ERRORS = {
+    1: "bad argument",
+    2: "AES calls too many. doesn't fit in the rows",
+    3: "not enough rows available",
+    4: "Keys should be scheduled",
+    5: "lookup input not in table",
+    6: "from_bytes returned None",
+}
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code):
+        super().__init__(f"oracle error {code}: {ERRORS.get(code, '?')}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the Makefile beside it (gcc only; no CUDA)."""
+    src_newer = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(os.path.join(_DIR, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("h2aes_oracle.cpp", "fr.hpp", "Makefile")
+    )
+    if force or src_newer:
+        subprocess.check_call(["make", "-C", _DIR, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        u64p = C.POINTER(C.c_uint64)
+        u8p = C.POINTER(C.c_uint8)
+        L.orc_new.restype = C.c_void_p
+        L.orc_new.argtypes = [C.c_int] * 4
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_set_record_copies.argtypes = [C.c_void_p, C.c_int]
+        L.orc_synthesize.argtypes = [C.c_void_p, u8p, u8p, C.c_uint64]
+        L.orc_num_copies.restype = C.c_uint64
+        L.orc_num_copies.argtypes = [C.c_void_p]
+        L.orc_num_regions.restype = C.c_uint64
+        L.orc_num_regions.argtypes = [C.c_void_p]
+        L.orc_get_copies.argtypes = [C.c_void_p, u64p]
+        L.orc_get_advice.argtypes = [C.c_void_p, C.c_int, u64p]
+        L.orc_get_fixed.argtypes = [C.c_void_p, C.c_int, u64p]
+        L.orc_get_selector.argtypes = [C.c_void_p, C.c_int, u8p]
+        L.orc_get_ciphertexts.argtypes = [C.c_void_p, u8p]
+        L.orc_get_round_keys.argtypes = [C.c_void_p, u8p]
+        L.orc_lookup.argtypes = [C.c_void_p, C.c_int] + [u64p] * 8
+        L.orc_mock_verify.argtypes = [C.c_void_p, u64p]
+        L.orc_mock_verify_ext.argtypes = [C.c_int] * 3 + [u64p, u64p, u8p, u64p, C.c_uint64, u64p]
+        L.orc_shape.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int32)]
+        L.orc_fr_from_u64.argtypes = [C.c_uint64, u64p]
+        for f in (L.orc_fr_mul, L.orc_fr_add, L.orc_xor_bytes):
+            f.argtypes = [u64p, u64p, u64p]
+        for f in (L.orc_fr_inv, L.orc_fr_to_canonical, L.orc_fr_from_canonical):
+            f.argtypes = [u64p, u64p]
+        L.orc_tables.argtypes = [C.c_int, u8p, u8p, u8p]
+        L.orc_bench_circuit.argtypes = (
+            [C.c_int] * 3 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int, C.c_int,
+                             C.POINTER(C.c_double), u64p]
+        )
+        _lib = L
+    return _lib
+
+
+def _u64(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+R_MONT = (1 << 256) % R_MOD
+
+
+def limbs_to_int(a) -> int:
+    a = np.asarray(a, dtype=np.uint64).reshape(-1)
+    return sum(int(a[i]) << (64 * i) for i in range(4))
+
+
+def int_to_limbs(v: int) -> np.ndarray:
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def fr_from_int(v: int) -> np.ndarray:
+    """canonical integer -> Montgomery limbs (pure Python big-int; independent of the C code)."""
+    return int_to_limbs((v % R_MOD) * R_MONT % R_MOD)
+
+
+def fr_to_int(limbs) -> int:
+    """Montgomery limbs -> canonical integer."""
+    return limbs_to_int(limbs) * pow(R_MONT, -1, R_MOD) % R_MOD
+
+
+def shape(kind: int, k: int, N: int) -> dict:
+    out = (C.c_int32 * 5)()
+    rc = lib().orc_shape(kind, k, N, out)
+    if rc:
+        raise OracleError(rc)
+    return dict(n_advice=out[0], n_fixed=out[1], n_selectors=out[2], n_lookups=out[3],
+                n_sets=out[4], n=1 << k, usable=(1 << k) - 6)
+
+
+def tables(fips: bool = False):
+    s = np.zeros(256, np.uint8)
+    m2 = np.zeros(256, np.uint8)
+    m3 = np.zeros(256, np.uint8)
+    lib().orc_tables(int(fips), _u8(s), _u8(m2), _u8(m3))
+    return s, m2, m3
+
+
+class Circuit:
+    """One synthesized circuit: the reference's `synthesize` replayed on the CPU."""
+
+    def __init__(self, kind: int, k: int, N: int, fips_sbox: bool = False):
+        self.kind, self.k, self.N = kind, k, N
+        self.n = 1 << k
+        self.info = shape(kind, k, N)
+        self._h = lib().orc_new(kind, k, N, int(fips_sbox))
+        if not self._h:
+            raise OracleError(1)
+        self.n_blocks = 0
+
+    def close(self):
+        if self._h:
+            lib().orc_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def synthesize(self, key, plaintexts=None):
+        key = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        assert key.size == 16
+        if plaintexts is None:
+            pts = np.zeros((0, 16), np.uint8)
+        else:
+            pts = np.ascontiguousarray(np.asarray(plaintexts, dtype=np.uint8).reshape(-1, 16))
+        self.n_blocks = pts.shape[0]
+        dummy = np.zeros(16, np.uint8)
+        rc = lib().orc_synthesize(self._h, _u8(key), _u8(pts if pts.size else dummy), self.n_blocks)
+        if rc:
+            raise OracleError(rc)
+        return self
+
+    def advice(self, col=None) -> np.ndarray:
+        if col is None:
+            return np.stack([self.advice(c) for c in range(self.info["n_advice"])])
+        out = np.zeros((self.n, 4), np.uint64)
+        rc = lib().orc_get_advice(self._h, col, _u64(out))
+        if rc:
+            raise OracleError(rc)
+        return out
+
+    def fixed(self, col=None) -> np.ndarray:
+        if col is None:
+            return np.stack([self.fixed(c) for c in range(self.info["n_fixed"])])
+        out = np.zeros((self.n, 4), np.uint64)
+        rc = lib().orc_get_fixed(self._h, col, _u64(out))
+        if rc:
+            raise OracleError(rc)
+        return out
+
+    def selectors(self, sel=None) -> np.ndarray:
+        if sel is None:
+            return np.stack([self.selectors(c) for c in range(self.info["n_selectors"])])
+        out = np.zeros(self.n, np.uint8)
+        rc = lib().orc_get_selector(self._h, sel, _u8(out))
+        if rc:
+            raise OracleError(rc)
+        return out
+
+    def copies(self) -> np.ndarray:
+        m = lib().orc_num_copies(self._h)
+        out = np.zeros((max(m, 1), 4), np.uint64)
+        lib().orc_get_copies(self._h, _u64(out))
+        return out[:m]
+
+    def num_regions(self) -> int:
+        return lib().orc_num_regions(self._h)
+
+    def ciphertexts(self) -> np.ndarray:
+        out = np.zeros((max(self.n_blocks, 1), 16), np.uint8)
+        lib().orc_get_ciphertexts(self._h, _u8(out))
+        return out[: self.n_blocks]
+
+    def round_keys(self) -> np.ndarray:
+        out = np.zeros(176, np.uint8)
+        lib().orc_get_round_keys(self._h, _u8(out))
+        return out
+
+    def lookup(self, idx: int, theta, beta, gamma, want=("A", "S", "Ap", "Sp", "Z")) -> dict:
+        """halo2 v0.3.0 commit_permuted + commit_product for lookup `idx` (Montgomery limbs)."""
+        bufs = {}
+        ptrs = []
+        null = C.POINTER(C.c_uint64)()
+        for name in ("A", "S", "Ap", "Sp", "Z"):
+            if name in want:
+                bufs[name] = np.zeros((self.n, 4), np.uint64)
+                ptrs.append(_u64(bufs[name]))
+            else:
+                ptrs.append(null)
+        th = np.ascontiguousarray(theta, dtype=np.uint64)
+        be = np.ascontiguousarray(beta, dtype=np.uint64)
+        ga = np.ascontiguousarray(gamma, dtype=np.uint64)
+        rc = lib().orc_lookup(self._h, idx, _u64(th), _u64(be), _u64(ga), *ptrs)
+        if rc:
+            raise OracleError(rc)
+        return bufs
+
+    def mock_verify(self):
+        where = np.zeros(2, np.uint64)
+        rc = lib().orc_mock_verify(self._h, _u64(where))
+        return rc, (int(where[0]), int(where[1]))
+
+
+def mock_verify_ext(kind, k, N, advice, fixed, selectors, copies):
+    """Restated MockProver over caller-supplied columns (e.g. read back from the GPU)."""
+    advice = np.ascontiguousarray(advice, dtype=np.uint64)
+    fixed = np.ascontiguousarray(fixed, dtype=np.uint64)
+    selectors = np.ascontiguousarray(selectors, dtype=np.uint8)
+    copies = np.ascontiguousarray(copies, dtype=np.uint64).reshape(-1, 4)
+    info = shape(kind, k, N)
+    n = 1 << k
+    assert advice.shape == (info["n_advice"], n, 4), advice.shape
+    assert fixed.shape == (info["n_fixed"], n, 4), fixed.shape
+    assert selectors.shape == (info["n_selectors"], n), selectors.shape
+    where = np.zeros(2, np.uint64)
+    cp = copies if copies.size else np.zeros((1, 4), np.uint64)
+    rc = lib().orc_mock_verify_ext(kind, k, N, _u64(advice), _u64(fixed), _u8(selectors),
+                                   _u64(cp), copies.shape[0], _u64(where))
+    return rc, (int(where[0]), int(where[1]))
+
+
+def bench_circuit(kind, k, N, key, plaintexts, theta, beta, gamma, threads=1, n_lookups=-1):
+    """Time one whole circuit on the CPU: (synthesize seconds, lookup seconds, Z[n-6] digest)."""
+    key = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+    pts = np.ascontiguousarray(np.asarray(plaintexts, dtype=np.uint8).reshape(-1, 16))
+    times = (C.c_double * 2)()
+    digest = np.zeros(4, np.uint64)
+    th = np.ascontiguousarray(theta, dtype=np.uint64)
+    be = np.ascontiguousarray(beta, dtype=np.uint64)
+    ga = np.ascontiguousarray(gamma, dtype=np.uint64)
+    dummy = np.zeros(16, np.uint8)
+    rc = lib().orc_bench_circuit(kind, k, N, _u8(key), _u8(pts if pts.size else dummy),
+                                 pts.shape[0], _u64(th), _u64(be), _u64(ga), threads, n_lookups,
+                                 times, _u64(digest))
+    if rc:
+        raise OracleError(rc)
+    return times[0], times[1], digest

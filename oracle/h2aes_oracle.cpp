@@ -1,0 +1,956 @@
+// TEST INFRASTRUCTURE — CPU oracle for the halo2-aes witness + lookup-helper-column path.
+//
+// This file is a CPU restatement of what the reference computes on this path, written region by
+// region the way the reference's `synthesize` drives halo2 (two passes per region under
+// SimpleFloorPlanner: a shape pass that records the touched columns, then the assignment pass).
+// It is deliberately NOT the closed-form layout the CUDA product uses: the two are independent
+// derivations of every (column,row,value), and tests/ compare them.
+//
+// What it follows (paths relative to /root/reference):
+//   * src/table.rs:18-192          load_enc_full_table
+//   * src/key_schedule.rs:80-224   schedule_keys / assign_first_round / assign_round
+//   * src/aes128.rs:143-356        schedule_key / encrypt / lcon / aes_callable + getters
+//   * src/chips/*.rs               xor / substitute / mul / range_check region bodies
+//   * src/utils.rs:8-33            xor_bytes / sub_byte / ROUND_CONSTANT
+//   * src/constant.rs              S_BOX (including its deviation from FIPS-197 at index 255),
+//                                  MUL_BY_2, MUL_BY_3, KEY_SCHEDULE_ROWS, AES_ROWS
+// Third-party behaviour that is NOT in /root/reference (un-vendored git dependency
+// halo2_proofs v0.3.0 @ 73408a140737d8336490452193b21f5a7a94e7de, Cargo.lock:741-743, and
+// halo2curves 0.6.1) is restated from its published algorithm and marked [UPSTREAM]:
+//   * circuit/floor_planner/single_pass.rs  region placement = max(next free row of touched cols)
+//   * circuit/table_layouter.rs + keygen fill_from_row  table padding with the offset-0 value
+//   * plonk/lookup/prover.rs  commit_permuted / permute_expression_pair / commit_product
+//   * dev.rs (MockProver::verify)  gate / lookup / permutation checks
+// PARITY STATUS: witness/fixed/selector values are pinned by the reference's own vectors
+// (EXPANDED key_schedule.rs:337-345, MockProver-satisfied zero/zero circuits, xor 5^12=9) plus
+// FIPS-197 App. B / C.1; the permuted/Z columns are "parity unpinned" — no reference test holds
+// their values, only algebraic invariants are available.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+// load this library.
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fr.hpp"
+
+namespace orc {
+
+// ---------------------------------------------------------------------------------------------
+// constants (src/constant.rs, src/utils.rs:28, src/table.rs:10-16)
+// ---------------------------------------------------------------------------------------------
+static const uint64_t KEY_SCHEDULE_ROWS = 1760;  // constant.rs:113
+static const uint64_t AES_ROWS = 1360;           // constant.rs:114
+static const uint64_t ROUND_CONSTANT[10] = {1, 2, 4, 8, 16, 32, 64, 128, 27, 54};  // utils.rs:28
+enum Tag { TAG_U8 = 1, TAG_XOR = 2, TAG_SBOX = 3, TAG_GFMUL2 = 4, TAG_GFMUL3 = 5 };  // table.rs:10
+
+struct ByteTables {
+    uint8_t sbox[256], mul2[256], mul3[256];
+};
+
+static uint8_t gf_xtime(uint8_t x) { return (uint8_t)((x << 1) ^ ((x & 0x80) ? 0x1b : 0)); }
+static uint8_t gf_mul(uint8_t a, uint8_t b) {
+    uint8_t p = 0;
+    for (int i = 0; i < 8; ++i) {
+        if (b & 1) p ^= a;
+        a = gf_xtime(a);
+        b >>= 1;
+    }
+    return p;
+}
+
+// The tables are generated from first principles (GF(2^8) inverse + affine map; xtime), then —
+// unless `fips` — entry 255 of the S-box is set to 23, which is what src/constant.rs:14 holds
+// (FIPS-197 says 0x16 = 22).  tests/test_oracle_golden.py checks all three tables byte for byte
+// against tests/golden/ref_tables.json, extracted from the reference's constant.rs.
+static ByteTables make_tables(bool fips) {
+    ByteTables t;
+    for (int x = 0; x < 256; ++x) {
+        uint8_t inv = 0;
+        if (x)
+            for (int y = 1; y < 256; ++y)
+                if (gf_mul((uint8_t)x, (uint8_t)y) == 1) { inv = (uint8_t)y; break; }
+        uint8_t s = inv;
+        for (int i = 1; i <= 4; ++i) s ^= (uint8_t)((inv << i) | (inv >> (8 - i)));
+        t.sbox[x] = s ^ 0x63;
+        t.mul2[x] = gf_xtime((uint8_t)x);
+        t.mul3[x] = gf_xtime((uint8_t)x) ^ (uint8_t)x;
+    }
+    if (!fips) t.sbox[255] = 23;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// circuit shapes
+// ---------------------------------------------------------------------------------------------
+enum Kind { KIND_AES = 0, KIND_KEYSCHED = 1 };
+enum ErrorCode {
+    ORC_OK = 0,
+    ORC_ERR_ARG = 1,
+    ORC_ERR_CAPACITY = 2,         // aes128.rs:160-162 panic!("AES calls too many...")
+    ORC_ERR_NOT_ENOUGH_ROWS = 3,  // [UPSTREAM] Error::NotEnoughRowsAvailable
+    ORC_ERR_KEYS_NOT_SCHEDULED = 4,  // aes128.rs:170 expect("Keys should be scheduled")
+    ORC_ERR_LOOKUP_INPUT_NOT_IN_TABLE = 5,  // [UPSTREAM] Error::ConstraintSystemFailure
+    ORC_ERR_FROM_BYTES = 6,                 // utils.rs:18 from_bytes(..).unwrap()
+};
+
+struct OrcError : std::runtime_error {
+    int code;
+    OrcError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+struct Shape {
+    int kind, k, N;
+    size_t n() const { return (size_t)1 << k; }
+    size_t usable() const { return n() - 6; }  // blinding_factors()=5, +1  [UPSTREAM]
+    int n_sets() const { return kind == KIND_AES ? N : 1; }
+    int n_advice() const { return 3 * n_sets() + 1; }
+    int n_fixed() const { return 5; }  // 4 table columns + round_constants
+    int n_complex_sel() const { return kind == KIND_AES ? 5 * N : 3; }
+    int n_selectors() const { return n_complex_sel() + 1; }  // + q_eq_rcon
+    int n_lookups() const { return n_complex_sel(); }
+    // selector/lookup index of op t (0 range,1 xor,2 sbox,3 mul2,4 mul3) in column set i:
+    //   aes128.rs:63-115 allocates them per set in this order; the key-schedule test/bench
+    //   circuit (key_schedule.rs:267-283, benches/key_schedule.rs:47-58) only has the first 3.
+    int sel(int set, int t) const { return kind == KIND_AES ? 5 * set + t : t; }
+    int sel_rcon() const { return n_complex_sel(); }
+    int words_column() const { return 3 * n_sets(); }  // key_schedule.rs:48, allocated last
+    int rc_column() const { return 4; }                // key_schedule.rs:49, after 4 table cols
+};
+
+struct AssignedCell {
+    int column;  // advice column index
+    size_t row;
+    Fr value;
+    bool known;  // false during the shape pass (Value::unknown())
+};
+
+struct Copy {
+    uint32_t col_a;  // advice column index (all copies on this path are advice<->advice)
+    uint64_t row_a;
+    uint32_t col_b;
+    uint64_t row_b;
+};
+
+class Synth;
+
+// One region as seen by an assignment closure.  [UPSTREAM] RegionShape (shape pass) and
+// SingleChipLayouterRegion (assignment pass).
+class Region {
+  public:
+    Synth *s;
+    bool shape_pass;
+    size_t start = 0;
+    std::vector<int> cols;  // RegionColumn ids touched (shape pass)
+    size_t row_count = 0;
+
+    void touch(int region_col, size_t offset);
+    void enable_selector(int sel, size_t offset);
+    AssignedCell assign_advice(int col, size_t offset, const std::function<Fr()> &to);
+    void assign_fixed(int col, size_t offset, const std::function<Fr()> &to);
+    AssignedCell copy_advice(const AssignedCell &src, int col, size_t offset);
+};
+
+class Synth {
+  public:
+    Shape sh;
+    ByteTables tb;
+    size_t n, usable;
+    std::vector<std::vector<Fr>> advice, fixed;
+    std::vector<std::vector<uint8_t>> selectors;
+    std::vector<Copy> copies;
+    std::vector<size_t> next_free;  // per RegionColumn: advice | fixed | selector
+    bool record_copies = true;
+    uint64_t n_regions = 0;
+
+    Synth(const Shape &shape, bool fips) : sh(shape), tb(make_tables(fips)) {
+        n = sh.n();
+        usable = sh.usable();
+        advice.assign(sh.n_advice(), std::vector<Fr>(n, FR_ZERO));
+        fixed.assign(sh.n_fixed(), std::vector<Fr>(n, FR_ZERO));
+        selectors.assign(sh.n_selectors(), std::vector<uint8_t>(n, 0));
+        next_free.assign(sh.n_advice() + sh.n_fixed() + sh.n_selectors(), 0);
+    }
+    int rc_advice(int c) const { return c; }
+    int rc_fixed(int c) const { return sh.n_advice() + c; }
+    int rc_selector(int c) const { return sh.n_advice() + sh.n_fixed() + c; }
+
+    void check_row(size_t row) const {
+        if (row >= usable)
+            throw OrcError(ORC_ERR_NOT_ENOUGH_ROWS, "row outside usable rows");
+    }
+
+    // [UPSTREAM] SingleChipLayouter::assign_region: run the closure on a RegionShape, place the
+    // region at the max next-free row of the columns it touched, then run it again for real.
+    template <class F>
+    auto assign_region(F &&f) -> decltype(f(std::declval<Region &>())) {
+        Region shape;
+        shape.s = this;
+        shape.shape_pass = true;
+        f(shape);
+        size_t region_start = 0;
+        for (int c : shape.cols) region_start = std::max(region_start, next_free[c]);
+        for (int c : shape.cols) next_free[c] = region_start + shape.row_count;
+        Region real;
+        real.s = this;
+        real.shape_pass = false;
+        real.start = region_start;
+        ++n_regions;
+        return f(real);
+    }
+};
+
+void Region::touch(int region_col, size_t offset) {
+    if (shape_pass) {
+        if (std::find(cols.begin(), cols.end(), region_col) == cols.end())
+            cols.push_back(region_col);
+        row_count = std::max(row_count, offset + 1);
+    }
+}
+void Region::enable_selector(int sel, size_t offset) {
+    if (shape_pass) return touch(s->rc_selector(sel), offset);
+    s->check_row(start + offset);
+    s->selectors[sel][start + offset] = 1;
+}
+AssignedCell Region::assign_advice(int col, size_t offset, const std::function<Fr()> &to) {
+    if (shape_pass) {
+        touch(s->rc_advice(col), offset);
+        return AssignedCell{col, offset, FR_ZERO, false};
+    }
+    s->check_row(start + offset);
+    Fr v = to();
+    s->advice[col][start + offset] = v;
+    return AssignedCell{col, start + offset, v, true};
+}
+void Region::assign_fixed(int col, size_t offset, const std::function<Fr()> &to) {
+    if (shape_pass) return touch(s->rc_fixed(col), offset);
+    s->check_row(start + offset);
+    s->fixed[col][start + offset] = to();
+}
+// [UPSTREAM] AssignedCell::copy_advice = assign_advice(value) + region.constrain_equal(cells).
+// constrain_equal does not affect the region shape.
+AssignedCell Region::copy_advice(const AssignedCell &src, int col, size_t offset) {
+    AssignedCell c = assign_advice(col, offset, [&] { return src.value; });
+    if (!shape_pass && s->record_copies)
+        s->copies.push_back(Copy{(uint32_t)c.column, c.row, (uint32_t)src.column, src.row});
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// byte helpers (src/utils.rs)
+// ---------------------------------------------------------------------------------------------
+// utils.rs:8-19: XOR all 32 canonical bytes, then Fp::from_bytes(..).unwrap().
+static Fr xor_bytes(const Fr &x, const Fr &y) {
+    uint64_t a[4], b[4], c[4];
+    fr_to_canonical(x, a);
+    fr_to_canonical(y, b);
+    for (int i = 0; i < 4; ++i) c[i] = a[i] ^ b[i];
+    Fr out;
+    if (!fr_from_canonical(c, &out)) throw OrcError(ORC_ERR_FROM_BYTES, "from_bytes None");
+    return out;
+}
+static uint8_t first_byte(const Fr &x) {  // `*v.to_bytes().first().unwrap()`
+    uint64_t a[4];
+    fr_to_canonical(x, a);
+    return (uint8_t)(a[0] & 0xff);
+}
+// utils.rs:22-24
+static Fr sub_byte(const ByteTables &tb, const Fr &x) { return fr_from_u64(tb.sbox[first_byte(x)]); }
+
+// ---------------------------------------------------------------------------------------------
+// chips (src/chips/*.rs) — each call is one 1-row region
+// ---------------------------------------------------------------------------------------------
+struct ChipCols {
+    int a0, a1, a2;  // advices[set][0..3]
+    int q_range, q_xor, q_sbox, q_mul2, q_mul3;
+};
+
+// u8_xor_chip.rs:63-100
+static AssignedCell chip_xor(Synth &s, const ChipCols &c, const AssignedCell &x,
+                             const AssignedCell &y) {
+    return s.assign_region([&](Region &r) {
+        r.enable_selector(c.q_xor, 0);
+        AssignedCell xc = r.copy_advice(x, c.a0, 0);
+        AssignedCell yc = r.copy_advice(y, c.a1, 0);
+        return r.assign_advice(c.a2, 0, [&] { return xor_bytes(xc.value, yc.value); });
+    });
+}
+// sbox_chip.rs:57-83
+static AssignedCell chip_sbox(Synth &s, const ChipCols &c, const AssignedCell &x) {
+    return s.assign_region([&](Region &r) {
+        r.enable_selector(c.q_sbox, 0);
+        AssignedCell xc = r.copy_advice(x, c.a0, 0);
+        return r.assign_advice(c.a1, 0, [&] { return sub_byte(s.tb, xc.value); });
+    });
+}
+// gf_mul_chip.rs:59-89 (macro instantiated for MUL_BY_2 / MUL_BY_3)
+static AssignedCell chip_mul(Synth &s, const ChipCols &c, int which, const AssignedCell &x) {
+    return s.assign_region([&](Region &r) {
+        r.enable_selector(which == 2 ? c.q_mul2 : c.q_mul3, 0);
+        r.copy_advice(x, c.a0, 0);
+        return r.assign_advice(c.a1, 0, [&] {
+            const uint8_t *dict = which == 2 ? s.tb.mul2 : s.tb.mul3;
+            return fr_from_u64(dict[first_byte(x.value)]);
+        });
+    });
+}
+// u8_range_check_chip.rs:51-70
+static void chip_range(Synth &s, const ChipCols &c, const AssignedCell &x) {
+    s.assign_region([&](Region &r) {
+        r.enable_selector(c.q_range, 0);
+        r.copy_advice(x, c.a0, 0);
+        return 0;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// table (src/table.rs:18-192) + [UPSTREAM] SimpleTableLayouter default/fill_from_row
+// ---------------------------------------------------------------------------------------------
+static void load_enc_full_table(Synth &s) {
+    auto &T = s.fixed;  // table columns are fixed columns 0..3
+    size_t first_unused = 256 + 256 + 65536 + 256 + 256 + 1;
+    if (first_unused > s.usable) throw OrcError(ORC_ERR_NOT_ENOUGH_ROWS, "table needs k>=17");
+    auto put = [&](size_t pos, uint64_t t0, uint64_t t1, uint64_t t2, uint64_t t3) {
+        T[0][pos] = fr_from_u64(t0);
+        T[1][pos] = fr_from_u64(t1);
+        T[2][pos] = fr_from_u64(t2);
+        T[3][pos] = fr_from_u64(t3);
+    };
+    size_t offset = 0;
+    for (int i = 0; i < 256; ++i) put(offset + i, TAG_U8, i, 0, 0);  // :23-50
+    offset += 256;
+    for (int i = 0; i < 256; ++i) put(offset + i, TAG_SBOX, i, s.tb.sbox[i], 0);  // :53-81
+    offset += 256;
+    size_t l = offset;
+    for (int i = 0; i < 256; ++i)
+        for (int j = 0; j < 256; ++j) put(l++, TAG_XOR, i, j, i ^ j);  // :84-115
+    offset += 65536;
+    for (int i = 0; i < 256; ++i) put(offset + i, TAG_GFMUL2, i, s.tb.mul2[i], 0);  // :118-145
+    offset += 256;
+    for (int i = 0; i < 256; ++i) put(offset + i, TAG_GFMUL3, i, s.tb.mul3[i], 0);  // :148-175
+    offset += 256;
+    put(offset, 0, 0, 0, 0);  // :178-188 "assign zero row"
+    // [UPSTREAM] every table column is padded over the remaining usable rows with the value
+    // assigned at offset 0 of that column.
+    for (int c = 0; c < 4; ++c) {
+        Fr def = T[c][0];
+        for (size_t row = first_unused; row < s.usable; ++row) T[c][row] = def;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// key schedule (src/key_schedule.rs)
+// ---------------------------------------------------------------------------------------------
+typedef std::vector<AssignedCell> Cells;
+
+static Cells ks_assign_first_round(Synth &s, const uint8_t key[16]) {  // :98-118
+    int w = s.sh.words_column();
+    return s.assign_region([&](Region &r) {
+        Cells words;
+        for (int i = 0; i < 16; ++i)
+            words.push_back(r.assign_advice(w, i, [&] { return fr_from_u64(key[i]); }));
+        return words;
+    });
+}
+
+static Cells ks_assign_round(Synth &s, const ChipCols &c, int round, const Cells &prev) {  // :122-224
+    int w = s.sh.words_column();
+    Cells words;
+    Cells shifted = s.assign_region([&](Region &r) {  // :138-154
+        static const int order[4] = {13, 14, 15, 12};
+        Cells out;
+        for (int i = 0; i < 4; ++i) out.push_back(r.copy_advice(prev[order[i]], w, i));
+        return out;
+    });
+    Cells subbed;
+    for (auto &b : shifted) subbed.push_back(chip_sbox(s, c, b));  // :156-159
+    Fr rc = fr_from_u64(ROUND_CONSTANT[round - 1]);                // :161, utils.rs:31-33
+    Cells rc_assigned = s.assign_region([&](Region &r) {           // :162-188
+        Cells res;
+        r.enable_selector(s.sh.sel_rcon(), 0);
+        r.assign_fixed(s.sh.rc_column(), 0, [&] { return rc; });
+        res.push_back(r.assign_advice(w, 0, [&] { return rc; }));
+        for (int i = 0; i < 3; ++i)
+            res.push_back(r.assign_advice(w, i + 1, [&] { return fr_from_u64(0); }));
+        return res;
+    });
+    Cells rconned;
+    for (int i = 0; i < 4; ++i) rconned.push_back(chip_xor(s, c, subbed[i], rc_assigned[i]));  // :190-194
+    Cells next_word;
+    for (int i = 0; i < 4; ++i) next_word.push_back(chip_xor(s, c, prev[i], rconned[i]));  // :197-202
+    words.insert(words.end(), next_word.begin(), next_word.end());
+    for (int i = 1; i < 4; ++i) {  // :207-216
+        Cells nw;
+        for (int j = 0; j < 4; ++j) nw.push_back(chip_xor(s, c, prev[4 * i + j], next_word[j]));
+        next_word = nw;
+        words.insert(words.end(), next_word.begin(), next_word.end());
+    }
+    for (auto &b : words) chip_range(s, c, b);  // :218-221
+    return words;
+}
+
+static std::vector<Cells> schedule_keys(Synth &s, const ChipCols &c, const uint8_t key[16]) {  // :80-96
+    std::vector<Cells> words;
+    Cells round = ks_assign_first_round(s, key);
+    words.push_back(round);
+    for (int i = 1; i <= 10; ++i) {
+        round = ks_assign_round(s, c, i, round);
+        words.push_back(round);
+    }
+    return words;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FixedAes128Config (src/aes128.rs)
+// ---------------------------------------------------------------------------------------------
+struct AesConfig {
+    Synth *s;
+    bool have_keys = false;
+    std::vector<Cells> keys;
+    size_t current = 0;  // :36-39
+    uint64_t count = 0;  // :41-42
+
+    ChipCols cols(size_t set) const {
+        const Shape &sh = s->sh;
+        int i = (int)set;
+        return ChipCols{3 * i, 3 * i + 1, 3 * i + 2, sh.sel(i, 0), sh.sel(i, 1),
+                        sh.sel(i, 2), sh.sel(i, 3), sh.sel(i, 4)};
+    }
+
+    void schedule_key(const uint8_t key[16]) {  // :143-152; key schedule uses set 0 (:118-124)
+        keys = schedule_keys(*s, cols(0), key);
+        have_keys = true;
+    }
+
+    bool aes_callable() {  // :303-325
+        uint64_t max_row = (uint64_t)1 << s->sh.k;
+        if (current == 0) max_row -= KEY_SCHEDULE_ROWS;
+        if (max_row >= count * AES_ROWS + AES_ROWS) return true;
+        if (current < (size_t)s->sh.N - 1) {
+            current += 1;
+            count = 0;
+            return true;
+        }
+        return false;
+    }
+
+    AssignedCell lcon(const Cells &word, const int coeffs[4]) {  // :268-301
+        ChipCols c = cols(current);
+        Cells tmp;
+        for (int t = 0; t < 4; ++t) {
+            switch (coeffs[t]) {
+            case 1:
+                tmp.push_back(s->assign_region(
+                    [&](Region &r) { return r.copy_advice(word[t], c.a0, 0); }));
+                break;
+            case 2: tmp.push_back(chip_mul(*s, c, 2, word[t])); break;
+            case 3: tmp.push_back(chip_mul(*s, c, 3, word[t])); break;
+            default: throw OrcError(ORC_ERR_ARG, "col should be 1, 2, or 3.");
+            }
+        }
+        AssignedCell inter_1 = chip_xor(*s, c, tmp[0], tmp[1]);
+        AssignedCell inter_2 = chip_xor(*s, c, tmp[2], tmp[3]);
+        return chip_xor(*s, c, inter_1, inter_2);
+    }
+
+    Cells encrypt(const uint8_t plaintext[16]) {  // :154-265
+        if (!aes_callable())
+            throw OrcError(ORC_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+        count += 1;
+        if (!have_keys) throw OrcError(ORC_ERR_KEYS_NOT_SCHEDULED, "Keys should be scheduled");
+        ChipCols c = cols(current);
+        Cells assigned_plaintext = s->assign_region([&](Region &r) {  // :176-192
+            Cells out;
+            for (int i = 0; i < 16; ++i)
+                out.push_back(r.assign_advice(c.a0, i, [&] { return fr_from_u64(plaintext[i]); }));
+            return out;
+        });
+        Cells prev_round;
+        for (int i = 0; i < 16; ++i)
+            prev_round.push_back(chip_xor(*s, c, assigned_plaintext[i], keys[0][i]));  // :194-198
+        static const int matrix[4][4] = {{2, 3, 1, 1}, {1, 2, 3, 1}, {1, 1, 2, 3}, {3, 1, 1, 2}};
+        for (int no_round = 1; no_round < 11; ++no_round) {  // :201-262
+            Cells subbed_flat;
+            for (auto &b : prev_round) subbed_flat.push_back(chip_sbox(*s, c, b));  // :203-209
+            std::vector<Cells> shifted(4);  // :216-223
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) shifted[i].push_back(subbed_flat[4 * ((i + j) % 4) + j]);
+            std::vector<Cells> mixed;
+            if (no_round == 10) {
+                mixed = shifted;
+            } else {
+                for (auto &word : shifted) {  // :239-248
+                    Cells out;
+                    for (int col = 0; col < 4; ++col) out.push_back(lcon(word, matrix[col]));
+                    mixed.push_back(out);
+                }
+            }
+            Cells next;
+            for (int i = 0; i < 4; ++i)  // :250-261
+                for (int j = 0; j < 4; ++j)
+                    next.push_back(chip_xor(*s, c, mixed[i][j], keys[no_round][i * 4 + j]));
+            prev_round = next;
+        }
+        return prev_round;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// lookup arguments configured on this path, in `meta.lookup` order
+// ---------------------------------------------------------------------------------------------
+struct LookupDef {
+    int selector;   // complex selector index q
+    uint64_t tag;   // q * Fp::from(Tag)
+    int m;          // number of (input, table) pairs
+    int adv[3];     // advice columns of x, y, z (m-1 of them used)
+};
+
+static LookupDef lookup_def(const Shape &sh, int idx) {
+    int set = sh.kind == KIND_AES ? idx / 5 : 0;
+    int t = sh.kind == KIND_AES ? idx % 5 : idx;
+    LookupDef d;
+    d.selector = sh.sel(set, t);
+    d.adv[0] = 3 * set;
+    d.adv[1] = 3 * set + 1;
+    d.adv[2] = 3 * set + 2;
+    switch (t) {
+    case 0: d.tag = TAG_U8; d.m = 2; break;      // u8_range_check_chip.rs:35-43
+    case 1: d.tag = TAG_XOR; d.m = 4; break;     // u8_xor_chip.rs:41-53
+    case 2: d.tag = TAG_SBOX; d.m = 3; break;    // sbox_chip.rs:38-48
+    case 3: d.tag = TAG_GFMUL2; d.m = 3; break;  // gf_mul_chip.rs:40-50
+    default: d.tag = TAG_GFMUL3; d.m = 3; break;
+    }
+    return d;
+}
+
+struct Columns {  // a view over n-row columns, owned by a Synth or supplied by the caller
+    Shape sh;
+    std::vector<const Fr *> advice, fixed;
+    std::vector<const uint8_t *> selectors;
+};
+
+static Columns view_of(const Synth &s) {
+    Columns c;
+    c.sh = s.sh;
+    for (auto &v : s.advice) c.advice.push_back(v.data());
+    for (auto &v : s.fixed) c.fixed.push_back(v.data());
+    for (auto &v : s.selectors) c.selectors.push_back(v.data());
+    return c;
+}
+
+// canonical (non-Montgomery) value as a sortable key: [UPSTREAM] `Ord for Fr`
+struct Key {
+    uint64_t c[4];
+    bool operator<(const Key &o) const {
+        for (int i = 3; i >= 0; --i) {
+            if (c[i] != o.c[i]) return c[i] < o.c[i];
+        }
+        return false;
+    }
+    bool operator==(const Key &o) const { return !memcmp(c, o.c, 32); }
+};
+static Key key_of(const Fr &a) {
+    Key k;
+    fr_to_canonical(a, k.c);
+    return k;
+}
+static Fr fr_of(const Key &k) {
+    Fr a = {{k.c[0], k.c[1], k.c[2], k.c[3]}};
+    return fr_mul(a, FR_R2);
+}
+
+// [UPSTREAM] plonk/lookup/prover.rs Argument::commit_permuted (compress_expressions) :
+//   compressed = fold(expressions, 0, |acc, e| acc * theta + e)  over all n rows.
+// Input expressions here are q*tag, q*x[, q*y[, q*z]] with q the selector's 0/1 fixed column.
+static void compress_lookup(const Columns &c, const LookupDef &d, const Fr &theta,
+                            std::vector<Fr> &A, std::vector<Fr> &S) {
+    size_t n = c.sh.n();
+    A.assign(n, FR_ZERO);
+    S.assign(n, FR_ZERO);
+    Fr tag = fr_from_u64(d.tag);
+    for (size_t row = 0; row < n; ++row) {
+        Fr q = c.selectors[d.selector][row] ? FR_ONE : FR_ZERO;
+        Fr acc = fr_mul(q, tag);  // Expression::Scaled(q, tag); first fold step: 0*theta + e0
+        Fr tacc = c.fixed[0][row];
+        for (int j = 0; j + 1 < d.m; ++j) {
+            Fr e = fr_mul(q, c.advice[d.adv[j]][row]);  // Expression::Product(q, advice)
+            acc = fr_add(fr_mul(acc, theta), e);
+            tacc = fr_add(fr_mul(tacc, theta), c.fixed[1 + j][row]);
+        }
+        A[row] = acc;
+        S[row] = tacc;
+    }
+}
+
+// [UPSTREAM] plonk/lookup/prover.rs permute_expression_pair.  Rows >= usable (blinding rows,
+// random in halo2) are left zero here.
+static int permute_expression_pair(const Shape &sh, const std::vector<Fr> &A,
+                                   const std::vector<Fr> &S, std::vector<Fr> &Ap,
+                                   std::vector<Fr> &Sp) {
+    size_t n = sh.n(), usable = sh.usable();
+    std::vector<Key> in(usable);
+    for (size_t i = 0; i < usable; ++i) in[i] = key_of(A[i]);
+    std::sort(in.begin(), in.end());  // permuted_input_expression.sort()
+    std::map<Key, uint32_t> leftover;  // BTreeMap<Scalar, u32>
+    for (size_t i = 0; i < usable; ++i) leftover[key_of(S[i])] += 1;
+    std::vector<Key> tab(usable);
+    std::vector<uint8_t> filled(usable, 0);
+    std::vector<size_t> repeated;
+    for (size_t row = 0; row < usable; ++row) {
+        if (row == 0 || !(in[row] == in[row - 1])) {
+            tab[row] = in[row];
+            filled[row] = 1;
+            auto it = leftover.find(in[row]);
+            if (it == leftover.end() || it->second == 0) return ORC_ERR_LOOKUP_INPUT_NOT_IN_TABLE;
+            it->second -= 1;
+        } else {
+            repeated.push_back(row);
+        }
+    }
+    // "Populate permuted table at unfilled rows with leftover table elements": BTreeMap iterated
+    // ascending, rows popped from the END of repeated_input_rows.
+    for (auto &kv : leftover)
+        for (uint32_t t = 0; t < kv.second; ++t) {
+            tab[repeated.back()] = kv.first;
+            repeated.pop_back();
+        }
+    if (!repeated.empty()) return ORC_ERR_ARG;
+    Ap.assign(n, FR_ZERO);
+    Sp.assign(n, FR_ZERO);
+    for (size_t i = 0; i < usable; ++i) {
+        Ap[i] = fr_of(in[i]);
+        Sp[i] = fr_of(tab[i]);
+    }
+    return ORC_OK;
+}
+
+// [UPSTREAM] plonk/lookup/prover.rs Permuted::commit_product.  z has n-5 deterministic entries
+// (z[0]=1 ... z[n-6]); the 5 blinding entries are left zero here.
+static void commit_product(const Shape &sh, const std::vector<Fr> &A, const std::vector<Fr> &S,
+                           const std::vector<Fr> &Ap, const std::vector<Fr> &Sp, const Fr &beta,
+                           const Fr &gamma, std::vector<Fr> &Z) {
+    size_t n = sh.n();
+    std::vector<Fr> prod(n);
+    for (size_t i = 0; i < n; ++i) prod[i] = fr_mul(fr_add(beta, Ap[i]), fr_add(gamma, Sp[i]));
+    fr_batch_invert(prod);
+    for (size_t i = 0; i < n; ++i) {
+        prod[i] = fr_mul(prod[i], fr_add(A[i], beta));
+        prod[i] = fr_mul(prod[i], fr_add(S[i], gamma));
+    }
+    Z.assign(n, FR_ZERO);
+    Fr state = FR_ONE;
+    Z[0] = state;
+    for (size_t i = 1; i < n - 5; ++i) {
+        state = fr_mul(state, prod[i - 1]);
+        Z[i] = state;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// [UPSTREAM] MockProver::verify restated for this constraint system.
+// Returns 0 when satisfied; otherwise a failure class (100 gate, 200 lookup, 300 copy,
+// 400 assignment in unusable rows) and fills `where` with (index,row).
+// ---------------------------------------------------------------------------------------------
+static int mock_verify(const Columns &c, const Copy *copies, size_t n_copies, uint64_t where[2]) {
+    const Shape &sh = c.sh;
+    size_t n = sh.n(), usable = sh.usable();
+    where[0] = where[1] = 0;
+    // (iv) nothing may be assigned outside the usable rows
+    for (size_t row = usable; row < n; ++row) {
+        for (size_t a = 0; a < c.advice.size(); ++a)
+            if (!fr_is_zero(c.advice[a][row])) { where[0] = a; where[1] = row; return 400; }
+        for (size_t f = 0; f < c.fixed.size(); ++f)
+            if (!fr_is_zero(c.fixed[f][row])) { where[0] = f; where[1] = row; return 401; }
+        for (size_t q = 0; q < c.selectors.size(); ++q)
+            if (c.selectors[q][row]) { where[0] = q; where[1] = row; return 402; }
+    }
+    // (i) gate "Equality RC": q_eq_rcon * (words - round_constants) = 0  (key_schedule.rs:59-64)
+    for (size_t row = 0; row < usable; ++row) {
+        if (!c.selectors[sh.sel_rcon()][row]) continue;
+        if (c.advice[sh.words_column()][row] != c.fixed[sh.rc_column()][row]) {
+            where[0] = 0; where[1] = row; return 100;
+        }
+    }
+    // (ii) lookups: every usable row's input tuple must be a row of the table tuple set
+    for (int li = 0; li < sh.n_lookups(); ++li) {
+        LookupDef d = lookup_def(sh, li);
+        std::vector<std::array<Key, 4>> table(usable);
+        for (size_t row = 0; row < usable; ++row)
+            for (int j = 0; j < 4; ++j)
+                table[row][j] = j < d.m ? key_of(c.fixed[j][row]) : Key{{0, 0, 0, 0}};
+        std::sort(table.begin(), table.end());
+        table.erase(std::unique(table.begin(), table.end()), table.end());
+        Key tagk = key_of(fr_from_u64(d.tag));
+        std::array<Key, 4> zero_t{};
+        bool zero_ok = std::binary_search(table.begin(), table.end(), zero_t);
+        for (size_t row = 0; row < usable; ++row) {
+            if (!c.selectors[d.selector][row]) {
+                if (!zero_ok) { where[0] = li; where[1] = row; return 200; }
+                continue;
+            }
+            std::array<Key, 4> t{};
+            t[0] = tagk;
+            for (int j = 0; j + 1 < d.m; ++j) t[1 + j] = key_of(c.advice[d.adv[j]][row]);
+            if (!std::binary_search(table.begin(), table.end(), t)) {
+                where[0] = li; where[1] = row; return 200;
+            }
+        }
+    }
+    // (iii) every copy constraint holds
+    for (size_t i = 0; i < n_copies; ++i) {
+        const Copy &cp = copies[i];
+        if (cp.col_a >= c.advice.size() || cp.col_b >= c.advice.size() || cp.row_a >= usable ||
+            cp.row_b >= usable) { where[0] = i; where[1] = cp.row_a; return 301; }
+        if (c.advice[cp.col_a][cp.row_a] != c.advice[cp.col_b][cp.row_b]) {
+            where[0] = i; where[1] = cp.row_a; return 300;
+        }
+    }
+    return 0;
+}
+
+struct Circuit {
+    Synth s;
+    AesConfig cfg;
+    std::vector<uint8_t> ciphertexts;
+    uint8_t round_keys[176];
+    Circuit(const Shape &sh, bool fips) : s(sh, fips) { cfg.s = &s; }
+};
+
+// The `synthesize` bodies: aes128.rs:389-402 / main.rs:42-54 / benches/aes128.rs:44-56 (AES) and
+// key_schedule.rs:296-315 / benches/key_schedule.rs:72-84 (key schedule only).
+static void synthesize(Circuit &c, const uint8_t key[16], const uint8_t *pts, uint64_t n_blocks) {
+    load_enc_full_table(c.s);
+    if (c.s.sh.kind == KIND_KEYSCHED) {
+        AesConfig &cfg = c.cfg;
+        cfg.keys = schedule_keys(c.s, cfg.cols(0), key);
+        cfg.have_keys = true;
+    } else {
+        c.cfg.schedule_key(key);
+    }
+    for (int r = 0; r < 11; ++r)
+        for (int i = 0; i < 16; ++i) c.round_keys[16 * r + i] = first_byte(c.cfg.keys[r][i].value);
+    c.ciphertexts.resize(16 * n_blocks);
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        Cells ct = c.cfg.encrypt(pts + 16 * b);
+        for (int i = 0; i < 16; ++i) c.ciphertexts[16 * b + i] = first_byte(ct[i].value);
+    }
+}
+
+}  // namespace orc
+
+// ---------------------------------------------------------------------------------------------
+// C interface for ctypes (tests/, bench.py cpu legs)
+// ---------------------------------------------------------------------------------------------
+using namespace orc;
+
+static Fr fr_load(const uint64_t *p) { return Fr{{p[0], p[1], p[2], p[3]}}; }
+
+extern "C" {
+
+int orc_shape(int kind, int k, int N, int32_t out[5]) {
+    if (k < 1 || k > 28 || N < 1 || (kind != KIND_AES && kind != KIND_KEYSCHED)) return ORC_ERR_ARG;
+    Shape sh{kind, k, N};
+    out[0] = sh.n_advice();
+    out[1] = sh.n_fixed();
+    out[2] = sh.n_selectors();
+    out[3] = sh.n_lookups();
+    out[4] = sh.n_sets();
+    return ORC_OK;
+}
+
+void *orc_new(int kind, int k, int N, int fips_sbox) {
+    if (k < 4 || k > 26 || N < 1 || (kind != KIND_AES && kind != KIND_KEYSCHED)) return nullptr;
+    try {
+        return new Circuit(Shape{kind, k, N}, fips_sbox != 0);
+    } catch (...) { return nullptr; }
+}
+void orc_free(void *h) { delete (Circuit *)h; }
+
+void orc_set_record_copies(void *h, int on) { ((Circuit *)h)->s.record_copies = on != 0; }
+
+int orc_synthesize(void *h, const uint8_t *key, const uint8_t *pts, uint64_t n_blocks) {
+    Circuit *c = (Circuit *)h;
+    try {
+        synthesize(*c, key, pts, n_blocks);
+    } catch (const OrcError &e) { return e.code; }
+    return ORC_OK;
+}
+
+uint64_t orc_num_regions(void *h) { return ((Circuit *)h)->s.n_regions; }
+uint64_t orc_num_copies(void *h) { return ((Circuit *)h)->s.copies.size(); }
+int orc_get_copies(void *h, uint64_t *out) {  // 4 u64 per copy: col_a,row_a,col_b,row_b
+    Circuit *c = (Circuit *)h;
+    for (size_t i = 0; i < c->s.copies.size(); ++i) {
+        out[4 * i] = c->s.copies[i].col_a;
+        out[4 * i + 1] = c->s.copies[i].row_a;
+        out[4 * i + 2] = c->s.copies[i].col_b;
+        out[4 * i + 3] = c->s.copies[i].row_b;
+    }
+    return ORC_OK;
+}
+int orc_get_advice(void *h, int col, uint64_t *out) {
+    Circuit *c = (Circuit *)h;
+    if (col < 0 || col >= (int)c->s.advice.size()) return ORC_ERR_ARG;
+    memcpy(out, c->s.advice[col].data(), c->s.n * 32);
+    return ORC_OK;
+}
+int orc_get_fixed(void *h, int col, uint64_t *out) {
+    Circuit *c = (Circuit *)h;
+    if (col < 0 || col >= (int)c->s.fixed.size()) return ORC_ERR_ARG;
+    memcpy(out, c->s.fixed[col].data(), c->s.n * 32);
+    return ORC_OK;
+}
+int orc_get_selector(void *h, int sel, uint8_t *out) {
+    Circuit *c = (Circuit *)h;
+    if (sel < 0 || sel >= (int)c->s.selectors.size()) return ORC_ERR_ARG;
+    memcpy(out, c->s.selectors[sel].data(), c->s.n);
+    return ORC_OK;
+}
+int orc_get_ciphertexts(void *h, uint8_t *out) {
+    Circuit *c = (Circuit *)h;
+    memcpy(out, c->ciphertexts.data(), c->ciphertexts.size());
+    return ORC_OK;
+}
+int orc_get_round_keys(void *h, uint8_t *out) {
+    memcpy(out, ((Circuit *)h)->round_keys, 176);
+    return ORC_OK;
+}
+
+// A, S, A', S', Z for lookup `idx` of the circuit's own columns; any output may be NULL.
+int orc_lookup(void *h, int idx, const uint64_t *theta, const uint64_t *beta,
+               const uint64_t *gamma, uint64_t *A, uint64_t *S, uint64_t *Ap, uint64_t *Sp,
+               uint64_t *Z) {
+    Circuit *c = (Circuit *)h;
+    if (idx < 0 || idx >= c->s.sh.n_lookups()) return ORC_ERR_ARG;
+    Columns cols = view_of(c->s);
+    LookupDef d = lookup_def(c->s.sh, idx);
+    std::vector<Fr> a, s, ap, sp, z;
+    compress_lookup(cols, d, fr_load(theta), a, s);
+    int rc = permute_expression_pair(c->s.sh, a, s, ap, sp);
+    if (rc) return rc;
+    size_t bytes = c->s.n * 32;
+    if (Z) {
+        commit_product(c->s.sh, a, s, ap, sp, fr_load(beta), fr_load(gamma), z);
+        memcpy(Z, z.data(), bytes);
+    }
+    if (A) memcpy(A, a.data(), bytes);
+    if (S) memcpy(S, s.data(), bytes);
+    if (Ap) memcpy(Ap, ap.data(), bytes);
+    if (Sp) memcpy(Sp, sp.data(), bytes);
+    return ORC_OK;
+}
+
+// Restated MockProver on the circuit's own columns.
+int orc_mock_verify(void *h, uint64_t where[2]) {
+    Circuit *c = (Circuit *)h;
+    Columns cols = view_of(c->s);
+    return mock_verify(cols, c->s.copies.data(), c->s.copies.size(), where);
+}
+
+// Restated MockProver on caller-supplied columns (e.g. copied back from the GPU):
+// advice  = n_advice   columns of n Fr, contiguous column-major
+// fixed   = 5          columns of n Fr (4 table columns, round_constants)
+// selectors = n_selectors columns of n bytes (0/1)
+// copies  = 4 u64 per copy constraint
+int orc_mock_verify_ext(int kind, int k, int N, const uint64_t *advice, const uint64_t *fixed,
+                        const uint8_t *selectors, const uint64_t *copies, uint64_t n_copies,
+                        uint64_t where[2]) {
+    Shape sh{kind, k, N};
+    size_t n = sh.n();
+    Columns cols;
+    cols.sh = sh;
+    for (int a = 0; a < sh.n_advice(); ++a) cols.advice.push_back((const Fr *)advice + (size_t)a * n);
+    for (int f = 0; f < sh.n_fixed(); ++f) cols.fixed.push_back((const Fr *)fixed + (size_t)f * n);
+    for (int q = 0; q < sh.n_selectors(); ++q) cols.selectors.push_back(selectors + (size_t)q * n);
+    std::vector<Copy> cp(n_copies);
+    for (size_t i = 0; i < n_copies; ++i)
+        cp[i] = Copy{(uint32_t)copies[4 * i], copies[4 * i + 1], (uint32_t)copies[4 * i + 2],
+                     copies[4 * i + 3]};
+    return mock_verify(cols, cp.data(), cp.size(), where);
+}
+
+// ---- small Fr helpers so Python tests can do field arithmetic through the same code ----------
+void orc_fr_from_u64(uint64_t v, uint64_t out[4]) { Fr a = fr_from_u64(v); memcpy(out, a.l, 32); }
+void orc_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t out[4]) {
+    Fr r = fr_mul(fr_load(a), fr_load(b)); memcpy(out, r.l, 32);
+}
+void orc_fr_add(const uint64_t *a, const uint64_t *b, uint64_t out[4]) {
+    Fr r = fr_add(fr_load(a), fr_load(b)); memcpy(out, r.l, 32);
+}
+void orc_fr_inv(const uint64_t *a, uint64_t out[4]) { Fr r = fr_inv(fr_load(a)); memcpy(out, r.l, 32); }
+void orc_fr_to_canonical(const uint64_t *a, uint64_t out[4]) { fr_to_canonical(fr_load(a), out); }
+int orc_fr_from_canonical(const uint64_t *a, uint64_t out[4]) {
+    Fr r;
+    if (!fr_from_canonical(a, &r)) return ORC_ERR_FROM_BYTES;
+    memcpy(out, r.l, 32);
+    return ORC_OK;
+}
+// utils.rs:8-19 on two Fr values (golden: 5 ^ 12 == 9, utils.rs:41-47)
+int orc_xor_bytes(const uint64_t *x, const uint64_t *y, uint64_t out[4]) {
+    try {
+        Fr r = xor_bytes(fr_load(x), fr_load(y));
+        memcpy(out, r.l, 32);
+    } catch (const OrcError &e) { return e.code; }
+    return ORC_OK;
+}
+void orc_tables(int fips, uint8_t sbox[256], uint8_t mul2[256], uint8_t mul3[256]) {
+    ByteTables t = make_tables(fips != 0);
+    memcpy(sbox, t.sbox, 256);
+    memcpy(mul2, t.mul2, 256);
+    memcpy(mul3, t.mul3, 256);
+}
+
+// ---- CPU baseline: one whole circuit (synthesize + every lookup's A,S,A',S',Z), timed ----------
+// The reference's synthesize is strictly sequential (one thread).  The lookup arguments are
+// independent of one another, so `threads` > 1 runs them in parallel with OpenMP — an upper
+// bound on what halo2's rayon `parallelize` could extract.  times[0] = synthesize seconds,
+// times[1] = lookup seconds.  digest = XOR of all Z[n-6] limbs (forces the work; must be Fr(1)).
+int orc_bench_circuit(int kind, int k, int N, const uint8_t *key, const uint8_t *pts,
+                      uint64_t n_blocks, const uint64_t *theta, const uint64_t *beta,
+                      const uint64_t *gamma, int threads, int n_lookups_to_run, double times[2],
+                      uint64_t digest[4]) {
+    Shape sh{kind, k, N};
+    auto t0 = std::chrono::steady_clock::now();
+    Circuit *c = new Circuit(sh, false);
+    c->s.record_copies = false;  // the proving-time WitnessCollection ignores copy constraints
+    int rc = ORC_OK;
+    try {
+        synthesize(*c, key, pts, n_blocks);
+    } catch (const OrcError &e) { rc = e.code; }
+    auto t1 = std::chrono::steady_clock::now();
+    if (rc) { delete c; return rc; }
+    Columns cols = view_of(c->s);
+    int nl = n_lookups_to_run < 0 ? sh.n_lookups() : std::min(n_lookups_to_run, sh.n_lookups());
+    std::vector<Fr> last(nl, FR_ZERO);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
+    for (int li = 0; li < nl; ++li) {
+        LookupDef d = lookup_def(sh, li);
+        std::vector<Fr> a, s, ap, sp, z;
+        compress_lookup(cols, d, fr_load(theta), a, s);
+        if (permute_expression_pair(sh, a, s, ap, sp)) {
+#pragma omp atomic
+            bad += 1;
+            continue;
+        }
+        commit_product(sh, a, s, ap, sp, fr_load(beta), fr_load(gamma), z);
+        last[li] = z[sh.n() - 6];
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    times[0] = std::chrono::duration<double>(t1 - t0).count();
+    times[1] = std::chrono::duration<double>(t2 - t1).count();
+    digest[0] = digest[1] = digest[2] = digest[3] = 0;
+    for (auto &f : last)
+        for (int i = 0; i < 4; ++i) digest[i] ^= f.l[i];
+    delete c;
+    return bad ? ORC_ERR_LOOKUP_INPUT_NOT_IN_TABLE : ORC_OK;
+}
+
+}  // extern "C"
