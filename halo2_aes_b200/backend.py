@@ -1,0 +1,250 @@
+"""Device-side handles: thin Python objects over the C ABI (include/h2aes.h).
+
+torch is used only for device memory, streams and (in sharded.py) torch.distributed; every
+column is produced by the library's own sm_100a kernels.  Field elements live in int64 tensors
+of shape [..., 4] holding the 4 little-endian u64 Montgomery limbs of bn256 Fr, bit-compatible
+with halo2curves' `Fr` (view them as numpy uint64 on the host).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import KIND_AES, KIND_KEYSCHED, SBOX_REFERENCE, check, lib
+
+
+def _fr_arg(x):
+    """4 u64 Montgomery limbs -> ctypes pointer (keeps the array alive through the return)."""
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64).reshape(4))
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Context:
+    """One per (process, GPU): uploads the S-box and the byte -> Fr(Montgomery) table."""
+
+    def __init__(self, device: int = 0, sbox_mode: int = SBOX_REFERENCE):
+        if not torch.cuda.is_available():
+            raise RuntimeError("halo2_aes_b200 needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        check(lib().h2aes_ctx_create(device, sbox_mode, C.byref(h)))
+        self._h = h
+        self.use_stream(torch.cuda.current_stream(self.device))
+
+    def use_stream(self, stream: "torch.cuda.Stream"):
+        self.stream = stream
+        check(lib().h2aes_ctx_set_stream(self._h, C.c_void_p(stream.cuda_stream)), self._h)
+
+    def synchronize(self):
+        check(lib().h2aes_ctx_synchronize(self._h), self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().h2aes_ctx_kernel_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().h2aes_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Circuit:
+    """One halo2 circuit instance of shape (kind, k, N) resident on the GPU."""
+
+    def __init__(self, ctx: Context, kind: int, k: int, N: int = 1):
+        self.ctx = ctx
+        self.kind, self.k, self.N = kind, k, N
+        self.layout = _ffi.layout_query(kind, k, N)
+        self.n = self.layout["n_rows"]
+        self.n_blocks = 0
+        self.shard, self.n_shards = 0, 1
+        h = C.c_void_p()
+        check(lib().h2aes_circuit_create(ctx._h, kind, k, N, C.byref(h)), ctx._h)
+        self._h = h
+
+    # ---- helpers ----------------------------------------------------------------------------
+    @property
+    def rows(self) -> int:
+        """rows of every column held by this (shard of the) circuit"""
+        return self.n // self.n_shards
+
+    def _cols(self, ncols: int, out=None):
+        if out is None:
+            out = torch.empty((ncols, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
+        assert out.is_cuda and out.is_contiguous() and out.numel() == ncols * self.rows * 4
+        return out
+
+    def set_shard(self, shard: int, n_shards: int):
+        check(lib().h2aes_circuit_set_shard(self._h, shard, n_shards), self.ctx._h)
+        self.shard, self.n_shards = shard, n_shards
+
+    # ---- witness ------------------------------------------------------------------------------
+    def witness(self, key, plaintexts=None, out=None, want_ciphertexts=True):
+        """schedule_key(key) then encrypt(pt) for every 16-byte row of `plaintexts`.
+
+        plaintexts: uint8 CUDA tensor [B,16] (or None).  Returns (advice [n_advice, rows, 4],
+        ciphertexts [B,16] uint8 or None).  Asynchronous on the context's stream.
+        """
+        key_a = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        assert key_a.size == 16
+        B = 0 if plaintexts is None else plaintexts.shape[0]
+        if B:
+            assert plaintexts.is_cuda and plaintexts.dtype == torch.uint8 and plaintexts.is_contiguous()
+        advice = self._cols(self.layout["n_advice"], out)
+        cts = torch.empty((B, 16), dtype=torch.uint8, device=self.ctx.device) \
+            if (want_ciphertexts and B) else None
+        check(lib().h2aes_witness_dev(self._h, key_a.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                      _ptr(plaintexts) if B else None, B, _ptr(advice),
+                                      _ptr(cts)), self.ctx._h)
+        self.n_blocks = B
+        return advice, cts
+
+    def witness_host(self, key, plaintexts: np.ndarray, advice_out: np.ndarray,
+                     ciphertexts_out: np.ndarray | None = None):
+        """Same through the _host entry point: numpy in, numpy out, copies done by the library."""
+        key_a = np.ascontiguousarray(np.frombuffer(bytes(key), dtype=np.uint8))
+        pts = np.ascontiguousarray(plaintexts, dtype=np.uint8).reshape(-1, 16)
+        B = pts.shape[0]
+        assert advice_out.dtype == np.uint64 and advice_out.flags.c_contiguous
+        assert advice_out.size == self.layout["n_advice"] * self.rows * 4
+        check(lib().h2aes_witness_host(
+            self._h, key_a.ctypes.data_as(C.POINTER(C.c_uint8)),
+            C.c_void_p(pts.ctypes.data) if B else None, B, C.c_void_p(advice_out.ctypes.data),
+            C.c_void_p(ciphertexts_out.ctypes.data) if ciphertexts_out is not None else None),
+            self.ctx._h)
+        self.n_blocks = B
+        return advice_out
+
+    def round_keys(self) -> np.ndarray:
+        out = np.zeros(176, np.uint8)
+        check(lib().h2aes_round_keys(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))), self.ctx._h)
+        return out
+
+    # ---- input-independent columns ------------------------------------------------------------
+    def fixed_columns(self, n_blocks=None, want_fixed=True, want_selectors=True):
+        nb = self.n_blocks if n_blocks is None else n_blocks
+        fixed = self._cols(self.layout["n_fixed"]) if want_fixed else None
+        sel = self._cols(self.layout["n_selectors"]) if want_selectors else None
+        check(lib().h2aes_fixed_columns_dev(self._h, nb, _ptr(fixed), _ptr(sel)), self.ctx._h)
+        return fixed, sel
+
+    def copy_constraints(self, n_blocks=None):
+        nb = self.n_blocks if n_blocks is None else n_blocks
+        total = C.c_uint64()
+        check(lib().h2aes_copy_count(self.kind, nb, C.byref(total)))
+        out = torch.empty((total.value, 4), dtype=torch.int64, device=self.ctx.device)
+        check(lib().h2aes_copy_constraints_dev(self._h, nb, _ptr(out)), self.ctx._h)
+        return out
+
+    # ---- lookup helper columns ------------------------------------------------------------------
+    def lookup_permuted(self, theta, first=0, count=None, want_inputs=True, out=None):
+        """A, S, A', S' of lookups [first, first+count): dict of [count, n, 4] tensors."""
+        L = self.layout["n_lookups"]
+        count = L - first if count is None else count
+        names = (["A", "S"] if want_inputs else []) + ["Ap", "Sp"]
+        bufs = out or {}
+        for nm in names:
+            if nm not in bufs:
+                bufs[nm] = torch.empty((count, self.n, 4), dtype=torch.int64, device=self.ctx.device)
+        th, thp = _fr_arg(theta)
+        check(lib().h2aes_lookup_permuted_dev(self._h, thp, first, count, _ptr(bufs.get("A")),
+                                              _ptr(bufs.get("S")), _ptr(bufs["Ap"]),
+                                              _ptr(bufs["Sp"])), self.ctx._h)
+        return bufs
+
+    def lookup_product(self, beta, gamma, first=0, count=None, out=None):
+        L = self.layout["n_lookups"]
+        count = L - first if count is None else count
+        Z = out if out is not None else torch.empty((count, self.n, 4), dtype=torch.int64,
+                                                     device=self.ctx.device)
+        be, bep = _fr_arg(beta)
+        ga, gap = _fr_arg(gamma)
+        check(lib().h2aes_lookup_product_dev(self._h, bep, gap, first, count, _ptr(Z)), self.ctx._h)
+        return Z
+
+    def lookup_check(self):
+        """Synchronize and surface device-detected conditions (ERR_LOOKUP / ERR_ZERO_DENOM)."""
+        check(lib().h2aes_lookup_check(self._h), self.ctx._h)
+
+    # ---- row-sharded phases (see sharded.py for the collective plumbing) -----------------------
+    def shard_hist(self, theta) -> torch.Tensor:
+        th, thp = _fr_arg(theta)
+        p = C.c_void_p()
+        words = C.c_uint64()
+        check(lib().h2aes_lookup_hist_dev(self._h, thp, C.byref(p), C.byref(words)), self.ctx._h)
+        return _wrap_device_u32(p.value, words.value, self.ctx.device)
+
+    def shard_permuted(self, want_inputs=True, want_outputs=True):
+        L = self.layout["n_lookups"]
+        bufs = {}
+        if want_outputs:
+            for nm in (["A", "S"] if want_inputs else []) + ["Ap", "Sp"]:
+                bufs[nm] = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
+        check(lib().h2aes_lookup_permuted_shard_dev(self._h, _ptr(bufs.get("A")), _ptr(bufs.get("S")),
+                                                    _ptr(bufs.get("Ap")), _ptr(bufs.get("Sp"))),
+              self.ctx._h)
+        return bufs
+
+    def shard_partial(self, beta, gamma) -> torch.Tensor:
+        be, bep = _fr_arg(beta)
+        ga, gap = _fr_arg(gamma)
+        p = C.c_void_p()
+        check(lib().h2aes_lookup_partial_dev(self._h, bep, gap, C.byref(p)), self.ctx._h)
+        L = self.layout["n_lookups"]
+        return _wrap_device_i64(p.value, L * 4, self.ctx.device).view(L, 4)
+
+    def shard_product(self, gathered: torch.Tensor):
+        L = self.layout["n_lookups"]
+        assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == self.n_shards * L * 4
+        Z = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
+        check(lib().h2aes_lookup_product_shard_dev(self._h, _ptr(gathered), _ptr(Z)), self.ctx._h)
+        return Z
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().h2aes_circuit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _CudaArray:
+    """Expose library-owned device memory to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3,
+            "strides": None,
+        }
+
+
+def _wrap_device_u32(ptr: int, count: int, device) -> torch.Tensor:
+    # int32 view: sums of row counts stay far below 2^31 (n <= 2^26)
+    return torch.as_tensor(_CudaArray(ptr, count, "<i4"), device=device)
+
+
+def _wrap_device_i64(ptr: int, count: int, device) -> torch.Tensor:
+    return torch.as_tensor(_CudaArray(ptr, count, "<i8"), device=device)
+
+
+def to_host_u64(t: torch.Tensor) -> np.ndarray:
+    """int64 device tensor of limbs -> numpy uint64 array (same bits)."""
+    return t.cpu().numpy().view(np.uint64)

@@ -1,0 +1,827 @@
+// api.cu — the extern "C" boundary declared in include/h2aes.h.
+//
+// Host-side glue only: argument checking with the reference's error behaviour (capacity panic of
+// src/aes128.rs:160-162 -> H2AES_ERR_CAPACITY, encrypt-before-schedule_key of :170 ->
+// H2AES_ERR_NOT_SCHEDULED, halo2's NotEnoughRowsAvailable -> H2AES_ERR_ROWS), device workspace
+// management, and the launch order of the kernels in witness.cu / lookup.cu.  There is no CPU
+// implementation of any column here: without a CUDA device every compute entry point fails.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+namespace h2 {
+cudaError_t launch_build_frtab(h2aes_ctx *ctx);
+cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
+                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev,
+                           uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
+                         uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_copies(h2aes_circuit *c, uint64_t n_copies, uint64_t *out);
+cudaError_t launch_view_bins(h2aes_circuit *c);
+cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_lookup_bins(h2aes_circuit *c);
+cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
+                            uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_inv_tables(h2aes_circuit *c);
+cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
+                                 uint64_t *Z, uint64_t row_begin, uint64_t row_end, int mode);
+cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
+uint64_t grand_product_tiles(uint64_t rows);
+
+// S-box from first principles (GF(2^8) inverse + affine map); H2AES_SBOX_REFERENCE then applies
+// the one deviation src/constant.rs:14 has from FIPS-197 (entry 255 is 23, not 0x16).
+static void make_sbox(int mode, uint8_t sbox[256]) {
+    for (int x = 0; x < 256; ++x) {
+        uint8_t inv = 0;
+        if (x) {
+            for (int y = 1; y < 256; ++y) {
+                uint8_t a = (uint8_t)x, b = (uint8_t)y, p = 0;
+                for (int i = 0; i < 8; ++i) {
+                    if (b & 1) p ^= a;
+                    a = xtime(a);
+                    b >>= 1;
+                }
+                if (p == 1) { inv = (uint8_t)y; break; }
+            }
+        }
+        uint8_t s = inv;
+        for (int i = 1; i <= 4; ++i) s ^= (uint8_t)((inv << i) | (inv >> (8 - i)));
+        sbox[x] = (uint8_t)(s ^ 0x63);
+    }
+    if (mode == H2AES_SBOX_REFERENCE) sbox[255] = 23;
+}
+
+static bool shape_ok(int kind, int k, int N) {
+    if (kind != KIND_AES && kind != KIND_KEYSCHED) return false;
+    if (k < 1 || k > 28) return false;
+    if (kind == KIND_AES && (N < 1 || N > MAX_SETS)) return false;
+    return true;
+}
+static Shape make_shape(int kind, int k, int N) { return Shape{kind, k, kind == KIND_AES ? N : 1}; }
+// halo2: the 66561-row table (and the 6 unusable rows) must fit  [UPSTREAM NotEnoughRowsAvailable]
+static bool rows_ok(const Shape &sh) { return sh.k >= 17; }
+
+static fr_t fr_from_limbs(const uint64_t *p) {
+    fr_t a;
+    for (int i = 0; i < 4; ++i) {
+        a.v[2 * i] = (uint32_t)p[i];
+        a.v[2 * i + 1] = (uint32_t)(p[i] >> 32);
+    }
+    return a;
+}
+static void fr_to_limbs(const fr_t &a, uint64_t *p) {
+    for (int i = 0; i < 4; ++i) p[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+}  // namespace h2
+
+using namespace h2;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static int32_t cuda_fail(h2aes_ctx *ctx, cudaError_t e, const char *what) {
+    if (ctx) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        ctx->last_error = buf;
+    }
+    return e == cudaErrorMemoryAllocation ? H2AES_ERR_NOMEM : H2AES_ERR_CUDA;
+}
+static int32_t fail(h2aes_ctx *ctx, int32_t code, const char *what) {
+    if (ctx) ctx->last_error = what;
+    return code;
+}
+#define CU(ctx, call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+template <class T>
+static cudaError_t dalloc(T **p, size_t count) {
+    return cudaMalloc((void **)p, count * sizeof(T) ? count * sizeof(T) : 1);
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// host-only queries
+// ---------------------------------------------------------------------------------------------
+int32_t h2aes_abi_version(void) { return H2AES_ABI_VERSION; }
+
+const char *h2aes_status_string(int32_t s) {
+    switch (s) {
+    case H2AES_OK: return "ok";
+    case H2AES_ERR_ARG: return "bad argument";
+    case H2AES_ERR_CAPACITY: return "AES calls too many. doesn't fit in the rows";
+    case H2AES_ERR_ROWS: return "not enough rows available";
+    case H2AES_ERR_NOT_SCHEDULED: return "Keys should be scheduled";
+    case H2AES_ERR_LOOKUP: return "lookup input not in table";
+    case H2AES_ERR_CUDA: return "CUDA error";
+    case H2AES_ERR_NCCL: return "NCCL error";
+    case H2AES_ERR_NOMEM: return "out of device memory";
+    case H2AES_ERR_STATE: return "call order violated";
+    case H2AES_ERR_ZERO_DENOM: return "zero denominator in the lookup grand product";
+    default: return "unknown status";
+    }
+}
+
+int32_t h2aes_layout_query(int32_t kind, int32_t k, int32_t N, h2aes_layout *out) {
+    if (!out || !shape_ok(kind, k, N)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    memset(out, 0, sizeof *out);
+    out->kind = kind;
+    out->k = k;
+    out->n_sets = sh.n_sets();
+    out->n_advice = sh.n_advice();
+    out->n_fixed = sh.n_fixed();
+    out->n_selectors = sh.n_selectors();
+    out->n_lookups = sh.n_lookups();
+    out->n_rows = sh.n();
+    out->usable_rows = sh.usable();
+    out->table_rows = TABLE_ROWS;
+    out->key_schedule_rows = KEY_SCHEDULE_ROWS;
+    out->rows_per_block = AES_ROWS;
+    out->capacity_set0 = kind == KIND_AES ? sh.cap0() : 0;
+    out->capacity_set = kind == KIND_AES ? sh.cap() : 0;
+    out->capacity_blocks = sh.capacity();
+    out->copies_key_schedule = COPIES_KEY_SCHEDULE;
+    out->copies_per_block = COPIES_PER_BLOCK;
+    return H2AES_OK;
+}
+
+int32_t h2aes_block_position(int32_t k, int32_t N, uint64_t block, int32_t *set,
+                             uint64_t *start_row) {
+    if (!set || !start_row || !shape_ok(KIND_AES, k, N)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(KIND_AES, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    int s;
+    uint64_t r;
+    if (!block_position(sh, block, &s, &r)) return H2AES_ERR_CAPACITY;
+    *set = s;
+    *start_row = r;
+    return H2AES_OK;
+}
+
+int32_t h2aes_row_op(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t set,
+                     uint64_t row) {
+    if (!shape_ok(kind, k, N)) return -H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return -H2AES_ERR_ROWS;
+    if (set < 0 || set >= sh.n_sets() || row >= sh.n()) return -H2AES_ERR_ARG;
+    if (n_blocks > sh.capacity()) return -H2AES_ERR_CAPACITY;
+    return (int32_t)row_op(sh, n_blocks, set, row);
+}
+
+int32_t h2aes_copy_count(int32_t kind, uint64_t n_blocks, uint64_t *out) {
+    if (!out || (kind != KIND_AES && kind != KIND_KEYSCHED)) return H2AES_ERR_ARG;
+    if (kind == KIND_KEYSCHED && n_blocks) return H2AES_ERR_ARG;
+    *out = COPIES_KEY_SCHEDULE + COPIES_PER_BLOCK * n_blocks;
+    return H2AES_OK;
+}
+
+int32_t h2aes_copy_constraints_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
+                                    uint64_t first, uint64_t count, uint64_t *out) {
+    if (!shape_ok(kind, k, N) || (!out && count)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    if (kind == KIND_KEYSCHED && n_blocks) return H2AES_ERR_ARG;
+    if (n_blocks > sh.capacity()) return H2AES_ERR_CAPACITY;
+    const uint64_t total = COPIES_KEY_SCHEDULE + COPIES_PER_BLOCK * n_blocks;
+    if (first > total || count > total - first) return H2AES_ERR_ARG;
+    for (uint64_t i = 0; i < count; ++i) {
+        CopyPair cp;
+        if (!copy_pair(sh, first + i, &cp)) return H2AES_ERR_CAPACITY;
+        out[4 * i] = cp.dst.col;
+        out[4 * i + 1] = cp.dst.row;
+        out[4 * i + 2] = cp.src.col;
+        out[4 * i + 3] = cp.src.row;
+    }
+    return H2AES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+int32_t h2aes_ctx_create(int32_t device, int32_t sbox_mode, h2aes_ctx **out) {
+    if (!out || (sbox_mode != H2AES_SBOX_REFERENCE && sbox_mode != H2AES_SBOX_FIPS197))
+        return H2AES_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return H2AES_ERR_CUDA;
+    if (device < 0 || device >= count) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = new (std::nothrow) h2aes_ctx();
+    if (!ctx) return H2AES_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sbox_mode = sbox_mode;
+    make_sbox(sbox_mode, ctx->h_sbox);
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) !=
+            cudaSuccess ||
+        (e = dalloc(&ctx->d_sbox, 256)) != cudaSuccess ||
+        (e = dalloc(&ctx->d_frtab, 512)) != cudaSuccess ||
+        (e = cudaMemcpy(ctx->d_sbox, ctx->h_sbox, 256, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = launch_build_frtab(ctx)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        cudaFree(ctx->d_sbox);
+        cudaFree(ctx->d_frtab);
+        delete ctx;
+        return e == cudaErrorMemoryAllocation ? H2AES_ERR_NOMEM : H2AES_ERR_CUDA;
+    }
+    *out = ctx;
+    return H2AES_OK;
+}
+
+int32_t h2aes_ctx_destroy(h2aes_ctx *ctx) {
+    if (!ctx) return H2AES_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_sbox);
+    cudaFree(ctx->d_frtab);
+    delete ctx;
+    return H2AES_OK;
+}
+
+int32_t h2aes_ctx_set_stream(h2aes_ctx *ctx, void *stream) {
+    if (!ctx) return H2AES_ERR_ARG;
+    ctx->stream = (cudaStream_t)stream;
+    return H2AES_OK;
+}
+
+int32_t h2aes_ctx_synchronize(h2aes_ctx *ctx) {
+    if (!ctx) return H2AES_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2AES_OK;
+}
+
+const char *h2aes_ctx_last_error(h2aes_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+uint64_t h2aes_ctx_kernel_launches(h2aes_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t h2aes_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return H2AES_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? H2AES_ERR_NOMEM : H2AES_ERR_CUDA;
+    return H2AES_OK;
+}
+int32_t h2aes_host_free(void *p) {
+    if (!p) return H2AES_ERR_ARG;
+    return cudaFreeHost(p) == cudaSuccess ? H2AES_OK : H2AES_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// circuit
+// ---------------------------------------------------------------------------------------------
+static void circuit_free(h2aes_circuit *c) {
+    void *ptrs[] = {c->d_rk,       c->d_key,      c->d_states,   c->d_trace,    c->d_chal,
+                    c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
+                    c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
+                    c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
+                    c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
+                    c->d_tile_agg, c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, c->d_err,
+                    c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_err) cudaFreeHost(c->h_err);
+}
+
+int32_t h2aes_circuit_create(h2aes_ctx *ctx, int32_t kind, int32_t k, int32_t N,
+                             h2aes_circuit **out) {
+    if (!ctx || !out) return H2AES_ERR_ARG;
+    *out = nullptr;
+    if (!shape_ok(kind, k, N)) return fail(ctx, H2AES_ERR_ARG, "bad circuit shape");
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return fail(ctx, H2AES_ERR_ROWS, "k < 17: the lookup table does not fit");
+    if (k > 26) return fail(ctx, H2AES_ERR_ARG, "k > 26 is not supported");
+    CU(ctx, cudaSetDevice(ctx->device));
+    h2aes_circuit *c = new (std::nothrow) h2aes_circuit();
+    if (!c) return H2AES_ERR_NOMEM;
+    c->ctx = ctx;
+    c->sh = sh;
+    c->states_cap = sh.capacity() ? sh.capacity() : 1;
+    cudaError_t e;
+    if ((e = dalloc(&c->d_rk, 176)) != cudaSuccess || (e = dalloc(&c->d_key, 16)) != cudaSuccess ||
+        (e = dalloc(&c->d_states, c->states_cap * ST_BYTES)) != cudaSuccess ||
+        (e = dalloc(&c->d_trace, (size_t)sh.n_sets() * sh.n())) != cudaSuccess ||
+        (e = dalloc(&c->d_err, 8)) != cudaSuccess ||
+        (e = cudaHostAlloc((void **)&c->h_err, 8 * sizeof(uint32_t), cudaHostAllocDefault)) !=
+            cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_err, 0, 8 * sizeof(uint32_t), ctx->stream)) != cudaSuccess) {
+        circuit_free(c);
+        delete c;
+        return cuda_fail(ctx, e, "circuit workspace");
+    }
+    *out = c;
+    return H2AES_OK;
+}
+
+int32_t h2aes_circuit_destroy(h2aes_circuit *c) {
+    if (!c) return H2AES_ERR_ARG;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    circuit_free(c);
+    delete c;
+    return H2AES_OK;
+}
+
+static void shard_rows(const h2aes_circuit *c, uint64_t *begin, uint64_t *end) {
+    const uint64_t per = c->sh.n() / (uint64_t)c->n_shards;
+    *begin = per * (uint64_t)c->shard;
+    *end = *begin + per;
+}
+
+int32_t h2aes_circuit_set_shard(h2aes_circuit *c, int32_t shard, int32_t n_shards) {
+    if (!c) return H2AES_ERR_ARG;
+    if (n_shards < 1 || n_shards > 64 || (n_shards & (n_shards - 1)) || shard < 0 ||
+        shard >= n_shards)
+        return fail(c->ctx, H2AES_ERR_ARG, "n_shards must be a power of two <= 64");
+    c->shard = shard;
+    c->n_shards = n_shards;
+    c->have_witness = c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
+    return H2AES_OK;
+}
+
+int32_t h2aes_witness_dev(h2aes_circuit *c, const uint8_t *key, const uint8_t *plaintexts_dev,
+                          uint64_t n_blocks, uint64_t *advice_dev, uint8_t *ciphertexts_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!key || !advice_dev || (n_blocks && !plaintexts_dev))
+        return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (c->sh.kind == KIND_KEYSCHED && n_blocks)
+        return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (n_blocks > c->sh.capacity())
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    CU(ctx, launch_witness(c, key, plaintexts_dev, n_blocks, advice_dev, ciphertexts_dev, rb, re));
+    c->n_blocks = n_blocks;
+    c->have_witness = true;
+    c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
+    return H2AES_OK;
+}
+
+static int32_t ensure_stage(h2aes_circuit *c, uint64_t bytes) {
+    if (c->stage_bytes >= bytes) return H2AES_OK;
+    if (c->d_stage) {
+        CU(c->ctx, cudaStreamSynchronize(c->ctx->stream));
+        cudaFree(c->d_stage);
+        c->d_stage = nullptr;
+        c->stage_bytes = 0;
+    }
+    CU(c->ctx, cudaMalloc(&c->d_stage, bytes));
+    c->stage_bytes = bytes;
+    return H2AES_OK;
+}
+
+int32_t h2aes_witness_host(h2aes_circuit *c, const uint8_t *key, const uint8_t *plaintexts,
+                           uint64_t n_blocks, uint64_t *advice, uint8_t *ciphertexts) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!key || !advice || (n_blocks && !plaintexts)) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (c->sh.kind == KIND_KEYSCHED && n_blocks)
+        return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (n_blocks > c->sh.capacity())
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (c->pt_cap < n_blocks || !c->d_pt) {
+        if (c->d_pt) cudaFree(c->d_pt);
+        if (c->d_ct) cudaFree(c->d_ct);
+        c->d_pt = c->d_ct = nullptr;
+        const uint64_t cap = n_blocks ? n_blocks : 1;
+        CU(ctx, dalloc(&c->d_pt, cap * 16));
+        CU(ctx, dalloc(&c->d_ct, cap * 16));
+        c->pt_cap = cap;
+    }
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    const uint64_t bytes = (uint64_t)c->sh.n_advice() * (re - rb) * 32;
+    int32_t rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    if (n_blocks)
+        CU(ctx, cudaMemcpyAsync(c->d_pt, plaintexts, n_blocks * 16, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    rc = h2aes_witness_dev(c, key, c->d_pt, n_blocks, (uint64_t *)c->d_stage, c->d_ct);
+    if (rc) return rc;
+    CU(ctx, cudaMemcpyAsync(advice, c->d_stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ciphertexts && n_blocks)
+        CU(ctx, cudaMemcpyAsync(ciphertexts, c->d_ct, n_blocks * 16, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2AES_OK;
+}
+
+int32_t h2aes_round_keys(h2aes_circuit *c, uint8_t *out176) {
+    if (!c || !out176) return H2AES_ERR_ARG;
+    if (!c->have_witness) return fail(c->ctx, H2AES_ERR_NOT_SCHEDULED, "Keys should be scheduled");
+    CU(c->ctx, cudaSetDevice(c->ctx->device));
+    CU(c->ctx, cudaMemcpyAsync(out176, c->d_rk, 176, cudaMemcpyDeviceToHost, c->ctx->stream));
+    CU(c->ctx, cudaStreamSynchronize(c->ctx->stream));
+    return H2AES_OK;
+}
+
+int32_t h2aes_fixed_columns_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
+                                uint64_t *selectors_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (c->sh.kind == KIND_KEYSCHED && n_blocks)
+        return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (n_blocks > c->sh.capacity())
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    if (!fixed_dev && !selectors_dev) return H2AES_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    CU(ctx, launch_fixed(c, n_blocks, fixed_dev, selectors_dev, rb, re));
+    return H2AES_OK;
+}
+
+int32_t h2aes_fixed_columns_host(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed,
+                                 uint64_t *selectors) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    const uint64_t fbytes = fixed ? (uint64_t)c->sh.n_fixed() * (re - rb) * 32 : 0;
+    const uint64_t sbytes = selectors ? (uint64_t)c->sh.n_selectors() * (re - rb) * 32 : 0;
+    int32_t rc = ensure_stage(c, fbytes + sbytes + 32);
+    if (rc) return rc;
+    uint64_t *df = fixed ? (uint64_t *)c->d_stage : nullptr;
+    uint64_t *ds = selectors ? (uint64_t *)((char *)c->d_stage + fbytes) : nullptr;
+    rc = h2aes_fixed_columns_dev(c, n_blocks, df, ds);
+    if (rc) return rc;
+    if (fixed) CU(ctx, cudaMemcpyAsync(fixed, df, fbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (selectors)
+        CU(ctx, cudaMemcpyAsync(selectors, ds, sbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2AES_OK;
+}
+
+int32_t h2aes_copy_constraints_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *copies_dev) {
+    if (!c || !copies_dev) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (c->sh.kind == KIND_KEYSCHED && n_blocks)
+        return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (n_blocks > c->sh.capacity())
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_copies(c, COPIES_KEY_SCHEDULE + COPIES_PER_BLOCK * n_blocks, copies_dev));
+    return H2AES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lookup helper columns
+// ---------------------------------------------------------------------------------------------
+static int32_t ensure_lookup_ws(h2aes_circuit *c) {
+    if (c->lk_alloc) return H2AES_OK;
+    h2aes_ctx *ctx = c->ctx;
+    const size_t L = (size_t)c->sh.n_lookups();
+    const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
+    c->n_tiles = grand_product_tiles(c->sh.n());
+    CU(ctx, dalloc(&c->d_chal, 4));
+    CU(ctx, dalloc(&c->d_val, VB));
+    CU(ctx, dalloc(&c->d_canon, VB));
+    CU(ctx, dalloc(&c->d_dval, VB));
+    CU(ctx, dalloc(&c->d_rank, VB));
+    CU(ctx, dalloc(&c->d_ts, VB));
+    CU(ctx, dalloc(&c->d_sorted, VB));
+    CU(ctx, dalloc(&c->d_slot, VB));
+    CU(ctx, dalloc(&c->d_head, VB));
+    CU(ctx, dalloc(&c->d_bhist, (size_t)N_VIEWS * (N_BUCKETS + 1)));
+    CU(ctx, dalloc(&c->d_bcur, (size_t)N_VIEWS * N_BUCKETS));
+    CU(ctx, dalloc(&c->d_viewmeta, (size_t)N_VIEWS * 8));
+    CU(ctx, dalloc(&c->d_ib, VB));
+    CU(ctx, dalloc(&c->d_ig, VB));
+    CU(ctx, dalloc(&c->d_nac, VB));
+    CU(ctx, dalloc(&c->d_cnt, LB));
+    CU(ctx, dalloc(&c->d_offz, LB));
+    CU(ctx, dalloc(&c->d_nzk, LB));
+    CU(ctx, dalloc(&c->d_loffz, LB));
+    CU(ctx, dalloc(&c->d_lk, LB));
+    CU(ctx, dalloc(&c->d_meta, L));
+    CU(ctx, dalloc(&c->d_tile_agg, L * c->n_tiles));
+    CU(ctx, dalloc(&c->d_tile_inc, L * c->n_tiles));
+    CU(ctx, dalloc(&c->d_tile_flag, L * c->n_tiles));
+    CU(ctx, dalloc(&c->d_tile_ctr, L));
+    CU(ctx, dalloc(&c->d_partial, L));
+    CU(ctx, dalloc(&c->d_carry, L));
+    c->lk_alloc = true;
+    return H2AES_OK;
+}
+
+// Device-side error flags raised by the lookup kernels are folded into the status here.
+static int32_t check_device_flags(h2aes_circuit *c) {
+    h2aes_ctx *ctx = c->ctx;
+    CU(ctx, cudaMemcpyAsync(c->h_err, c->d_err, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (c->h_err[0] || c->h_err[1])
+        CU(ctx, cudaMemsetAsync(c->d_err, 0, 8 * sizeof(uint32_t), ctx->stream));
+    if (c->h_err[0]) return fail(ctx, H2AES_ERR_ZERO_DENOM, "zero denominator in the grand product");
+    if (c->h_err[1]) return fail(ctx, H2AES_ERR_LOOKUP, "lookup input not in table");
+    return H2AES_OK;
+}
+
+static int32_t set_theta(h2aes_circuit *c, const uint64_t *theta, bool *changed) {
+    *changed = !c->have_theta || memcmp(c->theta, theta, 32) != 0;
+    if (*changed) {
+        memcpy(c->theta, theta, 32);
+        CU(c->ctx, cudaMemcpyAsync(c->d_chal, c->theta, 32, cudaMemcpyHostToDevice, c->ctx->stream));
+        c->have_theta = true;
+    }
+    return H2AES_OK;
+}
+
+static int32_t set_beta_gamma(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma) {
+    h2aes_ctx *ctx = c->ctx;
+    if (c->have_beta_gamma && !memcmp(c->beta, beta, 32) && !memcmp(c->gamma, gamma, 32))
+        return H2AES_OK;
+    memcpy(c->beta, beta, 32);
+    memcpy(c->gamma, gamma, 32);
+    CU(ctx, cudaMemcpyAsync(c->d_chal + 1, c->beta, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(c->d_chal + 2, c->gamma, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, launch_inv_tables(c));
+    c->have_beta_gamma = true;
+    return H2AES_OK;
+}
+
+int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32_t first,
+                                  int32_t count, uint64_t *A_dev, uint64_t *S_dev,
+                                  uint64_t *Ap_dev, uint64_t *Sp_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!theta || !Ap_dev || !Sp_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->sh.n_lookups())
+        return fail(ctx, H2AES_ERR_ARG, "lookup range");
+    if (!c->have_witness) return fail(ctx, H2AES_ERR_STATE, "lookup columns need a witness first");
+    if (c->n_shards != 1)
+        return fail(ctx, H2AES_ERR_STATE, "sharded circuit: use the *_shard_dev entry points");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = ensure_lookup_ws(c);
+    if (rc) return rc;
+    bool changed;
+    if ((rc = set_theta(c, theta, &changed))) return rc;
+    if (changed || !c->have_bins) {
+        CU(ctx, launch_view_bins(c));
+        CU(ctx, launch_lookup_hist(c, 0, c->sh.n()));
+        CU(ctx, launch_lookup_bins(c));
+        c->have_bins = true;
+        c->have_beta_gamma = false;
+    }
+    if (count)
+        CU(ctx, launch_permuted(c, first, count, A_dev, S_dev, Ap_dev, Sp_dev, 0, c->sh.n()));
+    return H2AES_OK;
+}
+
+int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                 int32_t first, int32_t count, uint64_t *Z_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!beta || !gamma || !Z_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->sh.n_lookups())
+        return fail(ctx, H2AES_ERR_ARG, "lookup range");
+    if (c->n_shards != 1)
+        return fail(ctx, H2AES_ERR_STATE, "sharded circuit: use the *_shard_dev entry points");
+    if (!c->have_witness || !c->have_bins)
+        return fail(ctx, H2AES_ERR_STATE, "the grand product needs the permuted columns first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = set_beta_gamma(c, beta, gamma);
+    if (rc) return rc;
+    if (count) CU(ctx, launch_grand_product(c, first, count, nullptr, Z_dev, 0, c->sh.n(), 0));
+    return H2AES_OK;
+}
+
+// _host variants: stage through device memory a bounded number of lookups at a time.
+static int lookups_per_stage(const h2aes_circuit *c, int ncols) {
+    const uint64_t per = (uint64_t)ncols * c->sh.n() * 32;
+    const uint64_t budget = 1ull << 30;
+    uint64_t m = budget / per;
+    return (int)(m < 1 ? 1 : m);
+}
+
+int32_t h2aes_lookup_permuted_host(h2aes_circuit *c, const uint64_t *theta, int32_t first,
+                                   int32_t count, uint64_t *A, uint64_t *S, uint64_t *Ap,
+                                   uint64_t *Sp) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!theta || !Ap || !Sp) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->sh.n_lookups())
+        return fail(ctx, H2AES_ERR_ARG, "lookup range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t col = c->sh.n() * 32;
+    const int ncols = 2 + (A ? 1 : 0) + (S ? 1 : 0);
+    const int step = lookups_per_stage(c, ncols);
+    for (int done = 0; done < count || done == 0; done += step) {
+        const int m = count - done < step ? count - done : step;
+        int32_t rc = ensure_stage(c, (uint64_t)ncols * (m > 0 ? m : 1) * col);
+        if (rc) return rc;
+        char *p = (char *)c->d_stage;
+        uint64_t *dA = nullptr, *dS = nullptr, *dAp, *dSp;
+        if (A) { dA = (uint64_t *)p; p += (uint64_t)m * col; }
+        if (S) { dS = (uint64_t *)p; p += (uint64_t)m * col; }
+        dAp = (uint64_t *)p; p += (uint64_t)m * col;
+        dSp = (uint64_t *)p;
+        rc = h2aes_lookup_permuted_dev(c, theta, first + done, m, dA, dS, dAp, dSp);
+        if (rc) return rc;
+        const uint64_t off = (uint64_t)done * c->sh.n() * 4, bytes = (uint64_t)m * col;
+        if (m > 0) {
+            if (A) CU(ctx, cudaMemcpyAsync(A + off, dA, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            if (S) CU(ctx, cudaMemcpyAsync(S + off, dS, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(Ap + off, dAp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(Sp + off, dSp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (count == 0) break;
+    }
+    return check_device_flags(c);
+}
+
+int32_t h2aes_lookup_product_host(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                  int32_t first, int32_t count, uint64_t *Z) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!beta || !gamma || !Z) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (first < 0 || count < 0 || first + count > c->sh.n_lookups())
+        return fail(ctx, H2AES_ERR_ARG, "lookup range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t col = c->sh.n() * 32;
+    const int step = lookups_per_stage(c, 1);
+    for (int done = 0; done < count; done += step) {
+        const int m = count - done < step ? count - done : step;
+        int32_t rc = ensure_stage(c, (uint64_t)m * col);
+        if (rc) return rc;
+        rc = h2aes_lookup_product_dev(c, beta, gamma, first + done, m, (uint64_t *)c->d_stage);
+        if (rc) return rc;
+        CU(ctx, cudaMemcpyAsync(Z + (uint64_t)done * c->sh.n() * 4, c->d_stage, (uint64_t)m * col,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return check_device_flags(c);
+}
+
+int32_t h2aes_lookup_check(h2aes_circuit *c) {
+    if (!c) return H2AES_ERR_ARG;
+    if (!c->lk_alloc) return H2AES_OK;
+    CU(c->ctx, cudaSetDevice(c->ctx->device));
+    return check_device_flags(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-sharded single circuit
+// ---------------------------------------------------------------------------------------------
+int32_t h2aes_lookup_hist_dev(h2aes_circuit *c, const uint64_t *theta, uint32_t **hist_dev,
+                              uint64_t *hist_words) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!theta || !hist_dev || !hist_words) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!c->have_witness) return fail(ctx, H2AES_ERR_STATE, "lookup columns need a witness first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = ensure_lookup_ws(c);
+    if (rc) return rc;
+    bool changed;
+    if ((rc = set_theta(c, theta, &changed))) return rc;
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    CU(ctx, launch_view_bins(c));
+    CU(ctx, launch_lookup_hist(c, rb, re));
+    c->have_hist = true;
+    c->have_bins = c->have_beta_gamma = c->have_partial = false;
+    *hist_dev = c->d_cnt;
+    *hist_words = (uint64_t)c->sh.n_lookups() * BIN_STRIDE;
+    return H2AES_OK;
+}
+
+int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint64_t *S_dev,
+                                        uint64_t *Ap_dev, uint64_t *Sp_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!c->have_hist) return fail(ctx, H2AES_ERR_STATE, "h2aes_lookup_hist_dev must run first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_lookup_bins(c));
+    c->have_bins = true;
+    if (Ap_dev && Sp_dev) {
+        uint64_t rb, re;
+        shard_rows(c, &rb, &re);
+        CU(ctx, launch_permuted(c, 0, c->sh.n_lookups(), A_dev, S_dev, Ap_dev, Sp_dev, rb, re));
+    } else if (Ap_dev || Sp_dev || A_dev || S_dev) {
+        return fail(ctx, H2AES_ERR_ARG, "A' and S' must both be given (or no output at all)");
+    }
+    return H2AES_OK;
+}
+
+int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                 uint64_t **partial_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!beta || !gamma || !partial_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!c->have_bins) return fail(ctx, H2AES_ERR_STATE, "permuted columns must be built first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = set_beta_gamma(c, beta, gamma);
+    if (rc) return rc;
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    const int L = c->sh.n_lookups();
+    CU(ctx, launch_grand_product(c, 0, L, nullptr, nullptr, rb, re, 1));
+    // the running product after the shard's last tile is the shard's partial product
+    const uint64_t tiles = grand_product_tiles(re - rb);
+    CU(ctx, cudaMemcpy2DAsync(c->d_partial, sizeof(fr_t), c->d_tile_inc + (tiles - 1),
+                              c->n_tiles * sizeof(fr_t), sizeof(fr_t), (size_t)L,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    c->have_partial = true;
+    *partial_dev = (uint64_t *)c->d_partial;
+    return H2AES_OK;
+}
+
+int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathered_dev,
+                                       uint64_t *Z_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!gathered_dev || !Z_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!c->have_partial) return fail(ctx, H2AES_ERR_STATE, "h2aes_lookup_partial_dev must run first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    CU(ctx, launch_shard_carry(c, gathered_dev));
+    CU(ctx, launch_grand_product(c, 0, c->sh.n_lookups(), c->d_carry, Z_dev, rb, re, 0));
+    return H2AES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug / test hooks (host evaluation of the shared host+device source)
+// ---------------------------------------------------------------------------------------------
+int32_t h2aes_dbg_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    if (!a || !b || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_mul(fr_from_limbs(a), fr_from_limbs(b)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_add(const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    if (!a || !b || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_add(fr_from_limbs(a), fr_from_limbs(b)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_sub(const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    if (!a || !b || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_sub(fr_from_limbs(a), fr_from_limbs(b)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out) {
+    if (!a || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_inv(fr_from_limbs(a)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out) {
+    if (!out) return H2AES_ERR_ARG;
+    fr_t a = fr_zero();
+    a.v[0] = (uint32_t)v;
+    a.v[1] = (uint32_t)(v >> 32);
+    fr_to_limbs(fr_mul(a, fr_r2()), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_to_canonical(const uint64_t *a, uint64_t *out) {
+    if (!a || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_to_canonical(fr_from_limbs(a)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_tables(int32_t sbox_mode, uint8_t *sbox256, uint8_t *mul2_256,
+                         uint8_t *mul3_256) {
+    if (sbox_mode != H2AES_SBOX_REFERENCE && sbox_mode != H2AES_SBOX_FIPS197) return H2AES_ERR_ARG;
+    if (sbox256) make_sbox(sbox_mode, sbox256);
+    for (int x = 0; x < 256; ++x) {
+        if (mul2_256) mul2_256[x] = gf_mul2((uint8_t)x);
+        if (mul3_256) mul3_256[x] = gf_mul3((uint8_t)x);
+    }
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_block_trace(int32_t sbox_mode, const uint8_t *round_keys176,
+                              const uint8_t *plaintext16, uint32_t *trace1360) {
+    if (!round_keys176 || !plaintext16 || !trace1360) return H2AES_ERR_ARG;
+    if (sbox_mode != H2AES_SBOX_REFERENCE && sbox_mode != H2AES_SBOX_FIPS197) return H2AES_ERR_ARG;
+    uint8_t sbox[256], st[ST_BYTES];
+    make_sbox(sbox_mode, sbox);
+    aes_block_states(sbox, round_keys176, plaintext16, st);
+    for (uint32_t q = 0; q < AES_ROWS; ++q) trace1360[q] = block_trace_word(st, round_keys176, q);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_key_schedule_trace(int32_t sbox_mode, const uint8_t *key16,
+                                     uint8_t *round_keys176, uint32_t *trace400,
+                                     uint8_t *words96) {
+    if (!key16 || !round_keys176) return H2AES_ERR_ARG;
+    if (sbox_mode != H2AES_SBOX_REFERENCE && sbox_mode != H2AES_SBOX_FIPS197) return H2AES_ERR_ARG;
+    uint8_t sbox[256];
+    make_sbox(sbox_mode, sbox);
+    expand_key(sbox, key16, round_keys176);
+    if (trace400)
+        for (uint32_t r = 0; r < KEY_SCHEDULE_ROWS; ++r)
+            trace400[r] = ks_trace_word(sbox, round_keys176, r);
+    if (words96)
+        for (uint32_t r = 0; r < (uint32_t)WORDS_ROWS; ++r)
+            words96[r] = (uint8_t)ks_words_byte(round_keys176, r);
+    return H2AES_OK;
+}
+
+}  // extern "C"

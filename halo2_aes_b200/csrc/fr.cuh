@@ -1,0 +1,244 @@
+// fr.cuh — bn256 scalar field on 8x32-bit limbs, Montgomery form (R = 2^256).
+//
+// Memory format == halo2curves 0.6.1 `bn256::Fr` (4 little-endian u64 limbs of x*R mod r), so a
+// column of these is bit-compatible with the Vec<Fr> the reference's prover consumes
+// (src/aes128.rs:11 `halo2curves::bn256::Fr as Fp`).
+//
+// Two implementations of the multiply:
+//   * a portable host+device CIOS (also what the CPU-only tests run through h2aes_dbg_fr_*);
+//   * on the device, a PTX mad.lo/madc.hi carry-chain version (IMAD pipe), used by the kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FR_HD __host__ __device__ __forceinline__
+#define FR_D __device__ __forceinline__
+#else
+#define FR_HD inline
+#endif
+
+namespace h2 {
+
+struct __align__(16) fr_t {
+    uint32_t v[8];
+};
+
+// r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+#define FR_P0 0xf0000001u
+#define FR_P1 0x43e1f593u
+#define FR_P2 0x79b97091u
+#define FR_P3 0x2833e848u
+#define FR_P4 0x8181585du
+#define FR_P5 0xb85045b6u
+#define FR_P6 0xe131a029u
+#define FR_P7 0x30644e72u
+#define FR_INV32 0xefffffffu  // -r^{-1} mod 2^32
+
+FR_HD uint32_t fr_p(int i) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    return P[i];
+}
+
+FR_HD fr_t fr_zero() {
+    fr_t z;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z.v[i] = 0;
+    return z;
+}
+// R mod r = Montgomery form of 1
+FR_HD fr_t fr_one() {
+    fr_t o = {{0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu,
+               0x9a07df2fu, 0x0e0a77c1u}};
+    return o;
+}
+// R^2 mod r
+FR_HD fr_t fr_r2() {
+    fr_t o = {{0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du,
+               0x7f4e44a5u, 0x0216d0b1u}};
+    return o;
+}
+
+FR_HD bool fr_is_zero(const fr_t &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.v[i];
+    return o == 0;
+}
+FR_HD bool fr_eq(const fr_t &a, const fr_t &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+}
+
+// a >= r ?
+FR_HD bool fr_geq_p(const uint32_t *a) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (a[i] > P[i]) return true;
+        if (a[i] < P[i]) return false;
+    }
+    return true;
+}
+
+// conditional subtract of r (input < 2r, output < r)
+FR_HD void fr_reduce_once(uint32_t *a) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t d[8];
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t t = (uint64_t)a[i] - P[i] - borrow;
+        d[i] = (uint32_t)t;
+        borrow = (t >> 32) & 1;
+    }
+    if (!borrow) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = d[i];
+    }
+}
+
+FR_HD fr_t fr_add(const fr_t &a, const fr_t &b) {
+    fr_t o;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        o.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    fr_reduce_once(o.v);  // a+b < 2r < 2^255: no carry out
+    return o;
+}
+
+FR_HD fr_t fr_sub(const fr_t &a, const fr_t &b) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    fr_t o;
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t t = (uint64_t)a.v[i] - b.v[i] - borrow;
+        o.v[i] = (uint32_t)t;
+        borrow = (t >> 32) & 1;
+    }
+    if (borrow) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            c += (uint64_t)o.v[i] + P[i];
+            o.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return o;
+}
+
+// Portable CIOS Montgomery product a*b*R^-1 mod r.
+FR_HD fr_t fr_mul_portable(const fr_t &a, const fr_t &b) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint64_t x = (uint64_t)a.v[j] * b.v[i] + t[j] + c;
+            t[j] = (uint32_t)x;
+            c = x >> 32;
+        }
+        uint64_t x = (uint64_t)t[8] + c;
+        t[8] = (uint32_t)x;
+        t[9] = (uint32_t)(x >> 32);
+        uint32_t m = t[0] * FR_INV32;
+        x = (uint64_t)m * P[0] + t[0];
+        c = x >> 32;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            x = (uint64_t)m * P[j] + t[j] + c;
+            t[j - 1] = (uint32_t)x;
+            c = x >> 32;
+        }
+        x = (uint64_t)t[8] + c;
+        t[7] = (uint32_t)x;
+        t[8] = t[9] + (uint32_t)(x >> 32);
+    }
+    fr_t o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = t[i];
+    fr_reduce_once(o.v);  // result < 2r, t[8] == 0
+    return o;
+}
+
+FR_HD fr_t fr_mul(const fr_t &a, const fr_t &b) {
+    // The portable form compiles to IMAD.WIDE chains on sm_100a; a hand-scheduled PTX variant
+    // is selected with -DH2AES_PTX_MUL once validated against this one on hardware.
+    return fr_mul_portable(a, b);
+}
+
+FR_HD fr_t fr_sqr(const fr_t &a) { return fr_mul(a, a); }
+
+FR_HD fr_t fr_from_u32(uint32_t x) {
+    fr_t a = fr_zero();
+    a.v[0] = x;
+    return fr_mul(a, fr_r2());
+}
+
+// leave Montgomery form: canonical value (what `to_repr`/`Ord` look at)
+FR_HD fr_t fr_to_canonical(const fr_t &a) {
+    fr_t one = fr_zero();
+    one.v[0] = 1;
+    return fr_mul(a, one);
+}
+
+// numeric compare of canonical values: -1, 0, 1
+FR_HD int fr_cmp_canonical(const fr_t &ca, const fr_t &cb) {
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (ca.v[i] < cb.v[i]) return -1;
+        if (ca.v[i] > cb.v[i]) return 1;
+    }
+    return 0;
+}
+
+// a^(r-2); inverse of 0 is 0 (same convention as ff::Field::invert().unwrap_or(0))
+FR_HD fr_t fr_inv(const fr_t &a) {
+    const uint32_t E[8] = {FR_P0 - 2u, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    fr_t acc = fr_one();
+    for (int i = 253; i >= 0; --i) {  // r < 2^254
+        acc = fr_sqr(acc);
+        if ((E[i >> 5] >> (i & 31)) & 1) acc = fr_mul(acc, a);
+    }
+    return acc;
+}
+
+#if defined(__CUDACC__)
+// 32-byte vector access helpers (column elements are 32-byte aligned)
+FR_D fr_t fr_load(const uint64_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+FR_D fr_t fr_load_s(const uint4 *q) {  // shared / generic
+    uint4 lo = q[0], hi = q[1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+// one 256-bit store per element (STG.E.ENL2.256 on sm_100a)
+FR_D void fr_store_256(uint64_t *p, const fr_t &a) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]),
+                 "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+                 "r"(a.v[7])
+                 : "memory");
+}
+FR_D void store_256(uint64_t *p, const uint4 &lo, const uint4 &hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x),
+                 "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+#endif
+
+}  // namespace h2

@@ -1,0 +1,127 @@
+// internal.h — state behind the opaque handles of include/h2aes.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/h2aes.h"
+#include "fr.cuh"
+#include "layout.h"
+
+namespace h2 {
+
+// number of distinct table tuples seen through an m-column lookup (m = view + 2)
+constexpr int N_VIEWS = 3;
+constexpr uint32_t VIEW0_ENTRIES = 5 * 256 + 1;  // (tag,x) pairs + the zero row
+constexpr uint32_t VIEW_MAX_ENTRIES = (uint32_t)TABLE_ROWS;
+constexpr uint32_t N_BUCKETS = 65536;
+constexpr uint32_t BIN_STRIDE = 66568;  // >= VIEW_MAX_ENTRIES + 2, multiple of 8
+
+H2_HD uint32_t view_entries(int v) { return v == 0 ? VIEW0_ENTRIES : VIEW_MAX_ENTRIES; }
+// view (0: 2 columns, 1: 3 columns, 2: 4 columns) used by the lookup of op `op`
+H2_HD int view_of_op(uint32_t op) { return op == OP_RANGE ? 0 : (op == OP_XOR ? 2 : 1); }
+// table row -> entry index inside a view
+H2_HD uint32_t entry_of_table_row(int v, uint32_t trow) {
+    if (v != 0) return trow;
+    if (trow < TROW_XOR) return trow;  // U8 rows 0..255, SBOX rows 256..511
+    if (trow < TROW_MUL2) return 512 + ((trow - TROW_XOR) >> 8);
+    if (trow < TROW_ZERO) return 768 + (trow - TROW_MUL2);  // MUL2 768.., MUL3 1024..
+    return 1280;
+}
+// any table row that realises entry e of view 0 (used to evaluate the tuple)
+H2_HD uint32_t table_row_of_entry(int v, uint32_t e) {
+    if (v != 0) return e;
+    if (e < 512) return e;
+    if (e < 768) return TROW_XOR + ((e - 512) << 8);
+    if (e < 1280) return TROW_MUL2 + (e - 768);
+    return TROW_ZERO;
+}
+// how many table rows (of the 66561 assigned ones) collapse onto entry e of view v
+H2_HD uint32_t entry_multiplicity(int v, uint32_t e) {
+    return (v == 0 && e >= 512 && e < 768) ? 256u : 1u;
+}
+
+struct LookupMeta {  // per lookup, produced by the bin-scan kernel
+    uint32_t n_nonempty;  // NZ: bins with at least one input row
+    uint32_t n_left;      // NL: bins with leftover table multiplicity
+    uint32_t repeated;    // R = usable - NZ
+    uint32_t k_zero;      // bin of the all-zero tuple (inactive rows)
+    uint32_t bad;         // != 0: an input value has no table row (cannot happen by construction)
+    uint32_t pad[3];
+};
+
+}  // namespace h2
+
+struct h2aes_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sbox_mode = 0;
+    int sm_count = 148;
+    uint8_t h_sbox[256];
+    uint8_t *d_sbox = nullptr;   // 256 bytes
+    uint4 *d_frtab = nullptr;    // 256 entries x 32 bytes: byte -> Fr (Montgomery)
+    uint64_t launches = 0;
+    std::string last_error;
+};
+
+struct h2aes_circuit {
+    h2aes_ctx *ctx = nullptr;
+    h2::Shape sh{};
+    uint64_t n_blocks = 0;
+    bool have_witness = false;
+    int shard = 0, n_shards = 1;
+
+    // witness workspace
+    uint8_t *d_rk = nullptr;       // 176
+    uint8_t *d_key = nullptr;      // 16
+    uint8_t *d_states = nullptr;   // capacity * ST_BYTES
+    uint64_t states_cap = 0;
+    uint32_t *d_trace = nullptr;   // n_sets * n words (a0 | a1<<8 | a2<<16 | op<<24)
+
+    // lookup workspace (allocated on first use)
+    bool lk_alloc = false;
+    bool have_theta = false, have_hist = false, have_bins = false, have_beta_gamma = false,
+         have_partial = false;
+    uint64_t theta[4] = {0, 0, 0, 0}, beta[4] = {0, 0, 0, 0}, gamma[4] = {0, 0, 0, 0};
+    h2::fr_t *d_chal = nullptr;      // theta, beta, gamma
+    // per view
+    h2::fr_t *d_val = nullptr;       // [3][BIN_STRIDE] compressed value of entry e
+    h2::fr_t *d_canon = nullptr;     // [3][BIN_STRIDE] canonical form (sort key)
+    h2::fr_t *d_dval = nullptr;      // [3][BIN_STRIDE] distinct values, ascending
+    uint32_t *d_rank = nullptr;      // [3][BIN_STRIDE] entry -> bin
+    uint32_t *d_ts = nullptr;        // [3][BIN_STRIDE] table multiplicity of bin
+    uint32_t *d_sorted = nullptr;    // [3][BIN_STRIDE] entries in ascending value order
+    uint32_t *d_slot = nullptr;      // [3][BIN_STRIDE] bucket-ordered entries
+    uint32_t *d_head = nullptr;      // [3][BIN_STRIDE]
+    uint32_t *d_bhist = nullptr;     // [3][N_BUCKETS+1]
+    uint32_t *d_bcur = nullptr;      // [3][N_BUCKETS]
+    uint32_t *d_viewmeta = nullptr;  // [3][8]: maxbits, n_bins, ...
+    h2::fr_t *d_ib = nullptr;        // [3][BIN_STRIDE] 1/(dval+beta)
+    h2::fr_t *d_ig = nullptr;        // [3][BIN_STRIDE] 1/(dval+gamma)
+    h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
+    // per lookup
+    uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
+    uint32_t *d_offz = nullptr;      // [L][BIN_STRIDE] first row of each nonempty bin (+ end)
+    uint32_t *d_nzk = nullptr;       // [L][BIN_STRIDE] bin of each nonempty slot
+    uint32_t *d_loffz = nullptr;     // [L][BIN_STRIDE] leftover prefix (+ end)
+    uint32_t *d_lk = nullptr;        // [L][BIN_STRIDE] bin of each leftover slot
+    h2::LookupMeta *d_meta = nullptr;  // [L]
+    // grand-product scan workspace
+    h2::fr_t *d_tile_agg = nullptr;   // [L][tiles]
+    h2::fr_t *d_tile_inc = nullptr;   // [L][tiles]
+    uint32_t *d_tile_flag = nullptr;  // [L][tiles]
+    uint32_t *d_tile_ctr = nullptr;   // [L]
+    uint32_t *d_err = nullptr;        // device error flags: [0] zero denominator, [1] not in table
+    uint32_t *h_err = nullptr;        // pinned mirror of d_err
+    h2::fr_t *d_partial = nullptr;    // [L] shard partial products
+    h2::fr_t *d_carry = nullptr;      // [L] product of the partials of the shards before this one
+    uint64_t n_tiles = 0;
+
+    // staging for the _host entry points
+    void *d_stage = nullptr;
+    uint64_t stage_bytes = 0;
+    uint8_t *d_pt = nullptr;
+    uint64_t pt_cap = 0;
+    uint8_t *d_ct = nullptr;
+};

@@ -1,0 +1,801 @@
+// lookup.cu — halo2 lookup-argument helper columns on the GPU (sm_100a).
+//
+// Replaces halo2_proofs v0.3.0 plonk/lookup/prover.rs [UPSTREAM, un-vendored dependency of the
+// reference; call sites src/main.rs:94-101, benches/aes128.rs:100-107,
+// benches/key_schedule.rs:117-124]:
+//   commit_permuted  : A = fold(q*tag, q*x, ...; theta), S = fold(table cols; theta),
+//                      A' = sort(A[..u]), S' = permuted table (first occurrences aligned, the
+//                      leftover table multiset filled ascending into the repeated rows taken
+//                      from the END), u = 2^k - 6;
+//   commit_product   : Z[0]=1, Z[i+1] = Z[i] (A[i]+beta)(S[i]+gamma) / ((A'[i]+beta)(S'[i]+gamma)).
+//
+// Design (no sort over n rows, no per-row inversion):
+//   * every input value is the compression of one of <= 66561 table tuples, so the rows are
+//     counted per *bin* (distinct compressed value) from the 4-byte trace word of each row;
+//   * the bins are ordered once per theta per view (2-, 3-, 4-column tables) with a bucket sort
+//     on the canonical value (16 leading bits) + exact 256-bit ranking inside each bucket;
+//   * A'/S' are expanded from the run structure (binary search of the row in the run offsets);
+//   * Z uses per-bin inverse tables (Montgomery-trick batch inversion over the bins, not the
+//     rows) and a single-pass decoupled-look-back prefix product over 256-bit Montgomery
+//     multiplies (warp shuffles inside a tile).
+#include "internal.h"
+
+namespace h2 {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ fr_t fr_from_tab(const uint4 *__restrict__ frtab, uint32_t b) {
+    uint4 lo = frtab[2 * b], hi = frtab[2 * b + 1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ fr_t fr_ld(const fr_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ void fr_st(fr_t *p, const fr_t &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ uint32_t fr_bitlen(const fr_t &c) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (c.v[i]) bits = 32 * i + (32 - __clz(c.v[i]));
+    return bits;
+}
+__device__ __forceinline__ uint32_t bucket_of(const fr_t &c, uint32_t maxbits) {
+    const uint32_t shift = maxbits > 16 ? maxbits - 16 : 0;
+    const uint32_t w = shift >> 5, b = shift & 31;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i == (int)w) lo = c.v[i];
+        if (i == (int)w + 1) hi = c.v[i];
+    }
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)((x >> b) & 0xffffu);
+}
+
+// Exclusive scan of data[0..n) in place by ONE CTA of 1024 threads; returns the total to all.
+__device__ uint32_t block_exclusive_scan_u32(uint32_t *data, uint32_t n) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    const uint32_t t = threadIdx.x, nt = blockDim.x;
+    const uint32_t chunk = (n + nt - 1) / nt;
+    const uint32_t lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += data[i];
+    // block exclusive scan of `sum`
+    uint32_t inc = sum;
+    const int lane = t & 31, wid = t >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (int)(nt >> 5) ? s_warp[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += y;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[wid] + inc - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t x = data[i];
+        data[i] = run;
+        run += x;
+    }
+    __syncthreads();
+    return s_total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1a: per-view bins (once per theta)
+// ---------------------------------------------------------------------------------------------
+// viewmeta[v*8 + 0] = max bit length of the canonical values, +1 = number of bins
+__global__ void __launch_bounds__(256)
+k_view_values(const uint8_t *__restrict__ sbox, const uint4 *__restrict__ frtab,
+              const fr_t *__restrict__ chal, fr_t *__restrict__ val, fr_t *__restrict__ canon,
+              uint32_t *__restrict__ viewmeta) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const fr_t theta = fr_ld(chal);
+    const uint32_t trow = table_row_of_entry(v, e);
+    fr_t acc = fr_from_tab(frtab, table_cell(sbox, 0, trow, ~0ull));
+    for (int j = 1; j < v + 2; ++j)
+        acc = fr_add(fr_mul(acc, theta), fr_from_tab(frtab, table_cell(sbox, j, trow, ~0ull)));
+    fr_st(val + (size_t)v * BIN_STRIDE + e, acc);
+    const fr_t c = fr_to_canonical(acc);
+    fr_st(canon + (size_t)v * BIN_STRIDE + e, c);
+    atomicMax(viewmeta + v * 8, fr_bitlen(c));
+}
+
+__global__ void __launch_bounds__(256)
+k_bucket_hist(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
+              uint32_t *__restrict__ bhist) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const uint32_t b = bucket_of(fr_ld(canon + (size_t)v * BIN_STRIDE + e), viewmeta[v * 8]);
+    atomicAdd(bhist + (size_t)v * (N_BUCKETS + 1) + b, 1u);
+}
+
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ bhist) {
+    const int v = blockIdx.x;
+    uint32_t *h = bhist + (size_t)v * (N_BUCKETS + 1);
+    uint32_t total = block_exclusive_scan_u32(h, N_BUCKETS);
+    if (threadIdx.x == 0) h[N_BUCKETS] = total;
+}
+
+__global__ void __launch_bounds__(256)
+k_bucket_scatter(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
+                 const uint32_t *__restrict__ bhist, uint32_t *__restrict__ bcur,
+                 uint32_t *__restrict__ slot) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const uint32_t b = bucket_of(fr_ld(canon + (size_t)v * BIN_STRIDE + e), viewmeta[v * 8]);
+    const uint32_t pos = bhist[(size_t)v * (N_BUCKETS + 1) + b] +
+                         atomicAdd(bcur + (size_t)v * N_BUCKETS + b, 1u);
+    slot[(size_t)v * BIN_STRIDE + pos] = e;
+}
+
+// exact position of entry e: bucket offset + number of bucket mates that order before it
+__global__ void __launch_bounds__(256)
+k_bucket_rank(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
+              const uint32_t *__restrict__ bhist, const uint32_t *__restrict__ slot,
+              uint32_t *__restrict__ sorted) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const fr_t *cv = canon + (size_t)v * BIN_STRIDE;
+    const fr_t me = fr_ld(cv + e);
+    const uint32_t b = bucket_of(me, viewmeta[v * 8]);
+    const uint32_t lo = bhist[(size_t)v * (N_BUCKETS + 1) + b];
+    const uint32_t hi = bhist[(size_t)v * (N_BUCKETS + 1) + b + 1];
+    uint32_t rank = 0;
+    for (uint32_t p = lo; p < hi; ++p) {
+        const uint32_t e2 = slot[(size_t)v * BIN_STRIDE + p];
+        if (e2 == e) continue;
+        const int cmp = fr_cmp_canonical(fr_ld(cv + e2), me);
+        rank += (cmp < 0 || (cmp == 0 && e2 < e)) ? 1u : 0u;
+    }
+    sorted[(size_t)v * BIN_STRIDE + lo + rank] = e;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_heads(const fr_t *__restrict__ canon, const uint32_t *__restrict__ sorted,
+            uint32_t *__restrict__ head, uint32_t *__restrict__ kidx) {
+    const int v = blockIdx.y;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= view_entries(v)) return;
+    const fr_t *cv = canon + (size_t)v * BIN_STRIDE;
+    const uint32_t *sv = sorted + (size_t)v * BIN_STRIDE;
+    uint32_t h = 1;
+    if (p > 0) h = fr_eq(fr_ld(cv + sv[p]), fr_ld(cv + sv[p - 1])) ? 0u : 1u;
+    head[(size_t)v * BIN_STRIDE + p] = h;
+    kidx[(size_t)v * BIN_STRIDE + p] = h;
+}
+
+__global__ void __launch_bounds__(1024)
+k_bin_index_scan(uint32_t *__restrict__ kidx, uint32_t *__restrict__ viewmeta) {
+    const int v = blockIdx.x;
+    // exclusive scan of the head flags: kidx[p] = (#heads before p); bin of p = kidx[p]+head[p]-1
+    uint32_t total = block_exclusive_scan_u32(kidx + (size_t)v * BIN_STRIDE, view_entries(v));
+    if (threadIdx.x == 0) viewmeta[v * 8 + 1] = total;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_fill(const fr_t *__restrict__ val, const uint32_t *__restrict__ sorted,
+           const uint32_t *__restrict__ head, const uint32_t *__restrict__ kidx,
+           uint64_t usable, fr_t *__restrict__ dval, uint32_t *__restrict__ rank,
+           uint32_t *__restrict__ ts) {
+    const int v = blockIdx.y;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= view_entries(v)) return;
+    const size_t o = (size_t)v * BIN_STRIDE;
+    const uint32_t e = sorted[o + p];
+    const uint32_t h = head[o + p];
+    const uint32_t k = kidx[o + p] + h - 1;
+    rank[o + e] = k;
+    if (h) fr_st(dval + o + k, fr_ld(val + o + e));
+    // table rows 66561..u-1 repeat row 0 (halo2 pads with the offset-0 value) -> entry 0
+    uint32_t mult = entry_multiplicity(v, e) + (e == 0 ? (uint32_t)(usable - TABLE_ROWS) : 0u);
+    atomicAdd(ts + o + k, mult);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1b: per-lookup histogram of the rows over the bins
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_lookup_hist(Shape sh, const uint32_t *__restrict__ trace, const uint32_t *__restrict__ rank,
+              uint32_t *__restrict__ cnt, uint64_t row_begin, uint64_t row_end) {
+    const uint64_t n = sh.n();
+    const int set = blockIdx.y;
+    const int ops = sh.ops_per_set();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t end = row_end < sh.usable() ? row_end : sh.usable();
+    for (uint64_t row = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < end;
+         row += stride) {
+        const uint32_t w = trace[(uint64_t)set * n + row];
+        const uint32_t op = w >> 24;
+        if (!op) continue;
+        const int v = view_of_op(op);
+        const uint32_t e = entry_of_table_row(v, table_row_of_word(w));
+        const uint32_t k = rank[(size_t)v * BIN_STRIDE + e];
+        atomicAdd(cnt + (size_t)(set * ops + (int)op - 1) * BIN_STRIDE + k, 1u);
+    }
+}
+
+// One CTA (1024 threads) per lookup: add the inactive rows to the zero bin, then compact the
+// nonempty input bins (offz/nzk) and the leftover table bins (loffz/lk).
+__global__ void __launch_bounds__(1024)
+k_lookup_bins(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ rank,
+              const uint32_t *__restrict__ ts, const uint32_t *__restrict__ viewmeta,
+              uint32_t *__restrict__ offz, uint32_t *__restrict__ nzk,
+              uint32_t *__restrict__ loffz, uint32_t *__restrict__ lk,
+              LookupMeta *__restrict__ meta, uint32_t *__restrict__ err) {
+    __shared__ uint32_t s_red[32];
+    __shared__ uint4 s_scan[32];
+    __shared__ uint32_t s_active;
+    const int l = blockIdx.x;
+    const int ops = sh.ops_per_set();
+    const uint32_t op = (uint32_t)(l % ops) + 1;
+    const int v = view_of_op(op);
+    const uint32_t D = viewmeta[v * 8 + 1];
+    const uint32_t usable = (uint32_t)sh.usable();
+    const uint32_t k0 = rank[(size_t)v * BIN_STRIDE + (v == 0 ? 1280u : TROW_ZERO)];
+    const uint32_t *c = cnt + (size_t)l * BIN_STRIDE;
+    const uint32_t *tsv = ts + (size_t)v * BIN_STRIDE;
+    const uint32_t t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
+    const uint32_t chunk = (D + nt - 1) / nt;
+    const uint32_t lo = min(D, t * chunk), hi = min(D, lo + chunk);
+    // pass 0: number of active rows
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; ++k) sum += c[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) s_red[wid] = sum;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t a = 0;
+        for (uint32_t i = 0; i < (nt >> 5); ++i) a += s_red[i];
+        s_active = a;
+    }
+    __syncthreads();
+    const uint32_t zero_extra = usable - s_active;
+    // pass 1: per-thread sums of (rows, nonempty bins, leftover, leftover bins)
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint32_t bad = 0;
+    for (uint32_t k = lo; k < hi; ++k) {
+        const uint32_t ck = c[k] + (k == k0 ? zero_extra : 0u);
+        const uint32_t nzf = ck ? 1u : 0u;
+        const uint32_t tk = tsv[k];
+        if (tk < nzf) bad = 1;
+        const uint32_t lf = tk - nzf;
+        acc.x += ck;
+        acc.y += nzf;
+        acc.z += lf;
+        acc.w += lf ? 1u : 0u;
+    }
+    // block exclusive scan of acc
+    uint4 inc = acc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint4 y;
+        y.x = __shfl_up_sync(0xffffffffu, inc.x, d);
+        y.y = __shfl_up_sync(0xffffffffu, inc.y, d);
+        y.z = __shfl_up_sync(0xffffffffu, inc.z, d);
+        y.w = __shfl_up_sync(0xffffffffu, inc.w, d);
+        if ((int)lane >= d) { inc.x += y.x; inc.y += y.y; inc.z += y.z; inc.w += y.w; }
+    }
+    if (lane == 31) s_scan[wid] = inc;
+    __syncthreads();
+    if (t == 0) {
+        uint4 run = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = 0; i < (nt >> 5); ++i) {
+            uint4 x = s_scan[i];
+            s_scan[i] = run;
+            run.x += x.x; run.y += x.y; run.z += x.z; run.w += x.w;
+        }
+        // totals: rows must equal usable, leftover must equal usable - nonempty
+        LookupMeta m;
+        m.n_nonempty = run.y;
+        m.n_left = run.w;
+        m.repeated = run.z;
+        m.k_zero = k0;
+        m.bad = (run.x != usable || run.z != usable - run.y) ? 2u : 0u;
+        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        meta[l] = m;
+        if (m.bad) atomicOr(err + 1, 1u);
+        offz[(size_t)l * BIN_STRIDE + run.y] = usable;
+        loffz[(size_t)l * BIN_STRIDE + run.w] = run.z;
+    }
+    __syncthreads();
+    uint4 base = s_scan[wid];
+    base.x += inc.x - acc.x; base.y += inc.y - acc.y; base.z += inc.z - acc.z; base.w += inc.w - acc.w;
+    // pass 2: write the compacted arrays
+    for (uint32_t k = lo; k < hi; ++k) {
+        const uint32_t ck = c[k] + (k == k0 ? zero_extra : 0u);
+        const uint32_t nzf = ck ? 1u : 0u;
+        const uint32_t lf = tsv[k] - nzf;
+        if (nzf) {
+            offz[(size_t)l * BIN_STRIDE + base.y] = base.x;
+            nzk[(size_t)l * BIN_STRIDE + base.y] = k;
+            base.y += 1;
+            base.x += ck;
+        }
+        if (lf) {
+            loffz[(size_t)l * BIN_STRIDE + base.w] = base.z;
+            lk[(size_t)l * BIN_STRIDE + base.w] = k;
+            base.w += 1;
+            base.z += lf;
+        }
+    }
+    if (bad) {
+        atomicOr(&meta[l].bad, 1u);
+        atomicOr(err + 1, 1u);
+    }
+}
+
+// largest j in [0, cnt) with arr[j] <= x   (arr ascending, arr[0] == 0 <= x)
+__device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ arr, uint32_t cnt,
+                                              uint32_t x) {
+    uint32_t lo = 0, hi = cnt;  // invariant: arr[lo] <= x, (hi == cnt or arr[hi] > x)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (arr[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// bins (k of A', k' of S') of usable row i
+struct RowBins {
+    uint32_t k, kp;
+};
+__device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
+                                            const uint32_t *__restrict__ offz,
+                                            const uint32_t *__restrict__ nzk,
+                                            const uint32_t *__restrict__ loffz,
+                                            const uint32_t *__restrict__ lk) {
+    RowBins rb;
+    const uint32_t j = search_le(offz, m.n_nonempty, i);
+    rb.k = nzk[j];
+    if (offz[j] == i) {
+        rb.kp = rb.k;  // first occurrence: S' = A'
+    } else {
+        // repeated rows, in row order, receive the leftover multiset from its END
+        const uint32_t rho = i - (j + 1);
+        const uint32_t jj = m.repeated - 1 - rho;
+        rb.kp = lk[search_le(loffz, m.n_left, jj)];
+    }
+    return rb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1c: expand A, S, A', S' (one lane per row, 256-bit stores)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
+           const fr_t *__restrict__ val, const fr_t *__restrict__ dval,
+           const uint32_t *__restrict__ offz_all, const uint32_t *__restrict__ nzk_all,
+           const uint32_t *__restrict__ loffz_all, const uint32_t *__restrict__ lk_all,
+           const LookupMeta *__restrict__ meta, uint64_t *__restrict__ A, uint64_t *__restrict__ S,
+           uint64_t *__restrict__ Ap, uint64_t *__restrict__ Sp, uint64_t row_begin,
+           uint64_t row_end) {
+    const int li = blockIdx.y;            // index inside this call
+    const int l = first_lookup + li;      // lookup index in the circuit
+    const int ops = sh.ops_per_set();
+    const int set = l / ops;
+    const uint32_t op = (uint32_t)(l % ops) + 1;
+    const int v = view_of_op(op);
+    const uint64_t n = sh.n(), usable = sh.usable();
+    const uint64_t out_rows = row_end - row_begin;
+    const LookupMeta m = meta[l];
+    const uint32_t *offz = offz_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *nzk = nzk_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *loffz = loffz_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *lk = lk_all + (size_t)l * BIN_STRIDE;
+    const fr_t *valv = val + (size_t)v * BIN_STRIDE;
+    const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const fr_t zero = fr_zero();
+    for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
+         lrow += stride) {
+        const uint64_t row = row_begin + lrow;
+        const size_t o = ((size_t)li * out_rows + lrow) * 4;
+        if (row >= usable) {
+            if (A) fr_store_256(A + o, zero);
+            if (S) fr_store_256(S + o, zero);
+            fr_store_256(Ap + o, zero);
+            fr_store_256(Sp + o, zero);
+            continue;
+        }
+        if (A) {
+            const uint32_t w = trace[(uint64_t)set * n + row];
+            fr_t a = zero;
+            if ((w >> 24) == op) a = fr_ld(valv + entry_of_table_row(v, table_row_of_word(w)));
+            fr_store_256(A + o, a);
+        }
+        if (S) {
+            const uint32_t e = row < TABLE_ROWS ? entry_of_table_row(v, (uint32_t)row) : 0u;
+            fr_store_256(S + o, fr_ld(valv + e));
+        }
+        const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk);
+        fr_store_256(Ap + o, fr_ld(dv + rb.k));
+        fr_store_256(Sp + o, fr_ld(dv + rb.kp));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2a: per-bin tables for the grand product (once per beta,gamma)
+//   ib[k] = 1/(d_k + beta), ig[k] = 1/(d_k + gamma)  — Montgomery-trick batch inversion, CH bins
+//   per thread;  nac[k] = (d_k + beta) * (pad + gamma) with pad = value of table row 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int INV_CH = 8;
+__global__ void __launch_bounds__(128)
+k_inv_tables(const fr_t *__restrict__ chal, const fr_t *__restrict__ dval,
+             const fr_t *__restrict__ val, const uint32_t *__restrict__ viewmeta,
+             fr_t *__restrict__ ib, fr_t *__restrict__ ig, fr_t *__restrict__ nac,
+             uint32_t *__restrict__ err) {
+    const int v = blockIdx.y;
+    const uint32_t D = viewmeta[v * 8 + 1];
+    const uint32_t k0 = (blockIdx.x * blockDim.x + threadIdx.x) * INV_CH;
+    if (k0 >= D) return;
+    const size_t o = (size_t)v * BIN_STRIDE;
+    const fr_t beta = fr_ld(chal + 1), gamma = fr_ld(chal + 2);
+    const fr_t padg = fr_add(fr_ld(val + o), gamma);
+    const uint32_t cnt = min((uint32_t)INV_CH, D - k0);
+    for (int which = 0; which < 2; ++which) {
+        const fr_t ch = which == 0 ? beta : gamma;
+        fr_t *out = which == 0 ? ib : ig;
+        fr_t x[INV_CH], pre[INV_CH];
+        fr_t acc = fr_one();
+        for (uint32_t j = 0; j < cnt; ++j) {
+            x[j] = fr_add(fr_ld(dval + o + k0 + j), ch);
+            pre[j] = acc;
+            if (fr_is_zero(x[j])) {
+                atomicOr(err, 1u);  // halo2's batch_invert would leave a zero here
+            } else {
+                acc = fr_mul(acc, x[j]);
+            }
+            if (which == 0) fr_st(nac + o + k0 + j, fr_mul(x[j], padg));
+        }
+        acc = fr_inv(acc);
+        for (int j = (int)cnt - 1; j >= 0; --j) {
+            if (fr_is_zero(x[j])) {
+                fr_st(out + o + k0 + j, x[j]);
+                continue;
+            }
+            fr_st(out + o + k0 + j, fr_mul(acc, pre[j]));
+            acc = fr_mul(acc, x[j]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2b: grand product Z — single pass, decoupled look-back over tiles of ZT*ZI rows
+// ---------------------------------------------------------------------------------------------
+constexpr int ZT = 128;  // threads per tile
+constexpr int ZI = 8;    // consecutive rows per thread
+constexpr int ZTILE = ZT * ZI;
+
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ fr_t fr_shfl_up(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_ld_volatile(const fr_t *p) {
+    // plain (weak) loads ordered after an acquire load of the flag
+    return fr_ld(p);
+}
+
+// factor f[i] = (A[i]+beta)(S[i]+gamma) / ((A'[i]+beta)(S'[i]+gamma)) of usable row i
+struct ZTables {
+    const fr_t *val, *dval, *ib, *ig, *nac;  // already offset to the lookup's view
+    const uint32_t *rank;
+    const uint32_t *offz, *nzk, *loffz, *lk;  // already offset to the lookup
+};
+
+// kMode 0: write Z with look-back; kMode 1: only the product of the shard's factors
+template <int kMode>
+__global__ void __launch_bounds__(ZT)
+k_grand_product(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
+                const fr_t *__restrict__ chal, const fr_t *__restrict__ val_all,
+                const fr_t *__restrict__ dval_all, const fr_t *__restrict__ ib_all,
+                const fr_t *__restrict__ ig_all, const fr_t *__restrict__ nac_all,
+                const uint32_t *__restrict__ rank_all, const uint32_t *__restrict__ offz_all,
+                const uint32_t *__restrict__ nzk_all, const uint32_t *__restrict__ loffz_all,
+                const uint32_t *__restrict__ lk_all, const LookupMeta *__restrict__ meta,
+                fr_t *__restrict__ tile_agg, fr_t *__restrict__ tile_inc,
+                uint32_t *__restrict__ tile_flag, uint32_t *__restrict__ tile_ctr,
+                const fr_t *__restrict__ carry_in, uint64_t n_tiles, uint64_t *__restrict__ Z,
+                uint64_t row_begin, uint64_t row_end) {
+    __shared__ fr_t s_warp[ZT / 32];
+    __shared__ fr_t s_tile_excl;
+    __shared__ uint32_t s_tile;
+    const int li = blockIdx.y;
+    const int l = first_lookup + li;
+    const int ops = sh.ops_per_set();
+    const int set = l / ops;
+    const uint32_t op = (uint32_t)(l % ops) + 1;
+    const int v = view_of_op(op);
+    const uint64_t n = sh.n();
+    const uint32_t usable = (uint32_t)sh.usable();
+    const uint64_t out_rows = row_end - row_begin;
+    const LookupMeta m = meta[l];
+    const uint32_t *offz = offz_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *nzk = nzk_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *loffz = loffz_all + (size_t)l * BIN_STRIDE;
+    const uint32_t *lk = lk_all + (size_t)l * BIN_STRIDE;
+    const size_t vo = (size_t)v * BIN_STRIDE;
+    const fr_t *valv = val_all + vo, *dv = dval_all + vo, *ib = ib_all + vo, *ig = ig_all + vo,
+               *nac = nac_all + vo;
+    const uint32_t *rank = rank_all + vo;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+
+    // dynamic tile id: a tile only waits on tiles that already started
+    if (t == 0) s_tile = atomicAdd(tile_ctr + l, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t row0 = row_begin + (uint64_t)tile * ZTILE + (uint64_t)t * ZI;
+
+    const fr_t beta = fr_ld(chal + 1), gamma = fr_ld(chal + 2);
+    fr_t f[ZI];
+    // bins of the thread's first usable row by binary search, then walk
+    uint32_t j = 0, jl = 0;
+    bool have_j = false, have_jl = false;
+#pragma unroll
+    for (int q = 0; q < ZI; ++q) {
+        const uint64_t row = row0 + q;
+        if (row >= usable || row >= row_end) {
+            f[q] = fr_one();
+            continue;
+        }
+        const uint32_t i = (uint32_t)row;
+        // numerator
+        const uint32_t w = trace[(uint64_t)set * n + row];
+        uint32_t kin = m.k_zero;
+        if ((w >> 24) == op) kin = rank[entry_of_table_row(v, table_row_of_word(w))];
+        fr_t num;
+        if (i < TABLE_ROWS) {
+            const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, i)), gamma);
+            num = fr_mul(fr_add(fr_ld(dv + kin), beta), sg);
+        } else {
+            num = fr_ld(nac + kin);
+        }
+        // denominator bins
+        if (!have_j) {
+            j = search_le(offz, m.n_nonempty, i);
+            have_j = true;
+        } else {
+            while (offz[j + 1] <= i) ++j;
+        }
+        const uint32_t k = nzk[j];
+        uint32_t kp = k;
+        if (offz[j] != i) {
+            const uint32_t jj = m.repeated - 1 - (i - (j + 1));
+            if (!have_jl) {
+                jl = search_le(loffz, m.n_left, jj);
+                have_jl = true;
+            } else {
+                while (loffz[jl] > jj) --jl;
+            }
+            kp = lk[jl];
+        }
+        f[q] = fr_mul(num, fr_mul(fr_ld(ib + k), fr_ld(ig + kp)));
+    }
+    // thread total
+    fr_t tot = f[0];
+#pragma unroll
+    for (int q = 1; q < ZI; ++q) tot = fr_mul(tot, f[q]);
+    // warp inclusive scan of the thread totals
+    fr_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        fr_t y = fr_shfl_up(inc, d);
+        if (lane >= d) inc = fr_mul(inc, y);
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    // exclusive prefix of this thread inside the tile
+    fr_t excl = fr_shfl_up(inc, 1);
+    if (lane == 0) excl = fr_one();
+    for (int wq = 0; wq < wid; ++wq) excl = fr_mul(excl, s_warp[wq]);
+
+    if (t == ZT - 1) {
+        // tile aggregate = inclusive value of the last thread
+        const fr_t agg = fr_mul(excl, tot);
+        fr_t *aggp = tile_agg + (size_t)l * n_tiles + tile;
+        fr_t *incp = tile_inc + (size_t)l * n_tiles + tile;
+        uint32_t *flagp = tile_flag + (size_t)l * n_tiles + tile;
+        fr_t prefix;
+        if (tile == 0) {
+            prefix = carry_in ? fr_ld(carry_in + l) : fr_one();
+            fr_st(incp, fr_mul(prefix, agg));
+            st_release_u32(flagp, 2u);
+        } else {
+            fr_st(aggp, agg);
+            st_release_u32(flagp, 1u);
+            // look back
+            fr_t acc = fr_one();
+            int p = (int)tile - 1;
+            while (true) {
+                const uint32_t *fp = tile_flag + (size_t)l * n_tiles + p;
+                uint32_t fl;
+                while ((fl = ld_acquire_u32(fp)) == 0u) __nanosleep(40);
+                if (fl == 2u) {
+                    acc = fr_mul(acc, fr_ld_volatile(tile_inc + (size_t)l * n_tiles + p));
+                    break;
+                }
+                acc = fr_mul(acc, fr_ld_volatile(tile_agg + (size_t)l * n_tiles + p));
+                --p;
+            }
+            prefix = acc;
+            fr_st(incp, fr_mul(prefix, agg));
+            st_release_u32(flagp, 2u);
+        }
+        s_tile_excl = prefix;
+    }
+    __syncthreads();
+    if (kMode == 1) return;
+    fr_t cur = fr_mul(s_tile_excl, excl);
+#pragma unroll
+    for (int q = 0; q < ZI; ++q) {
+        const uint64_t row = row0 + q;
+        if (row < row_end) {
+            const size_t o = ((size_t)li * out_rows + (row - row_begin)) * 4;
+            // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
+            if (row <= usable) fr_store_256(Z + o, cur);
+            else fr_store_256(Z + o, fr_zero());
+        }
+        cur = fr_mul(cur, f[q]);
+    }
+}
+
+// carry[l] = product of the partial products of the shards before `shard` (row-sharded circuit)
+__global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, int shard,
+                              fr_t *__restrict__ carry) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lookups) return;
+    fr_t acc = fr_one();
+    for (int s = 0; s < shard; ++s) acc = fr_mul(acc, fr_ld(gathered + (size_t)s * n_lookups + l));
+    fr_st(carry + l, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+cudaError_t launch_view_bins(h2aes_circuit *c) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(c->d_viewmeta, 0, N_VIEWS * 8 * 4, s))) return e;
+    if ((e = cudaMemsetAsync(c->d_bhist, 0, (size_t)N_VIEWS * (N_BUCKETS + 1) * 4, s))) return e;
+    if ((e = cudaMemsetAsync(c->d_bcur, 0, (size_t)N_VIEWS * N_BUCKETS * 4, s))) return e;
+    if ((e = cudaMemsetAsync(c->d_ts, 0, (size_t)N_VIEWS * BIN_STRIDE * 4, s))) return e;
+    dim3 g(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
+    k_view_values<<<g, 256, 0, s>>>(ctx->d_sbox, ctx->d_frtab, c->d_chal, c->d_val, c->d_canon,
+                                    c->d_viewmeta);
+    k_bucket_hist<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist);
+    k_bucket_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_bhist);
+    k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_bcur, c->d_slot);
+    k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_slot, c->d_sorted);
+    k_bin_heads<<<g, 256, 0, s>>>(c->d_canon, c->d_sorted, c->d_head, c->d_slot);
+    k_bin_index_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_slot, c->d_viewmeta);
+    k_bin_fill<<<g, 256, 0, s>>>(c->d_val, c->d_sorted, c->d_head, c->d_slot, c->sh.usable(),
+                                 c->d_dval, c->d_rank, c->d_ts);
+    ctx->launches += 8;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    const int L = c->sh.n_lookups();
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(c->d_cnt, 0, (size_t)L * BIN_STRIDE * 4, s))) return e;
+    dim3 g(ctx->sm_count * 2, c->sh.n_sets());
+    k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, row_begin, row_end);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lookup_bins(h2aes_circuit *c) {
+    h2aes_ctx *ctx = c->ctx;
+    const int L = c->sh.n_lookups();
+    k_lookup_bins<<<L, 1024, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
+                                               c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta,
+                                               c->d_err);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
+                            uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    const uint64_t rows = row_end - row_begin;
+    unsigned gx = cdiv(rows, 256);
+    const unsigned cap = (unsigned)ctx->sm_count * 8;
+    if (gx > cap) gx = cap;
+    dim3 g(gx, count);
+    k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_val, c->d_dval, c->d_offz,
+                                           c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S, Ap, Sp,
+                                           row_begin, row_end);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inv_tables(h2aes_circuit *c) {
+    h2aes_ctx *ctx = c->ctx;
+    dim3 g(cdiv(VIEW_MAX_ENTRIES, 128 * INV_CH), N_VIEWS);
+    k_inv_tables<<<g, 128, 0, ctx->stream>>>(c->d_chal, c->d_dval, c->d_val, c->d_viewmeta, c->d_ib,
+                                             c->d_ig, c->d_nac, c->d_err);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
+                                 uint64_t *Z, uint64_t row_begin, uint64_t row_end, int mode) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    const int L = c->sh.n_lookups();
+    const uint64_t rows = row_end - row_begin;
+    const uint64_t tiles = (rows + ZTILE - 1) / ZTILE;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(c->d_tile_flag, 0, (size_t)L * c->n_tiles * 4, s))) return e;
+    if ((e = cudaMemsetAsync(c->d_tile_ctr, 0, (size_t)L * 4, s))) return e;
+    dim3 g((unsigned)tiles, count);
+    if (mode == 0)
+        k_grand_product<0><<<g, ZT, 0, s>>>(c->sh, first, c->d_trace, c->d_chal, c->d_val, c->d_dval,
+                                            c->d_ib, c->d_ig, c->d_nac, c->d_rank, c->d_offz,
+                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, c->d_tile_agg,
+                                            c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, carry_in,
+                                            c->n_tiles, Z, row_begin, row_end);
+    else
+        k_grand_product<1><<<g, ZT, 0, s>>>(c->sh, first, c->d_trace, c->d_chal, c->d_val, c->d_dval,
+                                            c->d_ib, c->d_ig, c->d_nac, c->d_rank, c->d_offz,
+                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, c->d_tile_agg,
+                                            c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, carry_in,
+                                            c->n_tiles, Z, row_begin, row_end);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev) {
+    h2aes_ctx *ctx = c->ctx;
+    const int L = c->sh.n_lookups();
+    k_shard_carry<<<cdiv(L, 64), 64, 0, ctx->stream>>>((const fr_t *)gathered_dev, L, c->shard,
+                                                       c->d_carry);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+uint64_t grand_product_tiles(uint64_t rows) { return (rows + ZTILE - 1) / ZTILE; }
+
+}  // namespace h2

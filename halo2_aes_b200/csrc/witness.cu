@@ -1,0 +1,276 @@
+// witness.cu — advice / fixed / selector / copy-constraint kernels (sm_100a).
+//
+// Replaces, for a whole circuit at a time, what the reference does region by region on one CPU
+// thread: schedule_key (src/key_schedule.rs:80-224), encrypt + lcon (src/aes128.rs:154-301),
+// the chips' assign closures (src/chips/*.rs), load_enc_full_table (src/table.rs:18-192).
+//
+// Kernels
+//   k_key_expand     1 warp: FIPS-197 key expansion with the context's S-box -> 176 bytes.
+//   k_block_states   half a warp per AES block: the 31 16-byte round states of the block.
+//   k_advice         the streaming kernel: one lane per row, computes the row's trace word from
+//                    the block's round states (closed form, layout.h), stores the word (4 B) and
+//                    the three Fr cells of the column set with one 256-bit store each, from a
+//                    256-entry byte->Fr(Montgomery) table in shared memory.  HBM-store bound:
+//                    (3*sets+1) * 2^k * 32 bytes per circuit.
+//   k_fixed          table columns, round_constants and selector columns (input independent).
+//   k_copies         the copy-constraint list (closed form).
+#include "internal.h"
+
+namespace h2 {
+
+struct Key16 {
+    uint8_t b[16];
+};
+
+__global__ void k_key_expand(const uint8_t *__restrict__ sbox, Key16 key, uint8_t *__restrict__ rk) {
+    __shared__ uint8_t s_sbox[256];
+    __shared__ uint8_t s_rk[176];
+    const int l = threadIdx.x;
+    for (int i = l; i < 256; i += 32) s_sbox[i] = sbox[i];
+    if (l < 16) s_rk[l] = key.b[l];
+    __syncwarp();
+    for (int r = 1; r <= 10; ++r) {
+        const uint8_t *p = s_rk + 16 * (r - 1);
+        uint8_t *o = s_rk + 16 * r;
+        if (l < 4) {
+            int rot = (13 + l) - (l == 3 ? 4 : 0);
+            o[l] = (uint8_t)(p[l] ^ s_sbox[p[rot]] ^ (l == 0 ? rcon(r - 1) : 0));
+        }
+        __syncwarp();
+        for (int i = 1; i < 4; ++i) {
+            if (l < 4) o[4 * i + l] = (uint8_t)(p[4 * i + l] ^ o[4 * (i - 1) + l]);
+            __syncwarp();
+        }
+    }
+    for (int i = l; i < 176; i += 32) rk[i] = s_rk[i];
+}
+
+// Half-warp per block; lane i of the half-warp owns state byte i = 4w+j.
+__global__ void __launch_bounds__(128)
+k_block_states(const uint8_t *__restrict__ sbox, const uint8_t *__restrict__ rk,
+               const uint8_t *__restrict__ pts, uint64_t n_blocks, uint8_t *__restrict__ states,
+               uint8_t *__restrict__ cts) {
+    __shared__ uint8_t s_sbox[256];
+    __shared__ uint8_t s_rk[176];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = sbox[i];
+    for (int i = threadIdx.x; i < 176; i += blockDim.x) s_rk[i] = rk[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, l = lane & 15, hb = lane & 16;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t blk = 2 * warp + (lane >> 4);
+    const bool live = blk < n_blocks;
+    const uint64_t bsafe = live ? blk : 0;
+    uint8_t *st = states + bsafe * ST_BYTES;
+    const int w = l >> 2, c = l & 3;
+    uint32_t pt = n_blocks ? pts[bsafe * 16 + l] : 0;
+    uint32_t s = pt ^ s_rk[l];
+    if (live) st[16 * ST_PT + l] = (uint8_t)pt;
+#pragma unroll 1
+    for (int r = 1; r <= 10; ++r) {
+        uint32_t sub = s_sbox[s];
+        if (live) {
+            st[16 * (ST_IN + r - 1) + l] = (uint8_t)s;
+            st[16 * (ST_SUB + r - 1) + l] = (uint8_t)sub;
+        }
+        if (r < 10) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                uint32_t x = __shfl_sync(0xffffffffu, sub, hb + 4 * ((w + t) & 3) + t);
+                int m = mix_coeff(c, t);
+                acc ^= m == 1 ? x : (m == 2 ? gf_mul2((uint8_t)x) : gf_mul3((uint8_t)x));
+            }
+            if (live) st[16 * (ST_MIX + r - 1) + l] = (uint8_t)acc;
+            s = acc ^ s_rk[16 * r + l];
+        } else {
+            uint32_t x = __shfl_sync(0xffffffffu, sub, hb + 4 * ((w + c) & 3) + c);
+            s = x ^ s_rk[160 + l];
+        }
+    }
+    if (live) {
+        st[16 * ST_CT + l] = (uint8_t)s;
+        st[16 * 31 + l] = 0;
+        if (cts) cts[blk * 16 + l] = (uint8_t)s;
+    }
+}
+
+// trace word of (set,row): key-schedule rows, AES block rows, or nothing
+__device__ __forceinline__ uint32_t advice_word(const Shape &sh, uint64_t n_blocks, int set,
+                                                uint64_t row, const uint8_t *s_sbox,
+                                                const uint8_t *s_rk,
+                                                const uint8_t *__restrict__ states) {
+    if (set == 0 && row < KEY_SCHEDULE_ROWS) return ks_trace_word(s_sbox, s_rk, (uint32_t)row);
+    if (sh.kind != KIND_AES) return 0;
+    uint32_t base = (uint32_t)sh.set_base(set);
+    if (row < base) return 0;
+    uint32_t rel = (uint32_t)row - base;
+    uint32_t b = rel / (uint32_t)AES_ROWS;
+    if (b >= sh.blocks_in_set(set, n_blocks)) return 0;
+    uint32_t q = rel - b * (uint32_t)AES_ROWS;
+    const uint8_t *st = states + (sh.first_block_of_set(set) + b) * ST_BYTES;
+    return block_trace_word(st, s_rk, q);
+}
+
+// One lane per row.  Work item = (column set | words column, chunk of 32 consecutive rows).
+// Output column c of the shard starts at advice + c * out_rows * 4 (u64 units).
+__global__ void __launch_bounds__(256)
+k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
+         const uint8_t *__restrict__ states, const uint8_t *__restrict__ sbox,
+         const uint4 *__restrict__ frtab, uint64_t *__restrict__ advice,
+         uint32_t *__restrict__ trace, uint64_t row_begin, uint64_t row_end) {
+    __shared__ uint4 s_fr[512];
+    __shared__ uint8_t s_rk[176];
+    __shared__ uint8_t s_sbox[256];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_fr[i] = frtab[i];
+    for (int i = threadIdx.x; i < 176; i += blockDim.x) s_rk[i] = rk[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = sbox[i];
+    __syncthreads();
+    const uint64_t n = sh.n();
+    const int nsets = sh.n_sets();
+    const uint64_t out_rows = row_end - row_begin;
+    const uint64_t chunks = (out_rows + 31) >> 5;
+    const uint64_t total = chunks * (uint64_t)(nsets + 1);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    for (uint64_t item = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+         item < total; item += nwarps) {
+        const int set = (int)(item / chunks);
+        const uint64_t lrow = (item - (uint64_t)set * chunks) * 32 + lane;
+        if (lrow >= out_rows) continue;
+        const uint64_t row = row_begin + lrow;
+        if (set < nsets) {
+            const uint32_t word = advice_word(sh, n_blocks, set, row, s_sbox, s_rk, states);
+            trace[(uint64_t)set * n + row] = word;
+            uint64_t *o = advice + ((uint64_t)(3 * set) * out_rows + lrow) * 4;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint32_t b = (word >> (8 * j)) & 255u;
+                store_256(o + (uint64_t)j * out_rows * 4, s_fr[2 * b], s_fr[2 * b + 1]);
+            }
+        } else {
+            const uint32_t b = row < (uint64_t)WORDS_ROWS ? ks_words_byte(s_rk, (uint32_t)row) : 0;
+            uint64_t *o = advice + ((uint64_t)(3 * nsets) * out_rows + lrow) * 4;
+            store_256(o, s_fr[2 * b], s_fr[2 * b + 1]);
+        }
+    }
+}
+
+// Fixed columns (4 table columns + round_constants) and selector columns as Fr 0/1.
+__global__ void __launch_bounds__(256)
+k_fixed(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ sbox,
+        const uint4 *__restrict__ frtab, uint64_t *__restrict__ fixed,
+        uint64_t *__restrict__ selectors, uint64_t row_begin, uint64_t row_end) {
+    __shared__ uint4 s_fr[512];
+    __shared__ uint8_t s_sbox[256];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_fr[i] = frtab[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = sbox[i];
+    __syncthreads();
+    const uint64_t usable = sh.usable();
+    const uint64_t out_rows = row_end - row_begin;
+    const uint64_t chunks = (out_rows + 31) >> 5;
+    const int ncols = sh.n_fixed() + sh.n_selectors();
+    const uint64_t total = chunks * (uint64_t)ncols;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int ops = sh.ops_per_set();
+    for (uint64_t item = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+         item < total; item += nwarps) {
+        const int col = (int)(item / chunks);
+        const uint64_t lrow = (item - (uint64_t)col * chunks) * 32 + lane;
+        if (lrow >= out_rows) continue;
+        const uint64_t row = row_begin + lrow;
+        uint32_t v;
+        uint64_t *o;
+        if (col < 5) {
+            if (!fixed) continue;
+            v = col < 4 ? table_cell(s_sbox, col, row, usable) : rc_cell(row);
+            o = fixed + ((uint64_t)col * out_rows + lrow) * 4;
+        } else {
+            if (!selectors) continue;
+            const int q = col - 5;
+            if (q < sh.n_complex()) {
+                const int set = q / ops, t = q - set * ops;
+                v = row_op(sh, n_blocks, set, row) == (uint32_t)(t + 1) ? 1u : 0u;
+            } else {
+                int ri;
+                v = ks_is_rcon_row(row, &ri) ? 1u : 0u;
+            }
+            o = selectors + ((uint64_t)q * out_rows + lrow) * 4;
+        }
+        store_256(o, s_fr[2 * v], s_fr[2 * v + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_copies(Shape sh, uint64_t n_copies, uint64_t *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_copies; i += stride) {
+        CopyPair cp;
+        if (!copy_pair(sh, i, &cp)) continue;
+        ulonglong4 v;
+        v.x = cp.dst.col;
+        v.y = cp.dst.row;
+        v.z = cp.src.col;
+        v.w = cp.src.row;
+        uint4 lo = make_uint4((uint32_t)v.x, 0, (uint32_t)v.y, (uint32_t)(v.y >> 32));
+        uint4 hi = make_uint4((uint32_t)v.z, 0, (uint32_t)v.w, (uint32_t)(v.w >> 32));
+        store_256(out + 4 * i, lo, hi);
+    }
+}
+
+// byte -> Fr(Montgomery) table, built on the device once per context
+__global__ void k_build_frtab(uint4 *__restrict__ frtab) {
+    const int b = threadIdx.x;
+    fr_t f = fr_from_u32((uint32_t)b);
+    frtab[2 * b] = make_uint4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    frtab[2 * b + 1] = make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+static inline int grid_for(const h2aes_ctx *ctx, int ctas_per_sm) { return ctx->sm_count * ctas_per_sm; }
+
+cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
+    k_build_frtab<<<1, 256, 0, ctx->stream>>>(ctx->d_frtab);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
+                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev,
+                           uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    Key16 k16;
+    for (int i = 0; i < 16; ++i) k16.b[i] = key[i];
+    k_key_expand<<<1, 32, 0, ctx->stream>>>(ctx->d_sbox, k16, c->d_rk);
+    ctx->launches++;
+    if (n_blocks) {
+        const uint64_t blocks_per_cta = 8;
+        unsigned grid = (unsigned)((n_blocks + blocks_per_cta - 1) / blocks_per_cta);
+        k_block_states<<<grid, 128, 0, ctx->stream>>>(ctx->d_sbox, c->d_rk, pts_dev, n_blocks,
+                                                      c->d_states, cts_dev);
+        ctx->launches++;
+    }
+    k_advice<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
+                                                        ctx->d_sbox, ctx->d_frtab, advice_dev,
+                                                        c->d_trace, row_begin, row_end);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
+                         uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    k_fixed<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, ctx->d_sbox, ctx->d_frtab,
+                                                       fixed_dev, selectors_dev, row_begin, row_end);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_copies(h2aes_circuit *c, uint64_t n_copies, uint64_t *out) {
+    h2aes_ctx *ctx = c->ctx;
+    k_copies<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(c->sh, n_copies, out);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace h2

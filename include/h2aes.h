@@ -1,0 +1,246 @@
+/*
+ * h2aes.h — C ABI of the B200 witness-generation backend for tkmct/halo2-aes.
+ *
+ * This is the drop-in boundary: everything a Rust `build.rs`/`extern "C"` block (or cgo, JNI,
+ * ctypes ...) needs to replace the CPU assignment done by the reference's chips.  The reference
+ * has no FFI of its own; each entry point below names the reference interface it stands in for
+ * (paths relative to the reference repository).  See INTEGRATION.md for the Rust-side binding.
+ *
+ * Conventions
+ *   - every function returns an int32 status (H2AES_OK == 0); nothing unwinds across the ABI;
+ *   - field elements are bn256 `Fr` exactly as halo2curves 0.6.1 lays them out in memory:
+ *     4 little-endian u64 limbs of x*R mod r (Montgomery form) — a column is `n` such elements,
+ *     bit-compatible with `Vec<Fr>` / `Polynomial<Fr, LagrangeCoeff>`;
+ *   - multi-column outputs are column-major `[column][row][4]`;
+ *   - `_dev` functions take DEVICE pointers for bulk data and are asynchronous on the context's
+ *     stream; `_host` functions take HOST pointers, do the copies themselves and return after
+ *     the result is in host memory.  Small inputs (keys, challenges) are always host pointers;
+ *   - buffers are caller-owned; the library never frees caller memory;
+ *   - a context (and its circuits) may be used from one host thread at a time;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     H2AES_ERR_CUDA.
+ */
+#ifndef H2AES_H
+#define H2AES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2AES_ABI_VERSION 1
+
+/* status codes */
+#define H2AES_OK 0
+#define H2AES_ERR_ARG 1            /* null pointer, bad kind/k/N, out-of-range index             */
+#define H2AES_ERR_CAPACITY 2       /* src/aes128.rs:160-162 panic!("AES calls too many...")      */
+#define H2AES_ERR_ROWS 3           /* halo2 Error::NotEnoughRowsAvailable (k < 17, or a block     */
+                                   /* would touch the last 6 rows)                                */
+#define H2AES_ERR_NOT_SCHEDULED 4  /* src/aes128.rs:170 expect("Keys should be scheduled")       */
+#define H2AES_ERR_LOOKUP 5         /* halo2 Error::ConstraintSystemFailure in                     */
+                                   /* permute_expression_pair (input value not in table)          */
+#define H2AES_ERR_CUDA 6
+#define H2AES_ERR_NCCL 7
+#define H2AES_ERR_NOMEM 8
+#define H2AES_ERR_STATE 9          /* call order: lookups before witness, product before permuted */
+#define H2AES_ERR_ZERO_DENOM 10    /* (A'+beta)(S'+gamma) == 0 for some row (prob. ~2^-230);      */
+                                   /* halo2's batch_invert would silently leave a zero there      */
+
+/* circuit kinds */
+#define H2AES_KIND_AES 0      /* FixedAes128Config<K,N>: src/aes128.rs:27-141                     */
+#define H2AES_KIND_KEYSCHED 1 /* key-schedule-only circuit: src/key_schedule.rs:242-320,          */
+                              /* benches/key_schedule.rs:26-89 (N is ignored, one column set)     */
+
+/* S-box data */
+#define H2AES_SBOX_REFERENCE 0 /* src/constant.rs:1-14 as committed: S_BOX[255] == 23             */
+#define H2AES_SBOX_FIPS197 1   /* FIPS-197 value 0x16 at index 255                                */
+
+/* per-row operation codes (which complex selector is enabled on a row of a column set) */
+#define H2AES_OP_NONE 0
+#define H2AES_OP_RANGE 1 /* == table.rs Tag::U8     */
+#define H2AES_OP_XOR 2   /* == table.rs Tag::Xor    */
+#define H2AES_OP_SBOX 3  /* == table.rs Tag::Sbox   */
+#define H2AES_OP_MUL2 4  /* == table.rs Tag::GfMul2 */
+#define H2AES_OP_MUL3 5  /* == table.rs Tag::GfMul3 */
+
+typedef struct h2aes_ctx h2aes_ctx;
+typedef struct h2aes_circuit h2aes_circuit;
+
+/* Result of h2aes_layout_query: what `configure` allocates and what the floor planner yields. */
+typedef struct h2aes_layout {
+    int32_t kind, k, n_sets;
+    int32_t n_advice;    /* 3*n_sets + 1 : advices[i][0..3] = 3i..3i+2, words_column last       */
+    int32_t n_fixed;     /* 5 : 4 table columns, then round_constants                            */
+    int32_t n_selectors; /* 5*N (+1 q_eq_rcon) for AES; 3 (+1) for KEYSCHED; index 5i+op-1       */
+    int32_t n_lookups;   /* == number of complex selectors, same order                           */
+    int32_t reserved;
+    uint64_t n_rows;             /* 2^k                                                           */
+    uint64_t usable_rows;        /* 2^k - 6 (blinding_factors() + 1)                              */
+    uint64_t table_rows;         /* 66561 assigned rows of load_enc_full_table                    */
+    uint64_t key_schedule_rows;  /* 400 rows of advices[0][0] actually used by schedule_key       */
+    uint64_t rows_per_block;     /* 1360 == constant.rs AES_ROWS                                  */
+    uint64_t capacity_set0;      /* floor((2^k - 1760)/1360)  (aes128.rs:303-325)                 */
+    uint64_t capacity_set;       /* floor(2^k/1360) for every later column set                    */
+    uint64_t capacity_blocks;    /* capacity_set0 + (N-1)*capacity_set                            */
+    uint64_t copies_key_schedule;/* 640                                                           */
+    uint64_t copies_per_block;   /* 1952                                                          */
+} h2aes_layout;
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-only queries (no GPU needed).
+ * ------------------------------------------------------------------------------------------- */
+int32_t h2aes_abi_version(void);
+const char *h2aes_status_string(int32_t status);
+
+/* replaces: FixedAes128Config::configure (aes128.rs:46-141) + Aes128KeyScheduleConfig::configure
+ * (key_schedule.rs:40-77) as far as column/selector/lookup counts and order go. */
+int32_t h2aes_layout_query(int32_t kind, int32_t k, int32_t N, h2aes_layout *out);
+
+/* replaces: aes_callable + get_advices (aes128.rs:303-356): the column set and the first row of
+ * advices[set][0] used by the `block`-th call of `encrypt`.  H2AES_ERR_CAPACITY past the end. */
+int32_t h2aes_block_position(int32_t k, int32_t N, uint64_t block, int32_t *set,
+                             uint64_t *start_row);
+
+/* which selector (H2AES_OP_*) the chips enable on `row` of column set `set` when `n_blocks`
+ * blocks have been encrypted; negative status on error.  (q.enable calls in src/chips/*.rs) */
+int32_t h2aes_row_op(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t set,
+                     uint64_t row);
+
+/* number of copy constraints recorded by schedule_key + n_blocks encrypts (640 + 1952*n). */
+int32_t h2aes_copy_count(int32_t kind, uint64_t n_blocks, uint64_t *out);
+
+/* copy constraints [first, first+count) as 4 u64 each: (advice col a, row a, advice col b,
+ * row b); replaces the constrain_equal calls made by copy_advice in the chips. Host buffer. */
+int32_t h2aes_copy_constraints_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
+                                    uint64_t first, uint64_t count, uint64_t *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Context: one per (process, GPU).  Uploads the S-box / GF tables and the 256-entry
+ * byte -> Fr(Montgomery) table (replaces src/constant.rs + every `Fp::from(x as u64)`).
+ * ------------------------------------------------------------------------------------------- */
+int32_t h2aes_ctx_create(int32_t device, int32_t sbox_mode, h2aes_ctx **out);
+int32_t h2aes_ctx_destroy(h2aes_ctx *ctx);
+/* `stream` is a cudaStream_t; NULL = the legacy default stream. */
+int32_t h2aes_ctx_set_stream(h2aes_ctx *ctx, void *stream);
+int32_t h2aes_ctx_synchronize(h2aes_ctx *ctx);
+const char *h2aes_ctx_last_error(h2aes_ctx *ctx);
+/* number of this library's kernels launched through `ctx` so far. */
+uint64_t h2aes_ctx_kernel_launches(h2aes_ctx *ctx);
+/* pinned host memory helpers for the _host entry points (optional; any host memory works). */
+int32_t h2aes_host_alloc(uint64_t bytes, void **out);
+int32_t h2aes_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Circuit: one halo2 circuit instance of shape (kind, k, N).  Holds device workspace (the
+ * compact per-row trace the lookup phases read, the per-lookup bin structures, round keys).
+ * ------------------------------------------------------------------------------------------- */
+int32_t h2aes_circuit_create(h2aes_ctx *ctx, int32_t kind, int32_t k, int32_t N,
+                             h2aes_circuit **out);
+int32_t h2aes_circuit_destroy(h2aes_circuit *c);
+
+/* replaces: FixedAes128Config::schedule_key (aes128.rs:143-152 -> key_schedule.rs:80-224)
+ * followed by n_blocks calls of FixedAes128Config::encrypt (aes128.rs:154-265, lcon :268-301).
+ *   key            host, 16 bytes
+ *   plaintexts     n_blocks*16 bytes (may be NULL when n_blocks == 0)
+ *   advice         n_advice columns * 2^k rows * 4 u64: every cell the chips assign, zero
+ *                  elsewhere (rows >= 2^k-6 are left zero: halo2 fills them with blinding)
+ *   ciphertexts    n_blocks*16 bytes = the values of the 16 cells `encrypt` returns; nullable
+ * For H2AES_KIND_KEYSCHED n_blocks must be 0. */
+int32_t h2aes_witness_dev(h2aes_circuit *c, const uint8_t *key, const uint8_t *plaintexts_dev,
+                          uint64_t n_blocks, uint64_t *advice_dev, uint8_t *ciphertexts_dev);
+int32_t h2aes_witness_host(h2aes_circuit *c, const uint8_t *key, const uint8_t *plaintexts,
+                           uint64_t n_blocks, uint64_t *advice, uint8_t *ciphertexts);
+
+/* the 176 expanded key bytes (values of the 11x16 cells schedule_keys returns). Host out. */
+int32_t h2aes_round_keys(h2aes_circuit *c, uint8_t *out176);
+
+/* replaces: load_enc_full_table (table.rs:18-192, + halo2's padding of table columns), the
+ * assign_fixed of round_constants (key_schedule.rs:169) and every Selector::enable.
+ *   fixed      5 columns (4 table columns, round_constants)
+ *   selectors  n_selectors columns of Fr 0/1, order = h2aes_layout.n_selectors
+ * Input-independent: depends only on the shape and n_blocks. Either pointer may be NULL. */
+int32_t h2aes_fixed_columns_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
+                                uint64_t *selectors_dev);
+int32_t h2aes_fixed_columns_host(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed,
+                                 uint64_t *selectors);
+
+/* device variant of h2aes_copy_constraints_host: all 640 + 1952*n_blocks copies. */
+int32_t h2aes_copy_constraints_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *copies_dev);
+
+/* replaces: halo2_proofs v0.3.0 plonk/lookup/prover.rs Argument::commit_permuted up to (not
+ * including) the commitments, for lookups [first, first+count) of the circuit's witness
+ * (call sites: main.rs:94-101, benches/aes128.rs:100-107, benches/key_schedule.rs:117-124).
+ *   theta      host, 4 u64 Montgomery limbs
+ *   A, S       compressed input / table expressions over all 2^k rows (nullable)
+ *   Ap, Sp     permuted input / table columns; rows >= 2^k-6 are left zero (halo2: blinding)
+ * each output is [count][2^k][4]. Requires a prior h2aes_witness_* on this circuit. */
+int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32_t first,
+                                  int32_t count, uint64_t *A_dev, uint64_t *S_dev,
+                                  uint64_t *Ap_dev, uint64_t *Sp_dev);
+int32_t h2aes_lookup_permuted_host(h2aes_circuit *c, const uint64_t *theta, int32_t first,
+                                   int32_t count, uint64_t *A, uint64_t *S, uint64_t *Ap,
+                                   uint64_t *Sp);
+
+/* replaces: plonk/lookup/prover.rs Permuted::commit_product up to the commitment.
+ *   Z  [count][2^k][4]; entries 0..2^k-6 are the grand product (Z[0]=1, Z[2^k-6]=1 for a
+ *      satisfied lookup), the last 5 (halo2: blinding) are left zero.
+ * Requires h2aes_lookup_permuted_* with the same theta to have run for these lookups. */
+int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                 int32_t first, int32_t count, uint64_t *Z_dev);
+int32_t h2aes_lookup_product_host(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                  int32_t first, int32_t count, uint64_t *Z);
+
+/* the _dev lookup entry points are asynchronous; conditions the kernels detect on the device
+ * (H2AES_ERR_LOOKUP, H2AES_ERR_ZERO_DENOM) are reported by this call, which synchronizes the
+ * stream.  The _host entry points call it themselves. */
+int32_t h2aes_lookup_check(h2aes_circuit *c);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded single circuit (one process per GPU, shard g of G owns rows
+ * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin
+ * histograms (summed) and one 32-byte partial product per shard per lookup (gathered); the
+ * library exposes them as plain device buffers so the caller can move them with NCCL
+ * (ncclAllReduce / ncclAllGather) — see INTEGRATION.md and halo2_aes_b200/sharded.py.
+ * Outputs hold only the shard's rows: [column][rows_per_shard][4].
+ * ------------------------------------------------------------------------------------------- */
+int32_t h2aes_circuit_set_shard(h2aes_circuit *c, int32_t shard, int32_t n_shards);
+/* phase 1a: local histogram of table-bin hits; *hist_dev/ *hist_words give the buffer to
+ * all-reduce (uint32 sum) across shards before phase 1b. */
+int32_t h2aes_lookup_hist_dev(h2aes_circuit *c, const uint64_t *theta, uint32_t **hist_dev,
+                              uint64_t *hist_words);
+/* phase 1b: after the all-reduce: expand this shard's rows of A, S, A', S' (all lookups). */
+int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint64_t *S_dev,
+                                        uint64_t *Ap_dev, uint64_t *Sp_dev);
+/* phase 2a: product of this shard's row factors, one Fr per lookup -> *partial_dev
+ * ([n_lookups][4]); all-gather them into [n_shards][n_lookups][4] before phase 2b. */
+int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                                 uint64_t **partial_dev);
+/* phase 2b: Z for this shard's rows given every shard's partial products. */
+int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathered_dev,
+                                       uint64_t *Z_dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Debug / test hooks: the same host+device source the kernels use, run on the host, so
+ * CPU-only tests can check the field arithmetic and closed-form layout without a GPU.
+ * ------------------------------------------------------------------------------------------- */
+int32_t h2aes_dbg_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t *out);
+int32_t h2aes_dbg_fr_add(const uint64_t *a, const uint64_t *b, uint64_t *out);
+int32_t h2aes_dbg_fr_sub(const uint64_t *a, const uint64_t *b, uint64_t *out);
+int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out);
+int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out);
+int32_t h2aes_dbg_fr_to_canonical(const uint64_t *a, uint64_t *out);
+int32_t h2aes_dbg_tables(int32_t sbox_mode, uint8_t *sbox256, uint8_t *mul2_256,
+                         uint8_t *mul3_256);
+/* host evaluation of the per-row trace word (a0 | a1<<8 | a2<<16 | op<<24) the witness
+ * kernels produce for one AES block, 1360 words; used to pin the device byte pipeline. */
+int32_t h2aes_dbg_block_trace(int32_t sbox_mode, const uint8_t *round_keys176,
+                              const uint8_t *plaintext16, uint32_t *trace1360);
+int32_t h2aes_dbg_key_schedule_trace(int32_t sbox_mode, const uint8_t *key16,
+                                     uint8_t *round_keys176, uint32_t *trace400,
+                                     uint8_t *words96);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2AES_H */
