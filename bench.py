@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py — AES-128 block witnesses/s (Fr advice + lookup helper columns) on B200.
+
+One "step" = one whole halo2 circuit of the reference's bench shape (K=20, N=5 column sets,
+filled to its capacity of 3853 AES blocks under one key; BASELINE config 4's per-GPU unit):
+    witness   : key schedule + 3853 x encrypt -> 16 advice columns (512 MiB)
+    permuted  : the 25 lookups' A', S' columns (1.56 GiB)      [theta]
+    product   : the 25 lookups' grand products Z (0.78 GiB)   [beta, gamma]
+With --gpus N every rank runs its own independent circuits (no data-path collective; weak
+scaling).  Output: ONE JSON line on rank 0 (see the contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0x68326165  # "h2ae"
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+K_BENCH, N_BENCH = 20, 5
+METRIC = "AES-128 block witnesses/sec (Fr advice + lookup columns A',S',Z)"
+UNIT = "blocks/s"
+
+
+def splitmix_bytes(seed: int, n: int) -> np.ndarray:
+    idx = np.arange((n + 7) // 8, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.view(np.uint8)[:n].copy()
+
+
+def seeded_fr(seed: int) -> np.ndarray:
+    v = int.from_bytes(splitmix_bytes(seed, 64).tobytes(), "little") % R_MOD
+    m = v * ((1 << 256) % R_MOD) % R_MOD
+    return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def measured_peak():
+    """HBM GB/s denominator: MEASURED_PEAKS.json if present, else the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------------
+def cpu_baseline_sample(threads: int, target_s: float = 12.0):
+    """The oracle port on the host cores: independent k=17,N=1 circuits of 95 blocks each (same
+    rows-per-block ratio as the benchmarked K=20 shape: 2^k/capacity = 1380 vs 1363), one
+    circuit per thread, with all lookups (A,S,A',S',Z) of each circuit."""
+    import oracle
+    oracle.build()
+    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
+    k, N, nb = 17, 1, 95
+    # one calibration circuit, then as many rounds of `threads` circuits as fit the target
+    keys = splitmix_bytes(SEED + 20, 16 * threads).reshape(threads, 16)
+    pts = splitmix_bytes(SEED + 21, 16 * nb * threads).reshape(threads, nb, 16)
+    sec1, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
+    rounds = max(1, min(8, int(target_s / max(sec1, 1e-3))))
+    keys = splitmix_bytes(SEED + 22, 16 * threads * rounds).reshape(-1, 16)
+    pts = splitmix_bytes(SEED + 23, 16 * nb * threads * rounds).reshape(threads * rounds, nb, 16)
+    sec, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
+    blocks = nb * threads * rounds
+    return {"value": blocks / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "seconds": sec,
+            "sample": f"{threads * rounds} independent k=17,N=1 circuits x 95 blocks (synthesize + "
+                      f"5 lookups A,S,A',S',Z each), one circuit per thread, CPU restatement "
+                      f"(oracle/), {blocks} blocks in {sec:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port: the Rust crate cannot be
+    compiled here — no cargo, un-vendored halo2_proofs) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
+    k, N, nb = 17, 1, 95
+
+    def step(i):
+        keys = splitmix_bytes(SEED + 100 + i, 16 * threads).reshape(threads, 16)
+        pts = splitmix_bytes(SEED + 200 + i, 16 * nb * threads).reshape(threads, nb, 16)
+        sec, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
+        return sec
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    total = time.perf_counter() - t0
+    blocks = nb * threads * args.steps
+    value = blocks / total
+    sample = (f"each step = {threads} independent k=17,N=1 circuits x 95 blocks (synthesize + 5 "
+              f"lookups A,S,A',S',Z), one circuit per host thread; CPU restatement of the "
+              f"reference (oracle/), the Rust crate itself is unbuildable here")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 -> bn256 Fr (4x u64 Montgomery)", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE config 4 unit: independent K=20,N=5 circuits filled to capacity "
+                        "(3853 AES-128 blocks under one key each): 16 advice columns + A',S',Z of "
+                        "all 25 lookups; random keys/plaintexts (SplitMix64 seed 0x68326165), "
+                        "seeded theta/beta/gamma",
+            "k": K_BENCH, "column_sets": N_BENCH, "blocks_per_circuit": 3853,
+            "circuits_per_step_per_gpu": 1, "partitioning": f"independent circuits x{n_gpus}",
+            "l2_policy": "outputs are 2.86 GiB per step (>> 126 MB L2) and never re-read"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from halo2_aes_b200 import _ffi
+    from halo2_aes_b200.backend import Circuit, Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = Context(local)
+    stream = torch.cuda.Stream(device=local)
+    ctx.use_stream(stream)
+    cir = Circuit(ctx, _ffi.KIND_AES, K_BENCH, N_BENCH)
+    lay = cir.layout
+    n, nb, L, nadv = lay["n_rows"], lay["capacity_blocks"], lay["n_lookups"], lay["n_advice"]
+    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
+    n_in = args.warmup + args.steps + 2
+    keys = splitmix_bytes(SEED + 1000 * (rank + 1), 16 * n_in).reshape(n_in, 16)
+    with torch.cuda.stream(stream):
+        pts_all = torch.from_numpy(
+            splitmix_bytes(SEED + 7000 * (rank + 1), 16 * nb * 2).reshape(2, nb, 16)).cuda()
+        advice = torch.empty((nadv, n, 4), dtype=torch.int64, device="cuda")
+        bufs = {"Ap": torch.empty((L, n, 4), dtype=torch.int64, device="cuda"),
+                "Sp": torch.empty((L, n, 4), dtype=torch.int64, device="cuda")}
+        Z = torch.empty((L, n, 4), dtype=torch.int64, device="cuda")
+    stream.synchronize()
+
+    phases = ("witness", "lookup_prep", "permuted", "product_prep", "product")
+
+    def step(i, ev=None):
+        # a fresh key per step; theta nudged per step so the per-theta bin build is not skipped
+        th_i = th.copy()
+        th_i[0] ^= np.uint64(i + 1)
+        with torch.cuda.stream(stream):
+            if ev: ev[0].record(stream)
+            cir.witness(keys[i].tobytes(), pts_all[i & 1], out=advice, want_ciphertexts=False)
+            if ev: ev[1].record(stream)
+            cir.lookup_permuted(th_i, first=0, count=0, want_inputs=False, out=bufs)
+            if ev: ev[2].record(stream)
+            cir.lookup_permuted(th_i, first=0, count=L, want_inputs=False, out=bufs)
+            if ev: ev[3].record(stream)
+            cir.lookup_product(be, ga, first=0, count=0, out=Z)
+            if ev: ev[4].record(stream)
+            cir.lookup_product(be, ga, first=0, count=L, out=Z)
+            if ev: ev[5].record(stream)
+
+    for i in range(args.warmup):
+        step(i)
+    stream.synchronize()
+    cir.lookup_check()
+    # sanity: every Z column closes at 1 (the lookup argument is satisfied)
+    one = torch.tensor([-0x5369cbe3b0000005, 0x36fc76959f60cd29, 0x666ea36f7879462e,
+                        0x0e0a77c19a07df2f], dtype=torch.int64, device="cuda")
+    assert bool((Z[:, n - 6] == one).all()), "Z[n-6] != 1 after warm-up"
+
+    sampler = ClockSampler(local)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    launches0 = ctx.kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i, evs[i])
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches - launches0
+    cir.lookup_check()
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    assert bool((Z[:, n - 6] == one).all()), "Z[n-6] != 1 after the timed region"
+
+    # ---- per-kernel roofline from the in-step events (rank 0) --------------------------------
+    peak, peak_src = measured_peak()
+    ph_ms = {p: statistics.mean(e[j].elapsed_time(e[j + 1]) for e in evs)
+             for j, p in enumerate(phases)}
+    alg = {  # algorithmic bytes per launch (DESIGN.md "Kernels")
+        "witness": nadv * n * 32 + nb * 16,                 # k_advice: every advice cell once
+        "permuted": 2 * L * n * 32,                         # k_permuted: A', S'
+        "product": L * n * 32,                              # k_grand_product: Z
+    }
+    kern = {"witness": "k_advice (+k_key_expand, k_block_states)", "permuted": "k_permuted",
+            "product": "k_grand_product"}
+    kernels = []
+    for p in ("witness", "permuted", "product"):
+        gbs = alg[p] / (ph_ms[p] * 1e-3) / 1e9
+        kernels.append({"kernel": kern[p], "ms": ph_ms[p], "algorithmic_bytes": alg[p],
+                        "achieved_gbs": gbs, "frac": gbs / peak})
+    dom = max(kernels, key=lambda x: x["ms"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"],
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "launch_ms": dom["ms"], "algorithmic_bytes": dom["algorithmic_bytes"]}
+    step_bytes = sum(alg.values())
+
+    # ---- end to end through the C ABI with HOST buffers (copies inside the timed region) -------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx, cir, stream, keys, th, be, ga, rank, world)
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cpu = cpu_baseline_sample(os.cpu_count() or 1)
+        blocks = nb * args.steps * world
+        out = {
+            "metric": METRIC, "value": blocks / (ms_total * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 -> bn256 Fr (4x u64 Montgomery)",
+            "data": "synthetic", "config": workload_config(world),
+            "roofline": roofline, "kernels": kernels,
+            "phase_ms": ph_ms,
+            "step_algorithmic_bytes": step_bytes,
+            "step_effective_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
+            "witness_only_blocks_per_s": nb / (ph_ms["witness"] * 1e-3),
+            "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, ctx, cir, stream, keys, th, be, ga, rank, world):
+    """Same step through the reference-facing _host entry points: plaintexts start in pinned
+    host memory, every produced column ends in pinned host memory."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from halo2_aes_b200 import _ffi
+    L_ = _ffi.lib()
+    lay = cir.layout
+    n, nb, L, nadv = lay["n_rows"], lay["capacity_blocks"], lay["n_lookups"], lay["n_advice"]
+    pts = torch.from_numpy(splitmix_bytes(SEED + 31 + rank, 16 * nb)).pin_memory()
+    adv = torch.empty((nadv, n, 4), dtype=torch.int64).pin_memory()
+    Ap = torch.empty((L, n, 4), dtype=torch.int64).pin_memory()
+    Sp = torch.empty((L, n, 4), dtype=torch.int64).pin_memory()
+    Zh = torch.empty((L, n, 4), dtype=torch.int64).pin_memory()
+    cts = torch.empty((nb, 16), dtype=torch.uint8).pin_memory()
+    u64p = C.POINTER(C.c_uint64)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+
+    def step(i):
+        key = np.ascontiguousarray(keys[i % len(keys)])
+        th_i = th.copy()
+        th_i[0] ^= np.uint64(i + 77)
+        _ffi.check(L_.h2aes_witness_host(cir._h, key.ctypes.data_as(C.POINTER(C.c_uint8)), vp(pts),
+                                         nb, vp(adv), vp(cts)), ctx._h)
+        _ffi.check(L_.h2aes_lookup_permuted_host(cir._h, th_i.ctypes.data_as(u64p), 0, L, None,
+                                                 None, vp(Ap), vp(Sp)), ctx._h)
+        _ffi.check(L_.h2aes_lookup_product_host(cir._h, be.ctypes.data_as(u64p),
+                                                ga.ctypes.data_as(u64p), 0, L, vp(Zh)), ctx._h)
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(1 + i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    one = [-0x5369cbe3b0000005, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f]
+    assert Zh[:, n - 6].tolist() == [one] * L, "e2e: Z[n-6] != 1"
+    d2h = (nadv + 3 * L) * n * 32 + nb * 16
+    return {"value": nb * steps * world / dt, "unit": UNIT, "steps": steps,
+            "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": nb * 16 + 16 + 3 * 32,
+            "d2h_bytes_per_step": d2h,
+            "api": "h2aes_witness_host + h2aes_lookup_permuted_host + h2aes_lookup_product_host "
+                   "(pinned host buffers; every column copied back)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,10 @@ def lib():
             [C.c_int] * 3 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int, C.c_int,
                              C.POINTER(C.c_double), u64p]
         )
+        L.orc_bench_batch.argtypes = (
+            [C.c_int] * 4 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int,
+                             C.POINTER(C.c_double), u64p]
+        )
         _lib = L
     return _lib
 
@@ -275,3 +279,21 @@ def bench_circuit(kind, k, N, key, plaintexts, theta, beta, gamma, threads=1, n_
     if rc:
         raise OracleError(rc)
     return times[0], times[1], digest
+
+
+def bench_batch(kind, k, N, keys, plaintexts, theta, beta, gamma, threads=1):
+    """Time `len(keys)` independent circuits, one per OpenMP thread: (seconds, digest)."""
+    keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint8).reshape(-1, 16))
+    n_circ = keys.shape[0]
+    pts = np.ascontiguousarray(np.asarray(plaintexts, dtype=np.uint8).reshape(n_circ, -1, 16))
+    nb = pts.shape[1]
+    sec = C.c_double()
+    digest = np.zeros(4, np.uint64)
+    th = np.ascontiguousarray(theta, dtype=np.uint64)
+    be = np.ascontiguousarray(beta, dtype=np.uint64)
+    ga = np.ascontiguousarray(gamma, dtype=np.uint64)
+    rc = lib().orc_bench_batch(kind, k, N, n_circ, _u8(keys), _u8(pts), nb, _u64(th), _u64(be),
+                               _u64(ga), threads, C.byref(sec), _u64(digest))
+    if rc:
+        raise OracleError(rc)
+    return sec.value, digest

@@ -953,4 +953,35 @@ int orc_bench_circuit(int kind, int k, int N, const uint8_t *key, const uint8_t 
     return bad ? ORC_ERR_LOOKUP_INPUT_NOT_IN_TABLE : ORC_OK;
 }
 
+
+// ---- CPU baseline on all host threads: `n_circuits` independent circuits (the multi-circuit
+// workload of BASELINE config 4), one circuit per OpenMP thread, each circuit run exactly like
+// orc_bench_circuit with threads=1.  keys = n_circuits*16 bytes, pts = n_circuits*n_blocks*16.
+// seconds_out = wall time of the whole batch.
+int orc_bench_batch(int kind, int k, int N, int n_circuits, const uint8_t *keys,
+                    const uint8_t *pts, uint64_t n_blocks, const uint64_t *theta,
+                    const uint64_t *beta, const uint64_t *gamma, int threads, double *seconds_out,
+                    uint64_t digest[4]) {
+    auto t0 = std::chrono::steady_clock::now();
+    int bad = 0;
+    uint64_t dg[4] = {0, 0, 0, 0};
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
+    for (int c = 0; c < n_circuits; ++c) {
+        double times[2];
+        uint64_t d[4];
+        int rc = orc_bench_circuit(kind, k, N, keys + 16 * (size_t)c,
+                                   pts + 16 * n_blocks * (size_t)c, n_blocks, theta, beta, gamma,
+                                   1, -1, times, d);
+#pragma omp critical
+        {
+            if (rc) bad = rc;
+            for (int i = 0; i < 4; ++i) dg[i] ^= d[i];
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    *seconds_out = std::chrono::duration<double>(t1 - t0).count();
+    for (int i = 0; i < 4; ++i) digest[i] = dg[i];
+    return bad;
+}
+
 }  // extern "C"
