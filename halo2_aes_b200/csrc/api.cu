@@ -29,6 +29,7 @@ cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const f
                                  uint64_t *Z, uint64_t row_begin, uint64_t row_end, int mode);
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
 uint64_t grand_product_tiles(uint64_t rows);
+cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
 
 // S-box from first principles (GF(2^8) inverse + affine map); H2AES_SBOX_REFERENCE then applies
 // the one deviation src/constant.rs:14 has from FIPS-197 (entry 255 is 23, not 0x16).
@@ -281,6 +282,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
+                    c->d_ibg,      c->d_ibp,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_tile_agg, c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -498,6 +500,8 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_ib, VB));
     CU(ctx, dalloc(&c->d_ig, VB));
     CU(ctx, dalloc(&c->d_nac, VB));
+    CU(ctx, dalloc(&c->d_ibg, VB));
+    CU(ctx, dalloc(&c->d_ibp, VB));
     CU(ctx, dalloc(&c->d_cnt, LB));
     CU(ctx, dalloc(&c->d_offz, LB));
     CU(ctx, dalloc(&c->d_nzk, LB));
@@ -785,6 +789,23 @@ int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out) {
 int32_t h2aes_dbg_fr_to_canonical(const uint64_t *a, uint64_t *out) {
     if (!a || !out) return H2AES_ERR_ARG;
     fr_to_limbs(fr_to_canonical(fr_from_limbs(a)), out);
+    return H2AES_OK;
+}
+int32_t h2aes_dbg_fr_mul_dev(h2aes_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t n,
+                             uint64_t *out) {
+    if (!ctx || !a || !b || !out || !n) return H2AES_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    fr_t *d = nullptr;
+    CU(ctx, dalloc(&d, 3 * n));
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(d + n, b, n * 32, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = launch_dbg_fr_mul(ctx, d, d + n, n, d + 2 * n)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out, d + 2 * n, n * 32, cudaMemcpyDeviceToHost, ctx->stream)) ==
+            cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "h2aes_dbg_fr_mul_dev");
     return H2AES_OK;
 }
 int32_t h2aes_dbg_tables(int32_t sbox_mode, uint8_t *sbox256, uint8_t *mul2_256,

@@ -172,10 +172,40 @@ FR_HD fr_t fr_mul_portable(const fr_t &a, const fr_t &b) {
     return o;
 }
 
+#if defined(__CUDACC__)
+// conditional subtract of r with one borrow chain (device)
+FR_D void fr_reduce_once_dev(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t &r4,
+                             uint32_t &r5, uint32_t &r6, uint32_t &r7) {
+    uint32_t d0, d1, d2, d3, d4, d5, d6, d7, keep;
+    asm("sub.cc.u32 %0, %9, 0xf0000001;\n\t"
+        "subc.cc.u32 %1, %10, 0x43e1f593;\n\t"
+        "subc.cc.u32 %2, %11, 0x79b97091;\n\t"
+        "subc.cc.u32 %3, %12, 0x2833e848;\n\t"
+        "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
+        "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+        "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
+        "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(d4), "=r"(d5), "=r"(d6), "=r"(d7), "=r"(keep)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7));
+    // keep == 0xffffffff when the subtraction borrowed (value was already < r)
+    r0 = keep ? r0 : d0; r1 = keep ? r1 : d1; r2 = keep ? r2 : d2; r3 = keep ? r3 : d3;
+    r4 = keep ? r4 : d4; r5 = keep ? r5 : d5; r6 = keep ? r6 : d6; r7 = keep ? r7 : d7;
+}
+#endif
+
+// Montgomery product.  Device: the generated even/odd carry-chain PTX (gen_fr_mul.py, ~150
+// IMAD.WIDE-class instructions); host: the portable CIOS above (same results, both < r).
 FR_HD fr_t fr_mul(const fr_t &a, const fr_t &b) {
-    // The portable form compiles to IMAD.WIDE chains on sm_100a; a hand-scheduled PTX variant
-    // is selected with -DH2AES_PTX_MUL once validated against this one on hardware.
+#if defined(__CUDA_ARCH__) && !defined(H2AES_PORTABLE_MUL)
+    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+#include "fr_mul_ptx.inc"
+    fr_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
+    fr_t o = {{r0, r1, r2, r3, r4, r5, r6, r7}};
+    return o;
+#else
     return fr_mul_portable(a, b);
+#endif
 }
 
 FR_HD fr_t fr_sqr(const fr_t &a) { return fr_mul(a, a); }

@@ -48,7 +48,8 @@ struct LookupMeta {  // per lookup, produced by the bin-scan kernel
     uint32_t repeated;    // R = usable - NZ
     uint32_t k_zero;      // bin of the all-zero tuple (inactive rows)
     uint32_t bad;         // != 0: an input value has no table row (cannot happen by construction)
-    uint32_t pad[3];
+    uint32_t k_pad;       // bin of table row 0 (the value halo2 pads the table with)
+    uint32_t pad[2];
 };
 
 }  // namespace h2
@@ -100,6 +101,8 @@ struct h2aes_circuit {
     h2::fr_t *d_ib = nullptr;        // [3][BIN_STRIDE] 1/(dval+beta)
     h2::fr_t *d_ig = nullptr;        // [3][BIN_STRIDE] 1/(dval+gamma)
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
+    h2::fr_t *d_ibg = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k]
+    h2::fr_t *d_ibp = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k_pad]
     // per lookup
     uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
     uint32_t *d_offz = nullptr;      // [L][BIN_STRIDE] first row of each nonempty bin (+ end)

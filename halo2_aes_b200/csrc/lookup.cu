@@ -318,8 +318,9 @@ k_lookup_bins(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__rest
         m.n_left = run.w;
         m.repeated = run.z;
         m.k_zero = k0;
+        m.k_pad = rank[(size_t)v * BIN_STRIDE];  // bin of table row 0 = the padding value
         m.bad = (run.x != usable || run.z != usable - run.y) ? 2u : 0u;
-        m.pad[0] = m.pad[1] = m.pad[2] = 0;
+        m.pad[0] = m.pad[1] = 0;
         meta[l] = m;
         if (m.bad) atomicOr(err + 1, 1u);
         offz[(size_t)l * BIN_STRIDE + run.y] = usable;
@@ -443,52 +444,131 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
 
 // ---------------------------------------------------------------------------------------------
 // phase 2a: per-bin tables for the grand product (once per beta,gamma)
-//   ib[k] = 1/(d_k + beta), ig[k] = 1/(d_k + gamma)  — Montgomery-trick batch inversion, CH bins
-//   per thread;  nac[k] = (d_k + beta) * (pad + gamma) with pad = value of table row 0.
+//   ib[k] = 1/(d_k + beta), ig[k] = 1/(d_k + gamma): Montgomery-trick batch inversion with ONE
+//   field inversion per CTA of INV_TILE bins (block-wide forward + reverse product scans);
+//   nac[k] = (d_k + beta) * (pad + gamma) with pad = value of table row 0 (numerator of every
+//   row past the table);  then k_inv_merge: ibg[k] = ib[k]*ig[k] (first occurrence: S' = A'),
+//   ibp[k] = ib[k]*ig[k_pad] (repeated row that received the padding value).
 // ---------------------------------------------------------------------------------------------
+constexpr int INV_T = 256;
 constexpr int INV_CH = 8;
-__global__ void __launch_bounds__(128)
+constexpr int INV_TILE = INV_T * INV_CH;
+
+__device__ __forceinline__ fr_t fr_shfl_up(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_shfl_down(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_shfl_xor(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+
+__global__ void __launch_bounds__(INV_T)
 k_inv_tables(const fr_t *__restrict__ chal, const fr_t *__restrict__ dval,
              const fr_t *__restrict__ val, const uint32_t *__restrict__ viewmeta,
              fr_t *__restrict__ ib, fr_t *__restrict__ ig, fr_t *__restrict__ nac,
              uint32_t *__restrict__ err) {
-    const int v = blockIdx.y;
+    __shared__ fr_t s_wtot[INV_T / 32];
+    __shared__ fr_t s_inv;
+    const int v = blockIdx.y, which = blockIdx.z;
     const uint32_t D = viewmeta[v * 8 + 1];
-    const uint32_t k0 = (blockIdx.x * blockDim.x + threadIdx.x) * INV_CH;
-    if (k0 >= D) return;
+    const uint32_t base = blockIdx.x * INV_TILE;
+    if (base >= D) return;  // whole CTA
     const size_t o = (size_t)v * BIN_STRIDE;
-    const fr_t beta = fr_ld(chal + 1), gamma = fr_ld(chal + 2);
-    const fr_t padg = fr_add(fr_ld(val + o), gamma);
-    const uint32_t cnt = min((uint32_t)INV_CH, D - k0);
-    for (int which = 0; which < 2; ++which) {
-        const fr_t ch = which == 0 ? beta : gamma;
-        fr_t *out = which == 0 ? ib : ig;
-        fr_t x[INV_CH], pre[INV_CH];
-        fr_t acc = fr_one();
-        for (uint32_t j = 0; j < cnt; ++j) {
-            x[j] = fr_add(fr_ld(dval + o + k0 + j), ch);
-            pre[j] = acc;
-            if (fr_is_zero(x[j])) {
-                atomicOr(err, 1u);  // halo2's batch_invert would leave a zero here
-            } else {
-                acc = fr_mul(acc, x[j]);
+    const fr_t ch = fr_ld(chal + 1 + which);
+    const fr_t padg = fr_add(fr_ld(val + o), fr_ld(chal + 2));
+    fr_t *out = which == 0 ? ib : ig;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const uint32_t k0 = base + (uint32_t)t * INV_CH;
+    const fr_t one = fr_one();
+
+    fr_t x[INV_CH], pre[INV_CH];  // pre[j] = x[0] * ... * x[j-1]
+    uint32_t zero_mask = 0;
+    fr_t tot = one;
+#pragma unroll
+    for (int j = 0; j < INV_CH; ++j) {
+        const uint32_t k = k0 + j;
+        fr_t xv = one;
+        if (k < D) {
+            xv = fr_add(fr_ld(dval + o + k), ch);
+            if (which == 0) fr_st(nac + o + k, fr_mul(xv, padg));
+            if (fr_is_zero(xv)) {  // halo2's batch_invert would leave a zero here
+                zero_mask |= 1u << j;
+                xv = one;
+                atomicOr(err, 1u);
             }
-            if (which == 0) fr_st(nac + o + k0 + j, fr_mul(x[j], padg));
         }
-        acc = fr_inv(acc);
-        for (int j = (int)cnt - 1; j >= 0; --j) {
-            if (fr_is_zero(x[j])) {
-                fr_st(out + o + k0 + j, x[j]);
-                continue;
-            }
-            fr_st(out + o + k0 + j, fr_mul(acc, pre[j]));
-            acc = fr_mul(acc, x[j]);
-        }
+        x[j] = xv;
+        pre[j] = tot;
+        tot = fr_mul(tot, xv);
+    }
+    // forward / reverse inclusive product scans of the thread totals inside the warp
+    fr_t finc = tot, rinc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const fr_t yu = fr_shfl_up(finc, d);
+        const fr_t yd = fr_shfl_down(rinc, d);
+        if (lane >= d) finc = fr_mul(finc, yu);
+        if (lane + d < 32) rinc = fr_mul(rinc, yd);
+    }
+    if (lane == 31) s_wtot[wid] = finc;
+    __syncthreads();
+    fr_t before = fr_shfl_up(finc, 1), after = fr_shfl_down(rinc, 1);
+    if (lane == 0) before = one;
+    if (lane == 31) after = one;
+    for (int w = 0; w < INV_T / 32; ++w) {
+        const fr_t wt = s_wtot[w];
+        if (w < wid) before = fr_mul(before, wt);
+        if (w > wid) after = fr_mul(after, wt);
+    }
+    if (wid == 0) {  // one inversion per CTA
+        fr_t all = s_wtot[0];
+        for (int w = 1; w < INV_T / 32; ++w) all = fr_mul(all, s_wtot[w]);
+        const fr_t inv = fr_inv(all);
+        if (lane == 0) s_inv = inv;
+    }
+    __syncthreads();
+    // 1 / (product of this thread's elements) = inv_all * (everything before) * (everything after)
+    fr_t run = fr_mul(fr_mul(s_inv, before), after);
+#pragma unroll
+    for (int j = INV_CH - 1; j >= 0; --j) {
+        const uint32_t k = k0 + j;
+        const fr_t r = fr_mul(run, pre[j]);
+        run = fr_mul(run, x[j]);
+        if (k < D) fr_st(out + o + k, ((zero_mask >> j) & 1u) ? fr_zero() : r);
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ rank,
+            const fr_t *__restrict__ ib, const fr_t *__restrict__ ig, fr_t *__restrict__ ibg,
+            fr_t *__restrict__ ibp) {
+    const int v = blockIdx.y;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= viewmeta[v * 8 + 1]) return;
+    const size_t o = (size_t)v * BIN_STRIDE;
+    const uint32_t k_pad = rank[o];  // bin of table row 0, the padding value
+    const fr_t b = fr_ld(ib + o + k);
+    fr_st(ibg + o + k, fr_mul(b, fr_ld(ig + o + k)));
+    fr_st(ibp + o + k, fr_mul(b, fr_ld(ig + o + k_pad)));
+}
+
 // ---------------------------------------------------------------------------------------------
-// phase 2b: grand product Z — single pass, decoupled look-back over tiles of ZT*ZI rows
+// phase 2b: grand product Z — single pass, decoupled look-back over tiles of ZT*ZI rows.
+//   per row: 1 multiply for the factor (table x table), 1 for the thread total, 1 for the
+//   running product that is stored.  Tiles of all lookups of the call are interleaved in the
+//   grid so that few tiles of the same lookup are in flight at once, and the look-back itself
+//   is done by a whole warp (32 predecessors per step, warp product reduction).
 // ---------------------------------------------------------------------------------------------
 constexpr int ZT = 128;  // threads per tile
 constexpr int ZI = 8;    // consecutive rows per thread
@@ -502,92 +582,85 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ fr_t fr_shfl_up(const fr_t &a, int d) {
-    fr_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
-    return r;
-}
-__device__ __forceinline__ fr_t fr_ld_volatile(const fr_t *p) {
-    // plain (weak) loads ordered after an acquire load of the flag
-    return fr_ld(p);
-}
 
-// factor f[i] = (A[i]+beta)(S[i]+gamma) / ((A'[i]+beta)(S'[i]+gamma)) of usable row i
-struct ZTables {
-    const fr_t *val, *dval, *ib, *ig, *nac;  // already offset to the lookup's view
-    const uint32_t *rank;
-    const uint32_t *offz, *nzk, *loffz, *lk;  // already offset to the lookup
+struct ZArgs {
+    Shape sh;
+    int first_lookup, count;
+    const uint32_t *trace;
+    const fr_t *chal;
+    const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
+    const uint32_t *rank;                                // [3][BIN_STRIDE]
+    const uint32_t *offz, *nzk, *loffz, *lk;             // [L][BIN_STRIDE]
+    const LookupMeta *meta;
+    fr_t *tile_agg, *tile_inc;
+    uint32_t *tile_flag, *tile_ctr;
+    const fr_t *carry_in;
+    uint64_t n_tiles;
+    uint64_t *Z;
+    uint64_t row_begin, row_end;
 };
 
 // kMode 0: write Z with look-back; kMode 1: only the product of the shard's factors
 template <int kMode>
-__global__ void __launch_bounds__(ZT)
-k_grand_product(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
-                const fr_t *__restrict__ chal, const fr_t *__restrict__ val_all,
-                const fr_t *__restrict__ dval_all, const fr_t *__restrict__ ib_all,
-                const fr_t *__restrict__ ig_all, const fr_t *__restrict__ nac_all,
-                const uint32_t *__restrict__ rank_all, const uint32_t *__restrict__ offz_all,
-                const uint32_t *__restrict__ nzk_all, const uint32_t *__restrict__ loffz_all,
-                const uint32_t *__restrict__ lk_all, const LookupMeta *__restrict__ meta,
-                fr_t *__restrict__ tile_agg, fr_t *__restrict__ tile_inc,
-                uint32_t *__restrict__ tile_flag, uint32_t *__restrict__ tile_ctr,
-                const fr_t *__restrict__ carry_in, uint64_t n_tiles, uint64_t *__restrict__ Z,
-                uint64_t row_begin, uint64_t row_end) {
+__global__ void __launch_bounds__(ZT) k_grand_product(const ZArgs a) {
     __shared__ fr_t s_warp[ZT / 32];
     __shared__ fr_t s_tile_excl;
     __shared__ uint32_t s_tile;
-    const int li = blockIdx.y;
-    const int l = first_lookup + li;
+    const Shape sh = a.sh;
+    const int li = blockIdx.x % a.count;  // lookups interleaved: consecutive CTAs, different lookups
+    const int l = a.first_lookup + li;
     const int ops = sh.ops_per_set();
     const int set = l / ops;
     const uint32_t op = (uint32_t)(l % ops) + 1;
     const int v = view_of_op(op);
     const uint64_t n = sh.n();
     const uint32_t usable = (uint32_t)sh.usable();
-    const uint64_t out_rows = row_end - row_begin;
-    const LookupMeta m = meta[l];
-    const uint32_t *offz = offz_all + (size_t)l * BIN_STRIDE;
-    const uint32_t *nzk = nzk_all + (size_t)l * BIN_STRIDE;
-    const uint32_t *loffz = loffz_all + (size_t)l * BIN_STRIDE;
-    const uint32_t *lk = lk_all + (size_t)l * BIN_STRIDE;
+    const uint64_t out_rows = a.row_end - a.row_begin;
+    const LookupMeta m = a.meta[l];
+    const uint32_t *__restrict__ offz = a.offz + (size_t)l * BIN_STRIDE;
+    const uint32_t *__restrict__ nzk = a.nzk + (size_t)l * BIN_STRIDE;
+    const uint32_t *__restrict__ loffz = a.loffz + (size_t)l * BIN_STRIDE;
+    const uint32_t *__restrict__ lk = a.lk + (size_t)l * BIN_STRIDE;
     const size_t vo = (size_t)v * BIN_STRIDE;
-    const fr_t *valv = val_all + vo, *dv = dval_all + vo, *ib = ib_all + vo, *ig = ig_all + vo,
-               *nac = nac_all + vo;
-    const uint32_t *rank = rank_all + vo;
+    const fr_t *__restrict__ valv = a.val + vo, *__restrict__ dv = a.dval + vo,
+                             *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
+                             *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
+                             *__restrict__ ibp = a.ibp + vo;
+    const uint32_t *__restrict__ rank = a.rank + vo;
+    const uint32_t *__restrict__ trace = a.trace + (uint64_t)set * n;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const fr_t one = fr_one();
 
-    // dynamic tile id: a tile only waits on tiles that already started
-    if (t == 0) s_tile = atomicAdd(tile_ctr + l, 1u);
+    // dynamic tile id: a tile only ever waits on tiles that already started
+    if (t == 0) s_tile = atomicAdd(a.tile_ctr + l, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t row0 = row_begin + (uint64_t)tile * ZTILE + (uint64_t)t * ZI;
+    const uint64_t row0 = a.row_begin + (uint64_t)tile * ZTILE + (uint64_t)t * ZI;
 
-    const fr_t beta = fr_ld(chal + 1), gamma = fr_ld(chal + 2);
+    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
     fr_t f[ZI];
-    // bins of the thread's first usable row by binary search, then walk
     uint32_t j = 0, jl = 0;
     bool have_j = false, have_jl = false;
 #pragma unroll
     for (int q = 0; q < ZI; ++q) {
         const uint64_t row = row0 + q;
-        if (row >= usable || row >= row_end) {
-            f[q] = fr_one();
+        if (row >= usable || row >= a.row_end) {
+            f[q] = one;
             continue;
         }
         const uint32_t i = (uint32_t)row;
-        // numerator
-        const uint32_t w = trace[(uint64_t)set * n + row];
+        // numerator (A[i]+beta)(S[i]+gamma)
+        const uint32_t w = trace[row];
         uint32_t kin = m.k_zero;
         if ((w >> 24) == op) kin = rank[entry_of_table_row(v, table_row_of_word(w))];
         fr_t num;
-        if (i < TABLE_ROWS) {
+        if (i >= TABLE_ROWS) {
+            num = fr_ld(nac + kin);
+        } else {
             const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, i)), gamma);
             num = fr_mul(fr_add(fr_ld(dv + kin), beta), sg);
-        } else {
-            num = fr_ld(nac + kin);
         }
-        // denominator bins
+        // denominator 1/((A'[i]+beta)(S'[i]+gamma)): bins of row i, by search then by walking
         if (!have_j) {
             j = search_le(offz, m.n_nonempty, i);
             have_j = true;
@@ -595,8 +668,10 @@ k_grand_product(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             while (offz[j + 1] <= i) ++j;
         }
         const uint32_t k = nzk[j];
-        uint32_t kp = k;
-        if (offz[j] != i) {
+        fr_t den;
+        if (offz[j] == i) {
+            den = fr_ld(ibg + k);  // first occurrence: S' = A'
+        } else {
             const uint32_t jj = m.repeated - 1 - (i - (j + 1));
             if (!have_jl) {
                 jl = search_le(loffz, m.n_left, jj);
@@ -604,61 +679,67 @@ k_grand_product(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             } else {
                 while (loffz[jl] > jj) --jl;
             }
-            kp = lk[jl];
+            const uint32_t kp = lk[jl];
+            if (kp == m.k_pad) den = fr_ld(ibp + k);
+            else den = fr_mul(fr_ld(ib + k), fr_ld(ig + kp));
         }
-        f[q] = fr_mul(num, fr_mul(fr_ld(ib + k), fr_ld(ig + kp)));
+        f[q] = fr_mul(num, den);
     }
-    // thread total
+    // thread total, warp inclusive scan of the totals
     fr_t tot = f[0];
 #pragma unroll
     for (int q = 1; q < ZI; ++q) tot = fr_mul(tot, f[q]);
-    // warp inclusive scan of the thread totals
     fr_t inc = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        fr_t y = fr_shfl_up(inc, d);
+        const fr_t y = fr_shfl_up(inc, d);
         if (lane >= d) inc = fr_mul(inc, y);
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     // exclusive prefix of this thread inside the tile
     fr_t excl = fr_shfl_up(inc, 1);
-    if (lane == 0) excl = fr_one();
+    if (lane == 0) excl = one;
     for (int wq = 0; wq < wid; ++wq) excl = fr_mul(excl, s_warp[wq]);
 
-    if (t == ZT - 1) {
-        // tile aggregate = inclusive value of the last thread
-        const fr_t agg = fr_mul(excl, tot);
-        fr_t *aggp = tile_agg + (size_t)l * n_tiles + tile;
-        fr_t *incp = tile_inc + (size_t)l * n_tiles + tile;
-        uint32_t *flagp = tile_flag + (size_t)l * n_tiles + tile;
-        fr_t prefix;
+    if (wid == ZT / 32 - 1) {  // the last warp publishes the tile and looks back
+        fr_t *aggp = a.tile_agg + (size_t)l * a.n_tiles + tile;
+        fr_t *incp = a.tile_inc + (size_t)l * a.n_tiles + tile;
+        uint32_t *flags = a.tile_flag + (size_t)l * a.n_tiles;
+        fr_t agg = one;
+        if (lane == 31) agg = fr_mul(excl, tot);  // tile aggregate
+        fr_t prefix = one;
         if (tile == 0) {
-            prefix = carry_in ? fr_ld(carry_in + l) : fr_one();
-            fr_st(incp, fr_mul(prefix, agg));
-            st_release_u32(flagp, 2u);
+            if (a.carry_in) prefix = fr_ld(a.carry_in + l);
         } else {
-            fr_st(aggp, agg);
-            st_release_u32(flagp, 1u);
-            // look back
-            fr_t acc = fr_one();
+            if (lane == 31) {
+                fr_st(aggp, agg);
+                st_release_u32(flags + tile, 1u);
+            }
             int p = (int)tile - 1;
             while (true) {
-                const uint32_t *fp = tile_flag + (size_t)l * n_tiles + p;
-                uint32_t fl;
-                while ((fl = ld_acquire_u32(fp)) == 0u) __nanosleep(40);
-                if (fl == 2u) {
-                    acc = fr_mul(acc, fr_ld_volatile(tile_inc + (size_t)l * n_tiles + p));
-                    break;
+                const int idx = p - lane;  // lane 0 = nearest predecessor
+                uint32_t fl = 2u;          // before the first tile: "inclusive" with value one
+                fr_t val_p = one;
+                if (idx >= 0) {
+                    while ((fl = ld_acquire_u32(flags + idx)) == 0u) __nanosleep(20);
+                    val_p = fr_ld((fl == 2u ? a.tile_inc : a.tile_agg) + (size_t)l * a.n_tiles + idx);
                 }
-                acc = fr_mul(acc, fr_ld_volatile(tile_agg + (size_t)l * n_tiles + p));
-                --p;
+                const uint32_t done = __ballot_sync(0xffffffffu, fl == 2u);
+                const int first = __ffs(done) - 1;  // nearest predecessor with an inclusive value
+                if (done && lane > first) val_p = one;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val_p = fr_mul(val_p, fr_shfl_xor(val_p, d));
+                prefix = fr_mul(prefix, val_p);
+                if (done) break;
+                p -= 32;
             }
-            prefix = acc;
-            fr_st(incp, fr_mul(prefix, agg));
-            st_release_u32(flagp, 2u);
         }
-        s_tile_excl = prefix;
+        if (lane == 31) {
+            fr_st(incp, fr_mul(prefix, agg));
+            st_release_u32(flags + tile, 2u);
+            s_tile_excl = prefix;
+        }
     }
     __syncthreads();
     if (kMode == 1) return;
@@ -666,13 +747,13 @@ k_grand_product(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
 #pragma unroll
     for (int q = 0; q < ZI; ++q) {
         const uint64_t row = row0 + q;
-        if (row < row_end) {
-            const size_t o = ((size_t)li * out_rows + (row - row_begin)) * 4;
+        if (row < a.row_end) {
+            const size_t o = ((size_t)li * out_rows + (row - a.row_begin)) * 4;
             // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
-            if (row <= usable) fr_store_256(Z + o, cur);
-            else fr_store_256(Z + o, fr_zero());
+            if (row <= usable) fr_store_256(a.Z + o, cur);
+            else fr_store_256(a.Z + o, fr_zero());
         }
-        cur = fr_mul(cur, f[q]);
+        if (q + 1 < ZI) cur = fr_mul(cur, f[q]);
     }
 }
 
@@ -753,10 +834,13 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
 
 cudaError_t launch_inv_tables(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
-    dim3 g(cdiv(VIEW_MAX_ENTRIES, 128 * INV_CH), N_VIEWS);
-    k_inv_tables<<<g, 128, 0, ctx->stream>>>(c->d_chal, c->d_dval, c->d_val, c->d_viewmeta, c->d_ib,
-                                             c->d_ig, c->d_nac, c->d_err);
-    ctx->launches += 1;
+    dim3 g(cdiv(VIEW_MAX_ENTRIES, INV_TILE), N_VIEWS, 2);
+    k_inv_tables<<<g, INV_T, 0, ctx->stream>>>(c->d_chal, c->d_dval, c->d_val, c->d_viewmeta,
+                                               c->d_ib, c->d_ig, c->d_nac, c->d_err);
+    dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
+    k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_ibg,
+                                             c->d_ibp);
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 
@@ -770,19 +854,27 @@ cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const f
     cudaError_t e;
     if ((e = cudaMemsetAsync(c->d_tile_flag, 0, (size_t)L * c->n_tiles * 4, s))) return e;
     if ((e = cudaMemsetAsync(c->d_tile_ctr, 0, (size_t)L * 4, s))) return e;
-    dim3 g((unsigned)tiles, count);
-    if (mode == 0)
-        k_grand_product<0><<<g, ZT, 0, s>>>(c->sh, first, c->d_trace, c->d_chal, c->d_val, c->d_dval,
-                                            c->d_ib, c->d_ig, c->d_nac, c->d_rank, c->d_offz,
-                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, c->d_tile_agg,
-                                            c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, carry_in,
-                                            c->n_tiles, Z, row_begin, row_end);
-    else
-        k_grand_product<1><<<g, ZT, 0, s>>>(c->sh, first, c->d_trace, c->d_chal, c->d_val, c->d_dval,
-                                            c->d_ib, c->d_ig, c->d_nac, c->d_rank, c->d_offz,
-                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, c->d_tile_agg,
-                                            c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, carry_in,
-                                            c->n_tiles, Z, row_begin, row_end);
+    ZArgs a;
+    a.sh = c->sh;
+    a.first_lookup = first;
+    a.count = count;
+    a.trace = c->d_trace;
+    a.chal = c->d_chal;
+    a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
+    a.ibg = c->d_ibg; a.ibp = c->d_ibp;
+    a.rank = c->d_rank;
+    a.offz = c->d_offz; a.nzk = c->d_nzk; a.loffz = c->d_loffz; a.lk = c->d_lk;
+    a.meta = c->d_meta;
+    a.tile_agg = c->d_tile_agg; a.tile_inc = c->d_tile_inc;
+    a.tile_flag = c->d_tile_flag; a.tile_ctr = c->d_tile_ctr;
+    a.carry_in = carry_in;
+    a.n_tiles = c->n_tiles;
+    a.Z = Z;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
+    const unsigned grid = (unsigned)(tiles * (uint64_t)count);
+    if (mode == 0) k_grand_product<0><<<grid, ZT, 0, s>>>(a);
+    else k_grand_product<1><<<grid, ZT, 0, s>>>(a);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -792,6 +884,17 @@ cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev) {
     const int L = c->sh.n_lookups();
     k_shard_carry<<<cdiv(L, 64), 64, 0, ctx->stream>>>((const fr_t *)gathered_dev, L, c->shard,
                                                        c->d_carry);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+__global__ void k_dbg_fr_mul(const fr_t *__restrict__ a, const fr_t *__restrict__ b, uint64_t n,
+                             fr_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_st(out + i, fr_mul(fr_ld(a + i), fr_ld(b + i)));
+}
+cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out) {
+    k_dbg_fr_mul<<<cdiv(n, 128), 128, 0, ctx->stream>>>(a, b, n, out);
     ctx->launches += 1;
     return cudaGetLastError();
 }

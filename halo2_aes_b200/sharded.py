@@ -1,0 +1,92 @@
+"""Multi-GPU partitioning of the path (one process per GPU, torch.distributed for plumbing).
+
+Two regimes (BASELINE configs 4 and 5):
+
+* independent circuits / AES batches: blocks are cut into whole circuits of the reference's
+  capacity and dealt round-robin to the ranks.  No data-path collective at all.
+* one large circuit, row-sharded: shard g of G owns rows [g*n/G, (g+1)*n/G) of every column.
+  The witness needs no exchange (every rank expands the key and the block states itself and
+  stores only its rows).  The lookup helper columns need exactly two small exchanges:
+    1. all-reduce(sum) of the per-lookup table-bin histogram (66568 u32 per lookup) before
+       A'/S' can be expanded, because the permuted columns are a global sort;
+    2. all-gather of one 32-byte partial product per shard per lookup, from which each shard
+       derives its carry-in for the grand product Z.
+  Both are KiB..MiB-sized and latency-bound on NVLink5/NVSwitch, so they go through NCCL as
+  they are; the bulk columns never leave the GPU that owns their rows.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+# ---------------------------------------------------------------------------------------------
+# independent circuits
+# ---------------------------------------------------------------------------------------------
+def split_into_circuits(n_blocks: int, capacity: int) -> list[tuple[int, int]]:
+    """[(first_block, count)] of the circuits needed for n_blocks AES blocks, each filled to the
+    reference's capacity rule (aes128.rs:303-325) except the last."""
+    if capacity <= 0:
+        raise ValueError("capacity must be positive")
+    return [(s, min(capacity, n_blocks - s)) for s in range(0, n_blocks, capacity)]
+
+
+def circuits_of_rank(n_circuits: int, rank: int, world: int) -> list[int]:
+    """round-robin deal of circuit indices to ranks"""
+    return list(range(rank, n_circuits, world))
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives of the row-sharded circuit (device-agnostic: NCCL on GPUs, gloo in the CPU tests)
+# ---------------------------------------------------------------------------------------------
+def allreduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
+    """in-place SUM of the [n_lookups * BIN_STRIDE] int32 bin histogram across shards"""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
+def allgather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """[n_lookups, 4] int64 per shard -> [n_shards, n_lookups, 4] on every shard"""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return partial.unsqueeze(0).contiguous()
+    world = dist.get_world_size(group)
+    flat = partial.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view((world,) + tuple(partial.shape))
+
+
+class RowShardedCircuit:
+    """One circuit spread over the ranks of `group` by rows."""
+
+    def __init__(self, ctx, kind: int, k: int, N: int, group=None):
+        from .backend import Circuit
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.circuit = Circuit(ctx, kind, k, N)
+        self.circuit.set_shard(self.rank, self.world)
+
+    @property
+    def row_range(self):
+        per = self.circuit.n // self.world
+        return per * self.rank, per * (self.rank + 1)
+
+    def witness(self, key, plaintexts=None, out=None):
+        """every rank passes the same key/plaintexts; returns this shard's rows of every advice
+        column ([n_advice, n/G, 4]).  No communication."""
+        return self.circuit.witness(key, plaintexts, out=out)
+
+    def fixed_columns(self, **kw):
+        return self.circuit.fixed_columns(**kw)
+
+    def lookup_columns(self, theta, beta, gamma, want_inputs=False):
+        c = self.circuit
+        hist = c.shard_hist(theta)
+        allreduce_histogram(hist, self.group)                 # exchange 1
+        cols = c.shard_permuted(want_inputs=want_inputs)
+        partial = c.shard_partial(beta, gamma)
+        gathered = allgather_partials(partial, self.group)    # exchange 2
+        cols["Z"] = c.shard_product(gathered)
+        return cols

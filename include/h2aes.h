@@ -230,6 +230,10 @@ int32_t h2aes_dbg_fr_sub(const uint64_t *a, const uint64_t *b, uint64_t *out);
 int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out);
 int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out);
 int32_t h2aes_dbg_fr_to_canonical(const uint64_t *a, uint64_t *out);
+/* n Montgomery products out[i] = a[i]*b[i] computed ON THE DEVICE by the kernels' multiply
+ * (host pointers; pins the generated PTX multiply against host arithmetic in the GPU tests). */
+int32_t h2aes_dbg_fr_mul_dev(h2aes_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t n,
+                             uint64_t *out);
 int32_t h2aes_dbg_tables(int32_t sbox_mode, uint8_t *sbox256, uint8_t *mul2_256,
                          uint8_t *mul3_256);
 /* host evaluation of the per-row trace word (a0 | a1<<8 | a2<<16 | op<<24) the witness

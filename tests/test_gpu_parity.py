@@ -206,3 +206,66 @@ def test_host_entry_points(gpu, orc, ffi, challenges):
         for nm, g in (("A", A), ("S", S), ("Ap", Ap), ("Sp", Sp), ("Z", Z)):
             assert (g[li] == r[nm]).all(), (nm, li)
     cir.close()
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G):
+    """BASELINE config 5 (one circuit row-sharded over G GPUs) with the G shards run one after
+    another on this GPU and the two exchanges (histogram sum, partial-product gather) done by
+    hand — the same entry points sharded.RowShardedCircuit drives over NCCL."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    theta, beta, gamma = challenges
+    k, N = 17, 2
+    pts = splitmix_bytes(SEED + 50, 16 * 120).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 51, 16).tobytes()
+    d_pts = torch.from_numpy(pts).cuda()
+    shards = [Circuit(gpu, ffi.KIND_AES, k, N) for _ in range(G)]
+    for g, c in enumerate(shards):
+        c.set_shard(g, G)
+    adv = [c.witness(key, d_pts)[0] for c in shards]
+    fx = [c.fixed_columns() for c in shards]
+    hists = [c.shard_hist(theta) for c in shards]
+    total = torch.stack(hists).sum(dim=0, dtype=torch.int32)
+    for h in hists:
+        h.copy_(total)                                    # all-reduce(sum)
+    perm = [c.shard_permuted(want_inputs=True) for c in shards]
+    parts = [c.shard_partial(beta, gamma).clone() for c in shards]
+    gathered = torch.stack(parts).contiguous()            # all-gather
+    Zs = [c.shard_product(gathered) for c in shards]
+    for c in shards:
+        c.lookup_check()
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
+    cat = lambda ts: np.concatenate([_host(t) for t in ts], axis=1)
+    assert (cat(adv) == ref.advice()).all()
+    assert (cat([f[0] for f in fx]) == ref.fixed()).all()
+    assert (_sel_bits(orc, cat([f[1] for f in fx])) == ref.selectors()).all()
+    got = {nm: cat([p[nm] for p in perm]) for nm in ("A", "S", "Ap", "Sp")}
+    gZ = cat(Zs)
+    for li in (0, 1, 2, 3, 4, 6, 7):
+        r = ref.lookup(li, theta, beta, gamma)
+        for nm in ("A", "S", "Ap", "Sp"):
+            assert (got[nm][li] == r[nm]).all(), (nm, li)
+        assert (gZ[li] == r["Z"]).all(), ("Z", li)
+    for c in shards:
+        c.close()
+
+
+def test_fr_mul_device_vs_bigint(gpu, orc, ffi):
+    """The generated PTX Montgomery multiply (csrc/fr_mul_ptx.inc) on the device against Python
+    big integers, including extreme operands."""
+    R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    rng = np.random.default_rng(SEED)
+    vals = [0, 1, 2, R_MOD - 1, R_MOD - 2, (1 << 254) % R_MOD, (1 << 256) % R_MOD, R_MOD >> 1]
+    a = vals * len(vals) + [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(4000)]
+    b = [y for y in vals for _ in vals] + [int.from_bytes(rng.bytes(32), "little") % R_MOD
+                                            for _ in range(4000)]
+    A = np.stack([orc.int_to_limbs(x) for x in a])
+    B = np.stack([orc.int_to_limbs(x) for x in b])
+    out = np.zeros_like(A)
+    u64p = C.POINTER(C.c_uint64)
+    ffi.check(ffi.lib().h2aes_dbg_fr_mul_dev(gpu._h, A.ctypes.data_as(u64p), B.ctypes.data_as(u64p),
+                                            len(a), out.ctypes.data_as(u64p)), gpu._h)
+    rinv = pow(1 << 256, -1, R_MOD)
+    for i in range(len(a)):
+        assert orc.limbs_to_int(out[i]) == a[i] * b[i] * rinv % R_MOD, i

@@ -1,0 +1,110 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic in halo2_aes_b200/sharded.py:
+the circuit partitioning of independent batches, and the two collectives of the row-sharded
+circuit, checked against the oracle's whole-circuit columns."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, SEED, seeded_fr, splitmix_bytes
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from halo2_aes_b200 import sharded
+
+        # ---- independent circuits (BASELINE config 4) -------------------------------------
+        circuits = sharded.split_into_circuits(10000, 3853)
+        assert circuits == [(0, 3853), (3853, 3853), (7706, 2294)]
+        mine = sharded.circuits_of_rank(len(circuits), rank, world)
+        counts = torch.tensor([sum(circuits[i][1] for i in mine)])
+        dist.all_reduce(counts)
+        assert int(counts) == 10000
+
+        # ---- row-sharded single circuit (BASELINE config 5), emulated with the oracle -------
+        k, u = 17, (1 << 17) - 6
+        n = 1 << k
+        th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
+        key = splitmix_bytes(SEED + 40, 16).tobytes()
+        pts = splitmix_bytes(SEED + 41, 16 * 40).reshape(-1, 16)
+        full = oracle.Circuit(oracle.KIND_AES, k, 1).synthesize(key, pts)
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        L = oracle.lib()
+        for li in (1, 2):
+            r = full.lookup(li, th, be, ga)
+            # exchange 1: histogram of the shard's input values over the distinct table values
+            tab_vals, tab_inv = np.unique(r["S"][:u], axis=0, return_inverse=True)
+            index = {v.tobytes(): i for i, v in enumerate(tab_vals)}
+            hist = torch.zeros(len(tab_vals), dtype=torch.int32)
+            for row in range(lo, min(hi, u)):
+                hist[index[r["A"][row].tobytes()]] += 1
+            sharded.allreduce_histogram(hist)
+            whole = np.zeros(len(tab_vals), np.int64)
+            for row in range(u):
+                whole[index[r["A"][row].tobytes()]] += 1
+            assert (hist.numpy() == whole).all()
+            assert int(hist.sum()) == u
+            # exchange 2: per-shard partial product of Z's factors, gathered, gives the carry-in
+            Z = r["Z"]
+            def fr_mul(a, b):
+                out = np.zeros(4, np.uint64)
+                L.orc_fr_mul(oracle._u64(np.ascontiguousarray(a)), oracle._u64(np.ascontiguousarray(b)),
+                             oracle._u64(out))
+                return out
+            def fr_inv(a):
+                out = np.zeros(4, np.uint64)
+                L.orc_fr_inv(oracle._u64(np.ascontiguousarray(a)), oracle._u64(out))
+                return out
+            last = min(hi, u)  # Z[last] / Z[lo] = product of the shard's factors
+            partial = fr_mul(Z[last], fr_inv(Z[lo]))
+            t = torch.from_numpy(partial.view(np.int64).copy()).view(1, 4)
+            gathered = sharded.allgather_partials(t)
+            assert gathered.shape == (world, 1, 4)
+            carry = oracle.fr_from_int(1)
+            for s in range(rank):
+                carry = fr_mul(carry, gathered[s, 0].numpy().view(np.uint64))
+            assert (carry == Z[lo]).all(), "carry-in of the shard != Z at its first row"
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_partition_helpers():
+    from halo2_aes_b200 import sharded
+    assert sharded.split_into_circuits(0, 10) == []
+    assert sharded.split_into_circuits(10, 10) == [(0, 10)]
+    assert sharded.split_into_circuits(11, 10) == [(0, 10), (10, 1)]
+    c = sharded.split_into_circuits(1 << 20, 3853)
+    assert len(c) == 273 and sum(x[1] for x in c) == 1 << 20   # 273 circuits
+    seen = sorted(i for r in range(8) for i in sharded.circuits_of_rank(273, r, 8))
+    assert seen == list(range(273))
+    with pytest.raises(ValueError):
+        sharded.split_into_circuits(5, 0)
