@@ -102,7 +102,7 @@ SIGNATURES = {
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "h2aes_lookup_hist_dev": (C.c_int32, [_vp, _u64p, C.POINTER(_vp), _u64p]),
     "h2aes_lookup_permuted_shard_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
-    "h2aes_lookup_partial_dev": (C.c_int32, [_vp, _u64p, _u64p, C.POINTER(_vp)]),
+    "h2aes_lookup_partial_dev": (C.c_int32, [_vp, _u64p, _u64p, _vp, C.POINTER(_vp)]),
     "h2aes_lookup_product_shard_dev": (C.c_int32, [_vp, _vp, _vp]),
     "h2aes_dbg_fr_mul": (C.c_int32, [_u64p, _u64p, _u64p]),
     "h2aes_dbg_fr_add": (C.c_int32, [_u64p, _u64p, _u64p]),

@@ -199,18 +199,20 @@ class Circuit:
               self.ctx._h)
         return bufs
 
-    def shard_partial(self, beta, gamma) -> torch.Tensor:
+    def shard_partial(self, beta, gamma):
+        """phase 2a: returns (Z buffer holding the factors, partial products [L,4])"""
         be, bep = _fr_arg(beta)
         ga, gap = _fr_arg(gamma)
-        p = C.c_void_p()
-        check(lib().h2aes_lookup_partial_dev(self._h, bep, gap, C.byref(p)), self.ctx._h)
         L = self.layout["n_lookups"]
-        return _wrap_device_i64(p.value, L * 4, self.ctx.device).view(L, 4)
+        Z = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
+        p = C.c_void_p()
+        check(lib().h2aes_lookup_partial_dev(self._h, bep, gap, _ptr(Z), C.byref(p)), self.ctx._h)
+        return Z, _wrap_device_i64(p.value, L * 4, self.ctx.device).view(L, 4)
 
-    def shard_product(self, gathered: torch.Tensor):
+    def shard_product(self, gathered: torch.Tensor, Z: torch.Tensor):
+        """phase 2b: finishes Z in place from every shard's partial products"""
         L = self.layout["n_lookups"]
         assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == self.n_shards * L * 4
-        Z = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
         check(lib().h2aes_lookup_product_shard_dev(self._h, _ptr(gathered), _ptr(Z)), self.ctx._h)
         return Z
 

@@ -25,10 +25,12 @@ cudaError_t launch_lookup_bins(h2aes_circuit *c);
 cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
                             uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end);
 cudaError_t launch_inv_tables(h2aes_circuit *c);
-cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                                 uint64_t *Z, uint64_t row_begin, uint64_t row_end, int mode);
+cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z,
+                             uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
+                            uint64_t *Z, uint64_t row_begin, uint64_t row_end);
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
-uint64_t grand_product_tiles(uint64_t rows);
+void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk);
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
 
 // S-box from first principles (GF(2^8) inverse + affine map); H2AES_SBOX_REFERENCE then applies
@@ -284,7 +286,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
-                    c->d_tile_agg, c->d_tile_inc, c->d_tile_flag, c->d_tile_ctr, c->d_err,
+                    c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -484,7 +486,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
     const size_t L = (size_t)c->sh.n_lookups();
     const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
-    c->n_tiles = grand_product_tiles(c->sh.n());
+    grand_product_ws(c->sh.n(), &c->zm, &c->znblk);
     CU(ctx, dalloc(&c->d_chal, 4));
     CU(ctx, dalloc(&c->d_val, VB));
     CU(ctx, dalloc(&c->d_canon, VB));
@@ -508,10 +510,9 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_loffz, LB));
     CU(ctx, dalloc(&c->d_lk, LB));
     CU(ctx, dalloc(&c->d_meta, L));
-    CU(ctx, dalloc(&c->d_tile_agg, L * c->n_tiles));
-    CU(ctx, dalloc(&c->d_tile_inc, L * c->n_tiles));
-    CU(ctx, dalloc(&c->d_tile_flag, L * c->n_tiles));
-    CU(ctx, dalloc(&c->d_tile_ctr, L));
+    CU(ctx, dalloc(&c->d_ztot, L * c->zm));
+    CU(ctx, dalloc(&c->d_zbagg, L * c->znblk));
+    CU(ctx, dalloc(&c->d_zbexcl, L * c->znblk));
     CU(ctx, dalloc(&c->d_partial, L));
     CU(ctx, dalloc(&c->d_carry, L));
     c->lk_alloc = true;
@@ -596,7 +597,10 @@ int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const u
     CU(ctx, cudaSetDevice(ctx->device));
     int32_t rc = set_beta_gamma(c, beta, gamma);
     if (rc) return rc;
-    if (count) CU(ctx, launch_grand_product(c, first, count, nullptr, Z_dev, 0, c->sh.n(), 0));
+    if (count) {
+        CU(ctx, launch_z_factors(c, first, count, Z_dev, 0, c->sh.n()));
+        CU(ctx, launch_z_finish(c, first, count, nullptr, Z_dev, 0, c->sh.n()));
+    }
     return H2AES_OK;
 }
 
@@ -719,24 +723,20 @@ int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint6
 }
 
 int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
-                                 uint64_t **partial_dev) {
+                                 uint64_t *Z_dev, uint64_t **partial_dev) {
     if (!c) return H2AES_ERR_ARG;
     h2aes_ctx *ctx = c->ctx;
-    if (!beta || !gamma || !partial_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!beta || !gamma || !Z_dev || !partial_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
     if (!c->have_bins) return fail(ctx, H2AES_ERR_STATE, "permuted columns must be built first");
     CU(ctx, cudaSetDevice(ctx->device));
     int32_t rc = set_beta_gamma(c, beta, gamma);
     if (rc) return rc;
     uint64_t rb, re;
     shard_rows(c, &rb, &re);
-    const int L = c->sh.n_lookups();
-    CU(ctx, launch_grand_product(c, 0, L, nullptr, nullptr, rb, re, 1));
-    // the running product after the shard's last tile is the shard's partial product
-    const uint64_t tiles = grand_product_tiles(re - rb);
-    CU(ctx, cudaMemcpy2DAsync(c->d_partial, sizeof(fr_t), c->d_tile_inc + (tiles - 1),
-                              c->n_tiles * sizeof(fr_t), sizeof(fr_t), (size_t)L,
-                              cudaMemcpyDeviceToDevice, ctx->stream));
+    // per-row factors go to Z_dev, their total per lookup (the shard's partial product) to d_partial
+    CU(ctx, launch_z_factors(c, 0, c->sh.n_lookups(), Z_dev, rb, re));
     c->have_partial = true;
+    c->partial_Z = Z_dev;
     *partial_dev = (uint64_t *)c->d_partial;
     return H2AES_OK;
 }
@@ -747,11 +747,14 @@ int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathere
     h2aes_ctx *ctx = c->ctx;
     if (!gathered_dev || !Z_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
     if (!c->have_partial) return fail(ctx, H2AES_ERR_STATE, "h2aes_lookup_partial_dev must run first");
+    if (Z_dev != c->partial_Z)
+        return fail(ctx, H2AES_ERR_ARG, "Z_dev must be the buffer given to h2aes_lookup_partial_dev");
     CU(ctx, cudaSetDevice(ctx->device));
     uint64_t rb, re;
     shard_rows(c, &rb, &re);
     CU(ctx, launch_shard_carry(c, gathered_dev));
-    CU(ctx, launch_grand_product(c, 0, c->sh.n_lookups(), c->d_carry, Z_dev, rb, re, 0));
+    CU(ctx, launch_z_finish(c, 0, c->sh.n_lookups(), c->d_carry, Z_dev, rb, re));
+    c->have_partial = false;
     return H2AES_OK;
 }
 

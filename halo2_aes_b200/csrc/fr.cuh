@@ -196,13 +196,23 @@ FR_D void fr_reduce_once_dev(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t 
 
 // Montgomery product.  Device: the generated even/odd carry-chain PTX (gen_fr_mul.py, ~150
 // IMAD.WIDE-class instructions); host: the portable CIOS above (same results, both < r).
-FR_HD fr_t fr_mul(const fr_t &a, const fr_t &b) {
-#if defined(__CUDA_ARCH__) && !defined(H2AES_PORTABLE_MUL)
+#if defined(__CUDACC__)
+// ONE out-of-line copy per translation unit: a kernel with a dozen inlined multiplies is
+// hundreds of KB of SASS and stalls on instruction fetch (ncu: stall_no_inst 36% in
+// k_grand_product); as a call the whole multiply stays resident in the instruction cache.
+// Operands and result travel in registers (structs of 8 x u32 by value).
+static __device__ __noinline__ fr_t fr_mul_call(fr_t a, fr_t b) {
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
 #include "fr_mul_ptx.inc"
     fr_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
     fr_t o = {{r0, r1, r2, r3, r4, r5, r6, r7}};
     return o;
+}
+#endif
+
+FR_HD fr_t fr_mul(const fr_t &a, const fr_t &b) {
+#if defined(__CUDA_ARCH__) && !defined(H2AES_PORTABLE_MUL)
+    return fr_mul_call(a, b);
 #else
     return fr_mul_portable(a, b);
 #endif

@@ -111,15 +111,15 @@ struct h2aes_circuit {
     uint32_t *d_lk = nullptr;        // [L][BIN_STRIDE] bin of each leftover slot
     h2::LookupMeta *d_meta = nullptr;  // [L]
     // grand-product scan workspace
-    h2::fr_t *d_tile_agg = nullptr;   // [L][tiles]
-    h2::fr_t *d_tile_inc = nullptr;   // [L][tiles]
-    uint32_t *d_tile_flag = nullptr;  // [L][tiles]
-    uint32_t *d_tile_ctr = nullptr;   // [L]
+    h2::fr_t *d_ztot = nullptr;       // [L][zm]   per-thread factor products / their prefixes
+    h2::fr_t *d_zbagg = nullptr;      // [L][znblk] block aggregates
+    h2::fr_t *d_zbexcl = nullptr;     // [L][znblk] exclusive prefixes of the block aggregates
     uint32_t *d_err = nullptr;        // device error flags: [0] zero denominator, [1] not in table
     uint32_t *h_err = nullptr;        // pinned mirror of d_err
     h2::fr_t *d_partial = nullptr;    // [L] shard partial products
     h2::fr_t *d_carry = nullptr;      // [L] product of the partials of the shards before this one
-    uint64_t n_tiles = 0;
+    uint64_t zm = 0, znblk = 0;
+    uint64_t *partial_Z = nullptr;    // Z buffer holding the factors between phases 2a and 2b
 
     // staging for the _host entry points
     void *d_stage = nullptr;

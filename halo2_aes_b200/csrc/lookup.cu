@@ -564,24 +564,21 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 2b: grand product Z — single pass, decoupled look-back over tiles of ZT*ZI rows.
-//   per row: 1 multiply for the factor (table x table), 1 for the thread total, 1 for the
-//   running product that is stored.  Tiles of all lookups of the call are interleaved in the
-//   grid so that few tiles of the same lookup are in flight at once, and the look-back itself
-//   is done by a whole warp (32 predecessors per step, warp product reduction).
+// phase 2b: grand product Z as factor -> scan -> propagate (no spin-waits, no barriers on the
+// hot path; ~3.2 Montgomery multiplies per row):
+//   k_z_factors    per row f = num * den (one table x table multiply), stored in the Z buffer;
+//                  per thread (ZI consecutive rows) the product of its factors -> tot[]
+//   k_z_reduce / k_z_blocks / k_z_down   exclusive product scan of tot[] (n/ZI elements per
+//                  lookup) in three small kernels; the total is the shard's partial product
+//   k_z_propagate  per thread: running product from its exclusive prefix, overwriting the
+//                  factors in the Z buffer with Z itself
+// The kernel is bound by integer-multiply issue, not by HBM.
 // ---------------------------------------------------------------------------------------------
-constexpr int ZT = 128;  // threads per tile
-constexpr int ZI = 8;    // consecutive rows per thread
-constexpr int ZTILE = ZT * ZI;
-
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+constexpr int ZI = 16;     // consecutive rows per thread
+constexpr int ZF_T = 128;  // threads per CTA, factor / propagate kernels
+constexpr int ZS_T = 256;  // scan kernels: threads per CTA
+constexpr int ZS_E = 16;   //               elements per thread
+constexpr int ZS_TILE = ZS_T * ZS_E;
 
 struct ZArgs {
     Shape sh;
@@ -592,28 +589,26 @@ struct ZArgs {
     const uint32_t *rank;                                // [3][BIN_STRIDE]
     const uint32_t *offz, *nzk, *loffz, *lk;             // [L][BIN_STRIDE]
     const LookupMeta *meta;
-    fr_t *tile_agg, *tile_inc;
-    uint32_t *tile_flag, *tile_ctr;
-    const fr_t *carry_in;
-    uint64_t n_tiles;
+    fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
+    fr_t *bagg;       // [count][nblk] block aggregates of tot
+    fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
+    fr_t *partial;    // [L] product of all factors of the row range
+    const fr_t *carry_in;  // [L] or null
+    uint64_t m, nblk;
     uint64_t *Z;
     uint64_t row_begin, row_end;
 };
 
-// kMode 0: write Z with look-back; kMode 1: only the product of the shard's factors
-template <int kMode>
-__global__ void __launch_bounds__(ZT) k_grand_product(const ZArgs a) {
-    __shared__ fr_t s_warp[ZT / 32];
-    __shared__ fr_t s_tile_excl;
-    __shared__ uint32_t s_tile;
+__global__ void __launch_bounds__(ZF_T) k_z_factors(const ZArgs a) {
+    const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
+    if (e >= a.m) return;
     const Shape sh = a.sh;
-    const int li = blockIdx.x % a.count;  // lookups interleaved: consecutive CTAs, different lookups
+    const int li = blockIdx.y;
     const int l = a.first_lookup + li;
     const int ops = sh.ops_per_set();
     const int set = l / ops;
     const uint32_t op = (uint32_t)(l % ops) + 1;
     const int v = view_of_op(op);
-    const uint64_t n = sh.n();
     const uint32_t usable = (uint32_t)sh.usable();
     const uint64_t out_rows = a.row_end - a.row_begin;
     const LookupMeta m = a.meta[l];
@@ -627,25 +622,20 @@ __global__ void __launch_bounds__(ZT) k_grand_product(const ZArgs a) {
                              *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
                              *__restrict__ ibp = a.ibp + vo;
     const uint32_t *__restrict__ rank = a.rank + vo;
-    const uint32_t *__restrict__ trace = a.trace + (uint64_t)set * n;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const fr_t one = fr_one();
-
-    // dynamic tile id: a tile only ever waits on tiles that already started
-    if (t == 0) s_tile = atomicAdd(a.tile_ctr + l, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t row0 = a.row_begin + (uint64_t)tile * ZTILE + (uint64_t)t * ZI;
-
+    const uint32_t *__restrict__ trace = a.trace + (uint64_t)set * sh.n();
     const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
-    fr_t f[ZI];
+    const uint64_t row0 = a.row_begin + e * ZI;
+    uint64_t *__restrict__ zout = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
+
+    fr_t tot = fr_one();
     uint32_t j = 0, jl = 0;
     bool have_j = false, have_jl = false;
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < ZI; ++q) {
         const uint64_t row = row0 + q;
-        if (row >= usable || row >= a.row_end) {
-            f[q] = one;
+        if (row >= a.row_end) break;
+        if (row >= usable) {  // blinding rows: factor one (their Z entries are zeroed later)
+            fr_store_256(zout + 4 * q, fr_one());
             continue;
         }
         const uint32_t i = (uint32_t)row;
@@ -683,77 +673,110 @@ __global__ void __launch_bounds__(ZT) k_grand_product(const ZArgs a) {
             if (kp == m.k_pad) den = fr_ld(ibp + k);
             else den = fr_mul(fr_ld(ib + k), fr_ld(ig + kp));
         }
-        f[q] = fr_mul(num, den);
+        const fr_t f = fr_mul(num, den);
+        fr_store_256(zout + 4 * q, f);
+        tot = fr_mul(tot, f);
     }
-    // thread total, warp inclusive scan of the totals
-    fr_t tot = f[0];
-#pragma unroll
-    for (int q = 1; q < ZI; ++q) tot = fr_mul(tot, f[q]);
-    fr_t inc = tot;
-#pragma unroll
+    fr_st(a.tot + (size_t)li * a.m + e, tot);
+}
+
+// block aggregate of ZS_TILE consecutive thread totals
+__global__ void __launch_bounds__(ZS_T) k_z_reduce(const ZArgs a) {
+    __shared__ fr_t s_w[ZS_T / 32];
+    const int li = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const fr_t *__restrict__ x = a.tot + (size_t)li * a.m;
+    const uint64_t base = (uint64_t)blockIdx.x * ZS_TILE + (uint64_t)t * ZS_E;
+    fr_t p = fr_one();
+#pragma unroll 1
+    for (int j = 0; j < ZS_E; ++j)
+        if (base + j < a.m) p = fr_mul(p, fr_ld(x + base + j));
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) p = fr_mul(p, fr_shfl_xor(p, d));
+    if (lane == 0) s_w[wid] = p;
+    __syncthreads();
+    if (t == 0) {
+        fr_t all = s_w[0];
+        for (int w = 1; w < ZS_T / 32; ++w) all = fr_mul(all, s_w[w]);
+        fr_st(a.bagg + (size_t)li * a.nblk + blockIdx.x, all);
+    }
+}
+
+// one warp per lookup: exclusive prefixes of the block aggregates, and the grand total
+__global__ void __launch_bounds__(32) k_z_blocks(const ZArgs a) {
+    const int li = blockIdx.x, lane = threadIdx.x;
+    const fr_t *__restrict__ g = a.bagg + (size_t)li * a.nblk;
+    fr_t *__restrict__ ex = a.bexcl + (size_t)li * a.nblk;
+    const uint64_t per = (a.nblk + 31) / 32;
+    const uint64_t lo = min(a.nblk, (uint64_t)lane * per), hi = min(a.nblk, lo + per);
+    fr_t acc = fr_one();
+    for (uint64_t b = lo; b < hi; ++b) acc = fr_mul(acc, fr_ld(g + b));
+    fr_t inc = acc;
+#pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         const fr_t y = fr_shfl_up(inc, d);
         if (lane >= d) inc = fr_mul(inc, y);
     }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    // exclusive prefix of this thread inside the tile
-    fr_t excl = fr_shfl_up(inc, 1);
-    if (lane == 0) excl = one;
-    for (int wq = 0; wq < wid; ++wq) excl = fr_mul(excl, s_warp[wq]);
-
-    if (wid == ZT / 32 - 1) {  // the last warp publishes the tile and looks back
-        fr_t *aggp = a.tile_agg + (size_t)l * a.n_tiles + tile;
-        fr_t *incp = a.tile_inc + (size_t)l * a.n_tiles + tile;
-        uint32_t *flags = a.tile_flag + (size_t)l * a.n_tiles;
-        fr_t agg = one;
-        if (lane == 31) agg = fr_mul(excl, tot);  // tile aggregate
-        fr_t prefix = one;
-        if (tile == 0) {
-            if (a.carry_in) prefix = fr_ld(a.carry_in + l);
-        } else {
-            if (lane == 31) {
-                fr_st(aggp, agg);
-                st_release_u32(flags + tile, 1u);
-            }
-            int p = (int)tile - 1;
-            while (true) {
-                const int idx = p - lane;  // lane 0 = nearest predecessor
-                uint32_t fl = 2u;          // before the first tile: "inclusive" with value one
-                fr_t val_p = one;
-                if (idx >= 0) {
-                    while ((fl = ld_acquire_u32(flags + idx)) == 0u) __nanosleep(20);
-                    val_p = fr_ld((fl == 2u ? a.tile_inc : a.tile_agg) + (size_t)l * a.n_tiles + idx);
-                }
-                const uint32_t done = __ballot_sync(0xffffffffu, fl == 2u);
-                const int first = __ffs(done) - 1;  // nearest predecessor with an inclusive value
-                if (done && lane > first) val_p = one;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val_p = fr_mul(val_p, fr_shfl_xor(val_p, d));
-                prefix = fr_mul(prefix, val_p);
-                if (done) break;
-                p -= 32;
-            }
-        }
-        if (lane == 31) {
-            fr_st(incp, fr_mul(prefix, agg));
-            st_release_u32(flags + tile, 2u);
-            s_tile_excl = prefix;
-        }
+    fr_t run = fr_shfl_up(inc, 1);
+    if (lane == 0) run = fr_one();
+    for (uint64_t b = lo; b < hi; ++b) {
+        fr_st(ex + b, run);
+        run = fr_mul(run, fr_ld(g + b));
     }
+    if (lane == 31) fr_st(a.partial + a.first_lookup + li, inc);
+}
+
+// thread totals -> exclusive prefixes (times the block prefix, times the shard carry-in)
+__global__ void __launch_bounds__(ZS_T) k_z_down(const ZArgs a) {
+    __shared__ fr_t s_w[ZS_T / 32];
+    const int li = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    fr_t *__restrict__ x = a.tot + (size_t)li * a.m;
+    const uint64_t base = (uint64_t)blockIdx.x * ZS_TILE + (uint64_t)t * ZS_E;
+    fr_t p = fr_one();
+#pragma unroll 1
+    for (int j = 0; j < ZS_E; ++j)
+        if (base + j < a.m) p = fr_mul(p, fr_ld(x + base + j));
+    fr_t inc = p;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const fr_t y = fr_shfl_up(inc, d);
+        if (lane >= d) inc = fr_mul(inc, y);
+    }
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
-    if (kMode == 1) return;
-    fr_t cur = fr_mul(s_tile_excl, excl);
-#pragma unroll
+    fr_t run = fr_shfl_up(inc, 1);
+    if (lane == 0) run = fr_one();
+    for (int w = 0; w < wid; ++w) run = fr_mul(run, s_w[w]);
+    fr_t bp = fr_ld(a.bexcl + (size_t)li * a.nblk + blockIdx.x);
+    if (a.carry_in) bp = fr_mul(bp, fr_ld(a.carry_in + a.first_lookup + li));
+    run = fr_mul(run, bp);
+#pragma unroll 1
+    for (int j = 0; j < ZS_E; ++j) {
+        if (base + j >= a.m) break;
+        const fr_t xv = fr_ld(x + base + j);
+        fr_st(x + base + j, run);
+        run = fr_mul(run, xv);
+    }
+}
+
+__global__ void __launch_bounds__(ZF_T) k_z_propagate(const ZArgs a) {
+    const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
+    if (e >= a.m) return;
+    const int li = blockIdx.y;
+    const uint32_t usable = (uint32_t)a.sh.usable();
+    const uint64_t out_rows = a.row_end - a.row_begin;
+    const uint64_t row0 = a.row_begin + e * ZI;
+    uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
+    fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
+#pragma unroll 1
     for (int q = 0; q < ZI; ++q) {
         const uint64_t row = row0 + q;
-        if (row < a.row_end) {
-            const size_t o = ((size_t)li * out_rows + (row - a.row_begin)) * 4;
-            // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
-            if (row <= usable) fr_store_256(a.Z + o, cur);
-            else fr_store_256(a.Z + o, fr_zero());
-        }
-        if (q + 1 < ZI) cur = fr_mul(cur, f[q]);
+        if (row >= a.row_end) break;
+        const fr_t f = fr_load(z + 4 * q);
+        // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
+        fr_store_256(z + 4 * q, row <= usable ? cur : fr_zero());
+        cur = fr_mul(cur, f);
     }
 }
 
@@ -844,16 +867,8 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                                 uint64_t *Z, uint64_t row_begin, uint64_t row_end, int mode) {
-    h2aes_ctx *ctx = c->ctx;
-    cudaStream_t s = ctx->stream;
-    const int L = c->sh.n_lookups();
-    const uint64_t rows = row_end - row_begin;
-    const uint64_t tiles = (rows + ZTILE - 1) / ZTILE;
-    cudaError_t e;
-    if ((e = cudaMemsetAsync(c->d_tile_flag, 0, (size_t)L * c->n_tiles * 4, s))) return e;
-    if ((e = cudaMemsetAsync(c->d_tile_ctr, 0, (size_t)L * 4, s))) return e;
+static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in, uint64_t *Z,
+                    uint64_t row_begin, uint64_t row_end) {
     ZArgs a;
     a.sh = c->sh;
     a.first_lookup = first;
@@ -865,17 +880,39 @@ cudaError_t launch_grand_product(h2aes_circuit *c, int first, int count, const f
     a.rank = c->d_rank;
     a.offz = c->d_offz; a.nzk = c->d_nzk; a.loffz = c->d_loffz; a.lk = c->d_lk;
     a.meta = c->d_meta;
-    a.tile_agg = c->d_tile_agg; a.tile_inc = c->d_tile_inc;
-    a.tile_flag = c->d_tile_flag; a.tile_ctr = c->d_tile_ctr;
+    a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
+    a.partial = c->d_partial;
     a.carry_in = carry_in;
-    a.n_tiles = c->n_tiles;
+    a.m = (row_end - row_begin + ZI - 1) / ZI;
+    a.nblk = (a.m + ZS_TILE - 1) / ZS_TILE;
     a.Z = Z;
     a.row_begin = row_begin;
     a.row_end = row_end;
-    const unsigned grid = (unsigned)(tiles * (uint64_t)count);
-    if (mode == 0) k_grand_product<0><<<grid, ZT, 0, s>>>(a);
-    else k_grand_product<1><<<grid, ZT, 0, s>>>(a);
-    ctx->launches += 1;
+    return a;
+}
+
+// factors into Z, thread totals, block aggregates, block prefixes, partial[first..first+count)
+cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z,
+                             uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
+    k_z_factors<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    k_z_reduce<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
+    k_z_blocks<<<count, 32, 0, s>>>(a);
+    ctx->launches += 3;
+    return cudaGetLastError();
+}
+
+// exclusive prefixes of the thread totals (with the shard carry-in), then Z in place
+cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
+                            uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    const ZArgs a = z_args(c, first, count, carry_in, Z, row_begin, row_end);
+    k_z_down<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
+    k_z_propagate<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 
@@ -899,6 +936,10 @@ cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint
     return cudaGetLastError();
 }
 
-uint64_t grand_product_tiles(uint64_t rows) { return (rows + ZTILE - 1) / ZTILE; }
+// workspace sizes of the grand-product scan for `rows` rows: thread totals, block aggregates
+void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk) {
+    *m = (rows + ZI - 1) / ZI;
+    *nblk = (*m + ZS_TILE - 1) / ZS_TILE;
+}
 
 }  // namespace h2

@@ -86,7 +86,7 @@ class RowShardedCircuit:
         hist = c.shard_hist(theta)
         allreduce_histogram(hist, self.group)                 # exchange 1
         cols = c.shard_permuted(want_inputs=want_inputs)
-        partial = c.shard_partial(beta, gamma)
+        Z, partial = c.shard_partial(beta, gamma)
         gathered = allgather_partials(partial, self.group)    # exchange 2
-        cols["Z"] = c.shard_product(gathered)
+        cols["Z"] = c.shard_product(gathered, Z)
         return cols

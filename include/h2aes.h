@@ -212,11 +212,13 @@ int32_t h2aes_lookup_hist_dev(h2aes_circuit *c, const uint64_t *theta, uint32_t 
 /* phase 1b: after the all-reduce: expand this shard's rows of A, S, A', S' (all lookups). */
 int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint64_t *S_dev,
                                         uint64_t *Ap_dev, uint64_t *Sp_dev);
-/* phase 2a: product of this shard's row factors, one Fr per lookup -> *partial_dev
- * ([n_lookups][4]); all-gather them into [n_shards][n_lookups][4] before phase 2b. */
+/* phase 2a: per-row factors of this shard's rows are written to Z_dev ([n_lookups][rows][4],
+ * intermediate data), and their product, one Fr per lookup, to *partial_dev ([n_lookups][4]);
+ * all-gather the partials into [n_shards][n_lookups][4] before phase 2b. */
 int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
-                                 uint64_t **partial_dev);
-/* phase 2b: Z for this shard's rows given every shard's partial products. */
+                                 uint64_t *Z_dev, uint64_t **partial_dev);
+/* phase 2b: turns the factors in Z_dev (the same buffer as in phase 2a) into Z for this
+ * shard's rows, given every shard's partial products. */
 int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathered_dev,
                                        uint64_t *Z_dev);
 

@@ -230,9 +230,9 @@ def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G):
     for h in hists:
         h.copy_(total)                                    # all-reduce(sum)
     perm = [c.shard_permuted(want_inputs=True) for c in shards]
-    parts = [c.shard_partial(beta, gamma).clone() for c in shards]
-    gathered = torch.stack(parts).contiguous()            # all-gather
-    Zs = [c.shard_product(gathered) for c in shards]
+    zp = [c.shard_partial(beta, gamma) for c in shards]
+    gathered = torch.stack([p.clone() for _, p in zp]).contiguous()   # all-gather
+    Zs = [c.shard_product(gathered, z) for c, (z, _) in zip(shards, zp)]
     for c in shards:
         c.lookup_check()
     ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
