@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "lib", "libh2aes.so")
+# H2AES_LIB selects another build of the same library (tuning experiments); never a fallback
+LIB_PATH = os.environ.get("H2AES_LIB") or os.path.join(_DIR, "lib", "libh2aes.so")
 
 OK = 0
 ERR_ARG, ERR_CAPACITY, ERR_ROWS, ERR_NOT_SCHEDULED, ERR_LOOKUP = 1, 2, 3, 4, 5

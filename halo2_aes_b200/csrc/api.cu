@@ -284,13 +284,14 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
-                    c->d_ibg,      c->d_ibp,
+                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_c0pow,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost(c->h_err);
+    delete[] c->code_valid;
 }
 
 int32_t h2aes_circuit_create(h2aes_ctx *ctx, int32_t kind, int32_t k, int32_t N,
@@ -504,6 +505,11 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_nac, VB));
     CU(ctx, dalloc(&c->d_ibg, VB));
     CU(ctx, dalloc(&c->d_ibp, VB));
+    CU(ctx, dalloc(&c->d_c0pow, L * 17));
+    CU(ctx, dalloc(&c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n()));
+    CU(ctx, dalloc(&c->d_codek, L * c->sh.n()));
+    CU(ctx, dalloc(&c->d_codep, L * c->sh.n()));
+    c->code_valid = new bool[L]();
     CU(ctx, dalloc(&c->d_cnt, LB));
     CU(ctx, dalloc(&c->d_offz, LB));
     CU(ctx, dalloc(&c->d_nzk, LB));
@@ -577,9 +583,12 @@ int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32
         CU(ctx, launch_lookup_bins(c));
         c->have_bins = true;
         c->have_beta_gamma = false;
+        for (int l = 0; l < c->sh.n_lookups(); ++l) c->code_valid[l] = false;
     }
-    if (count)
+    if (count) {
         CU(ctx, launch_permuted(c, first, count, A_dev, S_dev, Ap_dev, Sp_dev, 0, c->sh.n()));
+        for (int l = first; l < first + count; ++l) c->code_valid[l] = true;
+    }
     return H2AES_OK;
 }
 
@@ -597,6 +606,15 @@ int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const u
     CU(ctx, cudaSetDevice(ctx->device));
     int32_t rc = set_beta_gamma(c, beta, gamma);
     if (rc) return rc;
+    // per-row codes come from the permuted-column kernel; make them for lookups it has not seen
+    for (int l = first; l < first + count; ++l) {
+        if (c->code_valid[l]) continue;
+        int e = l;
+        while (e < first + count && !c->code_valid[e]) ++e;
+        CU(ctx, launch_permuted(c, l, e - l, nullptr, nullptr, nullptr, nullptr, 0, c->sh.n()));
+        for (int x = l; x < e; ++x) c->code_valid[x] = true;
+        l = e - 1;
+    }
     if (count) {
         CU(ctx, launch_z_factors(c, first, count, Z_dev, 0, c->sh.n()));
         CU(ctx, launch_z_finish(c, first, count, nullptr, Z_dev, 0, c->sh.n()));
@@ -710,15 +728,14 @@ int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint6
     h2aes_ctx *ctx = c->ctx;
     if (!c->have_hist) return fail(ctx, H2AES_ERR_STATE, "h2aes_lookup_hist_dev must run first");
     CU(ctx, cudaSetDevice(ctx->device));
+    if ((Ap_dev == nullptr) != (Sp_dev == nullptr) || (!Ap_dev && (A_dev || S_dev)))
+        return fail(ctx, H2AES_ERR_ARG, "A' and S' must both be given (or no output at all)");
     CU(ctx, launch_lookup_bins(c));
     c->have_bins = true;
-    if (Ap_dev && Sp_dev) {
-        uint64_t rb, re;
-        shard_rows(c, &rb, &re);
-        CU(ctx, launch_permuted(c, 0, c->sh.n_lookups(), A_dev, S_dev, Ap_dev, Sp_dev, rb, re));
-    } else if (Ap_dev || Sp_dev || A_dev || S_dev) {
-        return fail(ctx, H2AES_ERR_ARG, "A' and S' must both be given (or no output at all)");
-    }
+    uint64_t rb, re;
+    shard_rows(c, &rb, &re);
+    // with no outputs this still records the per-row codes the grand product reads
+    CU(ctx, launch_permuted(c, 0, c->sh.n_lookups(), A_dev, S_dev, Ap_dev, Sp_dev, rb, re));
     return H2AES_OK;
 }
 

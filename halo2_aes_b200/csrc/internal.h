@@ -79,6 +79,10 @@ struct h2aes_circuit {
     uint8_t *d_states = nullptr;   // capacity * ST_BYTES
     uint64_t states_cap = 0;
     uint32_t *d_trace = nullptr;   // n_sets * n words (a0 | a1<<8 | a2<<16 | op<<24)
+    uint32_t *d_tracek = nullptr;  // n_sets * n words (op<<24 | bin of the row's tuple), per theta
+    uint32_t *d_codek = nullptr;   // [L][n] bin of A' | class<<30, written by k_permuted
+    uint32_t *d_codep = nullptr;   // [L][n] bin of S' where class == OTHER
+    bool *code_valid = nullptr;    // [L] host flags: codes of lookup l match the current bins
 
     // lookup workspace (allocated on first use)
     bool lk_alloc = false;
@@ -103,6 +107,7 @@ struct h2aes_circuit {
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
     h2::fr_t *d_ibg = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k]
     h2::fr_t *d_ibp = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k_pad]
+    h2::fr_t *d_c0pow = nullptr;     // [L][17] powers of the constant row factor
     // per lookup
     uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
     uint32_t *d_offz = nullptr;      // [L][BIN_STRIDE] first row of each nonempty bin (+ end)

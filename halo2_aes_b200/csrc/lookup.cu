@@ -221,23 +221,30 @@ k_bin_fill(const fr_t *__restrict__ val, const uint32_t *__restrict__ sorted,
 // ---------------------------------------------------------------------------------------------
 // phase 1b: per-lookup histogram of the rows over the bins
 // ---------------------------------------------------------------------------------------------
+// Also writes tracek[set][row] = op<<24 | bin of the row's tuple (0 for inactive rows), which the
+// grand-product kernel reads instead of re-deriving the bin from the trace word.
 __global__ void __launch_bounds__(256)
 k_lookup_hist(Shape sh, const uint32_t *__restrict__ trace, const uint32_t *__restrict__ rank,
-              uint32_t *__restrict__ cnt, uint64_t row_begin, uint64_t row_end) {
+              uint32_t *__restrict__ cnt, uint32_t *__restrict__ tracek, uint64_t row_begin,
+              uint64_t row_end) {
     const uint64_t n = sh.n();
     const int set = blockIdx.y;
     const int ops = sh.ops_per_set();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t end = row_end < sh.usable() ? row_end : sh.usable();
-    for (uint64_t row = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < end;
+    const uint64_t usable = sh.usable();
+    for (uint64_t row = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end;
          row += stride) {
         const uint32_t w = trace[(uint64_t)set * n + row];
         const uint32_t op = w >> 24;
-        if (!op) continue;
-        const int v = view_of_op(op);
-        const uint32_t e = entry_of_table_row(v, table_row_of_word(w));
-        const uint32_t k = rank[(size_t)v * BIN_STRIDE + e];
-        atomicAdd(cnt + (size_t)(set * ops + (int)op - 1) * BIN_STRIDE + k, 1u);
+        uint32_t tk = 0;
+        if (op && row < usable) {
+            const int v = view_of_op(op);
+            const uint32_t e = entry_of_table_row(v, table_row_of_word(w));
+            const uint32_t k = rank[(size_t)v * BIN_STRIDE + e];
+            atomicAdd(cnt + (size_t)(set * ops + (int)op - 1) * BIN_STRIDE + k, 1u);
+            tk = (op << 24) | k;
+        }
+        tracek[(uint64_t)set * n + row] = tk;
     }
 }
 
@@ -364,9 +371,10 @@ __device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ arr, 
     return lo;
 }
 
-// bins (k of A', k' of S') of usable row i
+// bins (k of A', k' of S') of usable row i, and how S' relates to A'
+constexpr uint32_t CODE_FIRST = 0u, CODE_PAD = 1u, CODE_OTHER = 2u;  // stored in bits 30..31
 struct RowBins {
-    uint32_t k, kp;
+    uint32_t k, kp, cls;
 };
 __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
                                             const uint32_t *__restrict__ offz,
@@ -378,17 +386,22 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
     rb.k = nzk[j];
     if (offz[j] == i) {
         rb.kp = rb.k;  // first occurrence: S' = A'
+        rb.cls = CODE_FIRST;
     } else {
         // repeated rows, in row order, receive the leftover multiset from its END
         const uint32_t rho = i - (j + 1);
         const uint32_t jj = m.repeated - 1 - rho;
         rb.kp = lk[search_le(loffz, m.n_left, jj)];
+        rb.cls = rb.kp == m.k_pad ? CODE_PAD : CODE_OTHER;
     }
     return rb;
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 1c: expand A, S, A', S' (one lane per row, 256-bit stores)
+// phase 1c: expand A, S, A', S' (one lane per row, 256-bit stores).  Also records per row the
+// 4-byte code (bin of A' | class<<30) — and the bin of S' where it is neither A' nor the
+// padding value — so that the grand product does not repeat the searches.  With Ap == null only
+// the codes are produced.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
@@ -396,8 +409,8 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            const uint32_t *__restrict__ offz_all, const uint32_t *__restrict__ nzk_all,
            const uint32_t *__restrict__ loffz_all, const uint32_t *__restrict__ lk_all,
            const LookupMeta *__restrict__ meta, uint64_t *__restrict__ A, uint64_t *__restrict__ S,
-           uint64_t *__restrict__ Ap, uint64_t *__restrict__ Sp, uint64_t row_begin,
-           uint64_t row_end) {
+           uint64_t *__restrict__ Ap, uint64_t *__restrict__ Sp, uint32_t *__restrict__ codek,
+           uint32_t *__restrict__ codep, uint64_t row_begin, uint64_t row_end) {
     const int li = blockIdx.y;            // index inside this call
     const int l = first_lookup + li;      // lookup index in the circuit
     const int ops = sh.ops_per_set();
@@ -413,6 +426,8 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const uint32_t *lk = lk_all + (size_t)l * BIN_STRIDE;
     const fr_t *valv = val + (size_t)v * BIN_STRIDE;
     const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
+    uint32_t *__restrict__ ck = codek + (size_t)l * n;
+    uint32_t *__restrict__ cp = codep + (size_t)l * n;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const fr_t zero = fr_zero();
     for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
@@ -422,8 +437,11 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
         if (row >= usable) {
             if (A) fr_store_256(A + o, zero);
             if (S) fr_store_256(S + o, zero);
-            fr_store_256(Ap + o, zero);
-            fr_store_256(Sp + o, zero);
+            if (Ap) {
+                fr_store_256(Ap + o, zero);
+                fr_store_256(Sp + o, zero);
+            }
+            ck[row] = 0;
             continue;
         }
         if (A) {
@@ -437,8 +455,12 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             fr_store_256(S + o, fr_ld(valv + e));
         }
         const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk);
-        fr_store_256(Ap + o, fr_ld(dv + rb.k));
-        fr_store_256(Sp + o, fr_ld(dv + rb.kp));
+        ck[row] = rb.k | (rb.cls << 30);
+        if (rb.cls == CODE_OTHER) cp[row] = rb.kp;
+        if (Ap) {
+            fr_store_256(Ap + o, fr_ld(dv + rb.k));
+            fr_store_256(Sp + o, fr_ld(dv + rb.kp));
+        }
     }
 }
 
@@ -563,6 +585,25 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
     fr_st(ibp + o + k, fr_mul(b, fr_ld(ig + o + k_pad)));
 }
 
+// c0pow[l][j] = (nac[k_zero] * ibp[k_zero])^j, j = 0..ZI: the factor of a row that is inactive in
+// row order and sits in the zero run of A' with the padding value as S' (one lane per power)
+__global__ void __launch_bounds__(32)
+k_z_consts(Shape sh, const LookupMeta *__restrict__ meta, const fr_t *__restrict__ nac,
+           const fr_t *__restrict__ ibp, fr_t *__restrict__ c0pow, int zi) {
+    const int l = blockIdx.x, j = threadIdx.x;
+    if (j > zi) return;
+    const uint32_t op = (uint32_t)(l % sh.ops_per_set()) + 1;
+    const size_t vo = (size_t)view_of_op(op) * BIN_STRIDE;
+    const uint32_t kz = meta[l].k_zero;
+    const fr_t c0 = fr_mul(fr_ld(nac + vo + kz), fr_ld(ibp + vo + kz));
+    fr_t acc = fr_one(), base = c0;
+    for (int e = j; e; e >>= 1) {
+        if (e & 1) acc = fr_mul(acc, base);
+        base = fr_mul(base, base);
+    }
+    fr_st(c0pow + (size_t)l * (zi + 1) + j, acc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // phase 2b: grand product Z as factor -> scan -> propagate (no spin-waits, no barriers on the
 // hot path; ~3.2 Montgomery multiplies per row):
@@ -577,29 +618,46 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
 constexpr int ZI = 16;     // consecutive rows per thread
 constexpr int ZF_T = 128;  // threads per CTA, factor / propagate kernels
 constexpr int ZS_T = 256;  // scan kernels: threads per CTA
-constexpr int ZS_E = 16;   //               elements per thread
+constexpr int ZS_E = 4;    //               elements per thread (latency-bound: keep chains short)
 constexpr int ZS_TILE = ZS_T * ZS_E;
 
 struct ZArgs {
     Shape sh;
     int first_lookup, count;
-    const uint32_t *trace;
+ const uint32_t *tracek;          // [sets][n]  op<<24 | bin of the row's input tuple
+    const uint32_t *codek, *codep;   // [L][n]     bin of A' | class<<30 ; bin of S' (class OTHER)
     const fr_t *chal;
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
-    const uint32_t *rank;                                // [3][BIN_STRIDE]
-    const uint32_t *offz, *nzk, *loffz, *lk;             // [L][BIN_STRIDE]
     const LookupMeta *meta;
     fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
     fr_t *bagg;       // [count][nblk] block aggregates of tot
     fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
     fr_t *partial;    // [L] product of all factors of the row range
     const fr_t *carry_in;  // [L] or null
+    const fr_t *c0pow;     // [L][ZI+1] powers of the constant factor nac[k_zero]*ibp[k_zero]
     uint64_t m, nblk;
     uint64_t *Z;
     uint64_t row_begin, row_end;
 };
 
-__global__ void __launch_bounds__(ZF_T) k_z_factors(const ZArgs a) {
+__device__ __forceinline__ void ld16(const uint32_t *__restrict__ p, uint32_t (&w)[ZI]) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < ZI / 4; ++i) {
+        const uint4 x = q[i];
+        w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+    }
+}
+
+// Each thread owns ZI consecutive rows (row ranges are multiples of ZI).  Operands of row q+1
+// are gathered while the two multiplies of row q run.
+#ifndef ZF_OCC
+#define ZF_OCC 5
+#endif
+#ifndef ZP_OCC
+#define ZP_OCC 6
+#endif
+__global__ void __launch_bounds__(ZF_T, ZF_OCC) k_z_factors(const ZArgs a) {
     const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
     if (e >= a.m) return;
     const Shape sh = a.sh;
@@ -609,73 +667,100 @@ __global__ void __launch_bounds__(ZF_T) k_z_factors(const ZArgs a) {
     const int set = l / ops;
     const uint32_t op = (uint32_t)(l % ops) + 1;
     const int v = view_of_op(op);
+    const uint64_t n = sh.n();
     const uint32_t usable = (uint32_t)sh.usable();
     const uint64_t out_rows = a.row_end - a.row_begin;
-    const LookupMeta m = a.meta[l];
-    const uint32_t *__restrict__ offz = a.offz + (size_t)l * BIN_STRIDE;
-    const uint32_t *__restrict__ nzk = a.nzk + (size_t)l * BIN_STRIDE;
-    const uint32_t *__restrict__ loffz = a.loffz + (size_t)l * BIN_STRIDE;
-    const uint32_t *__restrict__ lk = a.lk + (size_t)l * BIN_STRIDE;
+    const uint32_t k_zero = a.meta[l].k_zero;
     const size_t vo = (size_t)v * BIN_STRIDE;
     const fr_t *__restrict__ valv = a.val + vo, *__restrict__ dv = a.dval + vo,
                              *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
                              *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
                              *__restrict__ ibp = a.ibp + vo;
-    const uint32_t *__restrict__ rank = a.rank + vo;
-    const uint32_t *__restrict__ trace = a.trace + (uint64_t)set * sh.n();
-    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
     const uint64_t row0 = a.row_begin + e * ZI;
     uint64_t *__restrict__ zout = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
+    const uint32_t *__restrict__ cp = a.codep + (uint64_t)l * n + row0;
 
     fr_t tot = fr_one();
-    uint32_t j = 0, jl = 0;
-    bool have_j = false, have_jl = false;
+    if (row0 < TABLE_ROWS || row0 + ZI > usable) {
+        // rows inside the table (S varies per row) or touching the blinding rows: general form
+        const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
 #pragma unroll 1
-    for (int q = 0; q < ZI; ++q) {
-        const uint64_t row = row0 + q;
-        if (row >= a.row_end) break;
-        if (row >= usable) {  // blinding rows: factor one (their Z entries are zeroed later)
-            fr_store_256(zout + 4 * q, fr_one());
-            continue;
-        }
-        const uint32_t i = (uint32_t)row;
-        // numerator (A[i]+beta)(S[i]+gamma)
-        const uint32_t w = trace[row];
-        uint32_t kin = m.k_zero;
-        if ((w >> 24) == op) kin = rank[entry_of_table_row(v, table_row_of_word(w))];
-        fr_t num;
-        if (i >= TABLE_ROWS) {
-            num = fr_ld(nac + kin);
-        } else {
-            const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, i)), gamma);
-            num = fr_mul(fr_add(fr_ld(dv + kin), beta), sg);
-        }
-        // denominator 1/((A'[i]+beta)(S'[i]+gamma)): bins of row i, by search then by walking
-        if (!have_j) {
-            j = search_le(offz, m.n_nonempty, i);
-            have_j = true;
-        } else {
-            while (offz[j + 1] <= i) ++j;
-        }
-        const uint32_t k = nzk[j];
-        fr_t den;
-        if (offz[j] == i) {
-            den = fr_ld(ibg + k);  // first occurrence: S' = A'
-        } else {
-            const uint32_t jj = m.repeated - 1 - (i - (j + 1));
-            if (!have_jl) {
-                jl = search_le(loffz, m.n_left, jj);
-                have_jl = true;
-            } else {
-                while (loffz[jl] > jj) --jl;
+        for (int q = 0; q < ZI; ++q) {
+            const uint32_t i = (uint32_t)(row0 + q);
+            if (i >= usable) {  // blinding rows: factor one (their Z entries are zeroed later)
+                fr_store_256(zout + 4 * q, fr_one());
+                continue;
             }
-            const uint32_t kp = lk[jl];
-            if (kp == m.k_pad) den = fr_ld(ibp + k);
-            else den = fr_mul(fr_ld(ib + k), fr_ld(ig + kp));
+            const uint32_t tkq = a.tracek[(uint64_t)set * n + i], ckq = a.codek[(uint64_t)l * n + i];
+            const uint32_t kin = (tkq >> 24) == op ? (tkq & 0xffffffu) : k_zero;
+            fr_t num;
+            if (i >= TABLE_ROWS) {
+                num = fr_ld(nac + kin);
+            } else {
+                const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, i)), gamma);
+                num = fr_mul(fr_add(fr_ld(dv + kin), beta), sg);
+            }
+            const uint32_t k = ckq & 0x3fffffffu, cls = ckq >> 30;
+            fr_t den;
+            if (cls == CODE_OTHER) den = fr_mul(fr_ld(ib + k), fr_ld(ig + cp[q]));
+            else den = fr_ld((cls == CODE_FIRST ? ibg : ibp) + k);
+            const fr_t f = fr_mul(num, den);
+            fr_store_256(zout + 4 * q, f);
+            tot = fr_mul(tot, f);
         }
-        const fr_t f = fr_mul(num, den);
-        fr_store_256(zout + 4 * q, f);
-        tot = fr_mul(tot, f);
+    } else {
+        // Fast path: f = nac[bin of A] * {ibg | ibp}[bin of A'].  Most rows of most lookups are
+        // "constant": inactive in row order (A = 0) AND inside the zero run of A' with the padding
+        // value as S', so f = c0 = nac[k_zero]*ibp[k_zero].  Those rows cost a store and no
+        // multiply; the thread's other rows are walked through a bit mask so that a warp runs as
+        // many multiply rounds as its busiest lane has non-constant rows, not ZI.
+        uint32_t tk[ZI], ck[ZI];
+        ld16(a.tracek + (uint64_t)set * n + row0, tk);
+        ld16(a.codek + (uint64_t)l * n + row0, ck);
+        const uint32_t c0code = k_zero | (CODE_PAD << 30);
+        const fr_t *__restrict__ c0pow = a.c0pow + (size_t)l * (ZI + 1);
+        const fr_t c0 = fr_ld(c0pow + 1);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int q = 0; q < ZI; ++q) {
+            const bool nonconst = (tk[q] >> 24) == op || ck[q] != c0code;
+            mask |= (nonconst ? 1u : 0u) << q;
+            if (!nonconst) fr_store_256(zout + 4 * q, c0);
+        }
+        tot = fr_ld(c0pow + (ZI - __popc(mask)));
+        const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n + row0;
+        const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n + row0;
+        auto load_den = [&](int q) -> fr_t {
+            const uint32_t c = ckp[q];
+            const uint32_t k = c & 0x3fffffffu, cls = c >> 30;
+            if (cls == CODE_OTHER) return fr_mul(fr_ld(ib + k), fr_ld(ig + cp[q]));
+            return fr_ld((cls == CODE_FIRST ? ibg : ibp) + k);
+        };
+        auto load_num = [&](int q) -> fr_t {
+            const uint32_t t = tkp[q];
+            return fr_ld(nac + ((t >> 24) == op ? (t & 0xffffffu) : k_zero));
+        };
+        if (mask) {
+            int q = __ffs(mask) - 1;
+            mask &= mask - 1;
+            fr_t num_n = load_num(q), den_n = load_den(q);
+#pragma unroll 1
+            while (true) {
+                const fr_t num = num_n, den = den_n;
+                const int qc = q;
+                const bool more = mask != 0;
+                if (more) {  // operands of the next non-constant row, in flight during the multiplies
+                    q = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    num_n = load_num(q);
+                    den_n = load_den(q);
+                }
+                const fr_t f = fr_mul(num, den);
+                fr_store_256(zout + 4 * qc, f);
+                tot = fr_mul(tot, f);
+                if (!more) break;
+            }
+        }
     }
     fr_st(a.tot + (size_t)li * a.m + e, tot);
 }
@@ -760,7 +845,7 @@ __global__ void __launch_bounds__(ZS_T) k_z_down(const ZArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(ZF_T) k_z_propagate(const ZArgs a) {
+__global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
     if (e >= a.m) return;
     const int li = blockIdx.y;
@@ -769,14 +854,25 @@ __global__ void __launch_bounds__(ZF_T) k_z_propagate(const ZArgs a) {
     const uint64_t row0 = a.row_begin + e * ZI;
     uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
     fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
-#pragma unroll 1
-    for (int q = 0; q < ZI; ++q) {
-        const uint64_t row = row0 + q;
-        if (row >= a.row_end) break;
-        const fr_t f = fr_load(z + 4 * q);
-        // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
-        fr_store_256(z + 4 * q, row <= usable ? cur : fr_zero());
-        cur = fr_mul(cur, f);
+    constexpr int PB = 4;  // factors fetched ahead of the multiply chain
+    fr_t f[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) f[j] = fr_load(z + 4 * j);
+#pragma unroll
+    for (int q = 0; q < ZI; q += PB) {
+        fr_t g[PB];
+#pragma unroll
+        for (int j = 0; j < PB; ++j) g[j] = f[j];
+        if (q + PB < ZI) {
+#pragma unroll
+            for (int j = 0; j < PB; ++j) f[j] = fr_load(z + 4 * (q + PB + j));
+        }
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
+            fr_store_256(z + 4 * (q + j), row0 + q + j <= usable ? cur : fr_zero());
+            if (q + j + 1 < ZI) cur = fr_mul(cur, g[j]);
+        }
     }
 }
 
@@ -825,7 +921,8 @@ cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t ro
     cudaError_t e;
     if ((e = cudaMemsetAsync(c->d_cnt, 0, (size_t)L * BIN_STRIDE * 4, s))) return e;
     dim3 g(ctx->sm_count * 2, c->sh.n_sets());
-    k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, row_begin, row_end);
+    k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, c->d_tracek, row_begin,
+                                    row_end);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -850,7 +947,7 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     dim3 g(gx, count);
     k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_val, c->d_dval, c->d_offz,
                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S, Ap, Sp,
-                                           row_begin, row_end);
+                                           c->d_codek, c->d_codep, row_begin, row_end);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -863,7 +960,10 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
     k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_ibg,
                                              c->d_ibp);
-    ctx->launches += 2;
+    k_z_consts<<<c->sh.n_lookups(), 32, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
+                                                          c->d_c0pow, ZI);
+    static_assert(ZI == 16, "d_c0pow is allocated as [L][17]");
+    ctx->launches += 3;
     return cudaGetLastError();
 }
 
@@ -873,16 +973,17 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.sh = c->sh;
     a.first_lookup = first;
     a.count = count;
-    a.trace = c->d_trace;
+    a.tracek = c->d_tracek;
+    a.codek = c->d_codek;
+    a.codep = c->d_codep;
     a.chal = c->d_chal;
     a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
     a.ibg = c->d_ibg; a.ibp = c->d_ibp;
-    a.rank = c->d_rank;
-    a.offz = c->d_offz; a.nzk = c->d_nzk; a.loffz = c->d_loffz; a.lk = c->d_lk;
     a.meta = c->d_meta;
     a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
     a.partial = c->d_partial;
     a.carry_in = carry_in;
+    a.c0pow = c->d_c0pow;
     a.m = (row_end - row_begin + ZI - 1) / ZI;
     a.nblk = (a.m + ZS_TILE - 1) / ZS_TILE;
     a.Z = Z;

@@ -103,7 +103,7 @@ int32_t h2aes_block_position(int32_t k, int32_t N, uint64_t block, int32_t *set,
                              uint64_t *start_row);
 
 /* which selector (H2AES_OP_*) the chips enable on `row` of column set `set` when `n_blocks`
- * blocks have been encrypted; negative status on error.  (q.enable calls in src/chips/*.rs) */
+ * blocks have been encrypted; negative status on error.  (q.enable calls in the chips, src/chips/) */
 int32_t h2aes_row_op(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t set,
                      uint64_t row);
 
