@@ -76,6 +76,7 @@ SIGNATURES = {
                                           C.POINTER(C.c_int32), _u64p]),
     "h2aes_row_op": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
                                   C.c_uint64]),
+    "h2aes_active_rows": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _u64p]),
     "h2aes_copy_count": (C.c_int32, [C.c_int32, C.c_uint64, _u64p]),
     "h2aes_copy_constraints_host": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                                  C.c_uint64, C.c_uint64, _u64p]),

@@ -31,6 +31,7 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
                             uint64_t *Z, uint64_t row_begin, uint64_t row_end);
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
 void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk);
+uint32_t lookup_bin_tiles();
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
 
 // S-box from first principles (GF(2^8) inverse + affine map); H2AES_SBOX_REFERENCE then applies
@@ -179,6 +180,18 @@ int32_t h2aes_row_op(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int3
     return (int32_t)row_op(sh, n_blocks, set, row);
 }
 
+int32_t h2aes_active_rows(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t lookup,
+                          uint64_t *out) {
+    if (!out || !shape_ok(kind, k, N)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    if (lookup < 0 || lookup >= sh.n_lookups()) return H2AES_ERR_ARG;
+    if (n_blocks > sh.capacity()) return H2AES_ERR_CAPACITY;
+    const int ops = sh.ops_per_set();
+    *out = active_rows(sh, n_blocks, lookup / ops, (uint32_t)(lookup % ops) + 1);
+    return H2AES_OK;
+}
+
 int32_t h2aes_copy_count(int32_t kind, uint64_t n_blocks, uint64_t *out) {
     if (!out || (kind != KIND_AES && kind != KIND_KEYSCHED)) return H2AES_ERR_ARG;
     if (kind == KIND_KEYSCHED && n_blocks) return H2AES_ERR_ARG;
@@ -285,6 +298,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_c0pow,
+                    c->d_canon_b,  c->d_active,   c->d_lbsum,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -491,6 +505,9 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_chal, 4));
     CU(ctx, dalloc(&c->d_val, VB));
     CU(ctx, dalloc(&c->d_canon, VB));
+    CU(ctx, dalloc(&c->d_canon_b, VB));
+    CU(ctx, dalloc(&c->d_active, L));
+    CU(ctx, dalloc(&c->d_lbsum, L * lookup_bin_tiles()));
     CU(ctx, dalloc(&c->d_dval, VB));
     CU(ctx, dalloc(&c->d_rank, VB));
     CU(ctx, dalloc(&c->d_ts, VB));
@@ -538,6 +555,17 @@ static int32_t check_device_flags(h2aes_circuit *c) {
     return H2AES_OK;
 }
 
+// rows with each lookup's selector enabled (closed form, layout.h) -> device, for k_lookup_bins
+static int32_t upload_active(h2aes_circuit *c) {
+    const int L = c->sh.n_lookups(), ops = c->sh.ops_per_set();
+    uint32_t host[5 * MAX_SETS];
+    for (int l = 0; l < L; ++l)
+        host[l] = (uint32_t)active_rows(c->sh, c->n_blocks, l / ops, (uint32_t)(l % ops) + 1);
+    CU(c->ctx, cudaMemcpyAsync(c->d_active, host, sizeof(uint32_t) * L, cudaMemcpyHostToDevice,
+                               c->ctx->stream));
+    return H2AES_OK;
+}
+
 static int32_t set_theta(h2aes_circuit *c, const uint64_t *theta, bool *changed) {
     *changed = !c->have_theta || memcmp(c->theta, theta, 32) != 0;
     if (*changed) {
@@ -578,6 +606,7 @@ int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32
     bool changed;
     if ((rc = set_theta(c, theta, &changed))) return rc;
     if (changed || !c->have_bins) {
+        if ((rc = upload_active(c))) return rc;
         CU(ctx, launch_view_bins(c));
         CU(ctx, launch_lookup_hist(c, 0, c->sh.n()));
         CU(ctx, launch_lookup_bins(c));
@@ -730,6 +759,8 @@ int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint6
     CU(ctx, cudaSetDevice(ctx->device));
     if ((Ap_dev == nullptr) != (Sp_dev == nullptr) || (!Ap_dev && (A_dev || S_dev)))
         return fail(ctx, H2AES_ERR_ARG, "A' and S' must both be given (or no output at all)");
+    int32_t rc = upload_active(c);
+    if (rc) return rc;
     CU(ctx, launch_lookup_bins(c));
     c->have_bins = true;
     uint64_t rb, re;

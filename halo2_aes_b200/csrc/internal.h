@@ -15,7 +15,8 @@ namespace h2 {
 constexpr int N_VIEWS = 3;
 constexpr uint32_t VIEW0_ENTRIES = 5 * 256 + 1;  // (tag,x) pairs + the zero row
 constexpr uint32_t VIEW_MAX_ENTRIES = (uint32_t)TABLE_ROWS;
-constexpr uint32_t N_BUCKETS = 65536;
+constexpr uint32_t BUCKET_BITS = 12;  // ~20 table values per bucket for a random theta
+constexpr uint32_t N_BUCKETS = 1u << BUCKET_BITS;
 constexpr uint32_t BIN_STRIDE = 66568;  // >= VIEW_MAX_ENTRIES + 2, multiple of 8
 
 H2_HD uint32_t view_entries(int v) { return v == 0 ? VIEW0_ENTRIES : VIEW_MAX_ENTRIES; }
@@ -93,6 +94,9 @@ struct h2aes_circuit {
     // per view
     h2::fr_t *d_val = nullptr;       // [3][BIN_STRIDE] compressed value of entry e
     h2::fr_t *d_canon = nullptr;     // [3][BIN_STRIDE] canonical form (sort key)
+    h2::fr_t *d_canon_b = nullptr;   // [3][BIN_STRIDE] the same in bucket order
+    uint32_t *d_active = nullptr;    // [L] rows with the lookup's selector enabled
+    uint4 *d_lbsum = nullptr;        // [L][tiles] per-tile sums for the run-structure kernels
     h2::fr_t *d_dval = nullptr;      // [3][BIN_STRIDE] distinct values, ascending
     uint32_t *d_rank = nullptr;      // [3][BIN_STRIDE] entry -> bin
     uint32_t *d_ts = nullptr;        // [3][BIN_STRIDE] table multiplicity of bin

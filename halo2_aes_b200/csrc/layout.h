@@ -307,6 +307,17 @@ H2_HD uint32_t row_op(const Shape &sh, uint64_t n_blocks, int set, uint64_t row)
     return block_row_op((uint32_t)(rel - b * AES_ROWS));
 }
 
+// rows on which the selector of (set, op) is enabled after schedule_key + n_blocks encrypts:
+// per key schedule 160 range / 200 xor / 40 sbox rows, per block 608 xor / 160 sbox / 144 mul2 /
+// 144 mul3 rows
+H2_HD uint64_t active_rows(const Shape &sh, uint64_t n_blocks, int set, uint32_t op) {
+    const uint64_t per_block[6] = {0, 0, 608, 160, 144, 144};
+    const uint64_t per_ks[6] = {0, 160, 200, 40, 0, 0};
+    uint64_t r = set == 0 ? per_ks[op] : 0;
+    if (sh.kind == KIND_AES) r += sh.blocks_in_set(set, n_blocks) * per_block[op];
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fixed columns: 4 table columns (src/table.rs:18-192 + [UPSTREAM] padding with the offset-0
 // value over the usable rows), then round_constants.  Value is a small integer (< 256).

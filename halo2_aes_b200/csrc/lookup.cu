@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t fr_bitlen(const fr_t &c) {
     return bits;
 }
 __device__ __forceinline__ uint32_t bucket_of(const fr_t &c, uint32_t maxbits) {
-    const uint32_t shift = maxbits > 16 ? maxbits - 16 : 0;
+    const uint32_t shift = maxbits > BUCKET_BITS ? maxbits - BUCKET_BITS : 0;
     const uint32_t w = shift >> 5, b = shift & 31;
     uint32_t lo = 0, hi = 0;
 #pragma unroll
@@ -58,48 +58,60 @@ __device__ __forceinline__ uint32_t bucket_of(const fr_t &c, uint32_t maxbits) {
         if (i == (int)w + 1) hi = c.v[i];
     }
     const uint64_t x = ((uint64_t)hi << 32) | lo;
-    return (uint32_t)((x >> b) & 0xffffu);
+    return (uint32_t)((x >> b) & (N_BUCKETS - 1));
 }
 
-// Exclusive scan of data[0..n) in place by ONE CTA of 1024 threads; returns the total to all.
+// Exclusive scan of data[0..n) in place by ONE CTA (<= 1024 threads); returns the total to all.
+// Rounds of SCAN_E*blockDim consecutive elements, thread t on SCAN_E consecutive elements of the
+// round (64 contiguous bytes per thread); few rounds because every round costs a block barrier
+// chain and a global-memory round trip.
+constexpr int SCAN_E = 16;
 __device__ uint32_t block_exclusive_scan_u32(uint32_t *data, uint32_t n) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_carry;
     const uint32_t t = threadIdx.x, nt = blockDim.x;
-    const uint32_t chunk = (n + nt - 1) / nt;
-    const uint32_t lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += data[i];
-    // block exclusive scan of `sum`
-    uint32_t inc = sum;
-    const int lane = t & 31, wid = t >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += y;
-    }
-    if (lane == 31) s_warp[wid] = inc;
+    const int lane = t & 31, wid = t >> 5, nw = nt >> 5;
+    if (t == 0) s_carry = 0;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t w = lane < (int)(nt >> 5) ? s_warp[lane] : 0;
-        uint32_t winc = w;
+    for (uint32_t base = 0; base < n; base += SCAN_E * nt) {
+        const uint32_t i = base + SCAN_E * t;
+        uint32_t v[SCAN_E];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_E; ++j) {
+            v[j] = i + j < n ? data[i + j] : 0u;
+            sum += v[j];
+        }
+        uint32_t inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
         }
-        s_warp[lane] = winc - w;
-        if (lane == 31) s_total = winc;
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t w = lane < nw ? s_warp[lane] : 0u;
+            uint32_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += y;
+            }
+            s_warp[lane] = winc - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        uint32_t run = s_carry + s_warp[wid] + inc - sum;
+#pragma unroll
+        for (int j = 0; j < SCAN_E; ++j) {
+            if (i + j < n) data[i + j] = run;
+            run += v[j];
+        }
+        __syncthreads();
+        if (t == nt - 1) s_carry = run;  // inclusive total through this round
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = s_warp[wid] + inc - sum;
-    for (uint32_t i = lo; i < hi; ++i) {
-        uint32_t x = data[i];
-        data[i] = run;
-        run += x;
-    }
-    __syncthreads();
-    return s_total;
+    return s_carry;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,73 +156,142 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ bhi
 __global__ void __launch_bounds__(256)
 k_bucket_scatter(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
                  const uint32_t *__restrict__ bhist, uint32_t *__restrict__ bcur,
-                 uint32_t *__restrict__ slot) {
+                 uint32_t *__restrict__ slot, fr_t *__restrict__ canon_b) {
     const int v = blockIdx.y;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= view_entries(v)) return;
-    const uint32_t b = bucket_of(fr_ld(canon + (size_t)v * BIN_STRIDE + e), viewmeta[v * 8]);
+    const fr_t me = fr_ld(canon + (size_t)v * BIN_STRIDE + e);
+    const uint32_t b = bucket_of(me, viewmeta[v * 8]);
     const uint32_t pos = bhist[(size_t)v * (N_BUCKETS + 1) + b] +
                          atomicAdd(bcur + (size_t)v * N_BUCKETS + b, 1u);
     slot[(size_t)v * BIN_STRIDE + pos] = e;
+    fr_st(canon_b + (size_t)v * BIN_STRIDE + pos, me);  // bucket mates contiguous for k_bucket_rank
 }
 
-// exact position of entry e: bucket offset + number of bucket mates that order before it
+// exact position of the entry at bucket slot p: bucket offset + number of bucket mates that order
+// before it (ties broken by entry index).  Buckets can be large: the 256 values tag*theta^2 +
+// x*theta + y, y = 0..255, of one x are consecutive integers and share their leading bits.  The
+// CTA stages the canonical values of every bucket its 256 slots touch in shared memory (window
+// of RANK_WIN entries; anything beyond falls back to global loads).
+constexpr uint32_t RANK_WIN = 1280;
 __global__ void __launch_bounds__(256)
-k_bucket_rank(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
+k_bucket_rank(const fr_t *__restrict__ canon_b, const uint32_t *__restrict__ viewmeta,
               const uint32_t *__restrict__ bhist, const uint32_t *__restrict__ slot,
               uint32_t *__restrict__ sorted) {
+    __shared__ uint4 s_c[2 * RANK_WIN];
+    __shared__ uint32_t s_lo, s_hi;
     const int v = blockIdx.y;
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= view_entries(v)) return;
-    const fr_t *cv = canon + (size_t)v * BIN_STRIDE;
-    const fr_t me = fr_ld(cv + e);
-    const uint32_t b = bucket_of(me, viewmeta[v * 8]);
-    const uint32_t lo = bhist[(size_t)v * (N_BUCKETS + 1) + b];
-    const uint32_t hi = bhist[(size_t)v * (N_BUCKETS + 1) + b + 1];
+    const uint32_t np = view_entries(v);
+    const uint32_t p0 = blockIdx.x * blockDim.x;
+    if (p0 >= np) return;
+    const fr_t *__restrict__ cb = canon_b + (size_t)v * BIN_STRIDE;
+    const uint32_t *__restrict__ sl = slot + (size_t)v * BIN_STRIDE;
+    const uint32_t *__restrict__ bh = bhist + (size_t)v * (N_BUCKETS + 1);
+    const uint32_t maxbits = viewmeta[v * 8];
+    if (threadIdx.x == 0) s_lo = bh[bucket_of(fr_ld(cb + p0), maxbits)];
+    if (threadIdx.x == 32) s_hi = bh[bucket_of(fr_ld(cb + min(p0 + blockDim.x, np) - 1), maxbits) + 1];
+    __syncthreads();
+    const uint32_t w_lo = s_lo, w_n = min(s_hi - s_lo, RANK_WIN);
+    for (uint32_t i = threadIdx.x; i < w_n; i += blockDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(cb + w_lo + i);
+        s_c[2 * i] = src[0];
+        s_c[2 * i + 1] = src[1];
+    }
+    __syncthreads();
+    const uint32_t p = p0 + threadIdx.x;
+    if (p >= np) return;
+    const fr_t me = fr_ld(cb + p);
+    const uint32_t e = sl[p];
+    const uint32_t b = bucket_of(me, maxbits);
+    const uint32_t lo = bh[b], hi = bh[b + 1];
     uint32_t rank = 0;
-    for (uint32_t p = lo; p < hi; ++p) {
-        const uint32_t e2 = slot[(size_t)v * BIN_STRIDE + p];
-        if (e2 == e) continue;
-        const int cmp = fr_cmp_canonical(fr_ld(cv + e2), me);
-        rank += (cmp < 0 || (cmp == 0 && e2 < e)) ? 1u : 0u;
+    for (uint32_t q = lo; q < hi; ++q) {
+        const uint32_t wq = q - w_lo;  // lo >= w_lo by construction
+        const fr_t other = wq < w_n ? fr_load_s(s_c + 2 * wq) : fr_ld(cb + q);
+        const int cmp = fr_cmp_canonical(other, me);
+        if (cmp < 0) rank += 1;
+        else if (cmp == 0 && q != p && sl[q] < e) rank += 1;
     }
     sorted[(size_t)v * BIN_STRIDE + lo + rank] = e;
 }
 
+// block-wide sum of one u32 per thread (all threads get the result); blockDim <= 1024
+__device__ __forceinline__ uint32_t block_sum_u32(uint32_t x, uint32_t *s_red /* [33] */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) s_red[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t y = lane < nw ? s_red[lane] : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+        if (lane == 0) s_red[32] = y;
+    }
+    __syncthreads();
+    const uint32_t r = s_red[32];
+    __syncthreads();
+    return r;
+}
+
+constexpr uint32_t HEAD_TILES = (VIEW_MAX_ENTRIES + 255) / 256;  // tiles of 256 sorted positions
+
+// head[p] = 1 where the value at sorted position p differs from its predecessor (a new bin
+// starts); tilesum[v][tile] = heads in the tile
 __global__ void __launch_bounds__(256)
 k_bin_heads(const fr_t *__restrict__ canon, const uint32_t *__restrict__ sorted,
-            uint32_t *__restrict__ head, uint32_t *__restrict__ kidx) {
+            uint32_t *__restrict__ head, uint32_t *__restrict__ tilesum) {
     const int v = blockIdx.y;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= view_entries(v)) return;
     const fr_t *cv = canon + (size_t)v * BIN_STRIDE;
     const uint32_t *sv = sorted + (size_t)v * BIN_STRIDE;
-    uint32_t h = 1;
-    if (p > 0) h = fr_eq(fr_ld(cv + sv[p]), fr_ld(cv + sv[p - 1])) ? 0u : 1u;
-    head[(size_t)v * BIN_STRIDE + p] = h;
-    kidx[(size_t)v * BIN_STRIDE + p] = h;
+    uint32_t h = 0;
+    if (p < view_entries(v)) {
+        h = 1;
+        if (p > 0) h = fr_eq(fr_ld(cv + sv[p]), fr_ld(cv + sv[p - 1])) ? 0u : 1u;
+        head[(size_t)v * BIN_STRIDE + p] = h;
+    }
+    const int cnt = __syncthreads_count((int)h);
+    if (threadIdx.x == 0) tilesum[v * HEAD_TILES + blockIdx.x] = (uint32_t)cnt;
 }
 
-__global__ void __launch_bounds__(1024)
-k_bin_index_scan(uint32_t *__restrict__ kidx, uint32_t *__restrict__ viewmeta) {
-    const int v = blockIdx.x;
-    // exclusive scan of the head flags: kidx[p] = (#heads before p); bin of p = kidx[p]+head[p]-1
-    uint32_t total = block_exclusive_scan_u32(kidx + (size_t)v * BIN_STRIDE, view_entries(v));
-    if (threadIdx.x == 0) viewmeta[v * 8 + 1] = total;
-}
-
+// bin index of every sorted position = heads before it (tile prefix summed on the fly from the
+// tile sums + ballot scan inside the tile); fills rank / dval / ts; CTA 0 records the bin count
 __global__ void __launch_bounds__(256)
 k_bin_fill(const fr_t *__restrict__ val, const uint32_t *__restrict__ sorted,
-           const uint32_t *__restrict__ head, const uint32_t *__restrict__ kidx,
+           const uint32_t *__restrict__ head, const uint32_t *__restrict__ tilesum,
            uint64_t usable, fr_t *__restrict__ dval, uint32_t *__restrict__ rank,
-           uint32_t *__restrict__ ts) {
+           uint32_t *__restrict__ ts, uint32_t *__restrict__ viewmeta) {
+    __shared__ uint32_t s_red[33];
+    __shared__ uint32_t s_wcnt[8];
     const int v = blockIdx.y;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= view_entries(v)) return;
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const uint32_t p = blockIdx.x * blockDim.x + t;
+    const uint32_t np = view_entries(v);
+    const uint32_t ntiles = (np + 255) / 256;
+    if (blockIdx.x >= ntiles) return;
+    const uint32_t *tsum = tilesum + v * HEAD_TILES;
+    uint32_t before = 0, all = 0;
+    for (uint32_t i = t; i < ntiles; i += blockDim.x) {
+        const uint32_t x = tsum[i];
+        all += x;
+        if (i < blockIdx.x) before += x;
+    }
+    const uint32_t tile_prefix = block_sum_u32(before, s_red);
+    if (blockIdx.x == 0) {
+        const uint32_t total = block_sum_u32(all, s_red);
+        if (t == 0) viewmeta[v * 8 + 1] = total;
+    }
     const size_t o = (size_t)v * BIN_STRIDE;
+    const uint32_t h = p < np ? head[o + p] : 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, h != 0);
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t in_tile = __popc(bal & ((1u << lane) - 1u));
+    for (uint32_t w = 0; w < wid; ++w) in_tile += s_wcnt[w];
+    if (p >= np) return;
     const uint32_t e = sorted[o + p];
-    const uint32_t h = head[o + p];
-    const uint32_t k = kidx[o + p] + h - 1;
+    const uint32_t k = tile_prefix + in_tile + h - 1;
     rank[o + e] = k;
     if (h) fr_st(dval + o + k, fr_ld(val + o + e));
     // table rows 66561..u-1 repeat row 0 (halo2 pads with the offset-0 value) -> entry 0
@@ -248,59 +329,110 @@ k_lookup_hist(Shape sh, const uint32_t *__restrict__ trace, const uint32_t *__re
     }
 }
 
-// One CTA (1024 threads) per lookup: add the inactive rows to the zero bin, then compact the
-// nonempty input bins (offz/nzk) and the leftover table bins (loffz/lk).
-__global__ void __launch_bounds__(1024)
-k_lookup_bins(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ rank,
-              const uint32_t *__restrict__ ts, const uint32_t *__restrict__ viewmeta,
-              uint32_t *__restrict__ offz, uint32_t *__restrict__ nzk,
-              uint32_t *__restrict__ loffz, uint32_t *__restrict__ lk,
-              LookupMeta *__restrict__ meta, uint32_t *__restrict__ err) {
-    __shared__ uint32_t s_red[32];
-    __shared__ uint4 s_scan[32];
-    __shared__ uint32_t s_active;
-    const int l = blockIdx.x;
-    const int ops = sh.ops_per_set();
-    const uint32_t op = (uint32_t)(l % ops) + 1;
+// Run structure of a lookup from its bin histogram: add the inactive rows to the zero bin, then
+// compact the nonempty input bins (offz/nzk: first row and bin of each run of A') and the
+// leftover table bins (loffz/lk).  Two kernels over tiles of LB_TILE bins: per-tile sums of
+// (rows, nonempty bins, leftover rows, leftover bins), then each tile sums the tiles before it
+// on the fly, scans its own bins and writes.  `active[l]` = rows on which the lookup's selector
+// is enabled: input independent, computed on the host from the layout.
+constexpr int LB_T = 256, LB_E = 4, LB_TILE = LB_T * LB_E;
+constexpr uint32_t LB_TILES = (VIEW_MAX_ENTRIES + LB_TILE - 1) / LB_TILE;  // 66
+
+struct BinItem {
+    uint32_t ck, lf;
+};
+__device__ __forceinline__ BinItem bin_item(uint32_t k, uint32_t D, uint32_t k0, uint32_t zero_extra,
+                                            const uint32_t *__restrict__ c,
+                                            const uint32_t *__restrict__ tsv, uint32_t *bad) {
+    BinItem it = {0u, 0u};
+    if (k < D) {
+        it.ck = c[k] + (k == k0 ? zero_extra : 0u);
+        const uint32_t nzf = it.ck ? 1u : 0u;
+        const uint32_t tk = tsv[k];
+        if (tk < nzf) *bad = 1u;  // an input value without a table row
+        it.lf = tk - nzf;
+    }
+    return it;
+}
+
+__global__ void __launch_bounds__(LB_T)
+k_lookup_tiles(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ rank,
+               const uint32_t *__restrict__ ts, const uint32_t *__restrict__ viewmeta,
+               const uint32_t *__restrict__ active, uint4 *__restrict__ tsum,
+               uint32_t *__restrict__ err) {
+    __shared__ uint32_t s_red[33];
+    const int l = blockIdx.y;
+    const uint32_t op = (uint32_t)(l % sh.ops_per_set()) + 1;
+    const int v = view_of_op(op);
+    const uint32_t D = viewmeta[v * 8 + 1];
+    const uint32_t k0 = rank[(size_t)v * BIN_STRIDE + (v == 0 ? 1280u : TROW_ZERO)];
+    const uint32_t zero_extra = (uint32_t)sh.usable() - active[l];
+    const uint32_t *__restrict__ c = cnt + (size_t)l * BIN_STRIDE;
+    const uint32_t *__restrict__ tsv = ts + (size_t)v * BIN_STRIDE;
+    const uint32_t kb = blockIdx.x * LB_TILE + threadIdx.x * LB_E;
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    uint32_t bad = 0;
+#pragma unroll
+    for (int j = 0; j < LB_E; ++j) {
+        const BinItem it = bin_item(kb + j, D, k0, zero_extra, c, tsv, &bad);
+        mine.x += it.ck;
+        mine.y += it.ck ? 1u : 0u;
+        mine.z += it.lf;
+        mine.w += it.lf ? 1u : 0u;
+    }
+    uint4 tot;
+    tot.x = block_sum_u32(mine.x, s_red);
+    tot.y = block_sum_u32(mine.y, s_red);
+    tot.z = block_sum_u32(mine.z, s_red);
+    tot.w = block_sum_u32(mine.w, s_red);
+    if (threadIdx.x == 0) tsum[(size_t)l * LB_TILES + blockIdx.x] = tot;
+    if (bad) atomicOr(err + 1, 1u);
+}
+
+__global__ void __launch_bounds__(LB_T)
+k_lookup_compact(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ rank,
+                 const uint32_t *__restrict__ ts, const uint32_t *__restrict__ viewmeta,
+                 const uint32_t *__restrict__ active, const uint4 *__restrict__ tsum,
+                 uint32_t *__restrict__ offz, uint32_t *__restrict__ nzk,
+                 uint32_t *__restrict__ loffz, uint32_t *__restrict__ lk,
+                 LookupMeta *__restrict__ meta, uint32_t *__restrict__ err) {
+    __shared__ uint32_t s_red[33];
+    __shared__ uint4 s_warp[LB_T / 32];
+    const int l = blockIdx.y;
+    const uint32_t op = (uint32_t)(l % sh.ops_per_set()) + 1;
     const int v = view_of_op(op);
     const uint32_t D = viewmeta[v * 8 + 1];
     const uint32_t usable = (uint32_t)sh.usable();
     const uint32_t k0 = rank[(size_t)v * BIN_STRIDE + (v == 0 ? 1280u : TROW_ZERO)];
-    const uint32_t *c = cnt + (size_t)l * BIN_STRIDE;
-    const uint32_t *tsv = ts + (size_t)v * BIN_STRIDE;
-    const uint32_t t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
-    const uint32_t chunk = (D + nt - 1) / nt;
-    const uint32_t lo = min(D, t * chunk), hi = min(D, lo + chunk);
-    // pass 0: number of active rows
-    uint32_t sum = 0;
-    for (uint32_t k = lo; k < hi; ++k) sum += c[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    if (lane == 0) s_red[wid] = sum;
-    __syncthreads();
-    if (t == 0) {
-        uint32_t a = 0;
-        for (uint32_t i = 0; i < (nt >> 5); ++i) a += s_red[i];
-        s_active = a;
-    }
-    __syncthreads();
-    const uint32_t zero_extra = usable - s_active;
-    // pass 1: per-thread sums of (rows, nonempty bins, leftover, leftover bins)
-    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint32_t zero_extra = usable - active[l];
+    const uint32_t *__restrict__ c = cnt + (size_t)l * BIN_STRIDE;
+    const uint32_t *__restrict__ tsv = ts + (size_t)v * BIN_STRIDE;
+    uint32_t *__restrict__ o_offz = offz + (size_t)l * BIN_STRIDE;
+    uint32_t *__restrict__ o_nzk = nzk + (size_t)l * BIN_STRIDE;
+    uint32_t *__restrict__ o_loffz = loffz + (size_t)l * BIN_STRIDE;
+    uint32_t *__restrict__ o_lk = lk + (size_t)l * BIN_STRIDE;
+    const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    // sums of the tiles before this one (LB_TILES <= blockDim: one tile per thread)
+    uint4 before = make_uint4(0, 0, 0, 0);
+    if (t < blockIdx.x) before = tsum[(size_t)l * LB_TILES + t];
+    uint4 carry;
+    carry.x = block_sum_u32(before.x, s_red);
+    carry.y = block_sum_u32(before.y, s_red);
+    carry.z = block_sum_u32(before.z, s_red);
+    carry.w = block_sum_u32(before.w, s_red);
+    const uint32_t kb = blockIdx.x * LB_TILE + t * LB_E;
+    BinItem it[LB_E];
+    uint4 mine = make_uint4(0, 0, 0, 0);
     uint32_t bad = 0;
-    for (uint32_t k = lo; k < hi; ++k) {
-        const uint32_t ck = c[k] + (k == k0 ? zero_extra : 0u);
-        const uint32_t nzf = ck ? 1u : 0u;
-        const uint32_t tk = tsv[k];
-        if (tk < nzf) bad = 1;
-        const uint32_t lf = tk - nzf;
-        acc.x += ck;
-        acc.y += nzf;
-        acc.z += lf;
-        acc.w += lf ? 1u : 0u;
+#pragma unroll
+    for (int j = 0; j < LB_E; ++j) {
+        it[j] = bin_item(kb + j, D, k0, zero_extra, c, tsv, &bad);
+        mine.x += it[j].ck;
+        mine.y += it[j].ck ? 1u : 0u;
+        mine.z += it[j].lf;
+        mine.w += it[j].lf ? 1u : 0u;
     }
-    // block exclusive scan of acc
-    uint4 inc = acc;
+    uint4 inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint4 y;
@@ -310,53 +442,44 @@ k_lookup_bins(Shape sh, const uint32_t *__restrict__ cnt, const uint32_t *__rest
         y.w = __shfl_up_sync(0xffffffffu, inc.w, d);
         if ((int)lane >= d) { inc.x += y.x; inc.y += y.y; inc.z += y.z; inc.w += y.w; }
     }
-    if (lane == 31) s_scan[wid] = inc;
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    if (t == 0) {
-        uint4 run = make_uint4(0, 0, 0, 0);
-        for (uint32_t i = 0; i < (nt >> 5); ++i) {
-            uint4 x = s_scan[i];
-            s_scan[i] = run;
-            run.x += x.x; run.y += x.y; run.z += x.z; run.w += x.w;
+    uint4 ex = make_uint4(carry.x + inc.x - mine.x, carry.y + inc.y - mine.y,
+                          carry.z + inc.z - mine.z, carry.w + inc.w - mine.w);
+    for (uint32_t w = 0; w < wid; ++w) {
+        const uint4 x = s_warp[w];
+        ex.x += x.x; ex.y += x.y; ex.z += x.z; ex.w += x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < LB_E; ++j) {
+        if (it[j].ck) {
+            o_offz[ex.y] = ex.x;
+            o_nzk[ex.y] = kb + j;
+            ex.x += it[j].ck;
+            ex.y += 1;
         }
-        // totals: rows must equal usable, leftover must equal usable - nonempty
+        if (it[j].lf) {
+            o_loffz[ex.w] = ex.z;
+            o_lk[ex.w] = kb + j;
+            ex.z += it[j].lf;
+            ex.w += 1;
+        }
+    }
+    // the thread holding the last bin knows the totals
+    if (kb < D && kb + LB_E >= D) {
         LookupMeta m;
-        m.n_nonempty = run.y;
-        m.n_left = run.w;
-        m.repeated = run.z;
+        m.n_nonempty = ex.y;
+        m.n_left = ex.w;
+        m.repeated = ex.z;
         m.k_zero = k0;
         m.k_pad = rank[(size_t)v * BIN_STRIDE];  // bin of table row 0 = the padding value
-        m.bad = (run.x != usable || run.z != usable - run.y) ? 2u : 0u;
+        // totals: rows must equal usable, leftover must equal usable - nonempty
+        m.bad = (ex.x != usable || ex.z != usable - ex.y) ? 2u : 0u;
         m.pad[0] = m.pad[1] = 0;
         meta[l] = m;
         if (m.bad) atomicOr(err + 1, 1u);
-        offz[(size_t)l * BIN_STRIDE + run.y] = usable;
-        loffz[(size_t)l * BIN_STRIDE + run.w] = run.z;
-    }
-    __syncthreads();
-    uint4 base = s_scan[wid];
-    base.x += inc.x - acc.x; base.y += inc.y - acc.y; base.z += inc.z - acc.z; base.w += inc.w - acc.w;
-    // pass 2: write the compacted arrays
-    for (uint32_t k = lo; k < hi; ++k) {
-        const uint32_t ck = c[k] + (k == k0 ? zero_extra : 0u);
-        const uint32_t nzf = ck ? 1u : 0u;
-        const uint32_t lf = tsv[k] - nzf;
-        if (nzf) {
-            offz[(size_t)l * BIN_STRIDE + base.y] = base.x;
-            nzk[(size_t)l * BIN_STRIDE + base.y] = k;
-            base.y += 1;
-            base.x += ck;
-        }
-        if (lf) {
-            loffz[(size_t)l * BIN_STRIDE + base.w] = base.z;
-            lk[(size_t)l * BIN_STRIDE + base.w] = k;
-            base.w += 1;
-            base.z += lf;
-        }
-    }
-    if (bad) {
-        atomicOr(&meta[l].bad, 1u);
-        atomicOr(err + 1, 1u);
+        o_offz[ex.y] = usable;
+        o_loffz[ex.w] = ex.z;
     }
 }
 
@@ -904,13 +1027,14 @@ cudaError_t launch_view_bins(h2aes_circuit *c) {
                                     c->d_viewmeta);
     k_bucket_hist<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist);
     k_bucket_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_bhist);
-    k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_bcur, c->d_slot);
-    k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_slot, c->d_sorted);
+    k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_bcur, c->d_slot,
+                                       c->d_canon_b);
+    k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon_b, c->d_viewmeta, c->d_bhist, c->d_slot, c->d_sorted);
+    // (d_slot is free again after k_bucket_rank: reused for the per-tile head counts)
     k_bin_heads<<<g, 256, 0, s>>>(c->d_canon, c->d_sorted, c->d_head, c->d_slot);
-    k_bin_index_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_slot, c->d_viewmeta);
     k_bin_fill<<<g, 256, 0, s>>>(c->d_val, c->d_sorted, c->d_head, c->d_slot, c->sh.usable(),
-                                 c->d_dval, c->d_rank, c->d_ts);
-    ctx->launches += 8;
+                                 c->d_dval, c->d_rank, c->d_ts, c->d_viewmeta);
+    ctx->launches += 7;
     return cudaGetLastError();
 }
 
@@ -930,10 +1054,13 @@ cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t ro
 cudaError_t launch_lookup_bins(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
-    k_lookup_bins<<<L, 1024, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
-                                               c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta,
-                                               c->d_err);
-    ctx->launches += 1;
+    dim3 g(LB_TILES, L);
+    k_lookup_tiles<<<g, LB_T, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
+                                                c->d_active, c->d_lbsum, c->d_err);
+    k_lookup_compact<<<g, LB_T, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
+                                                  c->d_active, c->d_lbsum, c->d_offz, c->d_nzk,
+                                                  c->d_loffz, c->d_lk, c->d_meta, c->d_err);
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 
@@ -1036,6 +1163,8 @@ cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint
     ctx->launches += 1;
     return cudaGetLastError();
 }
+
+uint32_t lookup_bin_tiles() { return LB_TILES; }
 
 // workspace sizes of the grand-product scan for `rows` rows: thread totals, block aggregates
 void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk) {

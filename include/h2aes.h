@@ -107,6 +107,11 @@ int32_t h2aes_block_position(int32_t k, int32_t N, uint64_t block, int32_t *set,
 int32_t h2aes_row_op(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t set,
                      uint64_t row);
 
+/* rows on which the selector of lookup `lookup` is enabled after schedule_key + n_blocks encrypts
+ * (the Selector::enable calls of the chips; input independent). */
+int32_t h2aes_active_rows(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks, int32_t lookup,
+                          uint64_t *out);
+
 /* number of copy constraints recorded by schedule_key + n_blocks encrypts (640 + 1952*n). */
 int32_t h2aes_copy_count(int32_t kind, uint64_t n_blocks, uint64_t *out);
 

@@ -207,3 +207,15 @@ def test_copy_constraints_equal_region_replay(ffi, orc, kind, k, N, nb):
     assert ffi.lib().h2aes_copy_constraints_host(kind, k, N, nb, 635, 10 if nb else 5, _p(part, u64p)) == 0
     assert (part[:5] == want[635:640]).all()
     assert ffi.lib().h2aes_copy_constraints_host(kind, k, N, nb, total.value, 1, _p(part, u64p)) == ffi.ERR_ARG
+
+
+def test_active_rows_equal_selector_sums(ffi, orc):
+    """h2aes_active_rows (closed form) == number of enabled rows of each complex selector."""
+    for kind, k, N, nb in ((1, 17, 1, 0), (0, 17, 1, 0), (0, 17, 2, 97), (0, 17, 2, 191)):
+        pts = np.zeros((nb, 16), np.uint8)
+        ref = orc.Circuit(kind, k, N).synthesize(bytes(16), pts if nb else None)
+        sel = ref.selectors()
+        for li in range(ref.info["n_lookups"]):
+            out = C.c_uint64()
+            assert ffi.lib().h2aes_active_rows(kind, k, N, nb, li, C.byref(out)) == 0
+            assert out.value == int(sel[li].sum()), (kind, N, nb, li)
