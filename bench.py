@@ -297,7 +297,7 @@ def run_b200(args):
         "permuted": 2 * L * n * 32,                         # k_permuted: A', S'
         "product": L * n * 32,                              # k_grand_product: Z
     }
-    kern = {"witness": "k_advice (+k_key_expand, k_block_states)", "permuted": "k_permuted",
+    kern = {"witness": "k_advice (+k_block_states)", "permuted": "k_permuted",
             "product": "k_grand_product"}
     kernels = []
     for p in ("witness", "permuted", "product"):

@@ -32,6 +32,7 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
 void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk);
 uint32_t lookup_bin_tiles();
+uint64_t run_index_stride(uint64_t n);
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
 
 // S-box from first principles (GF(2^8) inverse + affine map); H2AES_SBOX_REFERENCE then applies
@@ -298,7 +299,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_c0pow,
-                    c->d_canon_b,  c->d_active,   c->d_lbsum,
+                    c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -508,6 +509,9 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_canon_b, VB));
     CU(ctx, dalloc(&c->d_active, L));
     CU(ctx, dalloc(&c->d_lbsum, L * lookup_bin_tiles()));
+    c->idx_stride = run_index_stride(c->sh.n());
+    CU(ctx, dalloc(&c->d_jidx, L * c->idx_stride));
+    CU(ctx, dalloc(&c->d_lidx, L * c->idx_stride));
     CU(ctx, dalloc(&c->d_dval, VB));
     CU(ctx, dalloc(&c->d_rank, VB));
     CU(ctx, dalloc(&c->d_ts, VB));

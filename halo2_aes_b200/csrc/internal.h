@@ -96,6 +96,9 @@ struct h2aes_circuit {
     h2::fr_t *d_canon = nullptr;     // [3][BIN_STRIDE] canonical form (sort key)
     h2::fr_t *d_canon_b = nullptr;   // [3][BIN_STRIDE] the same in bucket order
     uint32_t *d_active = nullptr;    // [L] rows with the lookup's selector enabled
+    uint32_t *d_jidx = nullptr;      // [L][idx_stride] coarse index into offz (k_run_index)
+    uint32_t *d_lidx = nullptr;      // [L][idx_stride] coarse index into loffz
+    uint64_t idx_stride = 0;
     uint4 *d_lbsum = nullptr;        // [L][tiles] per-tile sums for the run-structure kernels
     h2::fr_t *d_dval = nullptr;      // [3][BIN_STRIDE] distinct values, ascending
     uint32_t *d_rank = nullptr;      // [3][BIN_STRIDE] entry -> bin

@@ -493,6 +493,40 @@ __device__ __forceinline__ uint32_t search_le(const uint32_t *__restrict__ arr, 
     }
     return lo;
 }
+// the same inside [lo, hi): the caller guarantees arr[lo] <= x and (hi == cnt or arr[hi] > x)
+__device__ __forceinline__ uint32_t search_le_in(const uint32_t *__restrict__ arr, uint32_t lo,
+                                                 uint32_t hi, uint32_t x) {
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (arr[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Coarse indices into the run tables, one entry per RUN_STEP rows, so that the per-row searches
+// of k_permuted look at <= RUN_STEP+1 neighbouring entries (L1-resident) instead of bisecting the
+// whole table through L2:  jidx[t] = run of A' containing row t*RUN_STEP,  lidx[t] = leftover
+// entry containing leftover position t*RUN_STEP.
+constexpr uint32_t RUN_SHIFT = 8, RUN_STEP = 1u << RUN_SHIFT;
+__global__ void __launch_bounds__(256)
+k_run_index(Shape sh, const LookupMeta *__restrict__ meta, const uint32_t *__restrict__ offz_all,
+            const uint32_t *__restrict__ loffz_all, uint32_t *__restrict__ jidx_all,
+            uint32_t *__restrict__ lidx_all, uint32_t stride) {
+    const int l = blockIdx.y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    const LookupMeta m = meta[l];
+    const uint32_t usable = (uint32_t)sh.usable();
+    const uint64_t pos = (uint64_t)t << RUN_SHIFT;
+    const uint32_t i = pos < usable ? (uint32_t)pos : usable - 1;
+    jidx_all[(size_t)l * stride + t] = search_le(offz_all + (size_t)l * BIN_STRIDE, m.n_nonempty, i);
+    uint32_t li = 0;
+    if (m.repeated) {
+        const uint32_t jj = pos < m.repeated ? (uint32_t)pos : m.repeated - 1;
+        li = search_le(loffz_all + (size_t)l * BIN_STRIDE, m.n_left, jj);
+    }
+    lidx_all[(size_t)l * stride + t] = li;
+}
 
 // bins (k of A', k' of S') of usable row i, and how S' relates to A'
 constexpr uint32_t CODE_FIRST = 0u, CODE_PAD = 1u, CODE_OTHER = 2u;  // stored in bits 30..31
@@ -503,9 +537,12 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
                                             const uint32_t *__restrict__ offz,
                                             const uint32_t *__restrict__ nzk,
                                             const uint32_t *__restrict__ loffz,
-                                            const uint32_t *__restrict__ lk) {
+                                            const uint32_t *__restrict__ lk,
+                                            const uint32_t *__restrict__ jidx,
+                                            const uint32_t *__restrict__ lidx) {
     RowBins rb;
-    const uint32_t j = search_le(offz, m.n_nonempty, i);
+    const uint32_t t = i >> RUN_SHIFT;
+    const uint32_t j = search_le_in(offz, jidx[t], jidx[t + 1] + 1, i);
     rb.k = nzk[j];
     if (offz[j] == i) {
         rb.kp = rb.k;  // first occurrence: S' = A'
@@ -514,7 +551,8 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
         // repeated rows, in row order, receive the leftover multiset from its END
         const uint32_t rho = i - (j + 1);
         const uint32_t jj = m.repeated - 1 - rho;
-        rb.kp = lk[search_le(loffz, m.n_left, jj)];
+        const uint32_t tt = jj >> RUN_SHIFT;
+        rb.kp = lk[search_le_in(loffz, lidx[tt], lidx[tt + 1] + 1, jj)];
         rb.cls = rb.kp == m.k_pad ? CODE_PAD : CODE_OTHER;
     }
     return rb;
@@ -533,7 +571,9 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            const uint32_t *__restrict__ loffz_all, const uint32_t *__restrict__ lk_all,
            const LookupMeta *__restrict__ meta, uint64_t *__restrict__ A, uint64_t *__restrict__ S,
            uint64_t *__restrict__ Ap, uint64_t *__restrict__ Sp, uint32_t *__restrict__ codek,
-           uint32_t *__restrict__ codep, uint64_t row_begin, uint64_t row_end) {
+           uint32_t *__restrict__ codep, const uint32_t *__restrict__ jidx_all,
+           const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, uint64_t row_begin,
+           uint64_t row_end) {
     const int li = blockIdx.y;            // index inside this call
     const int l = first_lookup + li;      // lookup index in the circuit
     const int ops = sh.ops_per_set();
@@ -551,6 +591,8 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
     uint32_t *__restrict__ ck = codek + (size_t)l * n;
     uint32_t *__restrict__ cp = codep + (size_t)l * n;
+    const uint32_t *__restrict__ jidx = jidx_all + (size_t)l * idx_stride;
+    const uint32_t *__restrict__ lidx = lidx_all + (size_t)l * idx_stride;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const fr_t zero = fr_zero();
     for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
@@ -577,7 +619,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             const uint32_t e = row < TABLE_ROWS ? entry_of_table_row(v, (uint32_t)row) : 0u;
             fr_store_256(S + o, fr_ld(valv + e));
         }
-        const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk);
+        const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
         ck[row] = rb.k | (rb.cls << 30);
         if (rb.cls == CODE_OTHER) cp[row] = rb.kp;
         if (Ap) {
@@ -1060,7 +1102,9 @@ cudaError_t launch_lookup_bins(h2aes_circuit *c) {
     k_lookup_compact<<<g, LB_T, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
                                                   c->d_active, c->d_lbsum, c->d_offz, c->d_nzk,
                                                   c->d_loffz, c->d_lk, c->d_meta, c->d_err);
-    ctx->launches += 2;
+    k_run_index<<<dim3(cdiv(c->idx_stride, 256), L), 256, 0, ctx->stream>>>(
+        c->sh, c->d_meta, c->d_offz, c->d_loffz, c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride);
+    ctx->launches += 3;
     return cudaGetLastError();
 }
 
@@ -1074,7 +1118,8 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     dim3 g(gx, count);
     k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_val, c->d_dval, c->d_offz,
                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S, Ap, Sp,
-                                           c->d_codek, c->d_codep, row_begin, row_end);
+                                           c->d_codek, c->d_codep, c->d_jidx, c->d_lidx,
+                                           (uint32_t)c->idx_stride, row_begin, row_end);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -1165,6 +1210,7 @@ cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint
 }
 
 uint32_t lookup_bin_tiles() { return LB_TILES; }
+uint64_t run_index_stride(uint64_t n) { return (n >> RUN_SHIFT) + 2; }
 
 // workspace sizes of the grand-product scan for `rows` rows: thread totals, block aggregates
 void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk) {

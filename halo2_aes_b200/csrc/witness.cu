@@ -5,8 +5,8 @@
 // the chips' assign closures (src/chips/*.rs), load_enc_full_table (src/table.rs:18-192).
 //
 // Kernels
-//   k_key_expand     1 warp: FIPS-197 key expansion with the context's S-box -> 176 bytes.
-//   k_block_states   half a warp per AES block: the 31 16-byte round states of the block.
+//   k_block_states   FIPS-197 key expansion with the context's S-box (warp 0 of every CTA, into
+//                    shared memory), then half a warp per AES block: the 31 16-byte round states.
 //   k_advice         the streaming kernel: one lane per row, computes the row's trace word from
 //                    the block's round states (closed form, layout.h), stores the word (4 B) and
 //                    the three Fr cells of the column set with one 256-bit store each, from a
@@ -22,39 +22,38 @@ struct Key16 {
     uint8_t b[16];
 };
 
-__global__ void k_key_expand(const uint8_t *__restrict__ sbox, Key16 key, uint8_t *__restrict__ rk) {
-    __shared__ uint8_t s_sbox[256];
-    __shared__ uint8_t s_rk[176];
-    const int l = threadIdx.x;
-    for (int i = l; i < 256; i += 32) s_sbox[i] = sbox[i];
-    if (l < 16) s_rk[l] = key.b[l];
-    __syncwarp();
-    for (int r = 1; r <= 10; ++r) {
-        const uint8_t *p = s_rk + 16 * (r - 1);
-        uint8_t *o = s_rk + 16 * r;
-        if (l < 4) {
-            int rot = (13 + l) - (l == 3 ? 4 : 0);
-            o[l] = (uint8_t)(p[l] ^ s_sbox[p[rot]] ^ (l == 0 ? rcon(r - 1) : 0));
-        }
-        __syncwarp();
-        for (int i = 1; i < 4; ++i) {
-            if (l < 4) o[4 * i + l] = (uint8_t)(p[4 * i + l] ^ o[4 * (i - 1) + l]);
-            __syncwarp();
-        }
-    }
-    for (int i = l; i < 176; i += 32) rk[i] = s_rk[i];
-}
-
-// Half-warp per block; lane i of the half-warp owns state byte i = 4w+j.
+// Key expansion (FIPS-197 with the context's S-box) by warp 0 of every CTA into shared memory
+// (176 bytes; cheaper than a separate launch), then half a warp per AES block: lane i of the
+// half-warp owns state byte i = 4w+j.  CTA 0 also publishes the round keys for k_advice.
 __global__ void __launch_bounds__(128)
-k_block_states(const uint8_t *__restrict__ sbox, const uint8_t *__restrict__ rk,
+k_block_states(const uint8_t *__restrict__ sbox, Key16 key, uint8_t *__restrict__ rk_out,
                const uint8_t *__restrict__ pts, uint64_t n_blocks, uint8_t *__restrict__ states,
                uint8_t *__restrict__ cts) {
     __shared__ uint8_t s_sbox[256];
     __shared__ uint8_t s_rk[176];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = sbox[i];
-    for (int i = threadIdx.x; i < 176; i += blockDim.x) s_rk[i] = rk[i];
+    if (threadIdx.x < 16) s_rk[threadIdx.x] = key.b[threadIdx.x];
     __syncthreads();
+    if (threadIdx.x < 32) {
+        const int l = threadIdx.x;
+        for (int r = 1; r <= 10; ++r) {
+            const uint8_t *p = s_rk + 16 * (r - 1);
+            uint8_t *o = s_rk + 16 * r;
+            if (l < 4) {
+                const int rot = (13 + l) - (l == 3 ? 4 : 0);
+                o[l] = (uint8_t)(p[l] ^ s_sbox[p[rot]] ^ (l == 0 ? rcon(r - 1) : 0));
+            }
+            __syncwarp();
+            for (int i = 1; i < 4; ++i) {
+                if (l < 4) o[4 * i + l] = (uint8_t)(p[4 * i + l] ^ o[4 * (i - 1) + l]);
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 176; i += blockDim.x) rk_out[i] = s_rk[i];
+    if (!n_blocks) return;
     const int lane = threadIdx.x & 31, l = lane & 15, hb = lane & 16;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t blk = 2 * warp + (lane >> 4);
@@ -62,7 +61,7 @@ k_block_states(const uint8_t *__restrict__ sbox, const uint8_t *__restrict__ rk,
     const uint64_t bsafe = live ? blk : 0;
     uint8_t *st = states + bsafe * ST_BYTES;
     const int w = l >> 2, c = l & 3;
-    uint32_t pt = n_blocks ? pts[bsafe * 16 + l] : 0;
+    uint32_t pt = pts[bsafe * 16 + l];
     uint32_t s = pt ^ s_rk[l];
     if (live) st[16 * ST_PT + l] = (uint8_t)pt;
 #pragma unroll 1
@@ -241,15 +240,11 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
     h2aes_ctx *ctx = c->ctx;
     Key16 k16;
     for (int i = 0; i < 16; ++i) k16.b[i] = key[i];
-    k_key_expand<<<1, 32, 0, ctx->stream>>>(ctx->d_sbox, k16, c->d_rk);
+    const uint64_t blocks_per_cta = 8;
+    unsigned grid = n_blocks ? (unsigned)((n_blocks + blocks_per_cta - 1) / blocks_per_cta) : 1u;
+    k_block_states<<<grid, 128, 0, ctx->stream>>>(ctx->d_sbox, k16, c->d_rk, pts_dev, n_blocks,
+                                                  c->d_states, cts_dev);
     ctx->launches++;
-    if (n_blocks) {
-        const uint64_t blocks_per_cta = 8;
-        unsigned grid = (unsigned)((n_blocks + blocks_per_cta - 1) / blocks_per_cta);
-        k_block_states<<<grid, 128, 0, ctx->stream>>>(ctx->d_sbox, c->d_rk, pts_dev, n_blocks,
-                                                      c->d_states, cts_dev);
-        ctx->launches++;
-    }
     k_advice<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
                                                         ctx->d_sbox, ctx->d_frtab, advice_dev,
                                                         c->d_trace, row_begin, row_end);
