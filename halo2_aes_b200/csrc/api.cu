@@ -526,7 +526,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_nac, VB));
     CU(ctx, dalloc(&c->d_ibg, VB));
     CU(ctx, dalloc(&c->d_ibp, VB));
-    CU(ctx, dalloc(&c->d_c0pow, L * 17));
+    CU(ctx, dalloc(&c->d_c0pow, L * 33));
     CU(ctx, dalloc(&c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n()));
     CU(ctx, dalloc(&c->d_codek, L * c->sh.n()));
     CU(ctx, dalloc(&c->d_codep, L * c->sh.n()));

@@ -114,7 +114,7 @@ struct h2aes_circuit {
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
     h2::fr_t *d_ibg = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k]
     h2::fr_t *d_ibp = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k_pad]
-    h2::fr_t *d_c0pow = nullptr;     // [L][17] powers of the constant row factor
+    h2::fr_t *d_c0pow = nullptr;     // [L][ZI+1 <= 33] powers of the constant row factor
     // per lookup
     uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
     uint32_t *d_offz = nullptr;      // [L][BIN_STRIDE] first row of each nonempty bin (+ end)

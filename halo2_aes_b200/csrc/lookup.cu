@@ -752,7 +752,7 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
 
 // c0pow[l][j] = (nac[k_zero] * ibp[k_zero])^j, j = 0..ZI: the factor of a row that is inactive in
 // row order and sits in the zero run of A' with the padding value as S' (one lane per power)
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 k_z_consts(Shape sh, const LookupMeta *__restrict__ meta, const fr_t *__restrict__ nac,
            const fr_t *__restrict__ ibp, fr_t *__restrict__ c0pow, int zi) {
     const int l = blockIdx.x, j = threadIdx.x;
@@ -780,7 +780,10 @@ k_z_consts(Shape sh, const LookupMeta *__restrict__ meta, const fr_t *__restrict
 //                  factors in the Z buffer with Z itself
 // The kernel is bound by integer-multiply issue, not by HBM.
 // ---------------------------------------------------------------------------------------------
-constexpr int ZI = 16;     // consecutive rows per thread
+#ifndef ZI_ROWS
+#define ZI_ROWS 32
+#endif
+constexpr int ZI = ZI_ROWS;  // consecutive rows per thread (<= 32: one mask word; row ranges are multiples)
 constexpr int ZF_T = 128;  // threads per CTA, factor / propagate kernels
 constexpr int ZS_T = 256;  // scan kernels: threads per CTA
 constexpr int ZS_E = 4;    //               elements per thread (latency-bound: keep chains short)
@@ -820,7 +823,7 @@ __device__ __forceinline__ void ld16(const uint32_t *__restrict__ p, uint32_t (&
 #define ZF_OCC 5
 #endif
 #ifndef ZP_OCC
-#define ZP_OCC 6
+#define ZP_OCC 5
 #endif
 __global__ void __launch_bounds__(ZF_T, ZF_OCC) k_z_factors(const ZArgs a) {
     const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
@@ -883,6 +886,7 @@ __global__ void __launch_bounds__(ZF_T, ZF_OCC) k_z_factors(const ZArgs a) {
         ld16(a.tracek + (uint64_t)set * n + row0, tk);
         ld16(a.codek + (uint64_t)l * n + row0, ck);
         const uint32_t c0code = k_zero | (CODE_PAD << 30);
+        static_assert(ZI <= 32, "mask");
         const fr_t *__restrict__ c0pow = a.c0pow + (size_t)l * (ZI + 1);
         const fr_t c0 = fr_ld(c0pow + 1);
         uint32_t mask = 0;
@@ -1019,11 +1023,15 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     const uint64_t row0 = a.row_begin + e * ZI;
     uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
     fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
-    constexpr int PB = 4;  // factors fetched ahead of the multiply chain
+#ifndef ZP_PB
+#define ZP_PB 4
+#endif
+    constexpr int PB = ZP_PB;  // factors fetched ahead of the multiply chain
+    static_assert(ZI % PB == 0, "ZI must be a multiple of the prefetch depth");
     fr_t f[PB];
 #pragma unroll
     for (int j = 0; j < PB; ++j) f[j] = fr_load(z + 4 * j);
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < ZI; q += PB) {
         fr_t g[PB];
 #pragma unroll
@@ -1036,7 +1044,7 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
         for (int j = 0; j < PB; ++j) {
             // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
             fr_store_256(z + 4 * (q + j), row0 + q + j <= usable ? cur : fr_zero());
-            if (q + j + 1 < ZI) cur = fr_mul(cur, g[j]);
+            cur = fr_mul(cur, g[j]);
         }
     }
 }
@@ -1132,9 +1140,9 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
     k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_ibg,
                                              c->d_ibp);
-    k_z_consts<<<c->sh.n_lookups(), 32, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
+    k_z_consts<<<c->sh.n_lookups(), 64, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
                                                           c->d_c0pow, ZI);
-    static_assert(ZI == 16, "d_c0pow is allocated as [L][17]");
+    static_assert(ZI <= 32 && ZI % 4 == 0, "d_c0pow is allocated as [L][33]; one mask word");
     ctx->launches += 3;
     return cudaGetLastError();
 }
