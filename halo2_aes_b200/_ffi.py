@@ -86,6 +86,8 @@ SIGNATURES = {
     "h2aes_ctx_synchronize": (C.c_int32, [_vp]),
     "h2aes_ctx_last_error": (C.c_char_p, [_vp]),
     "h2aes_ctx_kernel_launches": (C.c_uint64, [_vp]),
+    "h2aes_ctx_profile": (C.c_int32, [_vp, C.c_int32]),
+    "h2aes_ctx_profile_read": (C.c_int32, [_vp, C.c_char_p, C.c_uint64]),
     "h2aes_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(_vp)]),
     "h2aes_host_free": (C.c_int32, [_vp]),
     "h2aes_circuit_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),

@@ -50,6 +50,20 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib().h2aes_ctx_kernel_launches(self._h))
 
+    def profile(self, enable: bool = True):
+        """bracket every kernel of this context with CUDA events (h2aes_ctx_profile)"""
+        check(lib().h2aes_ctx_profile(self._h, int(enable)), self._h)
+
+    def profile_read(self) -> dict:
+        """{kernel: (launches, total_ms)} since profiling was enabled / last read"""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib().h2aes_ctx_profile_read(self._h, buf, len(buf)), self._h)
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, n, ms = ln.split()
+            out[name] = (int(n), float(ms))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             lib().h2aes_ctx_destroy(self._h)

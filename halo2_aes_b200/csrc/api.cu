@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <string>
+#include <vector>
 
 #include "internal.h"
 
@@ -277,6 +279,48 @@ int32_t h2aes_ctx_synchronize(h2aes_ctx *ctx) {
 
 const char *h2aes_ctx_last_error(h2aes_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 uint64_t h2aes_ctx_kernel_launches(h2aes_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t h2aes_ctx_profile(h2aes_ctx *ctx, int32_t enable) {
+    if (!ctx) return H2AES_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    ctx->profiling = enable != 0;
+    return H2AES_OK;
+}
+
+int32_t h2aes_ctx_profile_read(h2aes_ctx *ctx, char *buf, uint64_t cap) {
+    if (!ctx || !buf || !cap) return H2AES_ERR_ARG;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char *name; uint64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        size_t i = 0;
+        while (i < agg.size() && strcmp(agg[i].name, r.name)) ++i;
+        if (i == agg.size()) agg.push_back(Agg{r.name, 0, 0.0});
+        agg[i].n += 1;
+        agg[i].ms += ms;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    std::string s;
+    char line[160];
+    for (auto &a : agg) {
+        snprintf(line, sizeof line, "%s %llu %.6f\n", a.name, (unsigned long long)a.n, a.ms);
+        s += line;
+    }
+    if (s.size() + 1 > cap) return fail(ctx, H2AES_ERR_ARG, "profile buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return H2AES_OK;
+}
 
 int32_t h2aes_host_alloc(uint64_t bytes, void **out) {
     if (!out) return H2AES_ERR_ARG;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/h2aes.h"
 #include "fr.cuh"
@@ -55,8 +56,15 @@ struct LookupMeta {  // per lookup, produced by the bin-scan kernel
 
 }  // namespace h2
 
+struct h2aes_prof_rec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+
 struct h2aes_ctx {
     int device = 0;
+    bool profiling = false;                // h2aes_ctx_profile: CUDA events around every kernel
+    std::vector<h2aes_prof_rec> prof;
     cudaStream_t stream = nullptr;
     int sbox_mode = 0;
     int sm_count = 148;
@@ -140,3 +148,18 @@ struct h2aes_circuit {
     uint64_t pt_cap = 0;
     uint8_t *d_ct = nullptr;
 };
+
+// per-kernel timing hooks (no-ops unless h2aes_ctx_profile(ctx, 1) was called)
+static inline void prof_begin(h2aes_ctx *ctx, const char *name) {
+    if (!ctx->profiling) return;
+    h2aes_prof_rec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof.push_back(r);
+}
+static inline void prof_end(h2aes_ctx *ctx) {
+    if (!ctx->profiling || ctx->prof.empty()) return;
+    cudaEventRecord(ctx->prof.back().b, ctx->stream);
+}

@@ -1073,17 +1073,31 @@ cudaError_t launch_view_bins(h2aes_circuit *c) {
     if ((e = cudaMemsetAsync(c->d_bcur, 0, (size_t)N_VIEWS * N_BUCKETS * 4, s))) return e;
     if ((e = cudaMemsetAsync(c->d_ts, 0, (size_t)N_VIEWS * BIN_STRIDE * 4, s))) return e;
     dim3 g(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
+    prof_begin(ctx, "k_view_values");
     k_view_values<<<g, 256, 0, s>>>(ctx->d_sbox, ctx->d_frtab, c->d_chal, c->d_val, c->d_canon,
                                     c->d_viewmeta);
+    prof_end(ctx);
+    prof_begin(ctx, "k_bucket_hist");
     k_bucket_hist<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist);
+    prof_end(ctx);
+    prof_begin(ctx, "k_bucket_scan");
     k_bucket_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_bhist);
+    prof_end(ctx);
+    prof_begin(ctx, "k_bucket_scatter");
     k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_bcur, c->d_slot,
                                        c->d_canon_b);
+    prof_end(ctx);
+    prof_begin(ctx, "k_bucket_rank");
     k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon_b, c->d_viewmeta, c->d_bhist, c->d_slot, c->d_sorted);
+    prof_end(ctx);
     // (d_slot is free again after k_bucket_rank: reused for the per-tile head counts)
+    prof_begin(ctx, "k_bin_heads");
     k_bin_heads<<<g, 256, 0, s>>>(c->d_canon, c->d_sorted, c->d_head, c->d_slot);
+    prof_end(ctx);
+    prof_begin(ctx, "k_bin_fill");
     k_bin_fill<<<g, 256, 0, s>>>(c->d_val, c->d_sorted, c->d_head, c->d_slot, c->sh.usable(),
                                  c->d_dval, c->d_rank, c->d_ts, c->d_viewmeta);
+    prof_end(ctx);
     ctx->launches += 7;
     return cudaGetLastError();
 }
@@ -1095,8 +1109,10 @@ cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t ro
     cudaError_t e;
     if ((e = cudaMemsetAsync(c->d_cnt, 0, (size_t)L * BIN_STRIDE * 4, s))) return e;
     dim3 g(ctx->sm_count * 2, c->sh.n_sets());
+    prof_begin(ctx, "k_lookup_hist");
     k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, c->d_tracek, row_begin,
                                     row_end);
+    prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -1105,13 +1121,19 @@ cudaError_t launch_lookup_bins(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
     dim3 g(LB_TILES, L);
+    prof_begin(ctx, "k_lookup_tiles");
     k_lookup_tiles<<<g, LB_T, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
                                                 c->d_active, c->d_lbsum, c->d_err);
+    prof_end(ctx);
+    prof_begin(ctx, "k_lookup_compact");
     k_lookup_compact<<<g, LB_T, 0, ctx->stream>>>(c->sh, c->d_cnt, c->d_rank, c->d_ts, c->d_viewmeta,
                                                   c->d_active, c->d_lbsum, c->d_offz, c->d_nzk,
                                                   c->d_loffz, c->d_lk, c->d_meta, c->d_err);
+    prof_end(ctx);
+    prof_begin(ctx, "k_run_index");
     k_run_index<<<dim3(cdiv(c->idx_stride, 256), L), 256, 0, ctx->stream>>>(
         c->sh, c->d_meta, c->d_offz, c->d_loffz, c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride);
+    prof_end(ctx);
     ctx->launches += 3;
     return cudaGetLastError();
 }
@@ -1124,10 +1146,12 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     const unsigned cap = (unsigned)ctx->sm_count * 8;
     if (gx > cap) gx = cap;
     dim3 g(gx, count);
+    prof_begin(ctx, "k_permuted");
     k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_val, c->d_dval, c->d_offz,
                                            c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S, Ap, Sp,
                                            c->d_codek, c->d_codep, c->d_jidx, c->d_lidx,
                                            (uint32_t)c->idx_stride, row_begin, row_end);
+    prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -1135,13 +1159,19 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
 cudaError_t launch_inv_tables(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
     dim3 g(cdiv(VIEW_MAX_ENTRIES, INV_TILE), N_VIEWS, 2);
+    prof_begin(ctx, "k_inv_tables");
     k_inv_tables<<<g, INV_T, 0, ctx->stream>>>(c->d_chal, c->d_dval, c->d_val, c->d_viewmeta,
                                                c->d_ib, c->d_ig, c->d_nac, c->d_err);
+    prof_end(ctx);
     dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
+    prof_begin(ctx, "k_inv_merge");
     k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_ibg,
                                              c->d_ibp);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_consts");
     k_z_consts<<<c->sh.n_lookups(), 64, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
                                                           c->d_c0pow, ZI);
+    prof_end(ctx);
     static_assert(ZI <= 32 && ZI % 4 == 0, "d_c0pow is allocated as [L][33]; one mask word");
     ctx->launches += 3;
     return cudaGetLastError();
@@ -1178,9 +1208,15 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
     const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
+    prof_begin(ctx, "k_z_factors");
     k_z_factors<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_reduce");
     k_z_reduce<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_blocks");
     k_z_blocks<<<count, 32, 0, s>>>(a);
+    prof_end(ctx);
     ctx->launches += 3;
     return cudaGetLastError();
 }
@@ -1191,8 +1227,12 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
     const ZArgs a = z_args(c, first, count, carry_in, Z, row_begin, row_end);
+    prof_begin(ctx, "k_z_down");
     k_z_down<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_propagate");
     k_z_propagate<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();
 }
@@ -1200,8 +1240,10 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
+    prof_begin(ctx, "k_shard_carry");
     k_shard_carry<<<cdiv(L, 64), 64, 0, ctx->stream>>>((const fr_t *)gathered_dev, L, c->shard,
                                                        c->d_carry);
+    prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
 }
@@ -1212,7 +1254,9 @@ __global__ void k_dbg_fr_mul(const fr_t *__restrict__ a, const fr_t *__restrict_
     if (i < n) fr_st(out + i, fr_mul(fr_ld(a + i), fr_ld(b + i)));
 }
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out) {
+    prof_begin(ctx, "k_dbg_fr_mul");
     k_dbg_fr_mul<<<cdiv(n, 128), 128, 0, ctx->stream>>>(a, b, n, out);
+    prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
 }

@@ -229,7 +229,9 @@ __global__ void k_build_frtab(uint4 *__restrict__ frtab) {
 static inline int grid_for(const h2aes_ctx *ctx, int ctas_per_sm) { return ctx->sm_count * ctas_per_sm; }
 
 cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
+    prof_begin(ctx, "k_build_frtab");
     k_build_frtab<<<1, 256, 0, ctx->stream>>>(ctx->d_frtab);
+    prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -242,12 +244,16 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
     for (int i = 0; i < 16; ++i) k16.b[i] = key[i];
     const uint64_t blocks_per_cta = 8;
     unsigned grid = n_blocks ? (unsigned)((n_blocks + blocks_per_cta - 1) / blocks_per_cta) : 1u;
+    prof_begin(ctx, "k_block_states");
     k_block_states<<<grid, 128, 0, ctx->stream>>>(ctx->d_sbox, k16, c->d_rk, pts_dev, n_blocks,
                                                   c->d_states, cts_dev);
+    prof_end(ctx);
     ctx->launches++;
+    prof_begin(ctx, "k_advice");
     k_advice<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
                                                         ctx->d_sbox, ctx->d_frtab, advice_dev,
                                                         c->d_trace, row_begin, row_end);
+    prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -255,15 +261,19 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
 cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
                          uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end) {
     h2aes_ctx *ctx = c->ctx;
+    prof_begin(ctx, "k_fixed");
     k_fixed<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, ctx->d_sbox, ctx->d_frtab,
                                                        fixed_dev, selectors_dev, row_begin, row_end);
+    prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_copies(h2aes_circuit *c, uint64_t n_copies, uint64_t *out) {
     h2aes_ctx *ctx = c->ctx;
+    prof_begin(ctx, "k_copies");
     k_copies<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(c->sh, n_copies, out);
+    prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();
 }

@@ -132,6 +132,11 @@ int32_t h2aes_ctx_synchronize(h2aes_ctx *ctx);
 const char *h2aes_ctx_last_error(h2aes_ctx *ctx);
 /* number of this library's kernels launched through `ctx` so far. */
 uint64_t h2aes_ctx_kernel_launches(h2aes_ctx *ctx);
+/* per-kernel timing: with enable != 0 every kernel launched through `ctx` is bracketed by CUDA
+ * events on the context's stream; h2aes_ctx_profile_read synchronizes and writes one line
+ * "kernel_name launches total_ms" per kernel (first-launch order) into buf, then clears. */
+int32_t h2aes_ctx_profile(h2aes_ctx *ctx, int32_t enable);
+int32_t h2aes_ctx_profile_read(h2aes_ctx *ctx, char *buf, uint64_t cap);
 /* pinned host memory helpers for the _host entry points (optional; any host memory works). */
 int32_t h2aes_host_alloc(uint64_t bytes, void **out);
 int32_t h2aes_host_free(void *p);
