@@ -344,6 +344,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_c0pow,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
+                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_zmask,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -570,6 +571,9 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_nac, VB));
     CU(ctx, dalloc(&c->d_ibg, VB));
     CU(ctx, dalloc(&c->d_ibp, VB));
+    CU(ctx, dalloc(&c->d_nacp, VB));
+    CU(ctx, dalloc(&c->d_ibgz, VB));
+    CU(ctx, dalloc(&c->d_ibpz, VB));
     CU(ctx, dalloc(&c->d_c0pow, L * 33));
     CU(ctx, dalloc(&c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n()));
     CU(ctx, dalloc(&c->d_codek, L * c->sh.n()));
@@ -582,6 +586,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_lk, LB));
     CU(ctx, dalloc(&c->d_meta, L));
     CU(ctx, dalloc(&c->d_ztot, L * c->zm));
+    CU(ctx, dalloc(&c->d_zmask, L * c->zm));
     CU(ctx, dalloc(&c->d_zbagg, L * c->znblk));
     CU(ctx, dalloc(&c->d_zbexcl, L * c->znblk));
     CU(ctx, dalloc(&c->d_partial, L));

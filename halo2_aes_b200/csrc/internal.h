@@ -122,6 +122,9 @@ struct h2aes_circuit {
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
     h2::fr_t *d_ibg = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k]
     h2::fr_t *d_ibp = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k_pad]
+    h2::fr_t *d_nacp = nullptr;      // [3][BIN_STRIDE] nac[k]*ibp[k_zero]
+    h2::fr_t *d_ibgz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibg[k]
+    h2::fr_t *d_ibpz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibp[k]
     h2::fr_t *d_c0pow = nullptr;     // [L][ZI+1 <= 33] powers of the constant row factor
     // per lookup
     uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
@@ -131,6 +134,7 @@ struct h2aes_circuit {
     uint32_t *d_lk = nullptr;        // [L][BIN_STRIDE] bin of each leftover slot
     h2::LookupMeta *d_meta = nullptr;  // [L]
     // grand-product scan workspace
+    uint32_t *d_zmask = nullptr;      // [L][zm]   non-constant-row bit masks of the chunks
     h2::fr_t *d_ztot = nullptr;       // [L][zm]   per-thread factor products / their prefixes
     h2::fr_t *d_zbagg = nullptr;      // [L][znblk] block aggregates
     h2::fr_t *d_zbexcl = nullptr;     // [L][znblk] exclusive prefixes of the block aggregates

@@ -738,16 +738,28 @@ k_inv_tables(const fr_t *__restrict__ chal, const fr_t *__restrict__ dval,
 
 __global__ void __launch_bounds__(256)
 k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ rank,
-            const fr_t *__restrict__ ib, const fr_t *__restrict__ ig, fr_t *__restrict__ ibg,
-            fr_t *__restrict__ ibp) {
+            const fr_t *__restrict__ ib, const fr_t *__restrict__ ig, const fr_t *__restrict__ nac,
+            fr_t *__restrict__ ibg, fr_t *__restrict__ ibp, fr_t *__restrict__ nacp,
+            fr_t *__restrict__ ibgz, fr_t *__restrict__ ibpz) {
     const int v = blockIdx.y;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= viewmeta[v * 8 + 1]) return;
     const size_t o = (size_t)v * BIN_STRIDE;
     const uint32_t k_pad = rank[o];  // bin of table row 0, the padding value
+    const uint32_t k_zero = rank[o + (v == 0 ? 1280u : TROW_ZERO)];  // bin of the all-zero tuple
+    const fr_t ig_pad = fr_ld(ig + o + k_pad);
     const fr_t b = fr_ld(ib + o + k);
-    fr_st(ibg + o + k, fr_mul(b, fr_ld(ig + o + k)));
-    fr_st(ibp + o + k, fr_mul(b, fr_ld(ig + o + k_pad)));
+    const fr_t g = fr_mul(b, fr_ld(ig + o + k));
+    const fr_t p = fr_mul(b, ig_pad);
+    fr_st(ibg + o + k, g);
+    fr_st(ibp + o + k, p);
+    // one operand constant: an active row inside the zero run of A' (denominator ibp[k_zero]),
+    // an inactive row outside it (numerator nac[k_zero]) -> the factor is a table entry
+    const fr_t ibp_zero = fr_mul(fr_ld(ib + o + k_zero), ig_pad);
+    const fr_t nac_zero = fr_ld(nac + o + k_zero);
+    fr_st(nacp + o + k, fr_mul(fr_ld(nac + o + k), ibp_zero));
+    fr_st(ibgz + o + k, fr_mul(nac_zero, g));
+    fr_st(ibpz + o + k, fr_mul(nac_zero, p));
 }
 
 // c0pow[l][j] = (nac[k_zero] * ibp[k_zero])^j, j = 0..ZI: the factor of a row that is inactive in
@@ -796,7 +808,9 @@ struct ZArgs {
     const uint32_t *codek, *codep;   // [L][n]     bin of A' | class<<30 ; bin of S' (class OTHER)
     const fr_t *chal;
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
+    const fr_t *nacp, *ibgz, *ibpz;                      // [3][BIN_STRIDE] one-operand-constant factors
     const LookupMeta *meta;
+    uint32_t *chunkmask;  // [count][m] one bit per row of the chunk: factor is not the constant c0
     fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
     fr_t *bagg;       // [count][nblk] block aggregates of tot
     fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
@@ -808,26 +822,18 @@ struct ZArgs {
     uint64_t row_begin, row_end;
 };
 
-__device__ __forceinline__ void ld16(const uint32_t *__restrict__ p, uint32_t (&w)[ZI]) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-#pragma unroll
-    for (int i = 0; i < ZI / 4; ++i) {
-        const uint4 x = q[i];
-        w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
-    }
-}
-
-// Each thread owns ZI consecutive rows (row ranges are multiples of ZI).  Operands of row q+1
-// are gathered while the two multiplies of row q run.
-#ifndef ZF_OCC
-#define ZF_OCC 5
+// k_z_fill: one lane per row (coalesced 4-byte reads of the row's two code words, coalesced
+// 256-bit store of its factor).  Most rows are "constant": inactive in row order (A = 0) AND
+// inside the zero run of A' with the padding value as S', so f = c0 = nac[k_zero]*ibp[k_zero].
+// Of the rest, almost all have one constant operand and read their factor from a merged table
+// (k_inv_merge); only rows that are both active and outside the zero run (or inside the table
+// rows, where S varies) multiply.  Also emits one bit per row (non-constant) as a 32-bit word
+// per chunk of ZI rows for k_z_chunks.
+static_assert(ZI == 32, "one warp ballot = one chunk mask");
+#ifndef ZFILL_OCC
+#define ZFILL_OCC 6
 #endif
-#ifndef ZP_OCC
-#define ZP_OCC 5
-#endif
-__global__ void __launch_bounds__(ZF_T, ZF_OCC) k_z_factors(const ZArgs a) {
-    const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
-    if (e >= a.m) return;
+__global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
     const Shape sh = a.sh;
     const int li = blockIdx.y;
     const int l = a.first_lookup + li;
@@ -843,93 +849,98 @@ __global__ void __launch_bounds__(ZF_T, ZF_OCC) k_z_factors(const ZArgs a) {
     const fr_t *__restrict__ valv = a.val + vo, *__restrict__ dv = a.dval + vo,
                              *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
                              *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
-                             *__restrict__ ibp = a.ibp + vo;
-    const uint64_t row0 = a.row_begin + e * ZI;
-    uint64_t *__restrict__ zout = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
-    const uint32_t *__restrict__ cp = a.codep + (uint64_t)l * n + row0;
-
-    fr_t tot = fr_one();
-    if (row0 < TABLE_ROWS || row0 + ZI > usable) {
-        // rows inside the table (S varies per row) or touching the blinding rows: general form
-        const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
-#pragma unroll 1
-        for (int q = 0; q < ZI; ++q) {
-            const uint32_t i = (uint32_t)(row0 + q);
-            if (i >= usable) {  // blinding rows: factor one (their Z entries are zeroed later)
-                fr_store_256(zout + 4 * q, fr_one());
-                continue;
-            }
-            const uint32_t tkq = a.tracek[(uint64_t)set * n + i], ckq = a.codek[(uint64_t)l * n + i];
-            const uint32_t kin = (tkq >> 24) == op ? (tkq & 0xffffffu) : k_zero;
-            fr_t num;
-            if (i >= TABLE_ROWS) {
-                num = fr_ld(nac + kin);
-            } else {
-                const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, i)), gamma);
-                num = fr_mul(fr_add(fr_ld(dv + kin), beta), sg);
-            }
-            const uint32_t k = ckq & 0x3fffffffu, cls = ckq >> 30;
-            fr_t den;
-            if (cls == CODE_OTHER) den = fr_mul(fr_ld(ib + k), fr_ld(ig + cp[q]));
-            else den = fr_ld((cls == CODE_FIRST ? ibg : ibp) + k);
-            const fr_t f = fr_mul(num, den);
-            fr_store_256(zout + 4 * q, f);
-            tot = fr_mul(tot, f);
+                             *__restrict__ ibp = a.ibp + vo, *__restrict__ nacp = a.nacp + vo,
+                             *__restrict__ ibgz = a.ibgz + vo, *__restrict__ ibpz = a.ibpz + vo;
+    const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n;
+    const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n;
+    const uint32_t *__restrict__ cpp = a.codep + (uint64_t)l * n;
+    const uint32_t c0code = k_zero | (CODE_PAD << 30);
+    const fr_t c0 = fr_ld(a.c0pow + (size_t)l * (ZI + 1) + 1);
+    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
+    uint64_t *__restrict__ zout = a.Z + (size_t)li * out_rows * 4;
+    uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.m;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    // warp w handles chunks w, w + warps, ... ; chunk c = rows [row_begin + 32c, +32)
+    for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
+         c += warps) {
+        const uint64_t row = a.row_begin + c * ZI + lane;
+        // classify: 0 constant (c0), 1 single table entry at `src`, 2 nac[kin] * den, 3 table row
+        int kind = 1;
+        const fr_t *src = nullptr;
+        uint32_t kin = k_zero, k = 0, cls = CODE_FIRST;
+        if (row >= usable) {
+            kind = 4;  // blinding rows: factor one (their Z entries are zeroed later)
+        } else {
+            const uint32_t t = tkp[row], ck = ckp[row];
+            const bool active = (t >> 24) == op;
+            if (active) kin = t & 0xffffffu;
+            k = ck & 0x3fffffffu;
+            cls = ck >> 30;
+            if ((uint32_t)row < TABLE_ROWS) kind = 3;
+            else if (ck == c0code) { kind = active ? 1 : 0; src = nacp + kin; }
+            else if (!active && cls != CODE_OTHER) src = (cls == CODE_FIRST ? ibgz : ibpz) + k;
+            else kind = 2;
         }
-    } else {
-        // Fast path: f = nac[bin of A] * {ibg | ibp}[bin of A'].  Most rows of most lookups are
-        // "constant": inactive in row order (A = 0) AND inside the zero run of A' with the padding
-        // value as S', so f = c0 = nac[k_zero]*ibp[k_zero].  Those rows cost a store and no
-        // multiply; the thread's other rows are walked through a bit mask so that a warp runs as
-        // many multiply rounds as its busiest lane has non-constant rows, not ZI.
-        uint32_t tk[ZI], ck[ZI];
-        ld16(a.tracek + (uint64_t)set * n + row0, tk);
-        ld16(a.codek + (uint64_t)l * n + row0, ck);
-        const uint32_t c0code = k_zero | (CODE_PAD << 30);
-        static_assert(ZI <= 32, "mask");
-        const fr_t *__restrict__ c0pow = a.c0pow + (size_t)l * (ZI + 1);
-        const fr_t c0 = fr_ld(c0pow + 1);
-        uint32_t mask = 0;
-#pragma unroll
-        for (int q = 0; q < ZI; ++q) {
-            const bool nonconst = (tk[q] >> 24) == op || ck[q] != c0code;
-            mask |= (nonconst ? 1u : 0u) << q;
-            if (!nonconst) fr_store_256(zout + 4 * q, c0);
-        }
-        tot = fr_ld(c0pow + (ZI - __popc(mask)));
-        const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n + row0;
-        const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n + row0;
-        auto load_den = [&](int q) -> fr_t {
-            const uint32_t c = ckp[q];
-            const uint32_t k = c & 0x3fffffffu, cls = c >> 30;
-            if (cls == CODE_OTHER) return fr_mul(fr_ld(ib + k), fr_ld(ig + cp[q]));
-            return fr_ld((cls == CODE_FIRST ? ibg : ibp) + k);
-        };
-        auto load_num = [&](int q) -> fr_t {
-            const uint32_t t = tkp[q];
-            return fr_ld(nac + ((t >> 24) == op ? (t & 0xffffffu) : k_zero));
-        };
-        if (mask) {
-            int q = __ffs(mask) - 1;
-            mask &= mask - 1;
-            fr_t num_n = load_num(q), den_n = load_den(q);
-#pragma unroll 1
-            while (true) {
-                const fr_t num = num_n, den = den_n;
-                const int qc = q;
-                const bool more = mask != 0;
-                if (more) {  // operands of the next non-constant row, in flight during the multiplies
-                    q = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    num_n = load_num(q);
-                    den_n = load_den(q);
+        fr_t f = c0;
+        if (kind == 1) f = fr_ld(src);  // one gather for every single-table case
+        if (kind == 4) f = fr_one();
+        if (__any_sync(0xffffffffu, kind == 2 || kind == 3)) {
+            if (kind == 2 || kind == 3) {
+                fr_t den = fr_ld((cls == CODE_FIRST ? ibg : (cls == CODE_PAD ? ibp : ib)) + k);
+                fr_t num = fr_ld((kind == 3 ? dv : nac) + kin);
+                if (cls == CODE_OTHER) den = fr_mul(den, fr_ld(ig + cpp[row]));
+                if (kind == 3) {  // S[i] is a table row: (A+beta)(S+gamma)
+                    const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, (uint32_t)row)), gamma);
+                    num = fr_mul(fr_add(num, beta), sg);
                 }
-                const fr_t f = fr_mul(num, den);
-                fr_store_256(zout + 4 * qc, f);
-                tot = fr_mul(tot, f);
-                if (!more) break;
+                f = fr_mul(num, den);
             }
         }
+        fr_store_256(zout + (row - a.row_begin) * 4, f);
+        const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
+        if (lane == 0) cmask[c] = bal;
+    }
+}
+
+// k_z_chunks: one thread per chunk of ZI rows: product of the chunk's factors = c0^(constant
+// rows) * the non-constant factors (read back; their positions come from the chunk mask, so
+// several loads are in flight ahead of the multiply chain).
+__global__ void __launch_bounds__(128) k_z_chunks(const ZArgs a) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.m) return;
+    const int li = blockIdx.y;
+    const int l = a.first_lookup + li;
+    const uint64_t out_rows = a.row_end - a.row_begin;
+    const uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + e * ZI) * 4;
+    uint32_t mask = a.chunkmask[(size_t)li * a.m + e];
+    fr_t tot = fr_ld(a.c0pow + (size_t)l * (ZI + 1) + (ZI - __popc(mask)));
+    auto next_q = [&]() -> int {
+        if (!mask) return -1;
+        const int q = __ffs(mask) - 1;
+        mask &= mask - 1;
+        return q;
+    };
+    constexpr int D = 3;  // loads in flight
+    int q[D];
+    fr_t f[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        q[j] = next_q();
+        f[j] = fr_one();
+        if (q[j] >= 0) f[j] = fr_load(z + 4 * q[j]);
+    }
+#pragma unroll 1
+    while (q[0] >= 0) {
+        const fr_t cur = f[0];
+#pragma unroll
+        for (int j = 0; j + 1 < D; ++j) {
+            q[j] = q[j + 1];
+            f[j] = f[j + 1];
+        }
+        q[D - 1] = next_q();
+        if (q[D - 1] >= 0) f[D - 1] = fr_load(z + 4 * q[D - 1]);
+        tot = fr_mul(tot, cur);
     }
     fr_st(a.tot + (size_t)li * a.m + e, tot);
 }
@@ -1014,6 +1025,9 @@ __global__ void __launch_bounds__(ZS_T) k_z_down(const ZArgs a) {
     }
 }
 
+#ifndef ZP_OCC
+#define ZP_OCC 5
+#endif
 __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
     if (e >= a.m) return;
@@ -1165,8 +1179,8 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     prof_end(ctx);
     dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
     prof_begin(ctx, "k_inv_merge");
-    k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_ibg,
-                                             c->d_ibp);
+    k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_nac,
+                                             c->d_ibg, c->d_ibp, c->d_nacp, c->d_ibgz, c->d_ibpz);
     prof_end(ctx);
     prof_begin(ctx, "k_z_consts");
     k_z_consts<<<c->sh.n_lookups(), 64, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
@@ -1189,7 +1203,9 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.chal = c->d_chal;
     a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
     a.ibg = c->d_ibg; a.ibp = c->d_ibp;
+    a.nacp = c->d_nacp; a.ibgz = c->d_ibgz; a.ibpz = c->d_ibpz;
     a.meta = c->d_meta;
+    a.chunkmask = c->d_zmask;
     a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
     a.partial = c->d_partial;
     a.carry_in = carry_in;
@@ -1208,8 +1224,16 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
     const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
-    prof_begin(ctx, "k_z_factors");
-    k_z_factors<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    {
+        unsigned gx = cdiv(a.m, 8);  // 8 warps (chunks) per CTA pass
+        const unsigned cap = (unsigned)ctx->sm_count * 16;
+        if (gx > cap) gx = cap;
+        prof_begin(ctx, "k_z_fill");
+        k_z_fill<<<dim3(gx, count), 256, 0, s>>>(a);
+        prof_end(ctx);
+    }
+    prof_begin(ctx, "k_z_chunks");
+    k_z_chunks<<<dim3(cdiv(a.m, 128), count), 128, 0, s>>>(a);
     prof_end(ctx);
     prof_begin(ctx, "k_z_reduce");
     k_z_reduce<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
@@ -1217,7 +1241,7 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
     prof_begin(ctx, "k_z_blocks");
     k_z_blocks<<<count, 32, 0, s>>>(a);
     prof_end(ctx);
-    ctx->launches += 3;
+    ctx->launches += 4;
     return cudaGetLastError();
 }
 
