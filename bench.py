@@ -335,10 +335,14 @@ def run_b200(args):
     alg = {  # algorithmic bytes per launch; None: not a streaming kernel
         "k_advice": nadv * n * 32 + nb * 16,      # every advice cell written once (+ plaintexts)
         "k_permuted": 2 * L * n * 32,             # A', S'
-        "k_z_factors": L * n * 32,                # the per-row factor column it stores
+        "k_z_fill": L * n * 32,                   # the per-row factor column it stores
         "k_z_propagate": 2 * L * n * 32,          # factors read, Z written
         "k_lookup_hist": 2 * (nadv // 3) * n * 4, # trace words read, bin words written
     }
+    # Fr-arithmetic kernels: Montgomery multiplies per launch where the count is exact, against the
+    # multiply throughput measured on this chip (profiles/microbench/RESULTS.md: 67 Gmul/s)
+    MUL_PEAK_G = 67.0
+    muls = {"k_z_propagate": L * n}           # one multiply per row: the stored running product
     kernels = []
     for name, (cnt, ms) in prof.items():
         per_launch = ms / cnt
@@ -347,6 +351,10 @@ def run_b200(args):
         if name in alg:
             gbs = alg[name] / (per_launch * 1e-3) / 1e9
             row.update({"algorithmic_bytes": alg[name], "achieved_gbs": gbs, "frac": gbs / peak})
+        if name in muls:
+            gm = muls[name] / (per_launch * 1e-3) / 1e9
+            row.update({"fr_multiplies": muls[name], "achieved_gmul_s": gm,
+                        "imad_frac_of_measured_mul_peak": gm / MUL_PEAK_G})
         kernels.append(row)
     dom = max(kernels, key=lambda x: x["ms_per_step"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom.get("achieved_gbs"),
