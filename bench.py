@@ -335,14 +335,13 @@ def run_b200(args):
     alg = {  # algorithmic bytes per launch; None: not a streaming kernel
         "k_advice": nadv * n * 32 + nb * 16,      # every advice cell written once (+ plaintexts)
         "k_permuted": 2 * L * n * 32,             # A', S'
-        "k_z_fill": L * n * 32,                   # the per-row factor column it stores
-        "k_z_propagate": 2 * L * n * 32,          # factors read, Z written
+        "k_z_propagate": L * n * 32,              # Z written (non-constant factors read: data dependent)
         "k_lookup_hist": 2 * (nadv // 3) * n * 4, # trace words read, bin words written
     }
     # Fr-arithmetic kernels: Montgomery multiplies per launch where the count is exact, against the
     # multiply throughput measured on this chip (profiles/microbench/RESULTS.md: 67 Gmul/s)
     MUL_PEAK_G = 67.0
-    muls = {"k_z_propagate": L * n}           # one multiply per row: the stored running product
+    muls = {}  # (no kernel left with an input-independent multiply count)
     kernels = []
     for name, (cnt, ms) in prof.items():
         per_launch = ms / cnt

@@ -342,7 +342,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
-                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_c0pow,
+                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
                     c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_zmask,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
@@ -574,7 +574,6 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_nacp, VB));
     CU(ctx, dalloc(&c->d_ibgz, VB));
     CU(ctx, dalloc(&c->d_ibpz, VB));
-    CU(ctx, dalloc(&c->d_c0pow, L * 33));
     CU(ctx, dalloc(&c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n()));
     CU(ctx, dalloc(&c->d_codek, L * c->sh.n()));
     CU(ctx, dalloc(&c->d_codep, L * c->sh.n()));

@@ -762,25 +762,6 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
     fr_st(ibpz + o + k, fr_mul(nac_zero, p));
 }
 
-// c0pow[l][j] = (nac[k_zero] * ibp[k_zero])^j, j = 0..ZI: the factor of a row that is inactive in
-// row order and sits in the zero run of A' with the padding value as S' (one lane per power)
-__global__ void __launch_bounds__(64)
-k_z_consts(Shape sh, const LookupMeta *__restrict__ meta, const fr_t *__restrict__ nac,
-           const fr_t *__restrict__ ibp, fr_t *__restrict__ c0pow, int zi) {
-    const int l = blockIdx.x, j = threadIdx.x;
-    if (j > zi) return;
-    const uint32_t op = (uint32_t)(l % sh.ops_per_set()) + 1;
-    const size_t vo = (size_t)view_of_op(op) * BIN_STRIDE;
-    const uint32_t kz = meta[l].k_zero;
-    const fr_t c0 = fr_mul(fr_ld(nac + vo + kz), fr_ld(ibp + vo + kz));
-    fr_t acc = fr_one(), base = c0;
-    for (int e = j; e; e >>= 1) {
-        if (e & 1) acc = fr_mul(acc, base);
-        base = fr_mul(base, base);
-    }
-    fr_st(c0pow + (size_t)l * (zi + 1) + j, acc);
-}
-
 // ---------------------------------------------------------------------------------------------
 // phase 2b: grand product Z as factor -> scan -> propagate (no spin-waits, no barriers on the
 // hot path; ~3.2 Montgomery multiplies per row):
@@ -816,19 +797,19 @@ struct ZArgs {
     fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
     fr_t *partial;    // [L] product of all factors of the row range
     const fr_t *carry_in;  // [L] or null
-    const fr_t *c0pow;     // [L][ZI+1] powers of the constant factor nac[k_zero]*ibp[k_zero]
     uint64_t m, nblk;
     uint64_t *Z;
     uint64_t row_begin, row_end;
 };
 
-// k_z_fill: one lane per row (coalesced 4-byte reads of the row's two code words, coalesced
-// 256-bit store of its factor).  Most rows are "constant": inactive in row order (A = 0) AND
-// inside the zero run of A' with the padding value as S', so f = c0 = nac[k_zero]*ibp[k_zero].
-// Of the rest, almost all have one constant operand and read their factor from a merged table
+// k_z_fill: one lane per row (coalesced 4-byte reads of the row's two code words).  Most rows are
+// "constant": inactive in row order (A = 0, S = padding value) AND inside the zero run of A' with
+// the padding value as S' — numerator and denominator are the same two terms, so the factor is
+// EXACTLY ONE and the row costs no multiply and no store anywhere in the pipeline.  Of the other
+// rows almost all have one constant operand and read their factor from a merged table
 // (k_inv_merge); only rows that are both active and outside the zero run (or inside the table
-// rows, where S varies) multiply.  Also emits one bit per row (non-constant) as a 32-bit word
-// per chunk of ZI rows for k_z_chunks.
+// rows, where S varies) multiply.  Non-constant factors are stored at the row's slot of the Z
+// buffer; one bit per row (non-constant) goes to a 32-bit word per chunk of ZI rows.
 static_assert(ZI == 32, "one warp ballot = one chunk mask");
 #ifndef ZFILL_OCC
 #define ZFILL_OCC 6
@@ -855,7 +836,6 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
     const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n;
     const uint32_t *__restrict__ cpp = a.codep + (uint64_t)l * n;
     const uint32_t c0code = k_zero | (CODE_PAD << 30);
-    const fr_t c0 = fr_ld(a.c0pow + (size_t)l * (ZI + 1) + 1);
     const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
     uint64_t *__restrict__ zout = a.Z + (size_t)li * out_rows * 4;
     uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.m;
@@ -865,13 +845,11 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
     for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
          c += warps) {
         const uint64_t row = a.row_begin + c * ZI + lane;
-        // classify: 0 constant (c0), 1 single table entry at `src`, 2 nac[kin] * den, 3 table row
-        int kind = 1;
+        // classify: 0 factor one, 1 single table entry at `src`, 2 nac[kin] * den, 3 table row
+        int kind = 0;  // also the blinding rows (their Z entries are zeroed by k_z_propagate)
         const fr_t *src = nullptr;
         uint32_t kin = k_zero, k = 0, cls = CODE_FIRST;
-        if (row >= usable) {
-            kind = 4;  // blinding rows: factor one (their Z entries are zeroed later)
-        } else {
+        if (row < usable) {
             const uint32_t t = tkp[row], ck = ckp[row];
             const bool active = (t >> 24) == op;
             if (active) kin = t & 0xffffffu;
@@ -879,14 +857,13 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
             cls = ck >> 30;
             if ((uint32_t)row < TABLE_ROWS) kind = 3;
             else if (ck == c0code) { kind = active ? 1 : 0; src = nacp + kin; }
-            else if (!active && cls != CODE_OTHER) src = (cls == CODE_FIRST ? ibgz : ibpz) + k;
+            else if (!active && cls != CODE_OTHER) { kind = 1; src = (cls == CODE_FIRST ? ibgz : ibpz) + k; }
             else kind = 2;
         }
-        fr_t f = c0;
+        fr_t f;
         if (kind == 1) f = fr_ld(src);  // one gather for every single-table case
-        if (kind == 4) f = fr_one();
-        if (__any_sync(0xffffffffu, kind == 2 || kind == 3)) {
-            if (kind == 2 || kind == 3) {
+        if (__any_sync(0xffffffffu, kind >= 2)) {
+            if (kind >= 2) {
                 fr_t den = fr_ld((cls == CODE_FIRST ? ibg : (cls == CODE_PAD ? ibp : ib)) + k);
                 fr_t num = fr_ld((kind == 3 ? dv : nac) + kin);
                 if (cls == CODE_OTHER) den = fr_mul(den, fr_ld(ig + cpp[row]));
@@ -897,24 +874,35 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
                 f = fr_mul(num, den);
             }
         }
-        fr_store_256(zout + (row - a.row_begin) * 4, f);
+        if (kind != 0) fr_store_256(zout + (row - a.row_begin) * 4, f);
         const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
         if (lane == 0) cmask[c] = bal;
     }
+}
+
+// Thread slot -> chunk for the chunk-per-thread kernels.  The rows a lookup is active on repeat
+// with the AES block (1360 rows = 42.5 chunks), so chunks 85 apart have the same number of
+// non-constant rows; the 32 lanes of a warp take chunks r, r+85, r+170, ... and run the same
+// number of multiply rounds (everything outside the zero run of A' is non-constant anyway).
+constexpr uint64_t Z_PERIOD = 85;  // chunks: 2 AES blocks = 2720 rows
+__device__ __forceinline__ uint64_t z_slots(uint64_t m) { return Z_PERIOD * ((m + Z_PERIOD - 1) / Z_PERIOD); }
+__device__ __forceinline__ bool z_chunk_of_slot(uint64_t slot, uint64_t m, uint64_t *e) {
+    const uint64_t per = (m + Z_PERIOD - 1) / Z_PERIOD;
+    *e = slot / per + Z_PERIOD * (slot % per);
+    return slot < Z_PERIOD * per && *e < m;
 }
 
 // k_z_chunks: one thread per chunk of ZI rows: product of the chunk's factors = c0^(constant
 // rows) * the non-constant factors (read back; their positions come from the chunk mask, so
 // several loads are in flight ahead of the multiply chain).
 __global__ void __launch_bounds__(128) k_z_chunks(const ZArgs a) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.m) return;
+    uint64_t e;
+    if (!z_chunk_of_slot((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, a.m, &e)) return;
     const int li = blockIdx.y;
-    const int l = a.first_lookup + li;
     const uint64_t out_rows = a.row_end - a.row_begin;
     const uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + e * ZI) * 4;
     uint32_t mask = a.chunkmask[(size_t)li * a.m + e];
-    fr_t tot = fr_ld(a.c0pow + (size_t)l * (ZI + 1) + (ZI - __popc(mask)));
+    fr_t tot = fr_one();  // constant rows have factor one
     auto next_q = [&]() -> int {
         if (!mask) return -1;
         const int q = __ffs(mask) - 1;
@@ -1025,41 +1013,50 @@ __global__ void __launch_bounds__(ZS_T) k_z_down(const ZArgs a) {
     }
 }
 
+// k_z_propagate: one thread per chunk: Z[row] = running product, which changes only after a
+// non-constant row (mask bit): ZI stores, popc(mask) multiplies.  The factors sit in the Z buffer
+// at the rows they belong to and are fetched ahead of the multiply chain.
 #ifndef ZP_OCC
 #define ZP_OCC 5
 #endif
 __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
-    const uint64_t e = (uint64_t)blockIdx.x * ZF_T + threadIdx.x;
-    if (e >= a.m) return;
+    uint64_t e;
+    if (!z_chunk_of_slot((uint64_t)blockIdx.x * ZF_T + threadIdx.x, a.m, &e)) return;
     const int li = blockIdx.y;
     const uint32_t usable = (uint32_t)a.sh.usable();
     const uint64_t out_rows = a.row_end - a.row_begin;
     const uint64_t row0 = a.row_begin + e * ZI;
     uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
     fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
-#ifndef ZP_PB
-#define ZP_PB 4
-#endif
-    constexpr int PB = ZP_PB;  // factors fetched ahead of the multiply chain
-    static_assert(ZI % PB == 0, "ZI must be a multiple of the prefetch depth");
-    fr_t f[PB];
-#pragma unroll
-    for (int j = 0; j < PB; ++j) f[j] = fr_load(z + 4 * j);
+    uint32_t mask = a.chunkmask[(size_t)li * a.m + e];
+    // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
+    const int nvalid = row0 + ZI <= (uint64_t)usable + 1 ? ZI
+                       : (row0 > usable ? 0 : (int)(usable + 1 - row0));
+    int done = 0;  // rows [0, done) of the chunk are written
+    auto next_q = [&]() -> int {
+        if (!mask) return -1;
+        const int q = __ffs(mask) - 1;
+        mask &= mask - 1;
+        return q;
+    };
+    int q0 = next_q(), q1 = next_q();
+    fr_t f0 = fr_one(), f1 = fr_one();
+    if (q0 >= 0) f0 = fr_load(z + 4 * q0);
+    if (q1 >= 0) f1 = fr_load(z + 4 * q1);
 #pragma unroll 1
-    for (int q = 0; q < ZI; q += PB) {
-        fr_t g[PB];
-#pragma unroll
-        for (int j = 0; j < PB; ++j) g[j] = f[j];
-        if (q + PB < ZI) {
-#pragma unroll
-            for (int j = 0; j < PB; ++j) f[j] = fr_load(z + 4 * (q + PB + j));
-        }
-#pragma unroll
-        for (int j = 0; j < PB; ++j) {
-            // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
-            fr_store_256(z + 4 * (q + j), row0 + q + j <= usable ? cur : fr_zero());
-            cur = fr_mul(cur, g[j]);
-        }
+    while (true) {
+        // rows up to and including the next non-constant row q0 (or the chunk end) get `cur`
+        const int upto = q0 >= 0 ? q0 + 1 : ZI;
+        for (int q = done; q < upto; ++q)
+            fr_store_256(z + 4 * q, q < nvalid ? cur : fr_zero());
+        done = upto;
+        if (q0 < 0) break;
+        const fr_t f = f0;
+        q0 = q1;
+        f0 = f1;
+        q1 = next_q();
+        if (q1 >= 0) f1 = fr_load(z + 4 * q1);
+        cur = fr_mul(cur, f);
     }
 }
 
@@ -1182,12 +1179,7 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_nac,
                                              c->d_ibg, c->d_ibp, c->d_nacp, c->d_ibgz, c->d_ibpz);
     prof_end(ctx);
-    prof_begin(ctx, "k_z_consts");
-    k_z_consts<<<c->sh.n_lookups(), 64, 0, ctx->stream>>>(c->sh, c->d_meta, c->d_nac, c->d_ibp,
-                                                          c->d_c0pow, ZI);
-    prof_end(ctx);
-    static_assert(ZI <= 32 && ZI % 4 == 0, "d_c0pow is allocated as [L][33]; one mask word");
-    ctx->launches += 3;
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 
@@ -1209,7 +1201,6 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
     a.partial = c->d_partial;
     a.carry_in = carry_in;
-    a.c0pow = c->d_c0pow;
     a.m = (row_end - row_begin + ZI - 1) / ZI;
     a.nblk = (a.m + ZS_TILE - 1) / ZS_TILE;
     a.Z = Z;
@@ -1233,7 +1224,7 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
         prof_end(ctx);
     }
     prof_begin(ctx, "k_z_chunks");
-    k_z_chunks<<<dim3(cdiv(a.m, 128), count), 128, 0, s>>>(a);
+    k_z_chunks<<<dim3(cdiv(85 * ((a.m + 84) / 85), 128), count), 128, 0, s>>>(a);
     prof_end(ctx);
     prof_begin(ctx, "k_z_reduce");
     k_z_reduce<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
@@ -1255,7 +1246,7 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
     k_z_down<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
     prof_end(ctx);
     prof_begin(ctx, "k_z_propagate");
-    k_z_propagate<<<dim3(cdiv(a.m, ZF_T), count), ZF_T, 0, s>>>(a);
+    k_z_propagate<<<dim3(cdiv(85 * ((a.m + 84) / 85), ZF_T), count), ZF_T, 0, s>>>(a);
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();
