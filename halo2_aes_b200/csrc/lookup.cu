@@ -1217,7 +1217,12 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
     const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
     {
         unsigned gx = cdiv(a.m, 8);  // 8 warps (chunks) per CTA pass
-        const unsigned cap = (unsigned)ctx->sm_count * 16;
+#ifndef ZFILL_CAP
+#define ZFILL_CAP 4
+#endif
+        // few, long-lived CTAs: the per-CTA prologue (challenges, table pointers) is ~100
+        // instructions and a chunk only ~150
+        const unsigned cap = (unsigned)ctx->sm_count * ZFILL_CAP;
         if (gx > cap) gx = cap;
         prof_begin(ctx, "k_z_fill");
         k_z_fill<<<dim3(gx, count), 256, 0, s>>>(a);
