@@ -909,7 +909,10 @@ __global__ void __launch_bounds__(128) k_z_chunks(const ZArgs a) {
         mask &= mask - 1;
         return q;
     };
-    constexpr int D = 3;  // loads in flight
+#ifndef ZC_DEPTH
+#define ZC_DEPTH 2
+#endif
+    constexpr int D = ZC_DEPTH;  // loads in flight
     int q[D];
     fr_t f[D];
 #pragma unroll
@@ -1039,23 +1042,34 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
         mask &= mask - 1;
         return q;
     };
-    int q0 = next_q(), q1 = next_q();
-    fr_t f0 = fr_one(), f1 = fr_one();
-    if (q0 >= 0) f0 = fr_load(z + 4 * q0);
-    if (q1 >= 0) f1 = fr_load(z + 4 * q1);
+#ifndef ZP_DEPTH
+#define ZP_DEPTH 2
+#endif
+    constexpr int D = ZP_DEPTH;  // factor loads in flight ahead of the multiply chain
+    int qn[D];
+    fr_t fn[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        qn[j] = next_q();
+        fn[j] = fr_one();
+        if (qn[j] >= 0) fn[j] = fr_load(z + 4 * qn[j]);
+    }
 #pragma unroll 1
     while (true) {
-        // rows up to and including the next non-constant row q0 (or the chunk end) get `cur`
-        const int upto = q0 >= 0 ? q0 + 1 : ZI;
+        // rows up to and including the next non-constant row (or the chunk end) get `cur`
+        const int upto = qn[0] >= 0 ? qn[0] + 1 : ZI;
         for (int q = done; q < upto; ++q)
             fr_store_256(z + 4 * q, q < nvalid ? cur : fr_zero());
         done = upto;
-        if (q0 < 0) break;
-        const fr_t f = f0;
-        q0 = q1;
-        f0 = f1;
-        q1 = next_q();
-        if (q1 >= 0) f1 = fr_load(z + 4 * q1);
+        if (qn[0] < 0) break;
+        const fr_t f = fn[0];
+#pragma unroll
+        for (int j = 0; j + 1 < D; ++j) {
+            qn[j] = qn[j + 1];
+            fn[j] = fn[j + 1];
+        }
+        qn[D - 1] = next_q();
+        if (qn[D - 1] >= 0) fn[D - 1] = fr_load(z + 4 * qn[D - 1]);
         cur = fr_mul(cur, f);
     }
 }
