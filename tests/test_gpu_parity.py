@@ -269,3 +269,37 @@ def test_fr_mul_device_vs_bigint(gpu, orc, ffi):
     rinv = pow(1 << 256, -1, R_MOD)
     for i in range(len(a)):
         assert orc.limbs_to_int(out[i]) == a[i] * b[i] * rinv % R_MOD, i
+
+
+def test_bench_shape_full_capacity(gpu, orc, ffi, challenges):
+    """The benchmarked circuit itself (BASELINE config 4 unit: K=20, N=5, 3853 random blocks):
+    every advice column and one lookup of each kind against the oracle, all 25 grand products
+    through the size-independent closing property Z[n-6] == 1."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    theta, beta, gamma = challenges
+    k, N = 20, 5
+    nb = ffi.layout_query(ffi.KIND_AES, k, N)["capacity_blocks"]
+    assert nb == 3853
+    pts = splitmix_bytes(SEED + 70, 16 * nb).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 71, 16).tobytes()
+    cir = Circuit(gpu, ffi.KIND_AES, k, N)
+    advice, cts = cir.witness(key, torch.from_numpy(pts).cuda())
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
+    assert (cts.cpu().numpy() == ref.ciphertexts()).all()
+    for col in range(16):
+        assert (_host(advice[col]) == ref.advice(col)).all(), col
+    del advice
+    perm = cir.lookup_permuted(theta, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma)
+    cir.lookup_check()
+    one = orc.fr_from_int(1)
+    n = 1 << k
+    zend = _host(Z[:, n - 6])
+    assert (zend == one).all() and (_host(Z[:, 0]) == one).all()
+    for li in (0, 6, 12, 18, 24):   # range, xor, sbox, mul2, mul3 of sets 0..4
+        r = ref.lookup(li, theta, beta, gamma, want=("Ap", "Sp", "Z"))
+        assert (_host(perm["Ap"][li]) == r["Ap"]).all(), ("Ap", li)
+        assert (_host(perm["Sp"][li]) == r["Sp"]).all(), ("Sp", li)
+        assert (_host(Z[li]) == r["Z"]).all(), ("Z", li)
+    cir.close()
