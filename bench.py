@@ -331,17 +331,21 @@ def run_b200(args):
         step(args.warmup + args.steps + j, pipes[0], iso[j])
     prof = pipes[0].ctx.profile_read()
     pipes[0].ctx.profile(False)
+    nc = int(pipes[0].cir.lookup_stats().sum())  # rows whose grand-product factor is not one
     ph_iso = phase_table(iso)
     alg = {  # algorithmic bytes per launch; None: not a streaming kernel
         "k_advice": nadv * n * 32 + nb * 16,      # every advice cell written once (+ plaintexts)
         "k_permuted": 2 * L * n * 32,             # A', S'
-        "k_z_propagate": L * n * 32,              # Z written (non-constant factors read: data dependent)
+        "k_z_fill": L * n * 8 + nc * 32 + L * n // 8,   # 2 code words per row read; non-constant
+                                                         # factors + chunk masks written
+        "k_z_chunks": nc * 32 + L * (n // 32) * 36,     # non-constant factors + masks read, totals written
+        "k_z_propagate": L * n * 32 + nc * 32,          # Z written, non-constant factors read
         "k_lookup_hist": 2 * (nadv // 3) * n * 4, # trace words read, bin words written
     }
     # Fr-arithmetic kernels: Montgomery multiplies per launch where the count is exact, against the
     # multiply throughput measured on this chip (profiles/microbench/RESULTS.md: 67 Gmul/s)
     MUL_PEAK_G = 67.0
-    muls = {}  # (no kernel left with an input-independent multiply count)
+    muls = {"k_z_chunks": nc, "k_z_propagate": nc}  # one multiply per non-constant row each
     kernels = []
     for name, (cnt, ms) in prof.items():
         per_launch = ms / cnt
@@ -392,6 +396,7 @@ def run_b200(args):
             "step_algorithmic_bytes": step_bytes,
             "step_effective_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
             "witness_only_blocks_per_s": nb / (ph_iso["witness"] * 1e-3),
+            "nonconstant_rows": nc, "nonconstant_row_fraction": nc / (L * n),
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
         }
         emit(out)

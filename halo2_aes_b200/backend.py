@@ -190,6 +190,13 @@ class Circuit:
         check(lib().h2aes_lookup_product_dev(self._h, bep, gap, first, count, _ptr(Z)), self.ctx._h)
         return Z
 
+    def lookup_stats(self) -> np.ndarray:
+        """rows per lookup whose grand-product factor is not one (last product call)"""
+        out = np.zeros(self.layout["n_lookups"], np.uint64)
+        check(lib().h2aes_lookup_stats(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))),
+              self.ctx._h)
+        return out
+
     def lookup_check(self):
         """Synchronize and surface device-detected conditions (ERR_LOOKUP / ERR_ZERO_DENOM)."""
         check(lib().h2aes_lookup_check(self._h), self.ctx._h)

@@ -344,7 +344,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
-                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_zmask,
+                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -586,6 +586,8 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     CU(ctx, dalloc(&c->d_meta, L));
     CU(ctx, dalloc(&c->d_ztot, L * c->zm));
     CU(ctx, dalloc(&c->d_zmask, L * c->zm));
+    CU(ctx, dalloc(&c->d_znonconst, L));
+    CU(ctx, cudaMemsetAsync(c->d_znonconst, 0, L * 8, ctx->stream));
     CU(ctx, dalloc(&c->d_zbagg, L * c->znblk));
     CU(ctx, dalloc(&c->d_zbexcl, L * c->znblk));
     CU(ctx, dalloc(&c->d_partial, L));
@@ -769,6 +771,16 @@ int32_t h2aes_lookup_product_host(h2aes_circuit *c, const uint64_t *beta, const 
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return check_device_flags(c);
+}
+
+int32_t h2aes_lookup_stats(h2aes_circuit *c, uint64_t *nonconst_rows) {
+    if (!c || !nonconst_rows) return H2AES_ERR_ARG;
+    if (!c->lk_alloc) return fail(c->ctx, H2AES_ERR_STATE, "no grand product has run yet");
+    CU(c->ctx, cudaSetDevice(c->ctx->device));
+    CU(c->ctx, cudaMemcpyAsync(nonconst_rows, c->d_znonconst, sizeof(uint64_t) * c->sh.n_lookups(),
+                               cudaMemcpyDeviceToHost, c->ctx->stream));
+    CU(c->ctx, cudaStreamSynchronize(c->ctx->stream));
+    return H2AES_OK;
 }
 
 int32_t h2aes_lookup_check(h2aes_circuit *c) {

@@ -133,6 +133,7 @@ struct h2aes_circuit {
     uint32_t *d_lk = nullptr;        // [L][BIN_STRIDE] bin of each leftover slot
     h2::LookupMeta *d_meta = nullptr;  // [L]
     // grand-product scan workspace
+    unsigned long long *d_znonconst = nullptr;  // [L] rows whose factor is not one (last product)
     uint32_t *d_zmask = nullptr;      // [L][zm]   non-constant-row bit masks of the chunks
     h2::fr_t *d_ztot = nullptr;       // [L][zm]   per-thread factor products / their prefixes
     h2::fr_t *d_zbagg = nullptr;      // [L][znblk] block aggregates

@@ -791,7 +791,8 @@ struct ZArgs {
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
     const fr_t *nacp, *ibgz, *ibpz;                      // [3][BIN_STRIDE] one-operand-constant factors
     const LookupMeta *meta;
-    uint32_t *chunkmask;  // [count][m] one bit per row of the chunk: factor is not the constant c0
+    uint32_t *chunkmask;  // [count][m] one bit per row of the chunk: factor is not one
+    unsigned long long *nonconst;  // [L] rows with a factor other than one (statistics)
     fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
     fr_t *bagg;       // [count][nblk] block aggregates of tot
     fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
@@ -841,6 +842,7 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
     uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.m;
     const int lane = threadIdx.x & 31;
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    uint32_t n_nonconst = 0;
     // warp w handles chunks w, w + warps, ... ; chunk c = rows [row_begin + 32c, +32)
     for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
          c += warps) {
@@ -877,7 +879,9 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
         if (kind != 0) fr_store_256(zout + (row - a.row_begin) * 4, f);
         const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
         if (lane == 0) cmask[c] = bal;
+        n_nonconst += __popc(bal);
     }
+    if (lane == 0 && n_nonconst) atomicAdd(a.nonconst + l, (unsigned long long)n_nonconst);
 }
 
 // Thread slot -> chunk for the chunk-per-thread kernels.  The rows a lookup is active on repeat
@@ -1212,6 +1216,7 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.nacp = c->d_nacp; a.ibgz = c->d_ibgz; a.ibpz = c->d_ibpz;
     a.meta = c->d_meta;
     a.chunkmask = c->d_zmask;
+    a.nonconst = c->d_znonconst;
     a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
     a.partial = c->d_partial;
     a.carry_in = carry_in;
@@ -1229,6 +1234,8 @@ cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
     const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
+    cudaError_t e0 = cudaMemsetAsync(c->d_znonconst + first, 0, (size_t)count * 8, s);
+    if (e0) return e0;
     {
         unsigned gx = cdiv(a.m, 8);  // 8 warps (chunks) per CTA pass
 #ifndef ZFILL_CAP

@@ -206,6 +206,11 @@ int32_t h2aes_lookup_product_host(h2aes_circuit *c, const uint64_t *beta, const 
  * stream.  The _host entry points call it themselves. */
 int32_t h2aes_lookup_check(h2aes_circuit *c);
 
+/* statistics of the last grand product, per lookup: rows (of this shard) whose factor
+ * (A+beta)(S+gamma)/((A'+beta)(S'+gamma)) is not identically one — the rows that cost a multiply
+ * in each of the chunk-product and propagate kernels.  Host out, n_lookups entries; synchronizes. */
+int32_t h2aes_lookup_stats(h2aes_circuit *c, uint64_t *nonconst_rows);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-sharded single circuit (one process per GPU, shard g of G owns rows
  * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin
