@@ -113,6 +113,7 @@ SIGNATURES = {
     "h2aes_dbg_fr_add": (C.c_int32, [_u64p, _u64p, _u64p]),
     "h2aes_dbg_fr_sub": (C.c_int32, [_u64p, _u64p, _u64p]),
     "h2aes_dbg_fr_inv": (C.c_int32, [_u64p, _u64p]),
+    "h2aes_dbg_fr_inv_fermat": (C.c_int32, [_u64p, _u64p]),
     "h2aes_dbg_fr_from_u64": (C.c_int32, [C.c_uint64, _u64p]),
     "h2aes_dbg_fr_to_canonical": (C.c_int32, [_u64p, _u64p]),
     "h2aes_dbg_fr_mul_dev": (C.c_int32, [_vp, _u64p, _u64p, C.c_uint64, _u64p]),

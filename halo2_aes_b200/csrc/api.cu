@@ -893,6 +893,11 @@ int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out) {
     fr_to_limbs(fr_inv(fr_from_limbs(a)), out);
     return H2AES_OK;
 }
+int32_t h2aes_dbg_fr_inv_fermat(const uint64_t *a, uint64_t *out) {
+    if (!a || !out) return H2AES_ERR_ARG;
+    fr_to_limbs(fr_inv_fermat(fr_from_limbs(a)), out);
+    return H2AES_OK;
+}
 int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out) {
     if (!out) return H2AES_ERR_ARG;
     fr_t a = fr_zero();

@@ -168,6 +168,28 @@ k_bucket_scatter(const fr_t *__restrict__ canon, const uint32_t *__restrict__ vi
     fr_st(canon_b + (size_t)v * BIN_STRIDE + pos, me);  // bucket mates contiguous for k_bucket_rank
 }
 
+// branch-free 256-bit compare of canonical values: *lt = (a < b) from one borrow chain, *eq from
+// the OR of the difference words
+__device__ __forceinline__ void fr_lt_eq(const fr_t &a, const fr_t &b, uint32_t *lt, uint32_t *eq) {
+    uint32_t d0, d1, d2, d3, d4, d5, d6, d7, borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(d4), "=r"(d5), "=r"(d6), "=r"(d7),
+          "=r"(borrow)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+          "r"(a.v[6]), "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]),
+          "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    *lt = borrow & 1u;  // 0xffffffff when a - b borrowed
+    *eq = ((d0 | d1 | d2 | d3 | d4 | d5 | d6 | d7) == 0u) ? 1u : 0u;
+}
+
 // exact position of the entry at bucket slot p: bucket offset + number of bucket mates that order
 // before it (ties broken by entry index).  Buckets can be large: the 256 values tag*theta^2 +
 // x*theta + y, y = 0..255, of one x are consecutive integers and share their leading bits.  The
@@ -208,9 +230,10 @@ k_bucket_rank(const fr_t *__restrict__ canon_b, const uint32_t *__restrict__ vie
     for (uint32_t q = lo; q < hi; ++q) {
         const uint32_t wq = q - w_lo;  // lo >= w_lo by construction
         const fr_t other = wq < w_n ? fr_load_s(s_c + 2 * wq) : fr_ld(cb + q);
-        const int cmp = fr_cmp_canonical(other, me);
-        if (cmp < 0) rank += 1;
-        else if (cmp == 0 && q != p && sl[q] < e) rank += 1;
+        uint32_t lt, eq;
+        fr_lt_eq(other, me, &lt, &eq);
+        rank += lt;
+        if (eq && q != p && sl[q] < e) rank += 1;  // ties (equal values) ordered by entry index
     }
     sorted[(size_t)v * BIN_STRIDE + lo + rank] = e;
 }
@@ -899,7 +922,10 @@ __device__ __forceinline__ bool z_chunk_of_slot(uint64_t slot, uint64_t m, uint6
 // k_z_chunks: one thread per chunk of ZI rows: product of the chunk's factors = c0^(constant
 // rows) * the non-constant factors (read back; their positions come from the chunk mask, so
 // several loads are in flight ahead of the multiply chain).
-__global__ void __launch_bounds__(128) k_z_chunks(const ZArgs a) {
+#ifndef ZC_OCC
+#define ZC_OCC 4
+#endif
+__global__ void __launch_bounds__(128, ZC_OCC) k_z_chunks(const ZArgs a) {
     uint64_t e;
     if (!z_chunk_of_slot((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, a.m, &e)) return;
     const int li = blockIdx.y;
@@ -1062,6 +1088,9 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     while (true) {
         // rows up to and including the next non-constant row (or the chunk end) get `cur`
         const int upto = qn[0] >= 0 ? qn[0] + 1 : ZI;
+#ifdef EXP_NO_Z_STORE
+        if (upto == 99)
+#endif
         for (int q = done; q < upto; ++q)
             fr_store_256(z + 4 * q, q < nvalid ? cur : fr_zero());
         done = upto;

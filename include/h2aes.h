@@ -244,7 +244,8 @@ int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathere
 int32_t h2aes_dbg_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t *out);
 int32_t h2aes_dbg_fr_add(const uint64_t *a, const uint64_t *b, uint64_t *out);
 int32_t h2aes_dbg_fr_sub(const uint64_t *a, const uint64_t *b, uint64_t *out);
-int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out);
+int32_t h2aes_dbg_fr_inv(const uint64_t *a, uint64_t *out);        /* binary extended Euclid */
+int32_t h2aes_dbg_fr_inv_fermat(const uint64_t *a, uint64_t *out); /* a^(r-2), cross-check   */
 int32_t h2aes_dbg_fr_from_u64(uint64_t v, uint64_t *out);
 int32_t h2aes_dbg_fr_to_canonical(const uint64_t *a, uint64_t *out);
 /* n Montgomery products out[i] = a[i]*b[i] computed ON THE DEVICE by the kernels' multiply

@@ -219,3 +219,21 @@ def test_active_rows_equal_selector_sums(ffi, orc):
             out = C.c_uint64()
             assert ffi.lib().h2aes_active_rows(kind, k, N, nb, li, C.byref(out)) == 0
             assert out.value == int(sel[li].sum()), (kind, N, nb, li)
+
+
+def test_fr_inv_binary_gcd_vs_fermat_and_bigint(ffi, orc):
+    """fr_inv (binary extended Euclid, what k_inv_tables runs) == a^(r-2) == pow(a, -1, r)."""
+    L = ffi.lib()
+    rng = np.random.default_rng(SEED + 5)
+    vals = [0, 1, 2, 3, R_MOD - 1, R_MOD - 2, (R_MOD + 1) // 2, 1 << 253, (1 << 256) % R_MOD,
+            0xFFFFFFFF, 1 << 32, (1 << 64) - 1]
+    vals += [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(400)]
+    vals += [int(x) for x in rng.integers(1, 1 << 20, 50)]
+    out, out2 = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
+    for i, a in enumerate(vals):
+        A = orc.fr_from_int(a)
+        assert L.h2aes_dbg_fr_inv(_p(A, u64p), _p(out, u64p)) == 0
+        assert orc.fr_to_int(out) == (pow(a, -1, R_MOD) if a else 0), hex(a)
+        if i < 60:
+            assert L.h2aes_dbg_fr_inv_fermat(_p(A, u64p), _p(out2, u64p)) == 0
+            assert (out == out2).all()
