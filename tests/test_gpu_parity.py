@@ -303,3 +303,16 @@ def test_bench_shape_full_capacity(gpu, orc, ffi, challenges):
         assert (_host(perm["Sp"][li]) == r["Sp"]).all(), ("Sp", li)
         assert (_host(Z[li]) == r["Z"]).all(), ("Z", li)
     cir.close()
+
+
+@pytest.mark.parametrize("theta_int", [1, 2, 255])
+def test_degenerate_theta_merges_equal_values(gpu, orc, ffi, theta_int):
+    """With a tiny theta many different table tuples compress to the SAME field element
+    (theta = 1: tag+x+y+z).  halo2 works on values, not on table rows, so bins must be merged by
+    value and an input may match several table rows — the collision-heavy edge case of the
+    permuted columns."""
+    theta = orc.fr_from_int(theta_int)
+    beta, gamma = orc.fr_from_int(5), orc.fr_from_int(7)
+    pts = splitmix_bytes(SEED + 90, 16 * 30).reshape(-1, 16)
+    _run_case(gpu, orc, ffi, ffi.KIND_AES, 17, 1, splitmix_bytes(SEED + 91, 16).tobytes(), pts,
+              (theta, beta, gamma))
