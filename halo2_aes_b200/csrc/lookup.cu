@@ -912,7 +912,6 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
 // non-constant rows; the 32 lanes of a warp take chunks r, r+85, r+170, ... and run the same
 // number of multiply rounds (everything outside the zero run of A' is non-constant anyway).
 constexpr uint64_t Z_PERIOD = 85;  // chunks: 2 AES blocks = 2720 rows
-__device__ __forceinline__ uint64_t z_slots(uint64_t m) { return Z_PERIOD * ((m + Z_PERIOD - 1) / Z_PERIOD); }
 __device__ __forceinline__ bool z_chunk_of_slot(uint64_t slot, uint64_t m, uint64_t *e) {
     const uint64_t per = (m + Z_PERIOD - 1) / Z_PERIOD;
     *e = slot / per + Z_PERIOD * (slot % per);
@@ -1088,9 +1087,6 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     while (true) {
         // rows up to and including the next non-constant row (or the chunk end) get `cur`
         const int upto = qn[0] >= 0 ? qn[0] + 1 : ZI;
-#ifdef EXP_NO_Z_STORE
-        if (upto == 99)
-#endif
         for (int q = done; q < upto; ++q)
             fr_store_256(z + 4 * q, q < nvalid ? cur : fr_zero());
         done = upto;
