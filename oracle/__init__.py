@@ -84,6 +84,9 @@ def lib():
             [C.c_int] * 3 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int, C.c_int,
                              C.POINTER(C.c_double), u64p]
         )
+        L.orc_perm_shape.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int32)] * 3
+        L.orc_permutation.argtypes = [C.c_void_p, u64p, u64p, u64p, C.POINTER(C.c_uint32), u64p]
+        L.orc_domain_constants.argtypes = [C.c_int, u64p, u64p]
         L.orc_bench_batch.argtypes = (
             [C.c_int] * 4 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int,
                              C.POINTER(C.c_double), u64p]
@@ -130,6 +133,22 @@ def shape(kind: int, k: int, N: int) -> dict:
         raise OracleError(rc)
     return dict(n_advice=out[0], n_fixed=out[1], n_selectors=out[2], n_lookups=out[3],
                 n_sets=out[4], n=1 << k, usable=(1 << k) - 6)
+
+
+def perm_shape(kind: int, k: int, N: int) -> dict:
+    """columns of the permutation argument in enable_equality order, chunking"""
+    out = (C.c_int32 * 3)()
+    types = (C.c_int32 * 256)()
+    idx = (C.c_int32 * 256)()
+    lib().orc_perm_shape(kind, k, N, out, types, idx)
+    return dict(n_columns=out[0], chunk_len=out[1], n_sets=out[2],
+                columns=[("advice" if types[i] == 0 else "fixed", idx[i]) for i in range(out[0])])
+
+
+def domain_constants(k: int):
+    om, de = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
+    lib().orc_domain_constants(k, _u64(om), _u64(de))
+    return om, de
 
 
 def tables(fips: bool = False):
@@ -238,6 +257,29 @@ class Circuit:
         if rc:
             raise OracleError(rc)
         return bufs
+
+    def permutation(self, beta, gamma, want=("sigma", "mapping", "Z")) -> dict:
+        """halo2 v0.3.0 permutation argument: sigma columns (keygen), the (column, row) mapping
+        they encode, and the grand products Z_perm (one per chunk of 3 columns)."""
+        ps = perm_shape(self.kind, self.k, self.N)
+        out = {}
+        null64 = C.POINTER(C.c_uint64)()
+        null32 = C.POINTER(C.c_uint32)()
+        if "sigma" in want:
+            out["sigma"] = np.zeros((ps["n_columns"], self.n, 4), np.uint64)
+        if "mapping" in want:
+            out["mapping"] = np.zeros((ps["n_columns"], self.n, 2), np.uint32)
+        if "Z" in want:
+            out["Z"] = np.zeros((ps["n_sets"], self.n, 4), np.uint64)
+        be = np.ascontiguousarray(beta, dtype=np.uint64)
+        ga = np.ascontiguousarray(gamma, dtype=np.uint64)
+        rc = lib().orc_permutation(
+            self._h, _u64(be), _u64(ga), _u64(out["sigma"]) if "sigma" in out else null64,
+            out["mapping"].ctypes.data_as(C.POINTER(C.c_uint32)) if "mapping" in out else null32,
+            _u64(out["Z"]) if "Z" in out else null64)
+        if rc:
+            raise OracleError(rc)
+        return out
 
     def mock_verify(self):
         where = np.zeros(2, np.uint64)

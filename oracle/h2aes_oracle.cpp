@@ -654,6 +654,153 @@ static void commit_product(const Shape &sh, const std::vector<Fr> &A, const std:
 }
 
 // ---------------------------------------------------------------------------------------------
+// [UPSTREAM] permutation argument (plonk/permutation/keygen.rs Assembly + prover.rs commit),
+// halo2_proofs v0.3.0 without the "thread-safe-region" feature (the reference enables only
+// derive_serde, dev-graph, cost-estimator: Cargo.toml:14-18).  SURVEY 8(f) item 1.
+// ---------------------------------------------------------------------------------------------
+// halo2curves 0.6.1 bn256::Fr constants [UPSTREAM]: MULTIPLICATIVE_GENERATOR = 7, S = 28,
+// ROOT_OF_UNITY = 7^((r-1)/2^28), DELTA = 7^(2^28)  (both re-derived from 7 in
+// tests/test_oracle_golden.py).
+static const uint64_t ROOT_OF_UNITY_CANON[4] = {0xd34f1ed960c37c9cull, 0x3215cf6dd39329c8ull,
+                                                0x98865ea93dd31f74ull, 0x03ddb9f5166d18b7ull};
+static const uint64_t DELTA_CANON[4] = {0x870e56bbe533e9a2ull, 0x5b5f898e5e963f25ull,
+                                        0x64ec26aad4c86e71ull, 0x09226b6e22c6f0caull};
+
+static Fr fr_of_canon(const uint64_t c[4]) {
+    Fr o;
+    fr_from_canonical(c, &o);
+    return o;
+}
+// EvaluationDomain::new: omega = ROOT_OF_UNITY squared (S - k) times
+static Fr domain_omega(int k) {
+    Fr w = fr_of_canon(ROOT_OF_UNITY_CANON);
+    for (int i = k; i < 28; ++i) w = fr_mul(w, w);
+    return w;
+}
+
+struct PermColumn {
+    int type;   // 0 advice, 1 fixed
+    int index;
+};
+// order of the enable_equality calls: key_schedule.rs:52-57 (advices[0][0..3], words_column,
+// enable_constant(round_constants)), then aes128.rs:126-130 (every advice column)
+static std::vector<PermColumn> perm_columns(const Shape &sh) {
+    std::vector<PermColumn> c;
+    for (int j = 0; j < 3; ++j) c.push_back(PermColumn{0, j});
+    c.push_back(PermColumn{0, sh.words_column()});
+    c.push_back(PermColumn{1, sh.rc_column()});
+    if (sh.kind == KIND_AES)
+        for (int a = 3; a < 3 * sh.N; ++a) c.push_back(PermColumn{0, a});
+    return c;
+}
+// cs.degree() = max(permutation 3, lookups max(4, 2 + 2 + 1) = 5, gate 2..3) = 5 -> chunk_len 3
+static const int PERM_CHUNK = 3;
+
+// [UPSTREAM] permutation::keygen::Assembly
+struct Assembly {
+    size_t n;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> mapping, aux;
+    std::vector<std::vector<uint32_t>> sizes;
+    Assembly(size_t n_, size_t ncols) : n(n_) {
+        mapping.resize(ncols);
+        for (size_t i = 0; i < ncols; ++i) {
+            mapping[i].resize(n);
+            for (size_t j = 0; j < n; ++j) mapping[i][j] = {(uint32_t)i, (uint32_t)j};
+        }
+        aux = mapping;
+        sizes.assign(ncols, std::vector<uint32_t>(n, 1));
+    }
+    void copy(uint32_t lc, uint32_t lr, uint32_t rc, uint32_t rr) {
+        auto left_cycle = aux[lc][lr], right_cycle = aux[rc][rr];
+        if (left_cycle == right_cycle) return;
+        if (sizes[left_cycle.first][left_cycle.second] < sizes[right_cycle.first][right_cycle.second])
+            std::swap(left_cycle, right_cycle);
+        sizes[left_cycle.first][left_cycle.second] += sizes[right_cycle.first][right_cycle.second];
+        auto i = right_cycle;
+        while (true) {
+            aux[i.first][i.second] = left_cycle;
+            i = mapping[i.first][i.second];
+            if (i == right_cycle) break;
+        }
+        std::swap(mapping[lc][lr], mapping[rc][rr]);
+    }
+};
+
+// mapping after all of the circuit's copy constraints, in recording order
+static Assembly build_assembly(const Synth &syn, const std::vector<PermColumn> &cols) {
+    const Shape &sh = syn.sh;
+    std::vector<int> pos_of_advice(sh.n_advice(), -1);
+    for (size_t i = 0; i < cols.size(); ++i)
+        if (cols[i].type == 0) pos_of_advice[cols[i].index] = (int)i;
+    Assembly as(syn.n, cols.size());
+    for (const Copy &cp : syn.copies)  // constrain_equal(left = new cell, right = source cell)
+        as.copy((uint32_t)pos_of_advice[cp.col_a], (uint32_t)cp.row_a,
+                (uint32_t)pos_of_advice[cp.col_b], (uint32_t)cp.row_b);
+    return as;
+}
+
+// [UPSTREAM] Assembly::build_pk: sigma_i(omega^j) = delta^{i'} omega^{j'}, (i', j') = mapping[i][j]
+static void build_sigma(const Synth &syn, const std::vector<PermColumn> &cols,
+                        std::vector<std::vector<Fr>> &sigma, std::vector<uint32_t> *map_out) {
+    Assembly as = build_assembly(syn, cols);
+    const size_t n = syn.n;
+    const Fr omega = domain_omega(syn.sh.k), delta = fr_of_canon(DELTA_CANON);
+    std::vector<Fr> omega_pow(n), delta_pow(cols.size());
+    Fr cur = FR_ONE;
+    for (size_t j = 0; j < n; ++j) { omega_pow[j] = cur; cur = fr_mul(cur, omega); }
+    cur = FR_ONE;
+    for (size_t i = 0; i < cols.size(); ++i) { delta_pow[i] = cur; cur = fr_mul(cur, delta); }
+    sigma.assign(cols.size(), std::vector<Fr>(n));
+    if (map_out) map_out->assign(2 * cols.size() * n, 0);
+    for (size_t i = 0; i < cols.size(); ++i)
+        for (size_t j = 0; j < n; ++j) {
+            auto m = as.mapping[i][j];
+            sigma[i][j] = fr_mul(delta_pow[m.first], omega_pow[m.second]);
+            if (map_out) {
+                (*map_out)[2 * (i * n + j)] = m.first;
+                (*map_out)[2 * (i * n + j) + 1] = m.second;
+            }
+        }
+}
+
+// [UPSTREAM] permutation::Argument::commit: one grand product per chunk of PERM_CHUNK columns,
+// chained through last_z = z[n - 6].  The 5 blinding entries of every z are left zero here.
+static void permutation_product(const Columns &c, const std::vector<PermColumn> &cols,
+                                const std::vector<std::vector<Fr>> &sigma, const Fr &beta,
+                                const Fr &gamma, std::vector<std::vector<Fr>> &Z) {
+    const size_t n = c.sh.n();
+    const Fr omega = domain_omega(c.sh.k), delta = fr_of_canon(DELTA_CANON);
+    Fr deltaomega0 = FR_ONE, last_z = FR_ONE;
+    Z.clear();
+    for (size_t base = 0; base < cols.size(); base += PERM_CHUNK) {
+        const size_t cnt = std::min((size_t)PERM_CHUNK, cols.size() - base);
+        std::vector<Fr> mv(n, FR_ONE);
+        for (size_t t = 0; t < cnt; ++t) {
+            const PermColumn &pc = cols[base + t];
+            const Fr *v = pc.type == 0 ? c.advice[pc.index] : c.fixed[pc.index];
+            for (size_t i = 0; i < n; ++i)
+                mv[i] = fr_mul(mv[i], fr_add(fr_add(fr_mul(beta, sigma[base + t][i]), gamma), v[i]));
+        }
+        fr_batch_invert(mv);
+        for (size_t t = 0; t < cnt; ++t) {
+            const PermColumn &pc = cols[base + t];
+            const Fr *v = pc.type == 0 ? c.advice[pc.index] : c.fixed[pc.index];
+            Fr dw = deltaomega0;
+            for (size_t i = 0; i < n; ++i) {
+                mv[i] = fr_mul(mv[i], fr_add(fr_add(fr_mul(dw, beta), gamma), v[i]));
+                dw = fr_mul(dw, omega);
+            }
+            deltaomega0 = fr_mul(deltaomega0, delta);
+        }
+        std::vector<Fr> z(n, FR_ZERO);
+        z[0] = last_z;
+        for (size_t row = 1; row < n - 5; ++row) z[row] = fr_mul(z[row - 1], mv[row - 1]);
+        last_z = z[n - 6];
+        Z.push_back(std::move(z));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // [UPSTREAM] MockProver::verify restated for this constraint system.
 // Returns 0 when satisfied; otherwise a failure class (100 gate, 200 lookup, 300 copy,
 // 400 assignment in unusable rows) and fills `where` with (index,row).
@@ -874,6 +1021,46 @@ int orc_mock_verify_ext(int kind, int k, int N, const uint64_t *advice, const ui
         cp[i] = Copy{(uint32_t)copies[4 * i], copies[4 * i + 1], (uint32_t)copies[4 * i + 2],
                      copies[4 * i + 3]};
     return mock_verify(cols, cp.data(), cp.size(), where);
+}
+
+// permutation argument of the circuit's own columns: ncols/nsets via orc_perm_shape;
+// sigma [ncols][n][4], mapping [ncols][n][2] (u32 column position, row), Z [nsets][n][4]; any
+// output may be NULL.
+int orc_perm_shape(int kind, int k, int N, int32_t out[3], int32_t *col_types, int32_t *col_indices) {
+    Shape sh{kind, k, N};
+    std::vector<PermColumn> cols = perm_columns(sh);
+    out[0] = (int32_t)cols.size();
+    out[1] = PERM_CHUNK;
+    out[2] = (int32_t)((cols.size() + PERM_CHUNK - 1) / PERM_CHUNK);
+    for (size_t i = 0; i < cols.size(); ++i) {
+        if (col_types) col_types[i] = cols[i].type;
+        if (col_indices) col_indices[i] = cols[i].index;
+    }
+    return ORC_OK;
+}
+int orc_permutation(void *h, const uint64_t *beta, const uint64_t *gamma, uint64_t *sigma_out,
+                    uint32_t *mapping_out, uint64_t *Z_out) {
+    Circuit *c = (Circuit *)h;
+    std::vector<PermColumn> cols = perm_columns(c->s.sh);
+    std::vector<std::vector<Fr>> sigma, Z;
+    std::vector<uint32_t> map;
+    build_sigma(c->s, cols, sigma, mapping_out ? &map : nullptr);
+    const size_t n = c->s.n;
+    if (sigma_out)
+        for (size_t i = 0; i < cols.size(); ++i) memcpy(sigma_out + 4 * i * n, sigma[i].data(), n * 32);
+    if (mapping_out) memcpy(mapping_out, map.data(), map.size() * 4);
+    if (Z_out) {
+        Columns cv = view_of(c->s);
+        permutation_product(cv, cols, sigma, fr_load(beta), fr_load(gamma), Z);
+        for (size_t sidx = 0; sidx < Z.size(); ++sidx)
+            memcpy(Z_out + 4 * sidx * n, Z[sidx].data(), n * 32);
+    }
+    return ORC_OK;
+}
+void orc_domain_constants(int k, uint64_t omega[4], uint64_t delta[4]) {
+    Fr w = domain_omega(k), d = fr_of_canon(DELTA_CANON);
+    memcpy(omega, w.l, 32);
+    memcpy(delta, d.l, 32);
 }
 
 // ---- small Fr helpers so Python tests can do field arithmetic through the same code ----------
