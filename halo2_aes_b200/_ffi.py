@@ -80,6 +80,8 @@ SIGNATURES = {
     "h2aes_copy_count": (C.c_int32, [C.c_int32, C.c_uint64, _u64p]),
     "h2aes_copy_constraints_host": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                                  C.c_uint64, C.c_uint64, _u64p]),
+    "h2aes_perm_query": (C.c_int32, [C.c_int32] * 3 + [C.POINTER(C.c_int32)] * 5),
+    "h2aes_perm_mapping_host": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _u32p]),
     "h2aes_ctx_create": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "h2aes_ctx_destroy": (C.c_int32, [_vp]),
     "h2aes_ctx_set_stream": (C.c_int32, [_vp, _vp]),

@@ -7,6 +7,7 @@
 // implementation of any column here: without a CUDA device every compute entry point fails.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -218,6 +219,76 @@ int32_t h2aes_copy_constraints_host(int32_t kind, int32_t k, int32_t N, uint64_t
         out[4 * i + 1] = cp.dst.row;
         out[4 * i + 2] = cp.src.col;
         out[4 * i + 3] = cp.src.row;
+    }
+    return H2AES_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// permutation argument: host-side, input-independent bookkeeping (keygen side)
+// ---------------------------------------------------------------------------------------------
+int32_t h2aes_perm_query(int32_t kind, int32_t k, int32_t N, int32_t *n_columns, int32_t *chunk_len,
+                         int32_t *n_sets, int32_t *is_fixed, int32_t *column_index) {
+    if (!shape_ok(kind, k, N)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    const int nc = perm_n_columns(sh);
+    if (n_columns) *n_columns = nc;
+    if (chunk_len) *chunk_len = PERM_CHUNK;
+    if (n_sets) *n_sets = perm_n_sets(sh);
+    for (int p = 0; p < nc; ++p) {
+        int f, idx;
+        perm_column(sh, p, &f, &idx);
+        if (is_fixed) is_fixed[p] = f;
+        if (column_index) column_index[p] = idx;
+    }
+    return H2AES_OK;
+}
+
+// halo2 keygen `permutation::keygen::Assembly` [UPSTREAM, v0.3.0 without thread-safe-region]
+// replayed over the closed-form copy list: cell = position * n + row.  Sequential by nature
+// (each copy splices two cycles); runs once per (shape, n_blocks), never per proof.
+static int32_t build_perm_mapping(const Shape &sh, uint64_t n_blocks, std::vector<uint32_t> &mapping) {
+    const uint64_t n = sh.n();
+    const uint64_t cells = (uint64_t)perm_n_columns(sh) * n;
+    if (cells > 0xffffffffull) return H2AES_ERR_ARG;
+    std::vector<uint32_t> aux(cells), sizes(cells, 1u);
+    mapping.resize(cells);
+    for (uint64_t i = 0; i < cells; ++i) mapping[i] = aux[i] = (uint32_t)i;
+    const uint64_t total = COPIES_KEY_SCHEDULE + COPIES_PER_BLOCK * n_blocks;
+    for (uint64_t idx = 0; idx < total; ++idx) {
+        CopyPair cp;
+        if (!copy_pair(sh, idx, &cp)) return H2AES_ERR_CAPACITY;
+        // constrain_equal(left = the freshly assigned copy, right = the cell it was copied from)
+        const uint32_t left = (uint32_t)(perm_pos_of_advice(sh, (int)cp.dst.col) * n + cp.dst.row);
+        const uint32_t right = (uint32_t)(perm_pos_of_advice(sh, (int)cp.src.col) * n + cp.src.row);
+        uint32_t lc = aux[left], rc = aux[right];
+        if (lc == rc) continue;
+        if (sizes[lc] < sizes[rc]) std::swap(lc, rc);
+        sizes[lc] += sizes[rc];
+        uint32_t i = rc;
+        do {
+            aux[i] = lc;
+            i = mapping[i];
+        } while (i != rc);
+        std::swap(mapping[left], mapping[right]);
+    }
+    return H2AES_OK;
+}
+
+int32_t h2aes_perm_mapping_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
+                                uint32_t *mapping_out) {
+    if (!mapping_out || !shape_ok(kind, k, N)) return H2AES_ERR_ARG;
+    const Shape sh = make_shape(kind, k, N);
+    if (!rows_ok(sh)) return H2AES_ERR_ROWS;
+    if (kind == KIND_KEYSCHED && n_blocks) return H2AES_ERR_ARG;
+    if (n_blocks > sh.capacity()) return H2AES_ERR_CAPACITY;
+    std::vector<uint32_t> m;
+    int32_t rc = build_perm_mapping(sh, n_blocks, m);
+    if (rc) return rc;
+    const uint64_t n = sh.n();
+    for (uint64_t i = 0; i < m.size(); ++i) {  // (position, row) pairs like halo2's Vec<Vec<(usize,usize)>>
+        mapping_out[2 * i] = (uint32_t)(m[i] / n);
+        mapping_out[2 * i + 1] = (uint32_t)(m[i] % n);
     }
     return H2AES_OK;
 }

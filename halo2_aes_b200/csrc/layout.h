@@ -480,4 +480,28 @@ H2_HD bool copy_pair(const Shape &sh, uint64_t idx, CopyPair *out) {
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// permutation argument: columns in the order of the enable_equality calls —
+// key_schedule.rs:52-57 (advices[0][0..3], words_column, enable_constant(round_constants)), then
+// aes128.rs:126-130 (every advice column)  [UPSTREAM halo2 permutation::Argument::add_column]
+// ---------------------------------------------------------------------------------------------
+constexpr int PERM_CHUNK = 3;  // cs.degree() - 2 with degree 5 (lookup: 2 + input 2 + table 1)
+H2_HD int perm_n_columns(const Shape &sh) { return 3 * sh.n_sets() + 2; }
+H2_HD int perm_n_sets(const Shape &sh) { return (perm_n_columns(sh) + PERM_CHUNK - 1) / PERM_CHUNK; }
+// position p of the permutation -> (is_fixed, column index)
+H2_HD void perm_column(const Shape &sh, int p, int *is_fixed, int *index) {
+    *is_fixed = 0;
+    if (p < 3) *index = p;
+    else if (p == 3) *index = sh.words_column();
+    else if (p == 4) { *is_fixed = 1; *index = 4; }
+    else *index = p - 2;  // advice 3, 4, ... 3N-1
+}
+// advice column -> position in the permutation
+H2_HD int perm_pos_of_advice(const Shape &sh, int a) {
+    if (a < 3) return a;
+    if (a == sh.words_column()) return 3;
+    return a + 2;
+}
+
 }  // namespace h2

@@ -120,6 +120,21 @@ int32_t h2aes_copy_count(int32_t kind, uint64_t n_blocks, uint64_t *out);
 int32_t h2aes_copy_constraints_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
                                     uint64_t first, uint64_t count, uint64_t *out);
 
+/* ---- permutation (copy-constraint) argument — SURVEY 8(f) item 1 ---------------------------
+ * replaces (as far as the columns go): halo2_proofs v0.3.0 plonk/permutation/keygen.rs
+ * (Assembly::copy / build_pk) and plonk/permutation/prover.rs (Argument::commit), call sites
+ * keygen_vk/keygen_pk and create_proof (main.rs:78-101).
+ * Columns of the argument, in enable_equality order (key_schedule.rs:52-57, aes128.rs:126-130):
+ * advices[0][0..3], words_column, round_constants (fixed), then the remaining advice columns;
+ * chunk_len = cs.degree() - 2 = 3 columns per grand product.  Arrays: n_columns entries. */
+int32_t h2aes_perm_query(int32_t kind, int32_t k, int32_t N, int32_t *n_columns, int32_t *chunk_len,
+                         int32_t *n_sets, int32_t *is_fixed, int32_t *column_index);
+/* the cycle structure halo2's keygen builds from the copy constraints of schedule_key + n_blocks
+ * encrypts: mapping[(p*n + row)*2 + {0,1}] = (position, row) that cell (p,row) maps to.  Host
+ * out, n_columns * 2^k * 2 u32.  Input independent (shape + n_blocks only). */
+int32_t h2aes_perm_mapping_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
+                                uint32_t *mapping_out);
+
 /* ---------------------------------------------------------------------------------------------
  * Context: one per (process, GPU).  Uploads the S-box / GF tables and the 256-entry
  * byte -> Fr(Montgomery) table (replaces src/constant.rs + every `Fp::from(x as u64)`).

@@ -237,3 +237,24 @@ def test_fr_inv_binary_gcd_vs_fermat_and_bigint(ffi, orc):
         if i < 60:
             assert L.h2aes_dbg_fr_inv_fermat(_p(A, u64p), _p(out2, u64p)) == 0
             assert (out == out2).all()
+
+
+@pytest.mark.parametrize("kind,k,N,nb", [(1, 17, 1, 0), (0, 17, 1, 3), (0, 17, 2, 120)])
+def test_permutation_columns_and_mapping_equal_keygen_replay(ffi, orc, kind, k, N, nb):
+    """Permutation argument bookkeeping: column order and the cycle structure built
+    from the closed-form copy list == halo2's keygen Assembly replayed by the oracle over the
+    copies recorded region by region."""
+    L = ffi.lib()
+    nc, cl, ns = C.c_int32(), C.c_int32(), C.c_int32()
+    fx = (C.c_int32 * 256)()
+    ix = (C.c_int32 * 256)()
+    assert L.h2aes_perm_query(kind, k, N, C.byref(nc), C.byref(cl), C.byref(ns), fx, ix) == 0
+    ps = orc.perm_shape(kind, k, N)
+    assert (nc.value, cl.value, ns.value) == (ps["n_columns"], ps["chunk_len"], ps["n_sets"])
+    assert [("fixed" if fx[i] else "advice", ix[i]) for i in range(nc.value)] == ps["columns"]
+    pts = splitmix_bytes(SEED + 13, 16 * max(nb, 1)).reshape(-1, 16)[:nb]
+    ref = orc.Circuit(kind, k, N).synthesize(bytes(16), pts if nb else None)
+    want = ref.permutation(np.ones(4, np.uint64), np.ones(4, np.uint64), want=("mapping",))["mapping"]
+    got = np.zeros_like(want)
+    assert L.h2aes_perm_mapping_host(kind, k, N, nb, got.ctypes.data_as(u32p)) == 0
+    assert (got == want).all()
