@@ -357,10 +357,19 @@ def run_b200(args):
             row.update({"fr_multiplies": muls[name], "achieved_gmul_s": gm,
                         "imad_frac_of_measured_mul_peak": gm / MUL_PEAK_G})
         kernels.append(row)
+    # DRAM bytes per launch from the committed `ncu --set full` capture of the same workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu_traffic = json.load(f)["kernels"]
+    except Exception:
+        ncu_traffic = {}
+    for row in kernels:
+        if row["kernel"] in ncu_traffic:
+            row["traffic"] = ncu_traffic[row["kernel"]]["traffic"]
     dom = max(kernels, key=lambda x: x["ms_per_step"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom.get("achieved_gbs"),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": dom.get("frac"),
-                "traffic": None, "launch_ms": dom["ms"],
+                "traffic": dom.get("traffic"), "launch_ms": dom["ms"],
                 "algorithmic_bytes": dom.get("algorithmic_bytes"),
                 "measured": "CUDA events around every launch (h2aes_ctx_profile), un-overlapped "
                             "pass after the timed region",
