@@ -104,6 +104,8 @@ SIGNATURES = {
     "h2aes_lookup_permuted_host": (C.c_int32, [_vp, _u64p, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "h2aes_lookup_product_dev": (C.c_int32, [_vp, _u64p, _u64p, C.c_int32, C.c_int32, _vp]),
     "h2aes_lookup_product_host": (C.c_int32, [_vp, _u64p, _u64p, C.c_int32, C.c_int32, _vp]),
+    "h2aes_perm_sigma_dev": (C.c_int32, [_vp, C.c_uint64, _vp]),
+    "h2aes_perm_product_dev": (C.c_int32, [_vp, _u64p, _u64p, _vp, _vp]),
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),
     "h2aes_lookup_check": (C.c_int32, [_vp]),
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),

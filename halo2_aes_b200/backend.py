@@ -190,6 +190,33 @@ class Circuit:
         check(lib().h2aes_lookup_product_dev(self._h, bep, gap, first, count, _ptr(Z)), self.ctx._h)
         return Z
 
+    # ---- permutation argument -----------------------------------------------------------------
+    def perm_shape(self) -> dict:
+        nc, cl, ns = C.c_int32(), C.c_int32(), C.c_int32()
+        fx, ix = (C.c_int32 * 256)(), (C.c_int32 * 256)()
+        check(lib().h2aes_perm_query(self.kind, self.k, self.N, C.byref(nc), C.byref(cl), C.byref(ns),
+                                     fx, ix))
+        return dict(n_columns=nc.value, chunk_len=cl.value, n_sets=ns.value,
+                    columns=[("fixed" if fx[i] else "advice", ix[i]) for i in range(nc.value)])
+
+    def perm_sigma(self, n_blocks=None) -> torch.Tensor:
+        nb = self.n_blocks if n_blocks is None else n_blocks
+        out = torch.empty((self.perm_shape()["n_columns"], self.n, 4), dtype=torch.int64,
+                          device=self.ctx.device)
+        check(lib().h2aes_perm_sigma_dev(self._h, nb, _ptr(out)), self.ctx._h)
+        return out
+
+    def perm_product(self, beta, gamma, advice: torch.Tensor) -> torch.Tensor:
+        """Z_perm [n_sets, n, 4] from the advice columns of the last witness call"""
+        assert advice.is_cuda and advice.is_contiguous()
+        assert advice.numel() == self.layout["n_advice"] * self.n * 4
+        be, bep = _fr_arg(beta)
+        ga, gap = _fr_arg(gamma)
+        out = torch.empty((self.perm_shape()["n_sets"], self.n, 4), dtype=torch.int64,
+                          device=self.ctx.device)
+        check(lib().h2aes_perm_product_dev(self._h, bep, gap, _ptr(advice), _ptr(out)), self.ctx._h)
+        return out
+
     def lookup_stats(self) -> np.ndarray:
         """rows per lookup whose grand-product factor is not one (last product call)"""
         out = np.zeros(self.layout["n_lookups"], np.uint64)

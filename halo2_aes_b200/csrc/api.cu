@@ -35,6 +35,9 @@ cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
 void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk);
 uint32_t lookup_bin_tiles();
+cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta);
+cudaError_t launch_perm_sigma(h2aes_circuit *c, uint64_t *sigma_dev);
+cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, uint64_t *Zp);
 uint64_t run_index_stride(uint64_t n);
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
 
@@ -415,7 +418,8 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
-                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_zmask,    c->d_znonconst,
+                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_pmap,     c->d_wlo,
+                    c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -859,6 +863,106 @@ int32_t h2aes_lookup_check(h2aes_circuit *c) {
     if (!c->lk_alloc) return H2AES_OK;
     CU(c->ctx, cudaSetDevice(c->ctx->device));
     return check_device_flags(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// permutation argument on the device
+// ---------------------------------------------------------------------------------------------
+// halo2curves 0.6.1 bn256::Fr [UPSTREAM]: ROOT_OF_UNITY = 7^((r-1)/2^28), DELTA = 7^(2^28)
+static fr_t fr_from_canonical_limbs(const uint32_t c[8]) {
+    fr_t a;
+    for (int i = 0; i < 8; ++i) a.v[i] = c[i];
+    return fr_mul(a, fr_r2());
+}
+static fr_t domain_omega(int k) {  // EvaluationDomain::new: the 2^28-th root squared 28-k times
+    const uint32_t root[8] = {0x60c37c9cu, 0xd34f1ed9u, 0xd39329c8u, 0x3215cf6du,
+                              0x3dd31f74u, 0x98865ea9u, 0x166d18b7u, 0x03ddb9f5u};
+    fr_t w = fr_from_canonical_limbs(root);
+    for (int i = k; i < 28; ++i) w = fr_mul(w, w);
+    return w;
+}
+static fr_t domain_delta() {
+    const uint32_t d[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu,
+                           0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
+    return fr_from_canonical_limbs(d);
+}
+
+static int32_t ensure_lookup_ws(h2aes_circuit *c);
+
+static int32_t ensure_perm_ws(h2aes_circuit *c) {
+    h2aes_ctx *ctx = c->ctx;
+    if (c->sh.k > 24) return fail(ctx, H2AES_ERR_ARG, "permutation argument: k <= 24");
+    int32_t rc = ensure_lookup_ws(c);  // the grand-product scan workspace is shared
+    if (rc) return rc;
+    if (!c->perm_alloc) {
+        const size_t n = c->sh.n(), nc = (size_t)perm_n_columns(c->sh), ns = (size_t)perm_n_sets(c->sh);
+        CU(ctx, dalloc(&c->d_pmap, nc * n));
+        CU(ctx, dalloc(&c->d_wlo, 1024));
+        CU(ctx, dalloc(&c->d_whi, (n >> 10) + 1));
+        CU(ctx, dalloc(&c->d_dpow, nc));
+        CU(ctx, dalloc(&c->d_bdp, nc));
+        CU(ctx, dalloc(&c->d_pnum, ns * n));
+        CU(ctx, dalloc(&c->d_ppre, ns * n));
+        c->perm_alloc = true;
+    }
+    if (!c->perm_tables) {
+        CU(ctx, launch_perm_tables(c, domain_omega(c->sh.k), domain_delta()));
+        c->perm_tables = true;
+    }
+    return H2AES_OK;
+}
+
+// cycle structure of (shape, n_blocks) -> device, packed position << 24 | row
+static int32_t ensure_perm_mapping(h2aes_circuit *c, uint64_t n_blocks) {
+    h2aes_ctx *ctx = c->ctx;
+    if (c->perm_blocks == n_blocks) return H2AES_OK;
+    std::vector<uint32_t> m;
+    int32_t rc = build_perm_mapping(c->sh, n_blocks, m);
+    if (rc) return fail(ctx, rc, "permutation mapping");
+    const uint64_t n = c->sh.n();
+    for (auto &x : m) x = (uint32_t)((x / n) << 24) | (uint32_t)(x % n);
+    CU(ctx, cudaMemcpyAsync(c->d_pmap, m.data(), m.size() * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // `m` goes out of scope
+    c->perm_blocks = n_blocks;
+    return H2AES_OK;
+}
+
+int32_t h2aes_perm_sigma_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *sigma_dev) {
+    if (!c || !sigma_dev) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (c->sh.kind == KIND_KEYSCHED && n_blocks)
+        return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (n_blocks > c->sh.capacity())
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    if (c->n_shards != 1) return fail(ctx, H2AES_ERR_STATE, "permutation argument: unsharded only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = ensure_perm_ws(c);
+    if (rc) return rc;
+    if ((rc = ensure_perm_mapping(c, n_blocks))) return rc;
+    CU(ctx, launch_perm_sigma(c, sigma_dev));
+    return H2AES_OK;
+}
+
+int32_t h2aes_perm_product_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                               const uint64_t *advice_dev, uint64_t *Zp_dev) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!beta || !gamma || !advice_dev || !Zp_dev) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!c->have_witness) return fail(ctx, H2AES_ERR_STATE, "the permutation product needs a witness");
+    if (c->n_shards != 1) return fail(ctx, H2AES_ERR_STATE, "permutation argument: unsharded only");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int32_t rc = ensure_perm_ws(c);
+    if (rc) return rc;
+    if ((rc = ensure_perm_mapping(c, c->n_blocks))) return rc;
+    // beta, gamma share the challenge slots of the lookup product; its cached tables are dropped
+    memcpy(c->beta, beta, 32);
+    memcpy(c->gamma, gamma, 32);
+    c->have_beta_gamma = false;
+    CU(ctx, cudaMemcpyAsync(c->d_chal + 1, c->beta, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(c->d_chal + 2, c->gamma, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, launch_perm_product(c, advice_dev, Zp_dev));
+    return H2AES_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

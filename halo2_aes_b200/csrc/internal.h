@@ -145,6 +145,17 @@ struct h2aes_circuit {
     uint64_t zm = 0, znblk = 0;
     uint64_t *partial_Z = nullptr;    // Z buffer holding the factors between phases 2a and 2b
 
+    // permutation argument (allocated on first use)
+    bool perm_alloc = false, perm_tables = false;
+    uint64_t perm_blocks = ~0ull;     // n_blocks the mapping on the device was built for
+    uint32_t *d_pmap = nullptr;       // [n_cols][n] packed mapping: position << 24 | row
+    h2::fr_t *d_wlo = nullptr;        // [1024] omega^t
+    h2::fr_t *d_whi = nullptr;        // [n/1024] omega^(1024 b)
+    h2::fr_t *d_dpow = nullptr;       // [n_cols] delta^p
+    h2::fr_t *d_bdp = nullptr;        // [n_cols] beta * delta^p
+    h2::fr_t *d_pnum = nullptr;       // [n_sets][n] numerators
+    h2::fr_t *d_ppre = nullptr;       // [n_sets][n] running denominator products
+
     // staging for the _host entry points
     void *d_stage = nullptr;
     uint64_t stage_bytes = 0;

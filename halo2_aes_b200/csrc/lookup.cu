@@ -1327,6 +1327,288 @@ cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// permutation (copy-constraint) argument — SURVEY 8(f) item 1
+//   halo2_proofs v0.3.0 [UPSTREAM] plonk/permutation: sigma_p(omega^i) = delta^{p'} omega^{i'}
+//   with (p', i') = mapping[p][i] (keygen), and per chunk of 3 columns the grand product
+//     Z[i+1] = Z[i] * prod_t (v_t(i) + beta*delta^{p_t}*omega^i + gamma)
+//                   / prod_t (v_t(i) + beta*sigma_{p_t}(omega^i) + gamma),
+//   chunk s starting from the previous chunk's Z[n-6].
+//   A term whose cell maps to itself cancels; a row where all terms cancel has factor one.  The
+//   other rows: k_p_terms (numerator, denominator), k_p_invert (Montgomery-trick batch inversion,
+//   one field inversion per CTA), then the same chunk-total / scan / propagate kernels as the
+//   lookup grand product.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t W_LO_BITS = 10, W_LO = 1u << W_LO_BITS;  // omega^j = w_hi[j >> 10] * w_lo[j & 1023]
+constexpr uint32_t PMAP_ROW_BITS = 24;                       // packed mapping: position << 24 | row
+
+// w_lo[t] = omega^t (t < 1024), w_hi[b] = omega^(1024 b) (b < n/1024), dpow[p] = delta^p
+__global__ void __launch_bounds__(256)
+k_p_tables(fr_t omega, fr_t delta, uint32_t n_hi, int n_cols, fr_t *__restrict__ w_lo,
+           fr_t *__restrict__ w_hi, fr_t *__restrict__ dpow) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    auto pow_u32 = [](fr_t base, uint32_t e) {
+        fr_t acc = fr_one();
+        for (; e; e >>= 1) {
+            if (e & 1u) acc = fr_mul(acc, base);
+            base = fr_mul(base, base);
+        }
+        return acc;
+    };
+    if (t < W_LO) fr_st(w_lo + t, pow_u32(omega, t));
+    if (t < n_hi) {
+        fr_t step = omega;  // omega^1024
+        for (uint32_t i = 0; i < W_LO_BITS; ++i) step = fr_mul(step, step);
+        fr_st(w_hi + t, pow_u32(step, t));
+    }
+    if (t < (uint32_t)n_cols) fr_st(dpow + t, pow_u32(delta, t));
+}
+
+// bdp[p] = beta * delta^p
+__global__ void k_p_beta(const fr_t *__restrict__ chal, const fr_t *__restrict__ dpow, int n_cols,
+                         fr_t *__restrict__ bdp) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_cols) fr_st(bdp + p, fr_mul(fr_ld(chal + 1), fr_ld(dpow + p)));
+}
+
+__device__ __forceinline__ fr_t omega_pow(const fr_t *__restrict__ w_lo, const fr_t *__restrict__ w_hi,
+                                          uint32_t j) {
+    return fr_mul(fr_ld(w_hi + (j >> W_LO_BITS)), fr_ld(w_lo + (j & (W_LO - 1))));
+}
+
+// sigma columns [n_cols][n] from the packed mapping (keygen side)
+__global__ void __launch_bounds__(256)
+k_p_sigma(const uint32_t *__restrict__ pmap, uint64_t cells, const fr_t *__restrict__ w_lo,
+          const fr_t *__restrict__ w_hi, const fr_t *__restrict__ dpow, uint64_t *__restrict__ sigma) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        const uint32_t m = pmap[i];
+        const fr_t s = fr_mul(fr_ld(dpow + (m >> PMAP_ROW_BITS)),
+                              omega_pow(w_lo, w_hi, m & ((1u << PMAP_ROW_BITS) - 1)));
+        fr_store_256(sigma + 4 * i, s);
+    }
+}
+
+struct PArgs {
+    Shape sh;
+    int n_cols, n_sets;
+    const uint32_t *pmap;      // [n_cols][n] packed mapping
+    const uint64_t *advice;    // [n_advice][n][4] as produced by h2aes_witness_dev
+    const uint4 *frtab;        // byte -> Fr
+    const fr_t *chal;          // [1] beta, [2] gamma
+    const fr_t *w_lo, *w_hi, *bdp;
+    uint64_t *Z;               // [n_sets][n][4]: denominators, then factors, then Z
+    fr_t *num;                 // [n_sets][n] numerators of the non-constant rows
+    fr_t *pre;                 // [n_sets][n] running denominator products inside a chunk
+    uint32_t *chunkmask;       // [n_sets][m]
+    uint64_t m;
+};
+
+// value of permutation column `p` at `row`
+__device__ __forceinline__ fr_t perm_value(const PArgs &a, int p, uint64_t row) {
+    int is_fixed, idx;
+    perm_column(a.sh, p, &is_fixed, &idx);
+    if (is_fixed) return fr_from_tab(a.frtab, rc_cell(row));  // round_constants
+    return fr_load(a.advice + ((uint64_t)idx * a.sh.n() + row) * 4);
+}
+
+// per row of a column set: numerator and denominator over the terms whose cell is in a cycle
+__global__ void __launch_bounds__(256) k_p_terms(const PArgs a) {
+    const int s = blockIdx.y;
+    const uint64_t n = a.sh.n();
+    const uint32_t usable = (uint32_t)a.sh.usable();
+    const fr_t gamma = fr_ld(a.chal + 2);
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    uint64_t *__restrict__ zout = a.Z + (size_t)s * n * 4;
+    fr_t *__restrict__ numout = a.num + (size_t)s * n;
+    for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
+         c += warps) {
+        const uint64_t row = c * ZI + lane;
+        uint32_t moved = 0;  // bit t: term t's cell does not map to itself
+        uint32_t mp[PERM_CHUNK];
+        if (row < usable) {
+#pragma unroll
+            for (int t = 0; t < PERM_CHUNK; ++t) {
+                const int p = PERM_CHUNK * s + t;
+                mp[t] = 0;
+                if (p < a.n_cols) {
+                    mp[t] = a.pmap[(uint64_t)p * n + row];
+                    if (mp[t] != (((uint32_t)p << PMAP_ROW_BITS) | (uint32_t)row)) moved |= 1u << t;
+                }
+            }
+        }
+        if (moved) {
+            const fr_t wi = omega_pow(a.w_lo, a.w_hi, (uint32_t)row);
+            fr_t num = fr_one(), den = fr_one();
+            bool first = true;
+#pragma unroll
+            for (int t = 0; t < PERM_CHUNK; ++t) {
+                if (!((moved >> t) & 1u)) continue;
+                const int p = PERM_CHUNK * s + t;
+                const fr_t vg = fr_add(perm_value(a, p, row), gamma);
+                const fr_t tn = fr_add(fr_mul(fr_ld(a.bdp + p), wi), vg);
+                const fr_t ws = omega_pow(a.w_lo, a.w_hi, mp[t] & ((1u << PMAP_ROW_BITS) - 1));
+                const fr_t td = fr_add(fr_mul(fr_ld(a.bdp + (mp[t] >> PMAP_ROW_BITS)), ws), vg);
+                num = first ? tn : fr_mul(num, tn);
+                den = first ? td : fr_mul(den, td);
+                first = false;
+            }
+            fr_store_256(zout + row * 4, den);
+            fr_st(numout + row, num);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, moved != 0);
+        if (lane == 0) a.chunkmask[(size_t)s * a.m + c] = bal;
+    }
+}
+
+// factor = numerator / denominator for the non-constant rows: one thread per chunk walks its
+// rows (forward: running denominator products; the block shares ONE field inversion through
+// forward/reverse product scans of the thread totals; backward: individual inverses).
+constexpr int PI_T = 128;
+__global__ void __launch_bounds__(PI_T) k_p_invert(const PArgs a) {
+    __shared__ fr_t s_wtot[PI_T / 32];
+    __shared__ fr_t s_inv;
+    const int s = blockIdx.y;
+    const uint64_t n = a.sh.n();
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const uint64_t e = (uint64_t)blockIdx.x * PI_T + t;
+    const bool live = e < a.m;
+    const uint32_t mask = live ? a.chunkmask[(size_t)s * a.m + e] : 0u;
+    uint64_t *__restrict__ z = a.Z + ((size_t)s * n + (live ? e : 0) * ZI) * 4;
+    fr_t *__restrict__ num = a.num + (size_t)s * n + (live ? e : 0) * ZI;
+    fr_t *__restrict__ pre = a.pre + (size_t)s * n + (live ? e : 0) * ZI;
+    const fr_t one = fr_one();
+    fr_t tot = one;
+    for (uint32_t mm = mask; mm; mm &= mm - 1) {
+        const int q = __ffs(mm) - 1;
+        fr_st(pre + q, tot);
+        tot = fr_mul(tot, fr_load(z + 4 * q));
+    }
+    // forward / reverse inclusive product scans of the thread totals
+    fr_t finc = tot, rinc = tot;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const fr_t yu = fr_shfl_up(finc, d);
+        const fr_t yd = fr_shfl_down(rinc, d);
+        if (lane >= d) finc = fr_mul(finc, yu);
+        if (lane + d < 32) rinc = fr_mul(rinc, yd);
+    }
+    if (lane == 31) s_wtot[wid] = finc;
+    __syncthreads();
+    fr_t before = fr_shfl_up(finc, 1), after = fr_shfl_down(rinc, 1);
+    if (lane == 0) before = one;
+    if (lane == 31) after = one;
+    for (int w = 0; w < PI_T / 32; ++w) {
+        const fr_t wt = s_wtot[w];
+        if (w < wid) before = fr_mul(before, wt);
+        if (w > wid) after = fr_mul(after, wt);
+    }
+    if (wid == 0) {
+        fr_t all = s_wtot[0];
+        for (int w = 1; w < PI_T / 32; ++w) all = fr_mul(all, s_wtot[w]);
+        const fr_t inv = fr_inv(all);  // denominators are nonzero with overwhelming probability
+        if (lane == 0) s_inv = inv;
+    }
+    __syncthreads();
+    if (!mask) return;
+    fr_t run = fr_mul(fr_mul(s_inv, before), after);  // 1 / (product of this thread's denominators)
+    for (uint32_t mm = mask; mm;) {
+        const int q = 31 - __clz(mm);  // backward
+        mm &= ~(1u << q);
+        const fr_t den = fr_load(z + 4 * q);
+        const fr_t inv_den = fr_mul(run, fr_ld(pre + q));
+        run = fr_mul(run, den);
+        fr_store_256(z + 4 * q, fr_mul(fr_ld(num + q), inv_den));
+    }
+}
+
+// carry[s] = product of the totals of the sets before s (Z of set s starts at Z[n-6] of set s-1)
+__global__ void k_p_carry(const fr_t *__restrict__ partial, int n_sets, fr_t *__restrict__ carry) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sets) return;
+    fr_t acc = fr_one();
+    for (int j = 0; j < s; ++j) acc = fr_mul(acc, fr_ld(partial + j));
+    fr_st(carry + s, acc);
+}
+
+cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta) {
+    h2aes_ctx *ctx = c->ctx;
+    const uint32_t n_hi = (uint32_t)(c->sh.n() >> W_LO_BITS);
+    const int n_cols = perm_n_columns(c->sh);
+    const uint32_t threads = n_hi > W_LO ? n_hi : W_LO;
+    prof_begin(ctx, "k_p_tables");
+    k_p_tables<<<cdiv(threads, 256), 256, 0, ctx->stream>>>(omega, delta, n_hi, n_cols, c->d_wlo,
+                                                            c->d_whi, c->d_dpow);
+    prof_end(ctx);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_perm_sigma(h2aes_circuit *c, uint64_t *sigma_dev) {
+    h2aes_ctx *ctx = c->ctx;
+    const uint64_t cells = (uint64_t)perm_n_columns(c->sh) * c->sh.n();
+    prof_begin(ctx, "k_p_sigma");
+    k_p_sigma<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->d_pmap, cells, c->d_wlo, c->d_whi,
+                                                          c->d_dpow, sigma_dev);
+    prof_end(ctx);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, uint64_t *Zp) {
+    h2aes_ctx *ctx = c->ctx;
+    cudaStream_t s = ctx->stream;
+    const int n_cols = perm_n_columns(c->sh), n_sets = perm_n_sets(c->sh);
+    const uint64_t n = c->sh.n();
+    PArgs p;
+    p.sh = c->sh;
+    p.n_cols = n_cols;
+    p.n_sets = n_sets;
+    p.pmap = c->d_pmap;
+    p.advice = advice_dev;
+    p.frtab = ctx->d_frtab;
+    p.chal = c->d_chal;
+    p.w_lo = c->d_wlo; p.w_hi = c->d_whi; p.bdp = c->d_bdp;
+    p.Z = Zp;
+    p.num = c->d_pnum;
+    p.pre = c->d_ppre;
+    p.chunkmask = c->d_zmask;
+    p.m = n / ZI;
+    prof_begin(ctx, "k_p_beta");
+    k_p_beta<<<cdiv(n_cols, 64), 64, 0, s>>>(c->d_chal, c->d_dpow, n_cols, c->d_bdp);
+    prof_end(ctx);
+    prof_begin(ctx, "k_p_terms");
+    k_p_terms<<<dim3((unsigned)ctx->sm_count * 4, n_sets), 256, 0, s>>>(p);
+    prof_end(ctx);
+    prof_begin(ctx, "k_p_invert");
+    k_p_invert<<<dim3(cdiv(p.m, PI_T), n_sets), PI_T, 0, s>>>(p);
+    prof_end(ctx);
+    // chunk totals, scan, chaining of the sets, running products: the lookup machinery
+    ZArgs a = z_args(c, 0, n_sets, nullptr, Zp, 0, n);
+    prof_begin(ctx, "k_z_chunks");
+    k_z_chunks<<<dim3(cdiv(85 * ((a.m + 84) / 85), 128), n_sets), 128, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_reduce");
+    k_z_reduce<<<dim3((unsigned)a.nblk, n_sets), ZS_T, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_blocks");
+    k_z_blocks<<<n_sets, 32, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_p_carry");
+    k_p_carry<<<1, 64, 0, s>>>(c->d_partial, n_sets, c->d_carry);
+    prof_end(ctx);
+    a.carry_in = c->d_carry;
+    prof_begin(ctx, "k_z_down");
+    k_z_down<<<dim3((unsigned)a.nblk, n_sets), ZS_T, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_z_propagate");
+    k_z_propagate<<<dim3(cdiv(85 * ((a.m + 84) / 85), ZF_T), n_sets), ZF_T, 0, s>>>(a);
+    prof_end(ctx);
+    ctx->launches += 9;
+    return cudaGetLastError();
+}
+
 uint32_t lookup_bin_tiles() { return LB_TILES; }
 uint64_t run_index_stride(uint64_t n) { return (n >> RUN_SHIFT) + 2; }
 

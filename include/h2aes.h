@@ -226,6 +226,17 @@ int32_t h2aes_lookup_check(h2aes_circuit *c);
  * in each of the chunk-product and propagate kernels.  Host out, n_lookups entries; synchronizes. */
 int32_t h2aes_lookup_stats(h2aes_circuit *c, uint64_t *nonconst_rows);
 
+/* permutation argument on the device (unsharded circuits, k <= 24).
+ *   sigma_dev  [n_columns][2^k][4]: sigma_p(omega^i) = delta^p' * omega^i' (keygen side;
+ *              replaces Assembly::build_pk's `permutations`)
+ *   Zp_dev     [n_sets][2^k][4]: the grand products of Argument::commit, one per chunk of 3
+ *              columns, set s starting at set s-1's Z[2^k-6]; entries 0..2^k-6 deterministic,
+ *              the last 5 (halo2: blinding) left zero
+ *   advice_dev the [n_advice][2^k][4] buffer h2aes_witness_dev filled (rows >= 2^k-6 are not read) */
+int32_t h2aes_perm_sigma_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *sigma_dev);
+int32_t h2aes_perm_product_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
+                               const uint64_t *advice_dev, uint64_t *Zp_dev);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-sharded single circuit (one process per GPU, shard g of G owns rows
  * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin

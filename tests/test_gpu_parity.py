@@ -316,3 +316,38 @@ def test_degenerate_theta_merges_equal_values(gpu, orc, ffi, theta_int):
     pts = splitmix_bytes(SEED + 90, 16 * 30).reshape(-1, 16)
     _run_case(gpu, orc, ffi, ffi.KIND_AES, 17, 1, splitmix_bytes(SEED + 91, 16).tobytes(), pts,
               (theta, beta, gamma))
+
+
+@pytest.mark.parametrize("kind,k,N,nb", [(1, 17, 1, 0), (0, 17, 1, 1), (0, 17, 2, 120), (0, 18, 3, 400)])
+def test_permutation_argument(gpu, orc, ffi, challenges, kind, k, N, nb):
+    """SURVEY 8(f).1 — the copy-constraint argument: sigma columns (keygen) and the chained grand
+    products Z_perm against the oracle's restatement of halo2's Assembly / Argument::commit, plus
+    the closing property (last set's Z[n-6] == 1 because every copy constraint holds)."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    _, beta, gamma = challenges
+    key = splitmix_bytes(SEED + 95, 16).tobytes()
+    pts = splitmix_bytes(SEED + 96, 16 * max(nb, 1)).reshape(-1, 16)[:nb]
+    cir = Circuit(gpu, kind, k, N)
+    assert cir.perm_shape() == orc.perm_shape(kind, k, N)
+    advice, _ = cir.witness(key, torch.from_numpy(pts.copy()).cuda() if nb else None)
+    sigma = cir.perm_sigma()
+    Zp = cir.perm_product(beta, gamma, advice)
+    gpu.synchronize()
+    ref = orc.Circuit(kind, k, N).synthesize(key, pts if nb else None)
+    r = ref.permutation(beta, gamma, want=("sigma", "Z"))
+    assert (_host(sigma) == r["sigma"]).all(), "sigma"
+    gz = _host(Zp)
+    n = 1 << k
+    one = orc.fr_from_int(1)
+    assert (gz[0, 0] == one).all() and (gz[-1, n - 6] == one).all()
+    for s in range(gz.shape[0]):
+        bad = np.flatnonzero((gz[s] != r["Z"][s]).any(axis=1))
+        assert bad.size == 0, f"Z_perm set {s}: {bad.size} rows differ, first {bad[:5]}"
+    # the lookup product still works after the permutation product reused its challenge slots
+    theta = challenges[0]
+    cir.lookup_permuted(theta, first=1, count=1, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma, first=1, count=1)
+    cir.lookup_check()
+    assert (_host(Z)[0] == ref.lookup(1, theta, beta, gamma, want=("Z",))["Z"]).all()
+    cir.close()
