@@ -330,6 +330,29 @@ def run_b200(args):
     prof = pipes[0].ctx.profile_read()
     pipes[0].ctx.profile(False)
     nc = int(pipes[0].cir.lookup_stats().sum())  # rows whose grand-product factor is not one
+    # SURVEY 8(f).1, outside the step (the metric is advice + lookup columns): the permutation
+    # argument's grand products for the same circuit, timed the same way
+    perm = None
+    if not args.no_perm:
+        cirp = pipes[0].cir
+        pipes[0].ctx.profile(True)
+        with torch.cuda.stream(pipes[0].stream):
+            cirp.witness(pipes[0].keys[0].tobytes(), pipes[0].pts[0], out=pipes[0].advice,
+                         want_ciphertexts=False)
+            cirp.perm_product(be, ga, pipes[0].advice)   # first call also builds the keygen-side mapping
+            pipes[0].ctx.profile_read()
+            Zp = None
+            for _ in range(3):
+                Zp = cirp.perm_product(be, ga, pipes[0].advice)
+        pp = pipes[0].ctx.profile_read()
+        pipes[0].ctx.profile(False)
+        assert bool((Zp[-1, n - 6] == one).all()), "Z_perm does not close at 1"
+        ns = Zp.shape[0]
+        perm = {"n_sets": ns, "ms": sum(ms for _, ms in pp.values()) / 3,
+                "kernels_ms": {k: ms / 3 for k, (cnt, ms) in pp.items()},
+                "algorithmic_bytes": ns * n * 32,
+                "note": "h2aes_perm_product_dev on the benchmarked circuit; not part of `value`"}
+        del Zp
     ph_iso = phase_table(iso)
     alg = {  # algorithmic bytes per launch; None: not a streaming kernel
         "k_advice": nadv * n * 32 + nb * 16,      # every advice cell written once (+ plaintexts)
@@ -403,6 +426,7 @@ def run_b200(args):
             "step_algorithmic_bytes": step_bytes,
             "step_effective_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
             "witness_only_blocks_per_s": nb / (ph_iso["witness"] * 1e-3),
+            "permutation_product": perm,
             "nonconstant_rows": nc, "nonconstant_row_fraction": nc / (L * n),
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
         }
@@ -495,6 +519,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-perm", action="store_true")
     ap.add_argument("--pipelines", type=int, default=2,
                     help="independent circuits in flight per GPU (each on its own stream)")
     args = ap.parse_args()

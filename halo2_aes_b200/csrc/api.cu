@@ -419,7 +419,8 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
                     c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_pmap,     c->d_wlo,
-                    c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,     c->d_zmask,    c->d_znonconst,
+                    c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
+                    c->d_omega_tab,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -900,6 +901,7 @@ static int32_t ensure_perm_ws(h2aes_circuit *c) {
         CU(ctx, dalloc(&c->d_wlo, 1024));
         CU(ctx, dalloc(&c->d_whi, (n >> 10) + 1));
         CU(ctx, dalloc(&c->d_dpow, nc));
+        CU(ctx, dalloc(&c->d_omega_tab, n));
         CU(ctx, dalloc(&c->d_bdp, nc));
         CU(ctx, dalloc(&c->d_pnum, ns * n));
         CU(ctx, dalloc(&c->d_ppre, ns * n));

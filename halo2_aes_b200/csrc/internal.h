@@ -152,6 +152,7 @@ struct h2aes_circuit {
     h2::fr_t *d_wlo = nullptr;        // [1024] omega^t
     h2::fr_t *d_whi = nullptr;        // [n/1024] omega^(1024 b)
     h2::fr_t *d_dpow = nullptr;       // [n_cols] delta^p
+    h2::fr_t *d_omega_tab = nullptr;  // [n] omega^j
     h2::fr_t *d_bdp = nullptr;        // [n_cols] beta * delta^p
     h2::fr_t *d_pnum = nullptr;       // [n_sets][n] numerators
     h2::fr_t *d_ppre = nullptr;       // [n_sets][n] running denominator products

@@ -1376,6 +1376,15 @@ __device__ __forceinline__ fr_t omega_pow(const fr_t *__restrict__ w_lo, const f
     return fr_mul(fr_ld(w_hi + (j >> W_LO_BITS)), fr_ld(w_lo + (j & (W_LO - 1))));
 }
 
+// omega_tab[j] = omega^j for the whole domain (keygen side; 32 B per row)
+__global__ void __launch_bounds__(256)
+k_p_omega_tab(const fr_t *__restrict__ w_lo, const fr_t *__restrict__ w_hi, uint64_t n,
+              fr_t *__restrict__ tab) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        fr_st(tab + j, omega_pow(w_lo, w_hi, (uint32_t)j));
+}
+
 // sigma columns [n_cols][n] from the packed mapping (keygen side)
 __global__ void __launch_bounds__(256)
 k_p_sigma(const uint32_t *__restrict__ pmap, uint64_t cells, const fr_t *__restrict__ w_lo,
@@ -1397,6 +1406,7 @@ struct PArgs {
     const uint4 *frtab;        // byte -> Fr
     const fr_t *chal;          // [1] beta, [2] gamma
     const fr_t *w_lo, *w_hi, *bdp;
+    const fr_t *omega_tab;     // [n] omega^j
     uint64_t *Z;               // [n_sets][n][4]: denominators, then factors, then Z
     fr_t *num;                 // [n_sets][n] numerators of the non-constant rows
     fr_t *pre;                 // [n_sets][n] running denominator products inside a chunk
@@ -1439,7 +1449,7 @@ __global__ void __launch_bounds__(256) k_p_terms(const PArgs a) {
             }
         }
         if (moved) {
-            const fr_t wi = omega_pow(a.w_lo, a.w_hi, (uint32_t)row);
+            const fr_t wi = fr_ld(a.omega_tab + row);
             fr_t num = fr_one(), den = fr_one();
             bool first = true;
 #pragma unroll
@@ -1448,7 +1458,7 @@ __global__ void __launch_bounds__(256) k_p_terms(const PArgs a) {
                 const int p = PERM_CHUNK * s + t;
                 const fr_t vg = fr_add(perm_value(a, p, row), gamma);
                 const fr_t tn = fr_add(fr_mul(fr_ld(a.bdp + p), wi), vg);
-                const fr_t ws = omega_pow(a.w_lo, a.w_hi, mp[t] & ((1u << PMAP_ROW_BITS) - 1));
+                const fr_t ws = fr_ld(a.omega_tab + (mp[t] & ((1u << PMAP_ROW_BITS) - 1)));
                 const fr_t td = fr_add(fr_mul(fr_ld(a.bdp + (mp[t] >> PMAP_ROW_BITS)), ws), vg);
                 num = first ? tn : fr_mul(num, tn);
                 den = first ? td : fr_mul(den, td);
@@ -1541,7 +1551,11 @@ cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &
     k_p_tables<<<cdiv(threads, 256), 256, 0, ctx->stream>>>(omega, delta, n_hi, n_cols, c->d_wlo,
                                                             c->d_whi, c->d_dpow);
     prof_end(ctx);
-    ctx->launches += 1;
+    prof_begin(ctx, "k_p_omega_tab");
+    k_p_omega_tab<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->d_wlo, c->d_whi, c->sh.n(),
+                                                              c->d_omega_tab);
+    prof_end(ctx);
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 
@@ -1570,6 +1584,7 @@ cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, ui
     p.frtab = ctx->d_frtab;
     p.chal = c->d_chal;
     p.w_lo = c->d_wlo; p.w_hi = c->d_whi; p.bdp = c->d_bdp;
+    p.omega_tab = c->d_omega_tab;
     p.Z = Zp;
     p.num = c->d_pnum;
     p.pre = c->d_ppre;
