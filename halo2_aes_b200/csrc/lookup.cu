@@ -1475,7 +1475,10 @@ __global__ void __launch_bounds__(256) k_p_terms(const PArgs a) {
 // factor = numerator / denominator for the non-constant rows: one thread per chunk walks its
 // rows (forward: running denominator products; the block shares ONE field inversion through
 // forward/reverse product scans of the thread totals; backward: individual inverses).
-constexpr int PI_T = 128;
+#ifndef PI_THREADS
+#define PI_THREADS 128
+#endif
+constexpr int PI_T = PI_THREADS;
 __global__ void __launch_bounds__(PI_T) k_p_invert(const PArgs a) {
     __shared__ fr_t s_wtot[PI_T / 32];
     __shared__ fr_t s_inv;
