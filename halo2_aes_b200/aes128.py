@@ -457,6 +457,14 @@ class B200Prover:
     def copies(self):
         return self.circuit.copy_constraints()
 
+    def permutation_sigma(self):
+        """the sigma columns keygen derives from the copy constraints (pk.permutation)"""
+        return self.circuit.perm_sigma()
+
+    def permutation_product(self, beta, gamma):
+        """the chained grand products Z_perm of permutation::Argument::commit"""
+        return self.circuit.perm_product(beta, gamma, self.layouter.advice)
+
     def lookup_columns(self, theta, beta, gamma, want_inputs=True):
         out = self.circuit.lookup_permuted(theta, want_inputs=want_inputs)
         out["Z"] = self.circuit.lookup_product(beta, gamma)

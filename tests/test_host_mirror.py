@@ -136,6 +136,10 @@ def test_correct_encryption_reference_shape(ffi, orc, challenges):
     Z = to_host_u64(cols["Z"])
     n = 1 << 20
     assert (Z[:, 0] == one).all() and (Z[:, n - 6] == one).all()
+    del cols
+    Zp = to_host_u64(prover.permutation_product(beta, gamma))   # 11 columns -> 4 chained sets
+    assert Zp.shape[0] == 4 and (Zp[0, 0] == one).all() and (Zp[-1, n - 6] == one).all()
+    assert all((Zp[s, 0] == Zp[s - 1, n - 6]).all() for s in range(1, 4))
 
 
 @pytest.mark.gpu

@@ -150,3 +150,46 @@ def test_lookup_helper_invariants(orc, challenges):
             return np.sort(x[:u].view([("a", "u8"), ("b", "u8"), ("c", "u8"), ("d", "u8")]).ravel())
         assert (key(A) == key(Ap)).all() and (key(S) == key(Sp)).all()
         assert not Ap[u:].any() and not Sp[u:].any() and not Z[u + 1:].any()
+
+
+def test_domain_constants_rederived_from_the_generator(orc):
+    """halo2curves bn256::Fr [UPSTREAM]: MULTIPLICATIVE_GENERATOR = 7, S = 28; the oracle's
+    ROOT_OF_UNITY / DELTA constants equal 7^((r-1)/2^28) and 7^(2^28), and the domain generator of
+    a 2^k-row circuit has exact order 2^k."""
+    assert (R_MOD - 1) % (1 << 28) == 0 and ((R_MOD - 1) >> 28) % 2 == 1
+    for k in (17, 20, 22):
+        om, de = orc.domain_constants(k)
+        w, d = orc.fr_to_int(om), orc.fr_to_int(de)
+        assert d == pow(7, 1 << 28, R_MOD)
+        assert w == pow(pow(7, (R_MOD - 1) >> 28, R_MOD), 1 << (28 - k), R_MOD)
+        assert pow(w, 1 << k, R_MOD) == 1 and pow(w, 1 << (k - 1), R_MOD) == R_MOD - 1
+
+
+def test_permutation_argument_invariants(orc, challenges):
+    """No reference test pins sigma / Z_perm (parity unpinned): check what halo2's verifier relies
+    on — sigma is a permutation of the identity labels delta^p omega^i that only moves cells inside
+    copy cycles of equal values, the sets chain (Z_s[0] == Z_{s-1}[n-6]) and the last one closes
+    at 1 because every copy constraint holds."""
+    _, beta, gamma = challenges
+    k, N, nb = 17, 2, 110
+    c = orc.Circuit(orc.KIND_AES, k, N).synthesize(
+        splitmix_bytes(SEED + 30, 16), splitmix_bytes(SEED + 31, 16 * nb).reshape(-1, 16))
+    ps = orc.perm_shape(orc.KIND_AES, k, N)
+    assert ps["columns"][:5] == [("advice", 0), ("advice", 1), ("advice", 2), ("advice", 6), ("fixed", 4)]
+    assert ps["n_columns"] == 3 * N + 2 and ps["chunk_len"] == 3 and ps["n_sets"] == 3
+    r = c.permutation(beta, gamma)
+    n = 1 << k
+    m = r["mapping"].astype(np.int64)
+    flat = m[:, :, 0] * n + m[:, :, 1]
+    assert np.array_equal(np.sort(flat.ravel()), np.arange(ps["n_columns"] * n))   # a permutation
+    cols = [c.advice(i) if t == "advice" else c.fixed(i) for t, i in ps["columns"]]
+    vals = np.stack(cols)                                                     # [ncols, n, 4]
+    moved = flat != np.arange(ps["n_columns"] * n).reshape(ps["n_columns"], n)
+    src = vals.reshape(-1, 4)[flat[moved]]
+    assert (vals[moved] == src).all()                      # cycles only join equal values
+    one = orc.fr_from_int(1)
+    Z = r["Z"]
+    assert (Z[0, 0] == one).all() and (Z[-1, n - 6] == one).all()
+    for s in range(1, Z.shape[0]):
+        assert (Z[s, 0] == Z[s - 1, n - 6]).all()
+    assert not Z[:, n - 5:].any()
