@@ -110,6 +110,12 @@ static int32_t fail(h2aes_ctx *ctx, int32_t code, const char *what) {
         if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
     } while (0)
 
+// allocate once: a lazy workspace builder that failed half-way is simply called again
+#define DA(ptr, count)                              \
+    do {                                            \
+        if (!(ptr)) CU(ctx, dalloc(&(ptr), count)); \
+    } while (0)
+
 template <class T>
 static cudaError_t dalloc(T **p, size_t count) {
     return cudaMalloc((void **)p, count * sizeof(T) ? count * sizeof(T) : 1);
@@ -332,6 +338,10 @@ int32_t h2aes_ctx_create(int32_t device, int32_t sbox_mode, h2aes_ctx **out) {
 int32_t h2aes_ctx_destroy(h2aes_ctx *ctx) {
     if (!ctx) return H2AES_ERR_ARG;
     cudaSetDevice(ctx->device);
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
     cudaFree(ctx->d_sbox);
     cudaFree(ctx->d_frtab);
     delete ctx;
@@ -624,50 +634,50 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     const size_t L = (size_t)c->sh.n_lookups();
     const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
     grand_product_ws(c->sh.n(), &c->zm, &c->znblk);
-    CU(ctx, dalloc(&c->d_chal, 4));
-    CU(ctx, dalloc(&c->d_val, VB));
-    CU(ctx, dalloc(&c->d_canon, VB));
-    CU(ctx, dalloc(&c->d_canon_b, VB));
-    CU(ctx, dalloc(&c->d_active, L));
-    CU(ctx, dalloc(&c->d_lbsum, L * lookup_bin_tiles()));
+    DA(c->d_chal, 4);
+    DA(c->d_val, VB);
+    DA(c->d_canon, VB);
+    DA(c->d_canon_b, VB);
+    DA(c->d_active, L);
+    DA(c->d_lbsum, L * lookup_bin_tiles());
     c->idx_stride = run_index_stride(c->sh.n());
-    CU(ctx, dalloc(&c->d_jidx, L * c->idx_stride));
-    CU(ctx, dalloc(&c->d_lidx, L * c->idx_stride));
-    CU(ctx, dalloc(&c->d_dval, VB));
-    CU(ctx, dalloc(&c->d_rank, VB));
-    CU(ctx, dalloc(&c->d_ts, VB));
-    CU(ctx, dalloc(&c->d_sorted, VB));
-    CU(ctx, dalloc(&c->d_slot, VB));
-    CU(ctx, dalloc(&c->d_head, VB));
-    CU(ctx, dalloc(&c->d_bhist, (size_t)N_VIEWS * (N_BUCKETS + 1)));
-    CU(ctx, dalloc(&c->d_bcur, (size_t)N_VIEWS * N_BUCKETS));
-    CU(ctx, dalloc(&c->d_viewmeta, (size_t)N_VIEWS * 8));
-    CU(ctx, dalloc(&c->d_ib, VB));
-    CU(ctx, dalloc(&c->d_ig, VB));
-    CU(ctx, dalloc(&c->d_nac, VB));
-    CU(ctx, dalloc(&c->d_ibg, VB));
-    CU(ctx, dalloc(&c->d_ibp, VB));
-    CU(ctx, dalloc(&c->d_nacp, VB));
-    CU(ctx, dalloc(&c->d_ibgz, VB));
-    CU(ctx, dalloc(&c->d_ibpz, VB));
-    CU(ctx, dalloc(&c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n()));
-    CU(ctx, dalloc(&c->d_codek, L * c->sh.n()));
-    CU(ctx, dalloc(&c->d_codep, L * c->sh.n()));
+    DA(c->d_jidx, L * c->idx_stride);
+    DA(c->d_lidx, L * c->idx_stride);
+    DA(c->d_dval, VB);
+    DA(c->d_rank, VB);
+    DA(c->d_ts, VB);
+    DA(c->d_sorted, VB);
+    DA(c->d_slot, VB);
+    DA(c->d_head, VB);
+    DA(c->d_bhist, (size_t)N_VIEWS * (N_BUCKETS + 1));
+    DA(c->d_bcur, (size_t)N_VIEWS * N_BUCKETS);
+    DA(c->d_viewmeta, (size_t)N_VIEWS * 8);
+    DA(c->d_ib, VB);
+    DA(c->d_ig, VB);
+    DA(c->d_nac, VB);
+    DA(c->d_ibg, VB);
+    DA(c->d_ibp, VB);
+    DA(c->d_nacp, VB);
+    DA(c->d_ibgz, VB);
+    DA(c->d_ibpz, VB);
+    DA(c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n());
+    DA(c->d_codek, L * c->sh.n());
+    DA(c->d_codep, L * c->sh.n());
     c->code_valid = new bool[L]();
-    CU(ctx, dalloc(&c->d_cnt, LB));
-    CU(ctx, dalloc(&c->d_offz, LB));
-    CU(ctx, dalloc(&c->d_nzk, LB));
-    CU(ctx, dalloc(&c->d_loffz, LB));
-    CU(ctx, dalloc(&c->d_lk, LB));
-    CU(ctx, dalloc(&c->d_meta, L));
-    CU(ctx, dalloc(&c->d_ztot, L * c->zm));
-    CU(ctx, dalloc(&c->d_zmask, L * c->zm));
-    CU(ctx, dalloc(&c->d_znonconst, L));
+    DA(c->d_cnt, LB);
+    DA(c->d_offz, LB);
+    DA(c->d_nzk, LB);
+    DA(c->d_loffz, LB);
+    DA(c->d_lk, LB);
+    DA(c->d_meta, L);
+    DA(c->d_ztot, L * c->zm);
+    DA(c->d_zmask, L * c->zm);
+    DA(c->d_znonconst, L);
     CU(ctx, cudaMemsetAsync(c->d_znonconst, 0, L * 8, ctx->stream));
-    CU(ctx, dalloc(&c->d_zbagg, L * c->znblk));
-    CU(ctx, dalloc(&c->d_zbexcl, L * c->znblk));
-    CU(ctx, dalloc(&c->d_partial, L));
-    CU(ctx, dalloc(&c->d_carry, L));
+    DA(c->d_zbagg, L * c->znblk);
+    DA(c->d_zbexcl, L * c->znblk);
+    DA(c->d_partial, L);
+    DA(c->d_carry, L);
     c->lk_alloc = true;
     return H2AES_OK;
 }
@@ -897,14 +907,14 @@ static int32_t ensure_perm_ws(h2aes_circuit *c) {
     if (rc) return rc;
     if (!c->perm_alloc) {
         const size_t n = c->sh.n(), nc = (size_t)perm_n_columns(c->sh), ns = (size_t)perm_n_sets(c->sh);
-        CU(ctx, dalloc(&c->d_pmap, nc * n));
-        CU(ctx, dalloc(&c->d_wlo, 1024));
-        CU(ctx, dalloc(&c->d_whi, (n >> 10) + 1));
-        CU(ctx, dalloc(&c->d_dpow, nc));
-        CU(ctx, dalloc(&c->d_omega_tab, n));
-        CU(ctx, dalloc(&c->d_bdp, nc));
-        CU(ctx, dalloc(&c->d_pnum, ns * n));
-        CU(ctx, dalloc(&c->d_ppre, ns * n));
+        DA(c->d_pmap, nc * n);
+        DA(c->d_wlo, 1024);
+        DA(c->d_whi, (n >> 10) + 1);
+        DA(c->d_dpow, nc);
+        DA(c->d_omega_tab, n);
+        DA(c->d_bdp, nc);
+        DA(c->d_pnum, ns * n);
+        DA(c->d_ppre, ns * n);
         c->perm_alloc = true;
     }
     if (!c->perm_tables) {
