@@ -663,7 +663,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n());
     DA(c->d_codek, L * c->sh.n());
     DA(c->d_codep, L * c->sh.n());
-    c->code_valid = new bool[L]();
+    if (!c->code_valid) c->code_valid = new bool[L]();
     DA(c->d_cnt, LB);
     DA(c->d_offz, LB);
     DA(c->d_nzk, LB);
