@@ -428,7 +428,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
-                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_pmap,     c->d_wlo,
+                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_sgz,      c->d_pmap,     c->d_wlo,
                     c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
                     c->d_omega_tab,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
@@ -660,6 +660,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_nacp, VB);
     DA(c->d_ibgz, VB);
     DA(c->d_ibpz, VB);
+    DA(c->d_sgz, VB);
     DA(c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n());
     DA(c->d_codek, L * c->sh.n());
     DA(c->d_codep, L * c->sh.n());

@@ -125,6 +125,7 @@ struct h2aes_circuit {
     h2::fr_t *d_nacp = nullptr;      // [3][BIN_STRIDE] nac[k]*ibp[k_zero]
     h2::fr_t *d_ibgz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibg[k]
     h2::fr_t *d_ibpz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibp[k]
+    h2::fr_t *d_sgz = nullptr;       // [3][BIN_STRIDE] (val[e]+gamma)/(pad+gamma) per table entry
     // per lookup
     uint32_t *d_cnt = nullptr;       // [L][BIN_STRIDE] input rows per bin
     uint32_t *d_offz = nullptr;      // [L][BIN_STRIDE] first row of each nonempty bin (+ end)

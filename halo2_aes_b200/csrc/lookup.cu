@@ -763,14 +763,18 @@ __global__ void __launch_bounds__(256)
 k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ rank,
             const fr_t *__restrict__ ib, const fr_t *__restrict__ ig, const fr_t *__restrict__ nac,
             fr_t *__restrict__ ibg, fr_t *__restrict__ ibp, fr_t *__restrict__ nacp,
-            fr_t *__restrict__ ibgz, fr_t *__restrict__ ibpz) {
+            fr_t *__restrict__ ibgz, fr_t *__restrict__ ibpz, const fr_t *__restrict__ val,
+            const fr_t *__restrict__ chal, fr_t *__restrict__ sgz) {
     const int v = blockIdx.y;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= viewmeta[v * 8 + 1]) return;
     const size_t o = (size_t)v * BIN_STRIDE;
     const uint32_t k_pad = rank[o];  // bin of table row 0, the padding value
     const uint32_t k_zero = rank[o + (v == 0 ? 1280u : TROW_ZERO)];  // bin of the all-zero tuple
     const fr_t ig_pad = fr_ld(ig + o + k_pad);
+    // an inactive row inside the table rows AND inside the zero run of A' (S' = padding value):
+    // (0+beta)(S+gamma) / ((0+beta)(pad+gamma)) = (S+gamma)/(pad+gamma), per table entry
+    if (k < view_entries(v)) fr_st(sgz + o + k, fr_mul(fr_add(fr_ld(val + o + k), fr_ld(chal + 2)), ig_pad));
+    if (k >= viewmeta[v * 8 + 1]) return;
     const fr_t b = fr_ld(ib + o + k);
     const fr_t g = fr_mul(b, fr_ld(ig + o + k));
     const fr_t p = fr_mul(b, ig_pad);
@@ -813,6 +817,7 @@ struct ZArgs {
     const fr_t *chal;
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
     const fr_t *nacp, *ibgz, *ibpz;                      // [3][BIN_STRIDE] one-operand-constant factors
+    const fr_t *sgz;                                     // [3][BIN_STRIDE] per table entry (see k_inv_merge)
     const LookupMeta *meta;
     uint32_t *chunkmask;  // [count][m] one bit per row of the chunk: factor is not one
     unsigned long long *nonconst;  // [L] rows with a factor other than one (statistics)
@@ -855,7 +860,8 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
                              *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
                              *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
                              *__restrict__ ibp = a.ibp + vo, *__restrict__ nacp = a.nacp + vo,
-                             *__restrict__ ibgz = a.ibgz + vo, *__restrict__ ibpz = a.ibpz + vo;
+                             *__restrict__ ibgz = a.ibgz + vo, *__restrict__ ibpz = a.ibpz + vo,
+                             *__restrict__ sgz = a.sgz + vo;
     const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n;
     const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n;
     const uint32_t *__restrict__ cpp = a.codep + (uint64_t)l * n;
@@ -880,7 +886,10 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
             if (active) kin = t & 0xffffffu;
             k = ck & 0x3fffffffu;
             cls = ck >> 30;
-            if ((uint32_t)row < TABLE_ROWS) kind = 3;
+            if ((uint32_t)row < TABLE_ROWS) {
+                kind = 3;
+                if (!active && ck == c0code) { kind = 1; src = sgz + entry_of_table_row(v, (uint32_t)row); }
+            }
             else if (ck == c0code) { kind = active ? 1 : 0; src = nacp + kin; }
             else if (!active && cls != CODE_OTHER) { kind = 1; src = (cls == CODE_FIRST ? ibgz : ibpz) + k; }
             else kind = 2;
@@ -1220,7 +1229,8 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
     dim3 g2(cdiv(VIEW_MAX_ENTRIES, 256), N_VIEWS);
     prof_begin(ctx, "k_inv_merge");
     k_inv_merge<<<g2, 256, 0, ctx->stream>>>(c->d_viewmeta, c->d_rank, c->d_ib, c->d_ig, c->d_nac,
-                                             c->d_ibg, c->d_ibp, c->d_nacp, c->d_ibgz, c->d_ibpz);
+                                             c->d_ibg, c->d_ibp, c->d_nacp, c->d_ibgz, c->d_ibpz,
+                                             c->d_val, c->d_chal, c->d_sgz);
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();
@@ -1239,6 +1249,7 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
     a.ibg = c->d_ibg; a.ibp = c->d_ibp;
     a.nacp = c->d_nacp; a.ibgz = c->d_ibgz; a.ibpz = c->d_ibpz;
+    a.sgz = c->d_sgz;
     a.meta = c->d_meta;
     a.chunkmask = c->d_zmask;
     a.nonconst = c->d_znonconst;
