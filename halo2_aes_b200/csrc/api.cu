@@ -430,7 +430,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
                     c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_sgz,      c->d_pmap,     c->d_wlo,
                     c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
-                    c->d_omega_tab,     c->d_zmask,    c->d_znonconst,
+                    c->d_omega_tab,     c->d_pmask,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
@@ -915,6 +915,7 @@ static int32_t ensure_perm_ws(h2aes_circuit *c) {
         DA(c->d_omega_tab, n);
         DA(c->d_bdp, nc);
         DA(c->d_pnum, ns * n);
+        DA(c->d_pmask, ns * (n / 32));
         DA(c->d_ppre, ns * n);
         c->perm_alloc = true;
     }

@@ -89,7 +89,7 @@ struct h2aes_circuit {
     uint64_t states_cap = 0;
     uint32_t *d_trace = nullptr;   // n_sets * n words (a0 | a1<<8 | a2<<16 | op<<24)
     uint32_t *d_tracek = nullptr;  // n_sets * n words (op<<24 | bin of the row's tuple), per theta
-    uint32_t *d_codek = nullptr;   // [L][n] bin of A' | class<<30, written by k_permuted
+    uint32_t *d_codek = nullptr;   // [L][n] factor code of every row (fcode_pack), written by k_permuted
     uint32_t *d_codep = nullptr;   // [L][n] bin of S' where class == OTHER
     bool *code_valid = nullptr;    // [L] host flags: codes of lookup l match the current bins
 
@@ -156,6 +156,7 @@ struct h2aes_circuit {
     h2::fr_t *d_omega_tab = nullptr;  // [n] omega^j
     h2::fr_t *d_bdp = nullptr;        // [n_cols] beta * delta^p
     h2::fr_t *d_pnum = nullptr;       // [n_sets][n] numerators
+    uint32_t *d_pmask = nullptr;      // [n_sets][n/32] chunk masks of the permutation product
     h2::fr_t *d_ppre = nullptr;       // [n_sets][n] running denominator products
 
     // staging for the _host entry points

@@ -587,14 +587,27 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
 // padding value — so that the grand product does not repeat the searches.  With Ap == null only
 // the codes are produced.
 // ---------------------------------------------------------------------------------------------
+// factor code of a row for the grand product (bits 31..30 kind, 29..28 selector, 23..0 index):
+//   kind 0  factor exactly one (constant row)                       -> nothing to do
+//   kind 1  factor = one entry of a merged table: selector 0 nacp[bin of A], 1 ibgz[bin of A'],
+//           2 ibpz[bin of A'], 3 sgz[table entry of the row]
+//   kind 2  factor = nac[bin of A] * den(bin of A', class in the selector bits)
+//   kind 3  the same with S a table row: (A+beta)(S+gamma) * den
+constexpr uint32_t FK_ONE = 0u, FK_TABLE = 1u, FK_GENERAL = 2u, FK_TABLE_ROW = 3u;
+constexpr uint32_t FSEL_NACP = 0u, FSEL_IBGZ = 1u, FSEL_IBPZ = 2u, FSEL_SGZ = 3u;
+__device__ __forceinline__ uint32_t fcode_pack(uint32_t kind, uint32_t sel, uint32_t idx) {
+    return (kind << 30) | (sel << 28) | idx;
+}
+
 __global__ void __launch_bounds__(256)
 k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
-           const fr_t *__restrict__ val, const fr_t *__restrict__ dval,
-           const uint32_t *__restrict__ offz_all, const uint32_t *__restrict__ nzk_all,
-           const uint32_t *__restrict__ loffz_all, const uint32_t *__restrict__ lk_all,
-           const LookupMeta *__restrict__ meta, uint64_t *__restrict__ A, uint64_t *__restrict__ S,
-           uint64_t *__restrict__ Ap, uint64_t *__restrict__ Sp, uint32_t *__restrict__ codek,
-           uint32_t *__restrict__ codep, const uint32_t *__restrict__ jidx_all,
+           const uint32_t *__restrict__ tracek, const fr_t *__restrict__ val,
+           const fr_t *__restrict__ dval, const uint32_t *__restrict__ offz_all,
+           const uint32_t *__restrict__ nzk_all, const uint32_t *__restrict__ loffz_all,
+           const uint32_t *__restrict__ lk_all, const LookupMeta *__restrict__ meta,
+           uint64_t *__restrict__ A, uint64_t *__restrict__ S, uint64_t *__restrict__ Ap,
+           uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint32_t *__restrict__ codep,
+           uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
            const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, uint64_t row_begin,
            uint64_t row_end) {
     const int li = blockIdx.y;            // index inside this call
@@ -612,16 +625,21 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const uint32_t *lk = lk_all + (size_t)l * BIN_STRIDE;
     const fr_t *valv = val + (size_t)v * BIN_STRIDE;
     const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
-    uint32_t *__restrict__ ck = codek + (size_t)l * n;
+    uint32_t *__restrict__ fc = fcode + (size_t)l * n;
     uint32_t *__restrict__ cp = codep + (size_t)l * n;
+    uint32_t *__restrict__ zmk = zmask + (size_t)l * zm;
+    const uint32_t *__restrict__ tk = tracek + (uint64_t)set * n;
     const uint32_t *__restrict__ jidx = jidx_all + (size_t)l * idx_stride;
     const uint32_t *__restrict__ lidx = lidx_all + (size_t)l * idx_stride;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const fr_t zero = fr_zero();
+    // row ranges are multiples of 32 and a warp's 32 lanes sit on 32 consecutive rows, so one
+    // ballot per iteration is the non-constant mask of one chunk of the grand product
     for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
          lrow += stride) {
         const uint64_t row = row_begin + lrow;
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
+        uint32_t code = fcode_pack(FK_ONE, 0, 0);
         if (row >= usable) {
             if (A) fr_store_256(A + o, zero);
             if (S) fr_store_256(S + o, zero);
@@ -629,26 +647,42 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
                 fr_store_256(Ap + o, zero);
                 fr_store_256(Sp + o, zero);
             }
-            ck[row] = 0;
-            continue;
+        } else {
+            if (A) {
+                const uint32_t w = trace[(uint64_t)set * n + row];
+                fr_t a = zero;
+                if ((w >> 24) == op) a = fr_ld(valv + entry_of_table_row(v, table_row_of_word(w)));
+                fr_store_256(A + o, a);
+            }
+            if (S) {
+                const uint32_t e = row < TABLE_ROWS ? entry_of_table_row(v, (uint32_t)row) : 0u;
+                fr_store_256(S + o, fr_ld(valv + e));
+            }
+            const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
+            if (rb.cls == CODE_OTHER) cp[row] = rb.kp;
+            if (Ap) {
+                fr_store_256(Ap + o, fr_ld(dv + rb.k));
+                fr_store_256(Sp + o, fr_ld(dv + rb.kp));
+            }
+            // classify the row's grand-product factor (see fcode_pack)
+            const uint32_t t = tk[row];
+            const bool active = (t >> 24) == op;
+            const bool in_zero_run = rb.k == m.k_zero && rb.cls == CODE_PAD;
+            if (row < TABLE_ROWS) {
+                code = (!active && in_zero_run)
+                           ? fcode_pack(FK_TABLE, FSEL_SGZ, entry_of_table_row(v, (uint32_t)row))
+                           : fcode_pack(FK_TABLE_ROW, rb.cls, rb.k);
+            } else if (in_zero_run) {
+                if (active) code = fcode_pack(FK_TABLE, FSEL_NACP, t & 0xffffffu);
+            } else if (!active && rb.cls != CODE_OTHER) {
+                code = fcode_pack(FK_TABLE, rb.cls == CODE_FIRST ? FSEL_IBGZ : FSEL_IBPZ, rb.k);
+            } else {
+                code = fcode_pack(FK_GENERAL, rb.cls, rb.k);
+            }
         }
-        if (A) {
-            const uint32_t w = trace[(uint64_t)set * n + row];
-            fr_t a = zero;
-            if ((w >> 24) == op) a = fr_ld(valv + entry_of_table_row(v, table_row_of_word(w)));
-            fr_store_256(A + o, a);
-        }
-        if (S) {
-            const uint32_t e = row < TABLE_ROWS ? entry_of_table_row(v, (uint32_t)row) : 0u;
-            fr_store_256(S + o, fr_ld(valv + e));
-        }
-        const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
-        ck[row] = rb.k | (rb.cls << 30);
-        if (rb.cls == CODE_OTHER) cp[row] = rb.kp;
-        if (Ap) {
-            fr_store_256(Ap + o, fr_ld(dv + rb.k));
-            fr_store_256(Sp + o, fr_ld(dv + rb.kp));
-        }
+        fc[row] = code;
+        const uint32_t bal = __ballot_sync(0xffffffffu, (code >> 30) != FK_ONE);
+        if ((threadIdx.x & 31) == 0) zmk[lrow >> 5] = bal;
     }
 }
 
@@ -813,13 +847,14 @@ struct ZArgs {
     Shape sh;
     int first_lookup, count;
  const uint32_t *tracek;          // [sets][n]  op<<24 | bin of the row's input tuple
-    const uint32_t *codek, *codep;   // [L][n]     bin of A' | class<<30 ; bin of S' (class OTHER)
+    const uint32_t *fcode, *codep;   // [L][n]     factor code (k_permuted) ; bin of S' (class OTHER)
     const fr_t *chal;
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
     const fr_t *nacp, *ibgz, *ibpz;                      // [3][BIN_STRIDE] one-operand-constant factors
     const fr_t *sgz;                                     // [3][BIN_STRIDE] per table entry (see k_inv_merge)
     const LookupMeta *meta;
-    uint32_t *chunkmask;  // [count][m] one bit per row of the chunk: factor is not one
+    uint32_t *chunkmask;  // [*][mstride] one bit per row of the chunk: factor is not one
+    uint64_t mstride;     //              (lookup l at l*mstride; the permutation sets at s*mstride)
     unsigned long long *nonconst;  // [L] rows with a factor other than one (statistics)
     fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
     fr_t *bagg;       // [count][nblk] block aggregates of tot
@@ -831,14 +866,15 @@ struct ZArgs {
     uint64_t row_begin, row_end;
 };
 
-// k_z_fill: one lane per row (coalesced 4-byte reads of the row's two code words).  Most rows are
-// "constant": inactive in row order (A = 0, S = padding value) AND inside the zero run of A' with
-// the padding value as S' — numerator and denominator are the same two terms, so the factor is
-// EXACTLY ONE and the row costs no multiply and no store anywhere in the pipeline.  Of the other
-// rows almost all have one constant operand and read their factor from a merged table
-// (k_inv_merge); only rows that are both active and outside the zero run (or inside the table
-// rows, where S varies) multiply.  Non-constant factors are stored at the row's slot of the Z
-// buffer; one bit per row (non-constant) goes to a 32-bit word per chunk of ZI rows.
+// k_z_fill: materialises the non-constant factors.  k_permuted already classified every row
+// (fcode) and wrote one bit per row (factor != 1) as a 32-bit word per chunk of ZI rows.  Most
+// rows are "constant": inactive in row order (A = 0, S = padding value) AND inside the zero run
+// of A' with the padding value as S' — numerator and denominator are the same two terms, so the
+// factor is EXACTLY ONE and the row costs no multiply and no store anywhere in the pipeline;
+// chunks without any other row are skipped after reading their mask.  Of the other rows almost
+// all have one constant operand and copy their factor from a merged table (k_inv_merge); only
+// rows that are both active and outside the zero run (or inside the table rows, where S
+// varies) multiply.  Factors are stored at the row's slot of the Z buffer.
 static_assert(ZI == 32, "one warp ballot = one chunk mask");
 #ifndef ZFILL_OCC
 #define ZFILL_OCC 6
@@ -852,66 +888,52 @@ __global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
     const uint32_t op = (uint32_t)(l % ops) + 1;
     const int v = view_of_op(op);
     const uint64_t n = sh.n();
-    const uint32_t usable = (uint32_t)sh.usable();
     const uint64_t out_rows = a.row_end - a.row_begin;
     const uint32_t k_zero = a.meta[l].k_zero;
     const size_t vo = (size_t)v * BIN_STRIDE;
     const fr_t *__restrict__ valv = a.val + vo, *__restrict__ dv = a.dval + vo,
                              *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
                              *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
-                             *__restrict__ ibp = a.ibp + vo, *__restrict__ nacp = a.nacp + vo,
-                             *__restrict__ ibgz = a.ibgz + vo, *__restrict__ ibpz = a.ibpz + vo,
-                             *__restrict__ sgz = a.sgz + vo;
+                             *__restrict__ ibp = a.ibp + vo;
     const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n;
-    const uint32_t *__restrict__ ckp = a.codek + (uint64_t)l * n;
+    const uint32_t *__restrict__ fcp = a.fcode + (uint64_t)l * n;
     const uint32_t *__restrict__ cpp = a.codep + (uint64_t)l * n;
-    const uint32_t c0code = k_zero | (CODE_PAD << 30);
-    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
     uint64_t *__restrict__ zout = a.Z + (size_t)li * out_rows * 4;
-    uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.m;
+    const uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.mstride;
     const int lane = threadIdx.x & 31;
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     uint32_t n_nonconst = 0;
     // warp w handles chunks w, w + warps, ... ; chunk c = rows [row_begin + 32c, +32)
     for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
          c += warps) {
+        const uint32_t mask = cmask[c];
+        if (!mask) continue;  // every factor of the chunk is one
+        n_nonconst += __popc(mask);
         const uint64_t row = a.row_begin + c * ZI + lane;
-        // classify: 0 factor one, 1 single table entry at `src`, 2 nac[kin] * den, 3 table row
-        int kind = 0;  // also the blinding rows (their Z entries are zeroed by k_z_propagate)
-        const fr_t *src = nullptr;
-        uint32_t kin = k_zero, k = 0, cls = CODE_FIRST;
-        if (row < usable) {
-            const uint32_t t = tkp[row], ck = ckp[row];
-            const bool active = (t >> 24) == op;
-            if (active) kin = t & 0xffffffu;
-            k = ck & 0x3fffffffu;
-            cls = ck >> 30;
-            if ((uint32_t)row < TABLE_ROWS) {
-                kind = 3;
-                if (!active && ck == c0code) { kind = 1; src = sgz + entry_of_table_row(v, (uint32_t)row); }
-            }
-            else if (ck == c0code) { kind = active ? 1 : 0; src = nacp + kin; }
-            else if (!active && cls != CODE_OTHER) { kind = 1; src = (cls == CODE_FIRST ? ibgz : ibpz) + k; }
-            else kind = 2;
-        }
+        const uint32_t code = ((mask >> lane) & 1u) ? fcp[row] : 0u;
+        const uint32_t kind = code >> 30, sel = (code >> 28) & 3u, idx = code & 0xffffffu;
         fr_t f;
-        if (kind == 1) f = fr_ld(src);  // one gather for every single-table case
-        if (__any_sync(0xffffffffu, kind >= 2)) {
-            if (kind >= 2) {
+        if (kind == FK_TABLE) {
+            const fr_t *tab = sel == FSEL_NACP ? a.nacp : (sel == FSEL_IBGZ ? a.ibgz : (sel == FSEL_IBPZ ? a.ibpz : a.sgz));
+            f = fr_ld(tab + vo + idx);
+        }
+        if (__any_sync(0xffffffffu, kind >= FK_GENERAL)) {
+            if (kind >= FK_GENERAL) {
+                const uint32_t t = tkp[row];
+                const uint32_t kin = (t >> 24) == op ? (t & 0xffffffu) : k_zero;
+                const uint32_t cls = sel, k = idx;
                 fr_t den = fr_ld((cls == CODE_FIRST ? ibg : (cls == CODE_PAD ? ibp : ib)) + k);
-                fr_t num = fr_ld((kind == 3 ? dv : nac) + kin);
+                fr_t num = fr_ld((kind == FK_TABLE_ROW ? dv : nac) + kin);
                 if (cls == CODE_OTHER) den = fr_mul(den, fr_ld(ig + cpp[row]));
-                if (kind == 3) {  // S[i] is a table row: (A+beta)(S+gamma)
+                if (kind == FK_TABLE_ROW) {  // S[i] is a table row: (A+beta)(S+gamma)
+                    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
                     const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, (uint32_t)row)), gamma);
                     num = fr_mul(fr_add(num, beta), sg);
                 }
                 f = fr_mul(num, den);
             }
         }
-        if (kind != 0) fr_store_256(zout + (row - a.row_begin) * 4, f);
-        const uint32_t bal = __ballot_sync(0xffffffffu, kind != 0);
-        if (lane == 0) cmask[c] = bal;
-        n_nonconst += __popc(bal);
+        if (kind != FK_ONE) fr_store_256(zout + (row - a.row_begin) * 4, f);
     }
     if (lane == 0 && n_nonconst) atomicAdd(a.nonconst + l, (unsigned long long)n_nonconst);
 }
@@ -939,7 +961,7 @@ __global__ void __launch_bounds__(128, ZC_OCC) k_z_chunks(const ZArgs a) {
     const int li = blockIdx.y;
     const uint64_t out_rows = a.row_end - a.row_begin;
     const uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + e * ZI) * 4;
-    uint32_t mask = a.chunkmask[(size_t)li * a.m + e];
+    uint32_t mask = a.chunkmask[(size_t)li * a.mstride + e];
     fr_t tot = fr_one();  // constant rows have factor one
     auto next_q = [&]() -> int {
         if (!mask) return -1;
@@ -1069,7 +1091,7 @@ __global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
     const uint64_t row0 = a.row_begin + e * ZI;
     uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
     fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
-    uint32_t mask = a.chunkmask[(size_t)li * a.m + e];
+    uint32_t mask = a.chunkmask[(size_t)li * a.mstride + e];
     // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
     const int nvalid = row0 + ZI <= (uint64_t)usable + 1 ? ZI
                        : (row0 > usable ? 0 : (int)(usable + 1 - row0));
@@ -1210,10 +1232,11 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     if (gx > cap) gx = cap;
     dim3 g(gx, count);
     prof_begin(ctx, "k_permuted");
-    k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_val, c->d_dval, c->d_offz,
-                                           c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S, Ap, Sp,
-                                           c->d_codek, c->d_codep, c->d_jidx, c->d_lidx,
-                                           (uint32_t)c->idx_stride, row_begin, row_end);
+    k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
+                                           c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S,
+                                           Ap, Sp, c->d_codek, c->d_codep, c->d_zmask, c->zm,
+                                           c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride, row_begin,
+                                           row_end);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -1243,7 +1266,7 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.first_lookup = first;
     a.count = count;
     a.tracek = c->d_tracek;
-    a.codek = c->d_codek;
+    a.fcode = c->d_codek;
     a.codep = c->d_codep;
     a.chal = c->d_chal;
     a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
@@ -1251,7 +1274,8 @@ static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in
     a.nacp = c->d_nacp; a.ibgz = c->d_ibgz; a.ibpz = c->d_ibpz;
     a.sgz = c->d_sgz;
     a.meta = c->d_meta;
-    a.chunkmask = c->d_zmask;
+    a.chunkmask = c->d_zmask + (size_t)first * c->zm;
+    a.mstride = c->zm;
     a.nonconst = c->d_znonconst;
     a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
     a.partial = c->d_partial;
@@ -1602,7 +1626,7 @@ cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, ui
     p.Z = Zp;
     p.num = c->d_pnum;
     p.pre = c->d_ppre;
-    p.chunkmask = c->d_zmask;
+    p.chunkmask = c->d_pmask;
     p.m = n / ZI;
     prof_begin(ctx, "k_p_beta");
     k_p_beta<<<cdiv(n_cols, 64), 64, 0, s>>>(c->d_chal, c->d_dpow, n_cols, c->d_bdp);
@@ -1615,6 +1639,7 @@ cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, ui
     prof_end(ctx);
     // chunk totals, scan, chaining of the sets, running products: the lookup machinery
     ZArgs a = z_args(c, 0, n_sets, nullptr, Zp, 0, n);
+    a.chunkmask = c->d_pmask;  // the permutation's own masks ([n_sets][n/32])
     prof_begin(ctx, "k_z_chunks");
     k_z_chunks<<<dim3(cdiv(85 * ((a.m + 84) / 85), 128), n_sets), 128, 0, s>>>(a);
     prof_end(ctx);
