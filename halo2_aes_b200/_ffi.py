@@ -20,6 +20,8 @@ ERR_CUDA, ERR_NCCL, ERR_NOMEM, ERR_STATE, ERR_ZERO_DENOM = 6, 7, 8, 9, 10
 KIND_AES, KIND_KEYSCHED = 0, 1
 SBOX_REFERENCE, SBOX_FIPS197 = 0, 1
 OP_NONE, OP_RANGE, OP_XOR, OP_SBOX, OP_MUL2, OP_MUL3 = 0, 1, 2, 3, 4, 5
+DOMAIN_FFT, DOMAIN_LAGRANGE_TO_COEFF, DOMAIN_COEFF_TO_EXTENDED, DOMAIN_EXTENDED_TO_COEFF = 0, 1, 2, 3
+CS_DEGREE = 5  # cs.degree() of both circuits (lookups: 2 + 2 + 1)
 
 
 class Layout(C.Structure):
@@ -106,6 +108,14 @@ SIGNATURES = {
     "h2aes_lookup_product_host": (C.c_int32, [_vp, _u64p, _u64p, C.c_int32, C.c_int32, _vp]),
     "h2aes_perm_sigma_dev": (C.c_int32, [_vp, C.c_uint64, _vp]),
     "h2aes_perm_product_dev": (C.c_int32, [_vp, _u64p, _u64p, _vp, _vp]),
+    "h2aes_domain_query": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), _u64p]),
+    "h2aes_domain_create": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "h2aes_domain_destroy": (C.c_int32, [_vp]),
+    "h2aes_fft_dev": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32]),
+    "h2aes_lagrange_to_coeff_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "h2aes_coeff_to_extended_dev": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
+    "h2aes_extended_to_coeff_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "h2aes_domain_transform_host": (C.c_int32, [_vp, C.c_int32, _vp, C.c_int32, _vp]),
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),
     "h2aes_lookup_check": (C.c_int32, [_vp]),
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
@@ -161,6 +171,14 @@ def layout_query(kind: int, k: int, N: int) -> dict:
     out = Layout()
     check(lib().h2aes_layout_query(kind, k, N, C.byref(out)))
     return out.asdict()
+
+
+def domain_query(k: int, j: int = CS_DEGREE):
+    """(extended_k, quotient_len) of EvaluationDomain::new(j, k)"""
+    ek = C.c_int32()
+    q = C.c_uint64()
+    check(lib().h2aes_domain_query(j, k, C.byref(ek), C.byref(q)))
+    return ek.value, q.value
 
 
 def block_position(k: int, N: int, block: int):

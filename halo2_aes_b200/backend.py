@@ -276,6 +276,72 @@ class Circuit:
             pass
 
 
+class Domain:
+    """halo2's EvaluationDomain::new(j, k) on the GPU (poly/domain.rs [UPSTREAM]): the transforms
+    keygen_pk / create_proof apply to the columns the circuit kernels produce.  Columns are int64
+    CUDA tensors [ncols, len, 4]; the in-place calls return their argument."""
+
+    def __init__(self, ctx: Context, k: int, j: int = _ffi.CS_DEGREE):
+        self.ctx, self.k, self.j = ctx, k, j
+        self.extended_k, self.quotient_len = _ffi.domain_query(k, j)
+        self.n, self.extended_n = 1 << k, 1 << self.extended_k
+        h = C.c_void_p()
+        check(lib().h2aes_domain_create(ctx._h, j, k, C.byref(h)), ctx._h)
+        self._h = h
+
+    def _chk(self, t: torch.Tensor, length: int) -> int:
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.int64
+        assert t.dim() == 3 and t.shape[1] == length and t.shape[2] == 4, tuple(t.shape)
+        return t.shape[0]
+
+    def fft(self, cols: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+        """best_fft(a, omega | omega_inv, k) in place"""
+        check(lib().h2aes_fft_dev(self._h, _ptr(cols), self._chk(cols, self.n), int(inverse)), self.ctx._h)
+        return cols
+
+    def lagrange_to_coeff(self, cols: torch.Tensor) -> torch.Tensor:
+        check(lib().h2aes_lagrange_to_coeff_dev(self._h, _ptr(cols), self._chk(cols, self.n)), self.ctx._h)
+        return cols
+
+    def coeff_to_extended(self, coeff: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        nc = self._chk(coeff, self.n)
+        if out is None:
+            out = torch.empty((nc, self.extended_n, 4), dtype=torch.int64, device=self.ctx.device)
+        assert self._chk(out, self.extended_n) == nc
+        check(lib().h2aes_coeff_to_extended_dev(self._h, _ptr(coeff), nc, _ptr(out)), self.ctx._h)
+        return out
+
+    def extended_to_coeff(self, ext: torch.Tensor) -> torch.Tensor:
+        """in place; coefficients [quotient_len, extended_n) are zero afterwards"""
+        check(lib().h2aes_extended_to_coeff_dev(self._h, _ptr(ext), self._chk(ext, self.extended_n)),
+              self.ctx._h)
+        return ext
+
+    def transform_host(self, op: int, cols: np.ndarray) -> np.ndarray:
+        """h2aes_domain_transform_host: numpy uint64 [ncols, len_in, 4] -> [ncols, len_out, 4]"""
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        n_in = self.extended_n if op == _ffi.DOMAIN_EXTENDED_TO_COEFF else self.n
+        n_out = {_ffi.DOMAIN_FFT: self.n, _ffi.DOMAIN_LAGRANGE_TO_COEFF: self.n,
+                 _ffi.DOMAIN_COEFF_TO_EXTENDED: self.extended_n,
+                 _ffi.DOMAIN_EXTENDED_TO_COEFF: self.quotient_len}[op]
+        assert cols.ndim == 3 and cols.shape[1:] == (n_in, 4), cols.shape
+        out = np.empty((cols.shape[0], n_out, 4), dtype=np.uint64)
+        check(lib().h2aes_domain_transform_host(self._h, op, C.c_void_p(cols.ctypes.data), cols.shape[0],
+                                                C.c_void_p(out.ctypes.data)), self.ctx._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().h2aes_domain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _CudaArray:
     """Expose library-owned device memory to torch through __cuda_array_interface__."""
 

@@ -238,6 +238,43 @@ int32_t h2aes_perm_product_dev(h2aes_circuit *c, const uint64_t *beta, const uin
                                const uint64_t *advice_dev, uint64_t *Zp_dev);
 
 /* ---------------------------------------------------------------------------------------------
+ * Evaluation domain — SURVEY 8(f) items 3/4: the transforms on either side of the witness path.
+ * replaces: halo2_proofs v0.3.0 poly/domain.rs EvaluationDomain::{new, lagrange_to_coeff,
+ * coeff_to_extended, extended_to_coeff} and arithmetic.rs best_fft, as keygen_pk applies them to
+ * the fixed / sigma columns and create_proof to the advice, A', S', Z columns
+ * (call sites main.rs:78-101, benches/aes128.rs:91-107, benches/key_schedule.rs:108-124).
+ *   j   cs.degree() (5 for both circuits: the lookups are degree 2 + 2 + 1); quotient_poly_degree
+ *       = j - 1; extended_k = smallest with 2^extended_k >= 2^k * (j - 1)  (k + 2 here)
+ * Columns are [ncols][len][4] as everywhere else.  The extended domain is the coset
+ * zeta * <extended_omega>, zeta = Fr::ZETA = 7^((r-1)/3) (g_coset), exactly as halo2 evaluates it.
+ * Limits: 2 <= k, extended_k <= 22.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct h2aes_domain h2aes_domain;
+#define H2AES_DOMAIN_FFT 0               /* best_fft(a, omega, k): a'[i] = sum_t a[t] omega^(it)  */
+#define H2AES_DOMAIN_LAGRANGE_TO_COEFF 1 /* EvaluationDomain::lagrange_to_coeff                   */
+#define H2AES_DOMAIN_COEFF_TO_EXTENDED 2 /* EvaluationDomain::coeff_to_extended                   */
+#define H2AES_DOMAIN_EXTENDED_TO_COEFF 3 /* EvaluationDomain::extended_to_coeff                   */
+/* host-only: EvaluationDomain::new's extended_k and the length extended_to_coeff truncates to. */
+int32_t h2aes_domain_query(int32_t j, int32_t k, int32_t *extended_k, uint64_t *quotient_len);
+int32_t h2aes_domain_create(h2aes_ctx *ctx, int32_t j, int32_t k, h2aes_domain **out);
+int32_t h2aes_domain_destroy(h2aes_domain *d);
+/* in place on ncols columns of 2^k elements; inverse != 0 uses omega^-1 (no 1/n scaling). */
+int32_t h2aes_fft_dev(h2aes_domain *d, uint64_t *cols_dev, int32_t ncols, int32_t inverse);
+/* in place: evaluations over <omega> -> coefficients (inverse transform and the 1/n divisor). */
+int32_t h2aes_lagrange_to_coeff_dev(h2aes_domain *d, uint64_t *cols_dev, int32_t ncols);
+/* coeff_dev [ncols][2^k][4] -> ext_dev [ncols][2^extended_k][4]: coefficient t times zeta^t, zero
+ * padding, forward transform with extended_omega. */
+int32_t h2aes_coeff_to_extended_dev(h2aes_domain *d, const uint64_t *coeff_dev, int32_t ncols,
+                                    uint64_t *ext_dev);
+/* in place on [ncols][2^extended_k][4]: inverse transform, 1/2^extended_k, zeta^-t; the
+ * coefficients past quotient_len (halo2 truncates the vector there) are written as zero. */
+int32_t h2aes_extended_to_coeff_dev(h2aes_domain *d, uint64_t *ext_dev, int32_t ncols);
+/* any of the four with HOST buffers (copies inside): in = ncols columns of the op's input length,
+ * out = ncols columns of its output length (2^k, 2^k, 2^extended_k, quotient_len). */
+int32_t h2aes_domain_transform_host(h2aes_domain *d, int32_t op, const uint64_t *in, int32_t ncols,
+                                    uint64_t *out);
+
+/* ---------------------------------------------------------------------------------------------
  * Row-sharded single circuit (one process per GPU, shard g of G owns rows
  * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin
  * histograms (summed) and one 32-byte partial product per shard per lookup (gathered); the

@@ -87,6 +87,9 @@ def lib():
         L.orc_perm_shape.argtypes = [C.c_int] * 3 + [C.POINTER(C.c_int32)] * 3
         L.orc_permutation.argtypes = [C.c_void_p, u64p, u64p, u64p, C.POINTER(C.c_uint32), u64p]
         L.orc_domain_constants.argtypes = [C.c_int, u64p, u64p]
+        L.orc_domain_transform.restype = C.c_int64
+        L.orc_domain_transform.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
+        L.orc_domain_query.argtypes = [C.c_int, C.c_int, u64p]
         L.orc_bench_batch.argtypes = (
             [C.c_int] * 4 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int,
                              C.POINTER(C.c_double), u64p]
@@ -149,6 +152,37 @@ def domain_constants(k: int):
     om, de = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
     lib().orc_domain_constants(k, _u64(om), _u64(de))
     return om, de
+
+
+# [UPSTREAM] poly/domain.rs EvaluationDomain restated (oracle/h2aes_oracle.cpp: domain_new ...)
+FFT, LAGRANGE_TO_COEFF, COEFF_TO_EXTENDED, EXTENDED_TO_COEFF = 0, 1, 2, 3
+CS_DEGREE = 5  # cs.degree() of both circuits: the lookups have degree 2 + 2 + 1
+
+
+def domain_query(k: int, j: int = CS_DEGREE) -> dict:
+    out = np.zeros((8, 4), np.uint64)
+    ek = lib().orc_domain_query(j, k, _u64(out))
+    names = ("omega", "omega_inv", "extended_omega", "extended_omega_inv", "g_coset",
+             "g_coset_inv", "ifft_divisor", "extended_ifft_divisor")
+    d = {nm: out[i].copy() for i, nm in enumerate(names)}
+    d["extended_k"] = ek
+    d["quotient_poly_degree"] = j - 1
+    return d
+
+
+def domain_transform(op: int, k: int, a: np.ndarray, j: int = CS_DEGREE) -> np.ndarray:
+    """One column through best_fft / lagrange_to_coeff / coeff_to_extended / extended_to_coeff."""
+    a = np.ascontiguousarray(a, np.uint64)
+    ek = domain_query(k, j)["extended_k"]
+    n_in = (1 << ek) if op == EXTENDED_TO_COEFF else (1 << k)
+    assert a.shape == (n_in, 4), a.shape
+    n_out = {FFT: 1 << k, LAGRANGE_TO_COEFF: 1 << k, COEFF_TO_EXTENDED: 1 << ek,
+             EXTENDED_TO_COEFF: (1 << k) * (j - 1)}[op]
+    out = np.zeros((n_out, 4), np.uint64)
+    got = lib().orc_domain_transform(j, k, op, _u64(a), _u64(out))
+    if got != n_out:
+        raise OracleError(int(-got))
+    return out
 
 
 def tables(fips: bool = False):

@@ -1063,6 +1063,136 @@ void orc_domain_constants(int k, uint64_t omega[4], uint64_t delta[4]) {
     memcpy(delta, d.l, 32);
 }
 
+// ---------------------------------------------------------------------------------------------
+// [UPSTREAM] evaluation domain: halo2_proofs v0.3.0 poly/domain.rs (EvaluationDomain::new,
+// lagrange_to_coeff, coeff_to_extended, extended_to_coeff, distribute_powers_zeta) and
+// arithmetic.rs (best_fft, serial form).  SURVEY 8(f) items 3/4: the transforms keygen_pk applies
+// to the fixed/sigma columns and create_proof to advice, A', S', Z (call sites main.rs:78-101).
+// halo2curves 0.6.1 bn256::Fr::ZETA = 7^((r-1)/3) (re-derived in tests/test_oracle_golden.py).
+// ---------------------------------------------------------------------------------------------
+static const uint64_t ZETA_CANON[4] = {0x8b17ea66b99c90ddull, 0x5bfc41088d8daaa7ull,
+                                       0xb3c4d79d41a91758ull, 0x0ull};
+struct Domain {
+    int k, extended_k;
+    uint64_t n, quotient_poly_degree;
+    Fr omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv;
+    Fr ifft_divisor, extended_ifft_divisor;
+};
+// EvaluationDomain::new(j, k): quotient_poly_degree = j - 1; extended_k = smallest with
+// 2^extended_k >= n * (j - 1); extended_omega = ROOT_OF_UNITY squared (S - extended_k) times;
+// omega = extended_omega squared (extended_k - k) times
+static Domain domain_new(int j, int k) {
+    Domain d;
+    d.k = k;
+    d.n = 1ull << k;
+    d.quotient_poly_degree = (uint64_t)(j - 1);
+    d.extended_k = k;
+    while ((1ull << d.extended_k) < d.n * d.quotient_poly_degree) d.extended_k += 1;
+    Fr w = fr_of_canon(ROOT_OF_UNITY_CANON);
+    for (int i = d.extended_k; i < 28; ++i) w = fr_mul(w, w);
+    d.extended_omega = w;
+    for (int i = k; i < d.extended_k; ++i) w = fr_mul(w, w);
+    d.omega = w;
+    d.omega_inv = fr_inv(d.omega);
+    d.extended_omega_inv = fr_inv(d.extended_omega);
+    d.g_coset = fr_of_canon(ZETA_CANON);
+    d.g_coset_inv = fr_mul(d.g_coset, d.g_coset);
+    d.ifft_divisor = fr_inv(fr_from_u64(d.n));
+    d.extended_ifft_divisor = fr_inv(fr_from_u64(1ull << d.extended_k));
+    return d;
+}
+static uint64_t bitreverse(uint64_t v, int bits) {
+    uint64_t r = 0;
+    for (int i = 0; i < bits; ++i) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+// arithmetic.rs serial_fft: bit-reversal swap, then log_n butterfly layers with a running twiddle
+static void serial_fft(Fr *a, const Fr &omega, int log_n) {
+    const uint64_t n = 1ull << log_n;
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t rk = bitreverse(k, log_n);
+        if (k < rk) std::swap(a[rk], a[k]);
+    }
+    uint64_t m = 1;
+    for (int layer = 0; layer < log_n; ++layer) {
+        uint64_t e[4] = {n / (2 * m), 0, 0, 0};
+        const Fr w_m = fr_pow(omega, e);
+        for (uint64_t k = 0; k < n; k += 2 * m) {
+            Fr w = FR_ONE;
+            for (uint64_t j = 0; j < m; ++j) {
+                const Fr t = fr_mul(a[k + j + m], w);
+                a[k + j + m] = fr_sub(a[k + j], t);
+                a[k + j] = fr_add(a[k + j], t);
+                w = fr_mul(w, w_m);
+            }
+        }
+        m *= 2;
+    }
+}
+// EvaluationDomain::ifft
+static void domain_ifft(Fr *a, const Fr &omega_inv, int log_n, const Fr &divisor) {
+    serial_fft(a, omega_inv, log_n);
+    const uint64_t n = 1ull << log_n;
+    for (uint64_t i = 0; i < n; ++i) a[i] = fr_mul(a[i], divisor);
+}
+// distribute_powers_zeta: a[i] *= [1, c0, c1][i % 3] with (c0, c1) = (zeta, zeta^2) into the
+// coset and (zeta^2, zeta) out of it
+static void distribute_powers_zeta(const Domain &d, Fr *a, uint64_t len, bool into_coset) {
+    const Fr c0 = into_coset ? d.g_coset : d.g_coset_inv, c1 = into_coset ? d.g_coset_inv : d.g_coset;
+    for (uint64_t i = 0; i < len; ++i) {
+        const uint64_t r = i % 3;
+        if (r == 1) a[i] = fr_mul(a[i], c0);
+        if (r == 2) a[i] = fr_mul(a[i], c1);
+    }
+}
+
+// op: 0 best_fft(a, omega, k)            (coefficients -> evaluations over the 2^k domain)
+//     1 lagrange_to_coeff                  (in place, 2^k elements)
+//     2 coeff_to_extended                  (in: 2^k coefficients, out: 2^extended_k evaluations
+//                                           over the coset zeta * <extended_omega>)
+//     3 extended_to_coeff                  (in: 2^extended_k, out: n * (j-1) coefficients)
+// returns the number of output elements (or a negative error)
+int64_t orc_domain_transform(int j, int k, int op, const uint64_t *in, uint64_t *out) {
+    if (k < 1 || k > 26 || j < 2) return -ORC_ERR_ARG;
+    const Domain d = domain_new(j, k);
+    const uint64_t en = 1ull << d.extended_k;
+    if (op == 0 || op == 1) {
+        std::vector<Fr> a(d.n);
+        memcpy(a.data(), in, d.n * 32);
+        if (op == 0) serial_fft(a.data(), d.omega, k);
+        else domain_ifft(a.data(), d.omega_inv, k, d.ifft_divisor);
+        memcpy(out, a.data(), d.n * 32);
+        return (int64_t)d.n;
+    }
+    if (op == 2) {
+        std::vector<Fr> a(en, fr_from_u64(0));
+        memcpy(a.data(), in, d.n * 32);
+        distribute_powers_zeta(d, a.data(), d.n, true);
+        serial_fft(a.data(), d.extended_omega, d.extended_k);
+        memcpy(out, a.data(), en * 32);
+        return (int64_t)en;
+    }
+    if (op == 3) {
+        std::vector<Fr> a(en);
+        memcpy(a.data(), in, en * 32);
+        domain_ifft(a.data(), d.extended_omega_inv, d.extended_k, d.extended_ifft_divisor);
+        distribute_powers_zeta(d, a.data(), en, false);
+        const uint64_t keep = d.n * d.quotient_poly_degree;
+        memcpy(out, a.data(), keep * 32);
+        return (int64_t)keep;
+    }
+    return -ORC_ERR_ARG;
+}
+// omega, omega_inv, extended_omega, extended_omega_inv, g_coset, g_coset_inv, ifft_divisor,
+// extended_ifft_divisor (8 x 4 limbs); returns extended_k
+int orc_domain_query(int j, int k, uint64_t *out32) {
+    const Domain d = domain_new(j, k);
+    const Fr *f[8] = {&d.omega, &d.omega_inv, &d.extended_omega, &d.extended_omega_inv,
+                      &d.g_coset, &d.g_coset_inv, &d.ifft_divisor, &d.extended_ifft_divisor};
+    for (int i = 0; i < 8; ++i) memcpy(out32 + 4 * i, f[i]->l, 32);
+    return d.extended_k;
+}
+
 // ---- small Fr helpers so Python tests can do field arithmetic through the same code ----------
 void orc_fr_from_u64(uint64_t v, uint64_t out[4]) { Fr a = fr_from_u64(v); memcpy(out, a.l, 32); }
 void orc_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t out[4]) {
