@@ -116,6 +116,9 @@ SIGNATURES = {
     "h2aes_coeff_to_extended_dev": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
     "h2aes_extended_to_coeff_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
     "h2aes_domain_transform_host": (C.c_int32, [_vp, C.c_int32, _vp, C.c_int32, _vp]),
+    "h2aes_lookup_quotient_dev": (C.c_int32, [_vp, _vp, _u64p, _u64p, _u64p, _u64p, C.c_int32, C.c_int32,
+                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "h2aes_divide_by_vanishing_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),
     "h2aes_lookup_check": (C.c_int32, [_vp]),
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),

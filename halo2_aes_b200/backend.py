@@ -217,6 +217,24 @@ class Circuit:
         check(lib().h2aes_perm_product_dev(self._h, bep, gap, _ptr(advice), _ptr(out)), self.ctx._h)
         return out
 
+    def lookup_quotient(self, dom: "Domain", theta, beta, gamma, y, advice_ext, table_ext, sel_ext,
+                        Ap_ext, Sp_ext, Z_ext, values_ext, first=0):
+        """evaluate_h, lookup part (h2aes_lookup_quotient_dev): folds the five expressions of
+        lookups [first, first + len(Z_ext)) into `values_ext` ([2^extended_k, 4], in place)."""
+        count = Z_ext.shape[0]
+        en = dom.extended_n
+        for t, nc in ((advice_ext, self.layout["n_advice"]), (table_ext, 4), (sel_ext, count),
+                      (Ap_ext, count), (Sp_ext, count), (Z_ext, count)):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.int64
+            assert tuple(t.shape) == (nc, en, 4), (tuple(t.shape), nc)
+        assert values_ext.is_cuda and values_ext.is_contiguous() and tuple(values_ext.shape) == (en, 4)
+        keep = [_fr_arg(v) for v in (theta, beta, gamma, y)]
+        check(lib().h2aes_lookup_quotient_dev(self._h, dom._h, *[k[1] for k in keep], first, count,
+                                              _ptr(advice_ext), _ptr(table_ext), _ptr(sel_ext),
+                                              _ptr(Ap_ext), _ptr(Sp_ext), _ptr(Z_ext),
+                                              _ptr(values_ext)), self.ctx._h)
+        return values_ext
+
     def lookup_stats(self) -> np.ndarray:
         """rows per lookup whose grand-product factor is not one (last product call)"""
         out = np.zeros(self.layout["n_lookups"], np.uint64)
@@ -316,6 +334,16 @@ class Domain:
         check(lib().h2aes_extended_to_coeff_dev(self._h, _ptr(ext), self._chk(ext, self.extended_n)),
               self.ctx._h)
         return ext
+
+    def divide_by_vanishing(self, ext: torch.Tensor) -> torch.Tensor:
+        """EvaluationDomain::divide_by_vanishing_poly, in place on [ncols, 2^extended_k, 4]"""
+        check(lib().h2aes_divide_by_vanishing_dev(self._h, _ptr(ext), self._chk(ext, self.extended_n)),
+              self.ctx._h)
+        return ext
+
+    def to_extended(self, lagrange: torch.Tensor) -> torch.Tensor:
+        """Lagrange columns [ncols, 2^k, 4] -> their extended cosets (a copy goes to coefficient form)"""
+        return self.coeff_to_extended(self.lagrange_to_coeff(lagrange.clone()))
 
     def transform_host(self, op: int, cols: np.ndarray) -> np.ndarray:
         """h2aes_domain_transform_host: numpy uint64 [ncols, len_in, 4] -> [ncols, len_out, 4]"""

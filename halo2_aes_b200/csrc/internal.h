@@ -167,6 +167,19 @@ struct h2aes_circuit {
     uint8_t *d_ct = nullptr;
 };
 
+// evaluation domain (ntt.cu); the extended Lagrange columns are built on first use (quotient.cu)
+struct h2aes_domain {
+    h2aes_ctx *ctx = nullptr;
+    int j = 0, k = 0, extended_k = 0;
+    uint64_t n = 0, en = 0, quotient_len = 0;
+    h2::fr_t *d_tw = nullptr;       // [en] extended_omega^e
+    h2::fr_t *d_consts = nullptr;   // 4 groups of 3: coset in, 1/n, 1/en * zeta^-i, (spare)
+    h2::fr_t *d_scratch = nullptr;  // [batch][en]
+    int batch = 0;
+    h2::fr_t *d_lagrange = nullptr; // [3][en] l0, l_last, l_active_row on the extended coset
+    h2::fr_t *d_tinv = nullptr;     // [2^(extended_k-k)] 1 / ((zeta*extended_omega^i)^n - 1)
+};
+
 // per-kernel timing hooks (no-ops unless h2aes_ctx_profile(ctx, 1) was called)
 static inline void prof_begin(h2aes_ctx *ctx, const char *name) {
     if (!ctx->profiling) return;

@@ -159,15 +159,10 @@ k_ntt_twiddles(const fr_t *__restrict__ w_lo, const fr_t *__restrict__ w_hi, uin
 
 using namespace h2;
 
-struct h2aes_domain {
-    h2aes_ctx *ctx = nullptr;
-    int j = 0, k = 0, extended_k = 0;
-    uint64_t n = 0, en = 0, quotient_len = 0;
-    fr_t *d_tw = nullptr;       // [en] extended_omega^e
-    fr_t *d_consts = nullptr;   // 4 groups of 3: coset in, 1/n, 1/en * zeta^-i, (spare)
-    fr_t *d_scratch = nullptr;  // [batch][en]
-    int batch = 0;
-};
+namespace h2 {
+fr_t domain_zeta();
+fr_t domain_extended_omega(int extended_k);
+}
 
 namespace {
 
@@ -207,6 +202,18 @@ fr_t fr_from_u64_host(uint64_t x) {
     a.v[1] = (uint32_t)(x >> 32);
     return fr_mul(a, fr_r2());
 }
+
+}  // namespace
+namespace h2 {
+fr_t domain_zeta() { return zeta(); }
+// extended_omega = ROOT_OF_UNITY squared (S - extended_k) times
+fr_t domain_extended_omega(int extended_k) {
+    fr_t w = root_of_unity_2_28();
+    for (int i = extended_k; i < 28; ++i) w = fr_mul(w, w);
+    return w;
+}
+}  // namespace h2
+namespace {
 
 // EvaluationDomain::new: extended_k = smallest with 2^extended_k >= n * (j - 1)
 bool domain_shape(int j, int k, int *extended_k, uint64_t *quotient_len) {
@@ -312,9 +319,7 @@ int32_t h2aes_domain_create(h2aes_ctx *ctx, int32_t j, int32_t k, h2aes_domain *
         h2aes_domain_destroy(d);
         return dcuda(ctx, e, "domain: cudaMalloc");
     }
-    // extended_omega = ROOT_OF_UNITY squared (S - extended_k) times
-    fr_t w = root_of_unity_2_28();
-    for (int i = ek; i < 28; ++i) w = fr_mul(w, w);
+    const fr_t w = domain_extended_omega(ek);
     std::vector<fr_t> lo(1u << NTT_W_LO_BITS), hi(n_hi);
     lo[0] = fr_one();
     for (size_t t = 1; t < lo.size(); ++t) lo[t] = fr_mul(lo[t - 1], w);
@@ -356,6 +361,8 @@ int32_t h2aes_domain_destroy(h2aes_domain *d) {
     cudaFree(d->d_tw);
     cudaFree(d->d_consts);
     cudaFree(d->d_scratch);
+    cudaFree(d->d_lagrange);
+    cudaFree(d->d_tinv);
     delete d;
     return H2AES_OK;
 }

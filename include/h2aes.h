@@ -274,6 +274,33 @@ int32_t h2aes_extended_to_coeff_dev(h2aes_domain *d, uint64_t *ext_dev, int32_t 
 int32_t h2aes_domain_transform_host(h2aes_domain *d, int32_t op, const uint64_t *in, int32_t ncols,
                                     uint64_t *out);
 
+/* ---- lookup terms of the quotient polynomial — SURVEY 8(f) item 4 ---------------------------
+ * replaces: halo2_proofs v0.3.0 plonk/evaluation.rs Evaluator::evaluate_h, lookup part, for lookups
+ * [first, first+count) in meta.lookup order (call sites: create_proof, main.rs:94-101).  For each
+ * lookup the running accumulator takes five steps values = values*y + expr with the expressions
+ *   (1 - z) l0;  (z^2 - z) l_last;  (z(wX)(a'+beta)(s'+gamma) - z (A+beta)(S+gamma)) l_active_row;
+ *   (a' - s') l0;  (a' - s')(a' - a'(X/w)) l_active_row
+ * evaluated on the extended coset; A, S = theta-folds of the lookup's input expressions
+ * (q*tag, q*x, ...: src/chips/*.rs configure) and of its table columns.
+ *   d           domain (j = 5, k = the circuit's); l0 / l_last / l_active_row are built on first use
+ *               as keygen.rs does (blinding_factors = 5)
+ *   advice_ext  [n_advice][2^extended_k][4]  extended cosets of the advice polynomials
+ *   table_ext   [4][2^extended_k][4]         ... of the 4 table columns
+ *   sel_ext     [count][2^extended_k][4]     ... of the selectors of lookups first..first+count-1
+ *   Ap/Sp/Z_ext [count][2^extended_k][4]     ... of A', S', Z of the same lookups
+ *   theta, beta, gamma, y   host, 4 u64 Montgomery limbs each
+ *   values_ext  [2^extended_k][4] in/out: the accumulator (gates and permutation terms come first
+ *               in halo2's order; start from zero for the lookup terms alone) */
+int32_t h2aes_lookup_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const uint64_t *theta,
+                                  const uint64_t *beta, const uint64_t *gamma, const uint64_t *y,
+                                  int32_t first, int32_t count, const uint64_t *advice_ext,
+                                  const uint64_t *table_ext, const uint64_t *sel_ext,
+                                  const uint64_t *Ap_ext, const uint64_t *Sp_ext,
+                                  const uint64_t *Z_ext, uint64_t *values_ext);
+/* replaces: EvaluationDomain::divide_by_vanishing_poly: element i of every column times
+ * 1 / ((zeta * extended_omega^i)^n - 1).  In place on [ncols][2^extended_k][4]. */
+int32_t h2aes_divide_by_vanishing_dev(h2aes_domain *d, uint64_t *ext_dev, int32_t ncols);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-sharded single circuit (one process per GPU, shard g of G owns rows
  * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin

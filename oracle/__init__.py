@@ -90,6 +90,9 @@ def lib():
         L.orc_domain_transform.restype = C.c_int64
         L.orc_domain_transform.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
         L.orc_domain_query.argtypes = [C.c_int, C.c_int, u64p]
+        L.orc_lookup_quotient.argtypes = [C.c_void_p, C.c_int, C.c_int] + [u64p] * 5
+        L.orc_divide_by_vanishing.argtypes = [C.c_int, C.c_int, u64p]
+        L.orc_poly_eval.argtypes = [u64p, C.c_uint64, u64p, u64p]
         L.orc_bench_batch.argtypes = (
             [C.c_int] * 4 + [u8p, u8p, C.c_uint64, u64p, u64p, u64p, C.c_int,
                              C.POINTER(C.c_double), u64p]
@@ -182,6 +185,23 @@ def domain_transform(op: int, k: int, a: np.ndarray, j: int = CS_DEGREE) -> np.n
     got = lib().orc_domain_transform(j, k, op, _u64(a), _u64(out))
     if got != n_out:
         raise OracleError(int(-got))
+    return out
+
+
+def divide_by_vanishing(k: int, a: np.ndarray, j: int = CS_DEGREE) -> np.ndarray:
+    """EvaluationDomain::divide_by_vanishing_poly on one extended column (returns a copy)."""
+    a = np.array(a, dtype=np.uint64, order="C", copy=True)
+    assert a.shape == (1 << domain_query(k, j)["extended_k"], 4)
+    lib().orc_divide_by_vanishing(j, k, _u64(a))
+    return a
+
+
+def poly_eval(coeffs: np.ndarray, x) -> np.ndarray:
+    """Horner evaluation of a coefficient column at the field element x (Montgomery limbs)."""
+    coeffs = np.ascontiguousarray(coeffs, np.uint64)
+    xx = np.ascontiguousarray(x, np.uint64)
+    out = np.zeros(4, np.uint64)
+    lib().orc_poly_eval(_u64(coeffs), coeffs.shape[0], _u64(xx), _u64(out))
     return out
 
 
@@ -291,6 +311,20 @@ class Circuit:
         if rc:
             raise OracleError(rc)
         return bufs
+
+    def lookup_quotient(self, theta, beta, gamma, y, first=0, count=None, values=None) -> np.ndarray:
+        """halo2 v0.3.0 evaluate_h, lookup terms of lookups [first, first+count): the running
+        extended-domain accumulator `values` (zero when None) after those lookups."""
+        sh = shape(self.kind, self.k, self.N)
+        count = sh["n_lookups"] - first if count is None else count
+        en = 1 << domain_query(self.k)["extended_k"]
+        acc = np.zeros((en, 4), np.uint64) if values is None else np.array(values, np.uint64, order="C", copy=True)
+        assert acc.shape == (en, 4)
+        args = [np.ascontiguousarray(v, dtype=np.uint64) for v in (theta, beta, gamma, y)]
+        rc = lib().orc_lookup_quotient(self._h, first, count, *[_u64(v) for v in args], _u64(acc))
+        if rc:
+            raise OracleError(rc)
+        return acc
 
     def permutation(self, beta, gamma, want=("sigma", "mapping", "Z")) -> dict:
         """halo2 v0.3.0 permutation argument: sigma columns (keygen), the (column, row) mapping

@@ -1193,6 +1193,134 @@ int orc_domain_query(int j, int k, uint64_t *out32) {
     return d.extended_k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// [UPSTREAM] plonk/evaluation.rs Evaluator::evaluate_h, the lookup part, and
+// vanishing/prover.rs + poly/domain.rs divide_by_vanishing_poly (halo2_proofs v0.3.0).
+// SURVEY 8(f) item 4.  For every lookup, in meta.lookup order, with `values` the running
+// extended-domain accumulator and idx an extended row (r_next / r_prev = idx +- 2^(ek-k)):
+//   values = values*y + (1 - z) * l0
+//   values = values*y + (z^2 - z) * l_last
+//   values = values*y + (z[r_next] (a'+beta)(s'+gamma) - z (A+beta)(S+gamma)) * l_active_row
+//   values = values*y + (a' - s') * l0
+//   values = values*y + (a' - s')(a' - a'[r_prev]) * l_active_row
+// A, S = the theta-compressions of the input / table expressions evaluated on the extended
+// coset (q*tag, q*x, ... with q, x the cosets of the selector and advice polynomials).
+// l0, l_last, l_blind as keygen.rs builds them: one-hot Lagrange columns at row 0, row n-6 and
+// rows n-5.., taken to the extended coset; l_active_row = 1 - (l_last + l_blind).
+// ---------------------------------------------------------------------------------------------
+static const int BLINDING_FACTORS = 5;  // cs.blinding_factors() of both circuits (usable = n - 6)
+
+static std::vector<Fr> to_extended(const Domain &d, const Fr *lagrange) {
+    std::vector<Fr> a(1ull << d.extended_k, FR_ZERO);
+    memcpy(a.data(), lagrange, d.n * 32);
+    domain_ifft(a.data(), d.omega_inv, d.k, d.ifft_divisor);
+    distribute_powers_zeta(d, a.data(), d.n, true);
+    serial_fft(a.data(), d.extended_omega, d.extended_k);
+    return a;
+}
+
+struct ExtLagrange {
+    std::vector<Fr> l0, l_last, l_active_row;
+};
+static ExtLagrange ext_lagrange(const Domain &d) {
+    std::vector<Fr> v(d.n, FR_ZERO);
+    ExtLagrange e;
+    v[0] = FR_ONE;
+    e.l0 = to_extended(d, v.data());
+    v[0] = FR_ZERO;
+    v[d.n - BLINDING_FACTORS - 1] = FR_ONE;
+    e.l_last = to_extended(d, v.data());
+    v[d.n - BLINDING_FACTORS - 1] = FR_ZERO;
+    for (int i = 0; i < BLINDING_FACTORS; ++i) v[d.n - 1 - i] = FR_ONE;
+    std::vector<Fr> l_blind = to_extended(d, v.data());
+    const uint64_t en = 1ull << d.extended_k;
+    e.l_active_row.resize(en);
+    for (uint64_t i = 0; i < en; ++i)
+        e.l_active_row[i] = fr_sub(FR_ONE, fr_add(e.l_last[i], l_blind[i]));
+    return e;
+}
+
+// values (2^extended_k elements, in/out) accumulates lookups [first, first+count) of the
+// circuit's own columns; blinding rows of every column are zero, as everywhere in this oracle.
+int orc_lookup_quotient(void *h, int first, int count, const uint64_t *theta_,
+                        const uint64_t *beta_, const uint64_t *gamma_, const uint64_t *y_,
+                        uint64_t *values) {
+    Circuit *c = (Circuit *)h;
+    const Shape &sh = c->s.sh;
+    if (first < 0 || count < 0 || first + count > sh.n_lookups()) return ORC_ERR_ARG;
+    const Domain d = domain_new(5, sh.k);
+    const uint64_t en = 1ull << d.extended_k, n = d.n;
+    const int64_t rot = (int64_t)1 << (d.extended_k - d.k);
+    const Fr theta = fr_load(theta_), beta = fr_load(beta_), gamma = fr_load(gamma_), y = fr_load(y_);
+    const ExtLagrange L = ext_lagrange(d);
+    Columns cols = view_of(c->s);
+    std::vector<Fr> acc(en);
+    memcpy(acc.data(), values, en * 32);
+    std::vector<std::vector<Fr>> table_ext;
+    for (int t = 0; t < 4; ++t) table_ext.push_back(to_extended(d, cols.fixed[t]));
+    std::vector<Fr> tmp(n);
+    for (int li = first; li < first + count; ++li) {
+        const LookupDef def = lookup_def(sh, li);
+        std::vector<Fr> a, s, ap, sp, z;
+        compress_lookup(cols, def, theta, a, s);
+        int rc = permute_expression_pair(sh, a, s, ap, sp);
+        if (rc) return rc;
+        commit_product(sh, a, s, ap, sp, beta, gamma, z);
+        const std::vector<Fr> ap_e = to_extended(d, ap.data()), sp_e = to_extended(d, sp.data()),
+                              z_e = to_extended(d, z.data());
+        for (uint64_t i = 0; i < n; ++i) tmp[i] = cols.selectors[def.selector][i] ? FR_ONE : FR_ZERO;
+        const std::vector<Fr> q_e = to_extended(d, tmp.data());
+        std::vector<std::vector<Fr>> adv_e;
+        for (int jx = 0; jx + 1 < def.m; ++jx) adv_e.push_back(to_extended(d, cols.advice[def.adv[jx]]));
+        const Fr tag = fr_from_u64(def.tag);
+        for (uint64_t idx = 0; idx < en; ++idx) {
+            // the lookup's expressions on the extended coset, folded with theta
+            Fr in = fr_mul(q_e[idx], tag), tb = table_ext[0][idx];
+            for (int jx = 0; jx + 1 < def.m; ++jx) {
+                in = fr_add(fr_mul(in, theta), fr_mul(q_e[idx], adv_e[jx][idx]));
+                tb = fr_add(fr_mul(tb, theta), table_ext[1 + jx][idx]);
+            }
+            const Fr table_value = fr_mul(fr_add(in, beta), fr_add(tb, gamma));
+            const uint64_t r_next = (uint64_t)(((int64_t)idx + rot) % (int64_t)en);
+            const uint64_t r_prev = (uint64_t)(((int64_t)idx - rot + (int64_t)en) % (int64_t)en);
+            const Fr a_minus_s = fr_sub(ap_e[idx], sp_e[idx]);
+            Fr v = acc[idx];
+            v = fr_add(fr_mul(v, y), fr_mul(fr_sub(FR_ONE, z_e[idx]), L.l0[idx]));
+            v = fr_add(fr_mul(v, y), fr_mul(fr_sub(fr_mul(z_e[idx], z_e[idx]), z_e[idx]), L.l_last[idx]));
+            const Fr lhs = fr_mul(fr_mul(z_e[r_next], fr_add(ap_e[idx], beta)), fr_add(sp_e[idx], gamma));
+            v = fr_add(fr_mul(v, y), fr_mul(fr_sub(lhs, fr_mul(z_e[idx], table_value)), L.l_active_row[idx]));
+            v = fr_add(fr_mul(v, y), fr_mul(a_minus_s, L.l0[idx]));
+            v = fr_add(fr_mul(v, y), fr_mul(fr_mul(a_minus_s, fr_sub(ap_e[idx], ap_e[r_prev])), L.l_active_row[idx]));
+            acc[idx] = v;
+        }
+    }
+    memcpy(values, acc.data(), en * 32);
+    return ORC_OK;
+}
+
+// EvaluationDomain::divide_by_vanishing_poly: a[i] *= t_evaluations[i % 2^(ek-k)], the inverses of
+// (zeta * extended_omega^i)^n - 1  (in place, 2^extended_k elements)
+int orc_divide_by_vanishing(int j, int k, uint64_t *a_) {
+    const Domain d = domain_new(j, k);
+    const uint64_t en = 1ull << d.extended_k, period = 1ull << (d.extended_k - d.k);
+    std::vector<Fr> t(period);
+    uint64_t e[4] = {d.n, 0, 0, 0};
+    const Fr zn = fr_pow(d.g_coset, e), wn = fr_pow(d.extended_omega, e);
+    Fr cur = zn;
+    for (uint64_t i = 0; i < period; ++i) { t[i] = fr_inv(fr_sub(cur, FR_ONE)); cur = fr_mul(cur, wn); }
+    Fr *a = (Fr *)a_;
+    for (uint64_t i = 0; i < en; ++i) a[i] = fr_mul(a[i], t[i % period]);
+    return ORC_OK;
+}
+
+// Horner evaluation of a coefficient vector at x (eval_polynomial of arithmetic.rs)
+void orc_poly_eval(const uint64_t *coeffs, uint64_t len, const uint64_t *x_, uint64_t out[4]) {
+    const Fr x = fr_load(x_);
+    Fr acc = FR_ZERO;
+    for (uint64_t i = len; i-- > 0;) acc = fr_add(fr_mul(acc, x), fr_load(coeffs + 4 * i));
+    memcpy(out, acc.l, 32);
+}
+
 // ---- small Fr helpers so Python tests can do field arithmetic through the same code ----------
 void orc_fr_from_u64(uint64_t v, uint64_t out[4]) { Fr a = fr_from_u64(v); memcpy(out, a.l, 32); }
 void orc_fr_mul(const uint64_t *a, const uint64_t *b, uint64_t out[4]) {
