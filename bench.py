@@ -408,6 +408,20 @@ def run_b200(args):
         e2e = run_e2e(args, pipes[0].ctx, pipes[0].cir, pipes[0].stream, pipes[0].keys, th, be, ga,
                       rank, world)
 
+    # ---- what follows the witness path in the prover; reported, not timed
+    prover_side = None
+    if rank == 0 and world == 1 and not args.no_prover_side:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location(
+                "prover_side", os.path.join(ROOT, "profiles", "prover_side.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            with torch.cuda.stream(pipes[0].stream):
+                prover_side = mod.measure(pipes[0].ctx, lay["k"], lay["n_sets"])
+        except Exception as e:  # never lose the headline line to the extra measurement
+            prover_side = {"error": repr(e)}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -428,6 +442,7 @@ def run_b200(args):
             "witness_only_blocks_per_s": nb / (ph_iso["witness"] * 1e-3),
             "permutation_product": perm,
             "nonconstant_rows": nc, "nonconstant_row_fraction": nc / (L * n),
+            "prover_side": prover_side,
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
         }
         emit(out)
@@ -520,6 +535,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-perm", action="store_true")
+    ap.add_argument("--no-prover-side", action="store_true",
+                    help="skip the NTT / lookup-quotient measurement (SURVEY 8f items 3/4)")
     ap.add_argument("--pipelines", type=int, default=2,
                     help="independent circuits in flight per GPU (each on its own stream)")
     args = ap.parse_args()

@@ -201,12 +201,51 @@ FR_D void fr_reduce_once_dev(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t 
 // hundreds of KB of SASS and stalls on instruction fetch (ncu: stall_no_inst 36% in
 // k_grand_product); as a call the whole multiply stays resident in the instruction cache.
 // Operands and result travel in registers (structs of 8 x u32 by value).
-static __device__ __noinline__ fr_t fr_mul_call(fr_t a, fr_t b) {
+#ifndef FR_MUL_LINKAGE
+#define FR_MUL_LINKAGE __noinline__
+#endif
+static __device__ FR_MUL_LINKAGE fr_t fr_mul_call(fr_t a, fr_t b) {
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
 #include "fr_mul_ptx.inc"
     fr_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
     fr_t o = {{r0, r1, r2, r3, r4, r5, r6, r7}};
     return o;
+}
+// Two independent products in one call: the carry chains of the two multiplies interleave, so a
+// warp keeps the multiplier busy on its own (used where occupancy is bounded by shared memory).
+struct fr_pair_t {
+    fr_t x, y;
+};
+static __device__ FR_MUL_LINKAGE fr_pair_t fr_mul2_call(fr_t a, fr_t b, fr_t c, fr_t d) {
+    fr_pair_t o;
+    {
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+#include "fr_mul_ptx.inc"
+        fr_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
+        o.x = fr_t{{r0, r1, r2, r3, r4, r5, r6, r7}};
+    }
+    {
+        const fr_t a = c, b = d;
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+#include "fr_mul_ptx.inc"
+        fr_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
+        o.y = fr_t{{r0, r1, r2, r3, r4, r5, r6, r7}};
+    }
+    return o;
+}
+#endif
+
+#if defined(__CUDACC__)
+// x = x*b, y = y*d (device: one interleaved call; host: two portable products)
+FR_HD void fr_mul2(fr_t &x, const fr_t &b, fr_t &y, const fr_t &d) {
+#if defined(__CUDA_ARCH__) && !defined(H2AES_PORTABLE_MUL)
+    const fr_pair_t o = fr_mul2_call(x, b, y, d);
+    x = o.x;
+    y = o.y;
+#else
+    x = fr_mul_portable(x, b);
+    y = fr_mul_portable(y, d);
+#endif
 }
 #endif
 

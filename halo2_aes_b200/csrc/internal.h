@@ -173,6 +173,7 @@ struct h2aes_domain {
     int j = 0, k = 0, extended_k = 0;
     uint64_t n = 0, en = 0, quotient_len = 0;
     h2::fr_t *d_tw = nullptr;       // [en] extended_omega^e
+    h2::fr_t *d_ctw = nullptr;      // compact per-size tables omega_m^e at [m + e], m <= 2^11
     h2::fr_t *d_consts = nullptr;   // 4 groups of 3: coset in, 1/n, 1/en * zeta^-i, (spare)
     h2::fr_t *d_scratch = nullptr;  // [batch][en]
     int batch = 0;

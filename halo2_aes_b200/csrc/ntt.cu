@@ -13,8 +13,8 @@
 //   k_ntt_rows  for every row j1: n2-point transform over the contiguous index i2 in shared
 //               memory, stored transposed: X[j1 + n1*j2].
 // A CTA holds a 64 KiB tile (2048 elements: G columns / rows at a time, so global accesses are
-// G*32 contiguous bytes), does log2(tile transform) radix-2 stages on it with one Montgomery
-// multiply per butterfly, and touches HBM once per pass: 4 x 32 B per element per transform
+// G*32 contiguous bytes), does log2(tile transform) radix-2 stages on it, two at a time in
+// registers, with one Montgomery multiply per butterfly, and touches HBM once per pass: 4 x 32 B per element per transform
 // against (K/2 + 1) multiplies — the kernels are bound by integer-multiply issue.
 // Twiddles come from one table of extended_omega^e (e < 2^extended_k) per domain; the inverse
 // transform reads it backwards.  The coset shift (zeta^i, period 3) and the 1/N of the inverse
@@ -25,11 +25,21 @@
 #include <string>
 #include <vector>
 
+// few multiply sites per kernel here: inlined, they save the call's register shuffling (+13 %)
+#ifndef NTT_CALL_MUL
+#define FR_MUL_LINKAGE __forceinline__
+#endif
 #include "internal.h"
 
 namespace h2 {
 
-constexpr int NTT_T = 512;          // threads per CTA
+#ifndef NTT_THREADS
+#define NTT_THREADS 256
+#endif
+#ifndef NTT_OCC
+#define NTT_OCC 3
+#endif
+constexpr int NTT_T = NTT_THREADS;  // threads per CTA
 constexpr int NTT_TILE_LOG = 11;    // elements per shared-memory tile (64 KiB)
 constexpr int NTT_W_LO_BITS = 10;
 
@@ -58,6 +68,7 @@ struct NttArgs {
     int inverse;                     // read the table backwards: omega_N^-e
     int mul3;                        // multiply element x by c[x % 3] (pass A: on load; B: on store)
     const fr_t *tw;
+    const fr_t *ctw;                 // compact tables: omega_m^e, e < m, at ctw + m, m = 2..2^TILE_LOG
     const fr_t *c;                   // 3 constants (device)
 };
 
@@ -67,30 +78,68 @@ __device__ __forceinline__ fr_t ntt_twiddle(const NttArgs &a, uint64_t e) {
     return nfr_ld(a.tw + idx);
 }
 
-// log2(m) radix-2 decimation-in-time stages on 2^lg independent m-point arrays in shared memory
-// (array g at s + g*m, input in bit-reversed order, output in natural order)
+// log2(m) decimation-in-time stages on 2^lg independent m-point arrays in shared memory (array g
+// at s + g*m, input in bit-reversed order, output in natural order).  Two stages at a time: a
+// thread takes the 4 elements p, p+h, p+2h, p+3h through stages h and 2h in registers (4
+// multiplies, 3 twiddles, one barrier per two stages); an odd stage count starts with the
+// multiply-free stage h = 1 on its own.
 __device__ __forceinline__ void ntt_tile_stages(fr_t *s, int lg, int ks, const NttArgs &a) {
-    const uint32_t half_log = (uint32_t)(ks - 1);
-    const uint32_t total = 1u << (lg + ks - 1);  // butterflies per stage
-    for (int lh = 0; lh < ks; ++lh) {
+    // omega_m^(+-e) from the m-entry table of this transform size (32 KiB at m = 1024: stays in L1,
+    // unlike the strided walk through the domain-wide table)
+    const fr_t *__restrict__ ctw = a.ctw + (1u << ks);
+    const uint32_t mmask = (1u << ks) - 1;
+    auto stage_tw = [&](uint32_t e) { return nfr_ld(ctw + (a.inverse ? ((mmask + 1 - e) & mmask) : e)); };
+    int lh = 0;
+    if (ks & 1) {
         __syncthreads();
+        const uint32_t total = 1u << (lg + ks - 1);
         for (uint32_t b = threadIdx.x; b < total; b += NTT_T) {
-            const uint32_t g = b >> half_log, bb = b & ((1u << half_log) - 1);
-            const uint32_t j = bb & ((1u << lh) - 1), blk = bb >> lh;
-            const uint32_t p0 = (g << ks) + (blk << (lh + 1)) + j, p1 = p0 + (1u << lh);
-            const fr_t u = nfr_ld(s + p0);
-            fr_t t = nfr_ld(s + p1);
-            // omega_m^(j m / 2h) = omega_N^(j N / 2h); the first stage has j == 0 everywhere
-            if (lh > 0) t = fr_mul(t, ntt_twiddle(a, (uint64_t)j << (a.K - 1 - lh)));
-            nfr_st(s + p0, fr_add(u, t));
-            nfr_st(s + p1, fr_sub(u, t));
+            const fr_t u = nfr_ld(s + 2 * b), t = nfr_ld(s + 2 * b + 1);
+            nfr_st(s + 2 * b, fr_add(u, t));
+            nfr_st(s + 2 * b + 1, fr_sub(u, t));
+        }
+        lh = 1;
+    }
+    if (ks < 2) {
+        __syncthreads();
+        return;
+    }
+    const uint32_t quarter_log = (uint32_t)(ks - 2);
+    const uint32_t total = 1u << (lg + ks - 2);  // groups of 4 per round
+    for (; lh < ks; lh += 2) {
+        __syncthreads();
+        const uint32_t h = 1u << lh;
+        for (uint32_t b = threadIdx.x; b < total; b += NTT_T) {
+            const uint32_t g = b >> quarter_log, bb = b & ((1u << quarter_log) - 1);
+            const uint32_t j = bb & (h - 1), blk = bb >> lh;
+            fr_t *p = s + (g << ks) + (blk << (lh + 2)) + j;
+            fr_t x0 = nfr_ld(p), x1 = nfr_ld(p + h), x2 = nfr_ld(p + 2 * h), x3 = nfr_ld(p + 3 * h);
+            // stage h: (x0, x1) and (x2, x3), both with omega_N^(j N / 2h)
+            if (lh > 0) {
+                const fr_t w = stage_tw(j << (ks - 1 - lh));
+                fr_mul2(x1, w, x3, w);
+            }
+            fr_t t = x1;
+            x1 = fr_sub(x0, t);
+            x0 = fr_add(x0, t);
+            t = x3;
+            x3 = fr_sub(x2, t);
+            x2 = fr_add(x2, t);
+            // stage 2h: (x0, x2) with omega_N^(j N / 4h), (x1, x3) with omega_N^((j + h) N / 4h)
+            const fr_t w3 = stage_tw((j + h) << (ks - 2 - lh));
+            if (lh > 0) fr_mul2(x2, stage_tw(j << (ks - 2 - lh)), x3, w3);
+            else x3 = fr_mul(x3, w3);
+            nfr_st(p, fr_add(x0, x2));
+            nfr_st(p + 2 * h, fr_sub(x0, x2));
+            nfr_st(p + h, fr_add(x1, x3));
+            nfr_st(p + 3 * h, fr_sub(x1, x3));
         }
     }
     __syncthreads();
 }
 
 // pass A: columns i2 in [c0, c0 + 2^lg) of the n1 x n2 view; transform over i1, twiddle, in place
-__global__ void __launch_bounds__(NTT_T, 2) k_ntt_cols(const NttArgs a) {
+__global__ void __launch_bounds__(NTT_T, NTT_OCC) k_ntt_cols(const NttArgs a) {
     extern __shared__ uint4 ntt_smem[];
     fr_t *s = reinterpret_cast<fr_t *>(ntt_smem);
     const int ka = a.ka, kb = a.kb, lg = a.lg;
@@ -122,7 +171,7 @@ __global__ void __launch_bounds__(NTT_T, 2) k_ntt_cols(const NttArgs a) {
 }
 
 // pass B: rows j1 in [r0, r0 + 2^lg); transform over i2; X[j1 + n1*j2]
-__global__ void __launch_bounds__(NTT_T, 2) k_ntt_rows(const NttArgs a) {
+__global__ void __launch_bounds__(NTT_T, NTT_OCC) k_ntt_rows(const NttArgs a) {
     extern __shared__ uint4 ntt_smem[];
     fr_t *s = reinterpret_cast<fr_t *>(ntt_smem);
     const int ka = a.ka, kb = a.kb, lg = a.lg;
@@ -153,6 +202,16 @@ k_ntt_twiddles(const fr_t *__restrict__ w_lo, const fr_t *__restrict__ w_hi, uin
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
         nfr_st(tw + e, fr_mul(nfr_ld(w_hi + (e >> NTT_W_LO_BITS)),
                               nfr_ld(w_lo + (e & ((1u << NTT_W_LO_BITS) - 1)))));
+}
+
+// compact per-size tables: ctw[m + e] = omega_m^e = tw[e * (table entries / m)], m = 2..2^max_log
+__global__ void __launch_bounds__(256)
+k_ntt_compact_twiddles(const fr_t *__restrict__ tw, int table_log, int max_log, fr_t *__restrict__ ctw) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // heap index m + e
+    if (i < 2 || i >= (2u << max_log)) return;
+    const int ks = 31 - __clz(i);
+    const uint32_t e = i - (1u << ks);
+    nfr_st(ctw + i, nfr_ld(tw + ((uint64_t)e << (table_log - ks))));
 }
 
 }  // namespace h2
@@ -245,6 +304,7 @@ int32_t run_plan(h2aes_domain *d, const Plan &p, const uint64_t *in, uint64_t *o
     a.tw_mask = d->en - 1;
     a.inverse = p.inverse;
     a.tw = d->d_tw;
+    a.ctw = d->d_ctw;
     const int lga = std::min(NTT_TILE_LOG - ka, kb), lgb = std::min(NTT_TILE_LOG - kb, ka);
     const size_t smem_a = (size_t)32 << (lga + ka), smem_b = (size_t)32 << (lgb + kb);
     for (int c0 = 0; c0 < ncols; c0 += d->batch) {
@@ -312,6 +372,7 @@ int32_t h2aes_domain_create(h2aes_ctx *ctx, int32_t j, int32_t k, h2aes_domain *
     const uint64_t n_hi = (d->en >> NTT_W_LO_BITS) + 1;
     if ((e = cudaMalloc((void **)&d->d_tw, d->en * sizeof(fr_t))) ||
         (e = cudaMalloc((void **)&d->d_consts, 12 * sizeof(fr_t))) ||
+        (e = cudaMalloc((void **)&d->d_ctw, sizeof(fr_t) * (2u << NTT_TILE_LOG))) ||
         (e = cudaMalloc((void **)&d->d_scratch, (size_t)d->batch * d->en * sizeof(fr_t))) ||
         (e = cudaMalloc((void **)&d_lo, sizeof(fr_t) << NTT_W_LO_BITS)) ||
         (e = cudaMalloc((void **)&d_hi, n_hi * sizeof(fr_t)))) {
@@ -342,7 +403,9 @@ int32_t h2aes_domain_create(h2aes_ctx *ctx, int32_t j, int32_t k, h2aes_domain *
     prof_begin(ctx, "k_ntt_twiddles");
     k_ntt_twiddles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_lo, d_hi, d->en, d->d_tw);
     prof_end(ctx);
-    ctx->launches += 1;
+    const int max_log = std::min(NTT_TILE_LOG, ek);
+    k_ntt_compact_twiddles<<<((2u << max_log) + 255) / 256, 256, 0, ctx->stream>>>(d->d_tw, ek, max_log, d->d_ctw);
+    ctx->launches += 2;
     e = cudaStreamSynchronize(ctx->stream);  // lo/hi/c are host temporaries
     cudaFree(d_lo); cudaFree(d_hi);
     if (!e) e = cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
@@ -359,6 +422,7 @@ int32_t h2aes_domain_destroy(h2aes_domain *d) {
     if (!d) return H2AES_ERR_ARG;
     cudaSetDevice(d->ctx->device);
     cudaFree(d->d_tw);
+    cudaFree(d->d_ctw);
     cudaFree(d->d_consts);
     cudaFree(d->d_scratch);
     cudaFree(d->d_lagrange);

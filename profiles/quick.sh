@@ -1,7 +1,7 @@
 # quick GPU check used during optimisation: parity subset + bench with live per-kernel times
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest.log 2>&1; echo pytest=$?; tail -2 gpurun_out/pytest.log
-timeout 600 python bench.py --no-cpu --no-e2e ${BENCH_ARGS} > gpurun_out/quick.json 2> gpurun_out/quick.err; echo bench=$?; tail -3 gpurun_out/quick.err
+timeout 600 python bench.py --no-cpu --no-e2e --no-prover-side ${BENCH_ARGS} > gpurun_out/quick.json 2> gpurun_out/quick.err; echo bench=$?; tail -3 gpurun_out/quick.err
 python - <<'PY'
 import json
 d = json.load(open("gpurun_out/quick.json"))
