@@ -226,6 +226,28 @@ class Pipe:
 PHASES = ("witness", "lookup_prep", "permuted", "product_prep", "product")
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank on the CPUs next to its GPU's PCIe root, so the pinned host buffers of the
+    end-to-end leg (first touch) live on that NUMA node.  Returns the node (None: left alone)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -236,6 +258,7 @@ def run_b200(args):
     if world != args.gpus and world == 1:
         raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -429,6 +452,7 @@ def run_b200(args):
         blocks = nb * args.steps * world
         cfg = workload_config(world)
         cfg["circuits_in_flight_per_gpu"] = P
+        cfg["host_numa_node_rank0"] = numa
         out = {
             "metric": METRIC, "value": blocks / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
