@@ -235,6 +235,23 @@ class Circuit:
                                               _ptr(values_ext)), self.ctx._h)
         return values_ext
 
+    def gate_perm_quotient(self, dom: "Domain", beta, gamma, y, advice_ext, rc_ext, qrc_ext, sigma_ext,
+                           Zp_ext, values_ext):
+        """evaluate_h before the lookups (h2aes_gate_perm_quotient_dev): the Equality-RC gate and
+        the permutation argument's expressions folded into `values_ext` (in place)."""
+        en = dom.extended_n
+        ps = self.perm_shape()
+        for t, shape in ((advice_ext, (self.layout["n_advice"], en, 4)), (rc_ext, (en, 4)), (qrc_ext, (en, 4)),
+                         (sigma_ext, (ps["n_columns"], en, 4)), (Zp_ext, (ps["n_sets"], en, 4)),
+                         (values_ext, (en, 4))):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.int64 and tuple(t.shape) == shape, \
+                (tuple(t.shape), shape)
+        keep = [_fr_arg(v) for v in (beta, gamma, y)]
+        check(lib().h2aes_gate_perm_quotient_dev(self._h, dom._h, *[k[1] for k in keep], _ptr(advice_ext),
+                                                 _ptr(rc_ext), _ptr(qrc_ext), _ptr(sigma_ext),
+                                                 _ptr(Zp_ext), _ptr(values_ext)), self.ctx._h)
+        return values_ext
+
     def lookup_stats(self) -> np.ndarray:
         """rows per lookup whose grand-product factor is not one (last product call)"""
         out = np.zeros(self.layout["n_lookups"], np.uint64)

@@ -1,4 +1,5 @@
-// quotient.cu — lookup terms of the quotient polynomial on the extended coset.
+// quotient.cu — the quotient polynomial's numerator on the extended coset: the gate and the
+// permutation expressions (k_gate_perm_quotient), then the lookup expressions (k_lookup_quotient).
 //
 // Replaces halo2_proofs v0.3.0 [UPSTREAM] plonk/evaluation.rs
 // Evaluator::evaluate_h, lookup part, and poly/domain.rs divide_by_vanishing_poly — the first
@@ -89,6 +90,67 @@ __global__ void __launch_bounds__(256, 2) k_lookup_quotient(const QArgs a) {
             v = fr_add(fr_mul(v, a.y), fr_mul(ams, l0));
             t = fr_mul(ams, fr_sub(ap, qfr_ld(apc + r_prev)));
             v = fr_add(fr_mul(v, a.y), fr_mul(t, l_act));
+        }
+        fr_store_256(reinterpret_cast<uint64_t *>(a.values + idx), v);
+    }
+}
+
+struct GPArgs {
+    Shape sh;
+    uint64_t en, rot;
+    const fr_t *advice;    // [n_advice][en]
+    const fr_t *rc;        // [en] round_constants
+    const fr_t *qrc;       // [en] q_eq_rcon as a fixed column
+    const fr_t *sigma;     // [n_columns][en]
+    const fr_t *Zp;        // [n_sets][en]
+    const fr_t *lagrange;  // [3][en]
+    const fr_t *tw;        // [en] extended_omega^idx
+    fr_t beta, gamma, y, beta_zeta, delta;
+    fr_t *values;
+};
+
+// evaluate_h before the lookups: the "Equality RC" gate (key_schedule.rs:59-64), then the
+// permutation argument's expressions (see the header comment of h2aes_gate_perm_quotient_dev)
+__global__ void __launch_bounds__(256, 2) k_gate_perm_quotient(const GPArgs a) {
+    const uint64_t en = a.en;
+    const int n_cols = perm_n_columns(a.sh), n_sets = perm_n_sets(a.sh);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const fr_t one = fr_one();
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < en; idx += stride) {
+        const uint64_t r_next = (idx + a.rot) & (en - 1);
+        const uint64_t r_last = (idx - (uint64_t)UNUSABLE_ROWS * a.rot) & (en - 1);
+        const fr_t l0 = qfr_ld(a.lagrange + idx), l_last = qfr_ld(a.lagrange + en + idx),
+                   l_act = qfr_ld(a.lagrange + 2 * en + idx);
+        fr_t v = qfr_ld(a.values + idx);
+        // gate: q_eq_rcon * (words_column - round_constants)
+        const fr_t words = qfr_ld(a.advice + (uint64_t)a.sh.words_column() * en + idx);
+        v = fr_add(fr_mul(v, a.y), fr_mul(qfr_ld(a.qrc + idx), fr_sub(words, qfr_ld(a.rc + idx))));
+        // l0 (1 - z_0);  l_last (z_last^2 - z_last);  l0 (z_i - z_{i-1}[r_last])
+        v = fr_add(fr_mul(v, a.y), fr_mul(fr_sub(one, qfr_ld(a.Zp + idx)), l0));
+        const fr_t zl = qfr_ld(a.Zp + (uint64_t)(n_sets - 1) * en + idx);
+        v = fr_add(fr_mul(v, a.y), fr_mul(fr_sub(fr_mul(zl, zl), zl), l_last));
+#pragma unroll 1
+        for (int si = 1; si < n_sets; ++si) {
+            const fr_t t = fr_sub(qfr_ld(a.Zp + (uint64_t)si * en + idx),
+                                  qfr_ld(a.Zp + (uint64_t)(si - 1) * en + r_last));
+            v = fr_add(fr_mul(v, a.y), fr_mul(t, l0));
+        }
+        // l_active_row (z_i[r_next] prod (v + beta sigma + gamma) - z_i prod (v + delta^p beta X + gamma))
+        fr_t cur = fr_mul(a.beta_zeta, qfr_ld(a.tw + idx));  // beta * X, X = zeta * extended_omega^idx
+#pragma unroll 1
+        for (int si = 0; si < n_sets; ++si) {
+            fr_t left = qfr_ld(a.Zp + (uint64_t)si * en + r_next), right = qfr_ld(a.Zp + (uint64_t)si * en + idx);
+#pragma unroll 1
+            for (int p = PERM_CHUNK * si; p < PERM_CHUNK * si + PERM_CHUNK && p < n_cols; ++p) {
+                int is_fixed, index;
+                perm_column(a.sh, p, &is_fixed, &index);
+                const fr_t val = qfr_ld(is_fixed ? a.rc + idx : a.advice + (uint64_t)index * en + idx);
+                const fr_t vg = fr_add(val, a.gamma);
+                left = fr_mul(left, fr_add(vg, fr_mul(a.beta, qfr_ld(a.sigma + (uint64_t)p * en + idx))));
+                right = fr_mul(right, fr_add(vg, cur));
+                cur = fr_mul(cur, a.delta);
+            }
+            v = fr_add(fr_mul(v, a.y), fr_mul(fr_sub(left, right), l_act));
         }
         fr_store_256(reinterpret_cast<uint64_t *>(a.values + idx), v);
     }
@@ -252,6 +314,48 @@ int32_t h2aes_lookup_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const uint6
     const unsigned grid = (unsigned)std::min<uint64_t>((a.en + 255) / 256, (uint64_t)ctx->sm_count * 16);
     prof_begin(ctx, "k_lookup_quotient");
     k_lookup_quotient<<<grid, 256, 0, ctx->stream>>>(a);
+    prof_end(ctx);
+    ctx->launches += 1;
+    QCU(ctx, cudaGetLastError());
+    return H2AES_OK;
+}
+
+int32_t h2aes_gate_perm_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const uint64_t *beta,
+                                     const uint64_t *gamma, const uint64_t *y,
+                                     const uint64_t *advice_ext, const uint64_t *rc_ext,
+                                     const uint64_t *qrc_ext, const uint64_t *sigma_ext,
+                                     const uint64_t *Zp_ext, uint64_t *values_ext) {
+    if (!c || !d) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (d->ctx != ctx) return qfail(ctx, H2AES_ERR_ARG, "quotient: domain and circuit of different contexts");
+    if (!beta || !gamma || !y || !advice_ext || !rc_ext || !qrc_ext || !sigma_ext || !Zp_ext || !values_ext)
+        return qfail(ctx, H2AES_ERR_ARG, "quotient: null pointer");
+    if (d->k != c->sh.k || d->j != 5) return qfail(ctx, H2AES_ERR_ARG, "quotient: domain must be (j=5, k of the circuit)");
+    if (c->n_shards != 1) return qfail(ctx, H2AES_ERR_STATE, "quotient: unsharded circuits only");
+    QCU(ctx, cudaSetDevice(ctx->device));
+    if (int32_t rc = ensure_lagrange(d)) return rc;
+    GPArgs a;
+    a.sh = c->sh;
+    a.en = d->en; a.rot = 1ull << (d->extended_k - d->k);
+    a.advice = reinterpret_cast<const fr_t *>(advice_ext);
+    a.rc = reinterpret_cast<const fr_t *>(rc_ext);
+    a.qrc = reinterpret_cast<const fr_t *>(qrc_ext);
+    a.sigma = reinterpret_cast<const fr_t *>(sigma_ext);
+    a.Zp = reinterpret_cast<const fr_t *>(Zp_ext);
+    a.lagrange = d->d_lagrange;
+    a.tw = d->d_tw;
+    a.beta = load_host(beta); a.gamma = load_host(gamma); a.y = load_host(y);
+    a.beta_zeta = fr_mul(a.beta, domain_zeta());
+    // halo2curves 0.6.1 bn256::Fr::DELTA = 7^(2^28) [UPSTREAM]
+    const uint32_t dl[8] = {0xe533e9a2u, 0x870e56bbu, 0x5e963f25u, 0x5b5f898eu,
+                            0xd4c86e71u, 0x64ec26aau, 0x22c6f0cau, 0x09226b6eu};
+    fr_t dc;
+    for (int i = 0; i < 8; ++i) dc.v[i] = dl[i];
+    a.delta = fr_mul(dc, fr_r2());
+    a.values = reinterpret_cast<fr_t *>(values_ext);
+    const unsigned grid = (unsigned)std::min<uint64_t>((a.en + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    prof_begin(ctx, "k_gate_perm_quotient");
+    k_gate_perm_quotient<<<grid, 256, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     QCU(ctx, cudaGetLastError());

@@ -297,6 +297,24 @@ int32_t h2aes_lookup_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const uint6
                                   const uint64_t *table_ext, const uint64_t *sel_ext,
                                   const uint64_t *Ap_ext, const uint64_t *Sp_ext,
                                   const uint64_t *Z_ext, uint64_t *values_ext);
+/* replaces: the part of Evaluator::evaluate_h that comes BEFORE the lookups in halo2's order:
+ *   custom gates  values = values*y + q_eq_rcon (words_column - round_constants)
+ *                 (create_gate "Equality RC", key_schedule.rs:59-64; the simple selector is a 0/1
+ *                 fixed column after keygen's compress_selectors)
+ *   permutation   values = values*y + (1 - z_0) l0
+ *                 values = values*y + (z_last^2 - z_last) l_last
+ *                 values = values*y + (z_i - z_{i-1}(w^-6 X)) l0                 for sets i >= 1
+ *                 values = values*y + (z_i(wX) prod_j (v_j + beta sigma_j + gamma)
+ *                                      - z_i(X) prod_j (v_j + delta^p beta X + gamma)) l_active_row
+ *   advice_ext  [n_advice][2^extended_k][4];  rc_ext, qrc_ext  [2^extended_k][4]: extended cosets of
+ *               round_constants and of the q_eq_rcon selector column;  sigma_ext [n_columns][..]
+ *               and Zp_ext [n_sets][..]: cosets of h2aes_perm_sigma_dev / h2aes_perm_product_dev
+ *               columns (h2aes_perm_query order).  values_ext in/out as above. */
+int32_t h2aes_gate_perm_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const uint64_t *beta,
+                                     const uint64_t *gamma, const uint64_t *y,
+                                     const uint64_t *advice_ext, const uint64_t *rc_ext,
+                                     const uint64_t *qrc_ext, const uint64_t *sigma_ext,
+                                     const uint64_t *Zp_ext, uint64_t *values_ext);
 /* replaces: EvaluationDomain::divide_by_vanishing_poly: element i of every column times
  * 1 / ((zeta * extended_omega^i)^n - 1).  In place on [ncols][2^extended_k][4]. */
 int32_t h2aes_divide_by_vanishing_dev(h2aes_domain *d, uint64_t *ext_dev, int32_t ncols);

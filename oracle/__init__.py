@@ -91,6 +91,7 @@ def lib():
         L.orc_domain_transform.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
         L.orc_domain_query.argtypes = [C.c_int, C.c_int, u64p]
         L.orc_lookup_quotient.argtypes = [C.c_void_p, C.c_int, C.c_int] + [u64p] * 5
+        L.orc_gate_perm_quotient.argtypes = [C.c_void_p] + [u64p] * 4
         L.orc_divide_by_vanishing.argtypes = [C.c_int, C.c_int, u64p]
         L.orc_poly_eval.argtypes = [u64p, C.c_uint64, u64p, u64p]
         L.orc_bench_batch.argtypes = (
@@ -322,6 +323,17 @@ class Circuit:
         assert acc.shape == (en, 4)
         args = [np.ascontiguousarray(v, dtype=np.uint64) for v in (theta, beta, gamma, y)]
         rc = lib().orc_lookup_quotient(self._h, first, count, *[_u64(v) for v in args], _u64(acc))
+        if rc:
+            raise OracleError(rc)
+        return acc
+
+    def gate_perm_quotient(self, beta, gamma, y, values=None) -> np.ndarray:
+        """halo2 v0.3.0 evaluate_h up to the lookups: the custom gate, then the permutation
+        argument's expressions, folded into `values` (zero when None)."""
+        en = 1 << domain_query(self.k)["extended_k"]
+        acc = np.zeros((en, 4), np.uint64) if values is None else np.array(values, np.uint64, order="C", copy=True)
+        args = [np.ascontiguousarray(v, dtype=np.uint64) for v in (beta, gamma, y)]
+        rc = lib().orc_gate_perm_quotient(self._h, *[_u64(v) for v in args], _u64(acc))
         if rc:
             raise OracleError(rc)
         return acc

@@ -1106,27 +1106,28 @@ static uint64_t bitreverse(uint64_t v, int bits) {
     for (int i = 0; i < bits; ++i) { r = (r << 1) | (v & 1); v >>= 1; }
     return r;
 }
-// arithmetic.rs serial_fft: bit-reversal swap, then log_n butterfly layers with a running twiddle
+// arithmetic.rs best_fft: bit-reversal swap, then log_n butterfly layers; layer m pairs
+// (k+j, k+j+m) with twiddle omega^(j n / 2m).  halo2 walks each block with a running twiddle (or
+// recurses per thread); here the twiddles come from one table of omega^t, t < n/2, and the
+// butterflies of a layer run under OpenMP — field arithmetic is exact, so the values are the same.
 static void serial_fft(Fr *a, const Fr &omega, int log_n) {
     const uint64_t n = 1ull << log_n;
     for (uint64_t k = 0; k < n; ++k) {
         const uint64_t rk = bitreverse(k, log_n);
         if (k < rk) std::swap(a[rk], a[k]);
     }
-    uint64_t m = 1;
+    std::vector<Fr> tw(n > 1 ? n / 2 : 1);
+    tw[0] = FR_ONE;
+    for (uint64_t t = 1; t < n / 2; ++t) tw[t] = fr_mul(tw[t - 1], omega);
     for (int layer = 0; layer < log_n; ++layer) {
-        uint64_t e[4] = {n / (2 * m), 0, 0, 0};
-        const Fr w_m = fr_pow(omega, e);
-        for (uint64_t k = 0; k < n; k += 2 * m) {
-            Fr w = FR_ONE;
-            for (uint64_t j = 0; j < m; ++j) {
-                const Fr t = fr_mul(a[k + j + m], w);
-                a[k + j + m] = fr_sub(a[k + j], t);
-                a[k + j] = fr_add(a[k + j], t);
-                w = fr_mul(w, w_m);
-            }
+        const uint64_t m = 1ull << layer, step = n >> (layer + 1);
+#pragma omp parallel for schedule(static) if (n >= 4096)
+        for (int64_t b = 0; b < (int64_t)(n / 2); ++b) {
+            const uint64_t j = (uint64_t)b & (m - 1), k = ((uint64_t)b >> layer) << (layer + 1);
+            const Fr t = fr_mul(a[k + j + m], tw[j * step]);
+            a[k + j + m] = fr_sub(a[k + j], t);
+            a[k + j] = fr_add(a[k + j], t);
         }
-        m *= 2;
     }
 }
 // EvaluationDomain::ifft
@@ -1293,6 +1294,81 @@ int orc_lookup_quotient(void *h, int first, int count, const uint64_t *theta_,
             v = fr_add(fr_mul(v, y), fr_mul(fr_mul(a_minus_s, fr_sub(ap_e[idx], ap_e[r_prev])), L.l_active_row[idx]));
             acc[idx] = v;
         }
+    }
+    memcpy(values, acc.data(), en * 32);
+    return ORC_OK;
+}
+
+// [UPSTREAM] plonk/evaluation.rs evaluate_h, what comes BEFORE the lookups in halo2's order:
+//   custom gates  values = values*y + q_eq_rcon (words - round_constants)   (key_schedule.rs:59-64;
+//                 the simple selector is a 0/1 fixed column after compress_selectors)
+//   permutation   values = values*y + (1 - z_0) l0
+//                 values = values*y + (z_last^2 - z_last) l_last
+//                 values = values*y + (z_i - z_{i-1}[r_last]) l0                    for sets i >= 1
+//                 values = values*y + (z_i[r_next] prod_j (v_j + beta sigma_j + gamma)
+//                                      - z_i prod_j (v_j + delta^p beta X + gamma)) l_active_row
+//   with X = zeta * extended_omega^idx, r_last = idx - 6 * 2^(ek-k), p running over ALL columns.
+int orc_gate_perm_quotient(void *h, const uint64_t *beta_, const uint64_t *gamma_,
+                           const uint64_t *y_, uint64_t *values) {
+    Circuit *c = (Circuit *)h;
+    const Shape &sh = c->s.sh;
+    const Domain d = domain_new(5, sh.k);
+    const uint64_t en = 1ull << d.extended_k, n = d.n;
+    const int64_t rot = (int64_t)1 << (d.extended_k - d.k);
+    const Fr beta = fr_load(beta_), gamma = fr_load(gamma_), y = fr_load(y_);
+    const Fr delta = fr_of_canon(DELTA_CANON);
+    const ExtLagrange L = ext_lagrange(d);
+    Columns cols = view_of(c->s);
+    std::vector<Fr> acc(en);
+    memcpy(acc.data(), values, en * 32);
+    // gate
+    {
+        std::vector<Fr> tmp(n);
+        for (uint64_t i = 0; i < n; ++i) tmp[i] = cols.selectors[sh.sel_rcon()][i] ? FR_ONE : FR_ZERO;
+        const std::vector<Fr> q_e = to_extended(d, tmp.data()),
+                              w_e = to_extended(d, cols.advice[sh.words_column()]),
+                              rc_e = to_extended(d, cols.fixed[sh.rc_column()]);
+        for (uint64_t idx = 0; idx < en; ++idx)
+            acc[idx] = fr_add(fr_mul(acc[idx], y), fr_mul(q_e[idx], fr_sub(w_e[idx], rc_e[idx])));
+    }
+    // permutation
+    std::vector<PermColumn> pcols = perm_columns(sh);
+    std::vector<std::vector<Fr>> sigma, Z;
+    build_sigma(c->s, pcols, sigma, nullptr);
+    permutation_product(cols, pcols, sigma, beta, gamma, Z);
+    std::vector<std::vector<Fr>> z_e, sig_e, val_e;
+    for (auto &z : Z) z_e.push_back(to_extended(d, z.data()));
+    for (size_t p = 0; p < pcols.size(); ++p) {
+        sig_e.push_back(to_extended(d, sigma[p].data()));
+        const Fr *v = pcols[p].type == 0 ? cols.advice[pcols[p].index] : cols.fixed[pcols[p].index];
+        val_e.push_back(to_extended(d, v));
+    }
+    const size_t n_sets = z_e.size();
+    Fr beta_term = FR_ONE;  // extended_omega^idx
+    for (uint64_t idx = 0; idx < en; ++idx) {
+        const uint64_t r_next = (uint64_t)(((int64_t)idx + rot) % (int64_t)en);
+        const uint64_t r_last =
+            (uint64_t)((((int64_t)idx - (BLINDING_FACTORS + 1) * rot) % (int64_t)en + (int64_t)en) % (int64_t)en);
+        Fr v = acc[idx];
+        v = fr_add(fr_mul(v, y), fr_mul(fr_sub(FR_ONE, z_e[0][idx]), L.l0[idx]));
+        const Fr zl = z_e[n_sets - 1][idx];
+        v = fr_add(fr_mul(v, y), fr_mul(fr_sub(fr_mul(zl, zl), zl), L.l_last[idx]));
+        for (size_t si = 1; si < n_sets; ++si)
+            v = fr_add(fr_mul(v, y), fr_mul(fr_sub(z_e[si][idx], z_e[si - 1][r_last]), L.l0[idx]));
+        Fr current_delta = fr_mul(fr_mul(beta, d.g_coset), beta_term);  // delta_start * beta_term
+        for (size_t si = 0; si < n_sets; ++si) {
+            const size_t base = si * PERM_CHUNK, cnt = std::min((size_t)PERM_CHUNK, pcols.size() - base);
+            Fr left = z_e[si][r_next], right = z_e[si][idx];
+            for (size_t t = 0; t < cnt; ++t)
+                left = fr_mul(left, fr_add(fr_add(val_e[base + t][idx], fr_mul(beta, sig_e[base + t][idx])), gamma));
+            for (size_t t = 0; t < cnt; ++t) {
+                right = fr_mul(right, fr_add(fr_add(val_e[base + t][idx], current_delta), gamma));
+                current_delta = fr_mul(current_delta, delta);
+            }
+            v = fr_add(fr_mul(v, y), fr_mul(fr_sub(left, right), L.l_active_row[idx]));
+        }
+        acc[idx] = v;
+        beta_term = fr_mul(beta_term, d.extended_omega);
     }
     memcpy(values, acc.data(), en * 32);
     return ORC_OK;

@@ -1,6 +1,6 @@
 """Timing of the prover-side steps that follow the witness path at the
-bench shape: every column of one K=20, N=5 circuit to coefficient form and to the extended
-coset, the lookup terms of the quotient, division by the vanishing polynomial and the way back
+bench shape: every column of one K=20, N=5 circuit (advice, table, selectors, A'/S'/Z, sigma, Z_perm) to coefficient form and to the extended
+coset, the gate / permutation / lookup terms of the quotient, division by the vanishing polynomial and the way back
 to coefficients.  CUDA events on the context's stream, inputs resident in HBM.  Prints one JSON
 object; not part of the headline metric."""
 import json
@@ -50,8 +50,11 @@ def measure(ctx, K=20, N=5):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), r
 
+    sigma = cir.perm_sigma()
+    Zp = cir.perm_product(beta, gamma, advice)
     cols = {"advice": advice, "table": fixed[:4].contiguous(), "sel": sel[:L].contiguous(),
-            "Ap": perm["Ap"], "Sp": perm["Sp"], "Z": Z}
+            "Ap": perm["Ap"], "Sp": perm["Sp"], "Z": Z,
+            "rc_qrc": torch.stack([fixed[4], sel[L]]), "sigma": sigma, "Zp": Zp}
     ncols = sum(t.shape[0] for t in cols.values())
     dom.to_extended(cols["table"])  # warm-up (twiddles, kernel attributes)
     ctx.profile(True)
@@ -60,6 +63,8 @@ def measure(ctx, K=20, N=5):
     values = torch.zeros((en, 4), dtype=torch.int64, device="cuda")
     cir.lookup_quotient(dom, theta, beta, gamma, y, ext["advice"], ext["table"], ext["sel"][:1],
                         ext["Ap"][:1], ext["Sp"][:1], ext["Z"][:1], values.clone())  # Lagrange columns
+    ms_gp, _ = timed(lambda: cir.gate_perm_quotient(dom, beta, gamma, y, ext["advice"], ext["rc_qrc"][0],
+                                                    ext["rc_qrc"][1], ext["sigma"], ext["Zp"], values))
     ms_q, _ = timed(lambda: cir.lookup_quotient(dom, theta, beta, gamma, y, ext["advice"], ext["table"],
                                                 ext["sel"], ext["Ap"], ext["Sp"], ext["Z"], values))
     ms_div, _ = timed(lambda: dom.divide_by_vanishing(values[None]))
@@ -85,6 +90,8 @@ def measure(ctx, K=20, N=5):
         "lookup_quotient": {"ms": ms_q, "lookups": L, "fr_multiplies": mul_q, "gmul_s": mul_q / ms_q / 1e6,
                             "frac_of_mul_peak": mul_q / ms_q / 1e6 / FR_MUL_PEAK_G,
                             "algorithmic_bytes": bytes_q, "hbm_gbs": bytes_q / ms_q / 1e6},
+        "gate_perm_quotient": {"ms": ms_gp, "permutation_columns": int(sigma.shape[0]),
+                               "permutation_sets": int(Zp.shape[0])},
         "divide_by_vanishing": {"ms": ms_div, "hbm_gbs": 2 * en * 32 / ms_div / 1e6},
         "extended_to_coeff": {"ms": ms_e2c},
         "kernels": {k_: {"launches": v[0], "ms": v[1]} for k_, v in kern.items()},

@@ -67,6 +67,47 @@ def verifier_numerator(orc, ref, kind, k, lookups, theta, beta, gamma, y, x, sta
     return acc
 
 
+def verifier_gate_perm(orc, ref, kind, k, N, beta, gamma, y, x):
+    """the custom gate, then the permutation argument's expressions at the point x"""
+    n = 1 << k
+    w = pow(pow(7, (R_MOD - 1) >> 28, R_MOD), 1 << (28 - k), R_MOD)
+    delta = pow(7, 1 << 28, R_MOD)
+    be, ga, yy = (orc.fr_to_int(v) for v in (beta, gamma, y))
+    one = orc.fr_from_int(1)
+
+    def ev(col, at):
+        c = orc.domain_transform(orc.LAGRANGE_TO_COEFF, k, col)
+        return orc.fr_to_int(orc.poly_eval(c, orc.fr_from_int(at % R_MOD)))
+
+    sels, adv, fixed = ref.selectors(), ref.advice(), ref.fixed()
+    q = ev(np.where(sels[-1][:, None] != 0, one[None, :], np.uint64(0)), x)  # q_eq_rcon is last
+    acc = q * (ev(adv[-1], x) - ev(fixed[4], x)) % R_MOD  # words_column is the last advice column
+    l0 = lagrange_at(k, 0, x)
+    l_last = lagrange_at(k, n - 6, x)
+    l_active = (1 - l_last - sum(lagrange_at(k, n - 1 - i, x) for i in range(5))) % R_MOD
+    pr = ref.permutation(beta, gamma, want=("sigma", "Z"))
+    cols = orc.perm_shape(kind, k, N)["columns"]
+    z = [ev(zc, x) for zc in pr["Z"]]
+    z_next = [ev(zc, x * w) for zc in pr["Z"]]
+    z_last_rot = [ev(zc, x * pow(w, -6, R_MOD)) for zc in pr["Z"]]
+    acc = (acc * yy + (1 - z[0]) * l0) % R_MOD
+    acc = (acc * yy + (z[-1] * z[-1] - z[-1]) * l_last) % R_MOD
+    for i in range(1, len(z)):
+        acc = (acc * yy + (z[i] - z_last_rot[i - 1]) * l0) % R_MOD
+    cur = be * x % R_MOD
+    for i in range(len(z)):
+        left, right = z_next[i], z[i]
+        chunk = list(range(3 * i, min(3 * i + 3, len(cols))))
+        vals = [ev(adv[cols[p][1]] if cols[p][0] == "advice" else fixed[cols[p][1]], x) for p in chunk]
+        for p, v in zip(chunk, vals):
+            left = left * (v + be * ev(pr["sigma"][p], x) + ga) % R_MOD
+        for v in vals:
+            right = right * (v + cur + ga) % R_MOD
+            cur = cur * delta % R_MOD
+        acc = (acc * yy + (left - right) * l_active) % R_MOD
+    return acc
+
+
 def check_verifier_equation(orc, ref, kind, k, lookups, chal, values, x, start=0):
     """h = values / (X^n - 1) on the extended coset, to coefficients; h(x) (x^n - 1) == N(x)"""
     theta, beta, gamma, y = chal
@@ -89,13 +130,16 @@ def keysched(orc):
     return key, orc.Circuit(orc.KIND_KEYSCHED, 17, 1).synthesize(key, None)
 
 
-def test_oracle_quotient_satisfies_the_verifier_equation(orc, keysched, chal4):
+def test_oracle_full_numerator_satisfies_the_verifier_equation(orc, keysched, chal4):
+    """gate, permutation, lookups in halo2's order (evaluate_h of the whole constraint system)"""
     _, ref = keysched
-    # accumulated in two calls (lookup 0, then lookups 1..2 on top of it): one fold
-    part = ref.lookup_quotient(*chal4, first=0, count=1)
+    theta, beta, gamma, y = chal4
+    # lookups accumulated in two calls on top of the gate + permutation terms: one fold
+    part = ref.lookup_quotient(*chal4, first=0, count=1, values=ref.gate_perm_quotient(beta, gamma, y))
     values = ref.lookup_quotient(*chal4, first=1, count=2, values=part)
-    x = int.from_bytes(splitmix_bytes(SEED + 12, 40).tobytes(), "little") % R_MOD
-    check_verifier_equation(orc, ref, orc.KIND_KEYSCHED, 17, range(3), chal4, values, x)
+    x = int.from_bytes(splitmix_bytes(SEED + 13, 40).tobytes(), "little") % R_MOD
+    start = verifier_gate_perm(orc, ref, orc.KIND_KEYSCHED, 17, 1, beta, gamma, y, x)
+    check_verifier_equation(orc, ref, orc.KIND_KEYSCHED, 17, range(3), chal4, values, x, start=start)
 
 
 # ---- GPU --------------------------------------------------------------------------------------
@@ -186,6 +230,67 @@ def test_verifier_equation_two_column_sets(gpu, orc, ffi, chal4):
     assert lhs == rhs
 
 
+def gpu_full_numerator(gpu, ffi, kind, k, N, key, pts, chal):
+    """gate + permutation + every lookup, in halo2's order, all on the device; returns the
+    accumulator after the gate/permutation terms, after the lookups, and h's coefficients"""
+    import torch
+    from halo2_aes_b200.backend import Circuit, Domain
+    theta, beta, gamma, y = chal
+    cir = Circuit(gpu, kind, k, N)
+    d_pts = torch.from_numpy(np.ascontiguousarray(pts)).cuda() if pts is not None and len(pts) else None
+    advice, _ = cir.witness(key, d_pts)
+    fixed, sel = cir.fixed_columns()
+    L = cir.layout["n_lookups"]
+    perm = cir.lookup_permuted(theta, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma)
+    sigma = cir.perm_sigma()
+    Zp = cir.perm_product(beta, gamma, advice)
+    cir.lookup_check()
+    dom = Domain(gpu, k)
+    ext = {nm: dom.to_extended(t) for nm, t in
+           (("advice", advice), ("fixed", fixed), ("sel", sel), ("Ap", perm["Ap"]), ("Sp", perm["Sp"]),
+            ("Z", Z), ("sigma", sigma), ("Zp", Zp))}
+    values = torch.zeros((dom.extended_n, 4), dtype=torch.int64, device="cuda")
+    cir.gate_perm_quotient(dom, beta, gamma, y, ext["advice"], ext["fixed"][4], ext["sel"][L],
+                           ext["sigma"], ext["Zp"], values)
+    after_perm = _host(values)
+    cir.lookup_quotient(dom, theta, beta, gamma, y, ext["advice"], ext["fixed"][:4].contiguous(),
+                        ext["sel"][:L].contiguous(), ext["Ap"], ext["Sp"], ext["Z"], values)
+    after_lookups = _host(values)
+    h = _host(dom.extended_to_coeff(dom.divide_by_vanishing(values[None])))[0]
+    dom.close()
+    cir.close()
+    return after_perm, after_lookups, h
+
+
+@pytest.mark.gpu
+def test_full_numerator_key_schedule_equals_the_oracle(gpu, orc, ffi, keysched, chal4):
+    key, ref = keysched
+    theta, beta, gamma, y = chal4
+    after_perm, after_lookups, _ = gpu_full_numerator(gpu, ffi, ffi.KIND_KEYSCHED, 17, 1, key, None, chal4)
+    want = ref.gate_perm_quotient(beta, gamma, y)
+    bad = np.flatnonzero((after_perm != want).any(axis=1))
+    assert bad.size == 0, f"gate/permutation: {bad.size} extended rows differ, first {bad[:5]}"
+    assert (after_lookups == ref.lookup_quotient(*chal4, values=want)).all()
+
+
+@pytest.mark.gpu
+def test_full_numerator_verifier_equation_two_column_sets(gpu, orc, ffi, chal4):
+    """k=17, N=2, 150 blocks over both column sets (8 permutation columns in 3 chained sets, 10
+    lookups): the device's h satisfies the verifier's equation for the WHOLE constraint system."""
+    key = splitmix_bytes(SEED + 26, 16).tobytes()
+    pts = splitmix_bytes(SEED + 27, 150 * 16).reshape(150, 16)
+    theta, beta, gamma, y = chal4
+    ref = orc.Circuit(orc.KIND_AES, 17, 2).synthesize(key, pts)
+    _, _, h = gpu_full_numerator(gpu, ffi, ffi.KIND_AES, 17, 2, key, pts, chal4)
+    x = int.from_bytes(splitmix_bytes(SEED + 28, 40).tobytes(), "little") % R_MOD
+    hx = orc.fr_to_int(orc.poly_eval(h, orc.fr_from_int(x)))
+    lhs = hx * (pow(x, 1 << 17, R_MOD) - 1) % R_MOD
+    start = verifier_gate_perm(orc, ref, orc.KIND_AES, 17, 2, beta, gamma, y, x)
+    rhs = verifier_numerator(orc, ref, orc.KIND_AES, 17, range(10), theta, beta, gamma, y, x, start)
+    assert lhs == rhs
+
+
 @pytest.mark.gpu
 def test_quotient_error_behaviour(gpu, ffi):
     import ctypes as C
@@ -195,6 +300,7 @@ def test_quotient_error_behaviour(gpu, ffi):
     dom = Domain(gpu, 12)
     assert lib.h2aes_lookup_quotient_dev(cir._h, None, *[None] * 4, 0, 1, *[None] * 7) == ffi.ERR_ARG
     assert lib.h2aes_lookup_quotient_dev(cir._h, dom._h, *[None] * 4, 0, 1, *[None] * 7) == ffi.ERR_ARG
+    assert lib.h2aes_gate_perm_quotient_dev(cir._h, dom._h, *[None] * 9) == ffi.ERR_ARG
     assert lib.h2aes_divide_by_vanishing_dev(dom._h, None, 1) == ffi.ERR_ARG
     assert lib.h2aes_divide_by_vanishing_dev(None, None, 1) == ffi.ERR_ARG
     dom.close()
