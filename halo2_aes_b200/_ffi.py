@@ -120,6 +120,10 @@ SIGNATURES = {
                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "h2aes_gate_perm_quotient_dev": (C.c_int32, [_vp, _vp, _u64p, _u64p, _u64p, _vp, _vp, _vp, _vp, _vp, _vp]),
     "h2aes_divide_by_vanishing_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "h2aes_msm_create": (C.c_int32, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "h2aes_msm_destroy": (C.c_int32, [_vp]),
+    "h2aes_msm_dev": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
+    "h2aes_msm_host": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),
     "h2aes_lookup_check": (C.c_int32, [_vp]),
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),

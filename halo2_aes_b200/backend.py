@@ -387,6 +387,47 @@ class Domain:
             pass
 
 
+class Msm:
+    """best_multiexp over bn256 G1 on the GPU (h2aes_msm_*): commitments of Fr columns against a
+    fixed set of bases (halo2curves G1Affine: int64 CUDA tensor [n, 2, 4], x then y)."""
+
+    def __init__(self, ctx: Context, bases: torch.Tensor):
+        assert bases.is_cuda and bases.is_contiguous() and bases.dtype == torch.int64
+        assert bases.dim() == 3 and bases.shape[1:] == (2, 4), tuple(bases.shape)
+        self.ctx, self.bases, self.n = ctx, bases, bases.shape[0]  # keeps the bases alive
+        h = C.c_void_p()
+        check(lib().h2aes_msm_create(ctx._h, _ptr(bases), self.n, C.byref(h)), ctx._h)
+        self._h = h
+
+    def commit(self, cols: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """cols [ncols, n, 4] (device) -> [ncols, 2, 4] affine points (device); asynchronous"""
+        assert cols.is_cuda and cols.is_contiguous() and cols.dtype == torch.int64
+        assert cols.dim() == 3 and cols.shape[1:] == (self.n, 4), tuple(cols.shape)
+        if out is None:
+            out = torch.empty((cols.shape[0], 2, 4), dtype=torch.int64, device=self.ctx.device)
+        check(lib().h2aes_msm_dev(self._h, _ptr(cols), cols.shape[0], _ptr(out)), self.ctx._h)
+        return out
+
+    def commit_host(self, cols: np.ndarray) -> np.ndarray:
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        assert cols.ndim == 3 and cols.shape[1:] == (self.n, 4), cols.shape
+        out = np.empty((cols.shape[0], 2, 4), dtype=np.uint64)
+        check(lib().h2aes_msm_host(self._h, C.c_void_p(cols.ctypes.data), cols.shape[0],
+                                   C.c_void_p(out.ctypes.data)), self.ctx._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().h2aes_msm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _CudaArray:
     """Expose library-owned device memory to torch through __cuda_array_interface__."""
 

@@ -15,12 +15,19 @@ a Python model of the PTX carry flag against big-integer arithmetic (random and 
 operands), and only then prints the same list as one inline-asm block.
 
     python gen_fr_mul.py            # self-test, then (re)write fr_mul_ptx.inc
+    python gen_fr_mul.py fq         # the same for the base field Fq -> fq_mul_ptx.inc
 """
 import os
 import random
 import sys
 
-P = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+FIELDS = {
+    # bn256 scalar field (halo2curves bn256::Fr) and base field (bn256::Fq)
+    "fr": 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
+    "fq": 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47,
+}
+FIELD = sys.argv[1] if len(sys.argv) > 1 else "fr"
+P = FIELDS[FIELD]
 N = 8
 M32 = 0xFFFFFFFF
 PL = [(P >> (32 * i)) & M32 for i in range(N)]
@@ -155,7 +162,7 @@ def operand(x):
 
 
 def emit(ops):
-    lines = ["// GENERATED by gen_fr_mul.py (self-tested against big-integer arithmetic) — do not edit.",
+    lines = [f"// GENERATED by gen_fr_mul.py {FIELD} (self-tested against big-integer arithmetic) — do not edit.",
              "// Montgomery product r = a*b*2^-256 mod p on 8x32-bit limbs, r < 2p (caller reduces once).",
              "// Operands: %0-%7 = r (out), %8-%15 = a, %16-%23 = b.",
              "asm(\"{\\n\\t\"",
@@ -177,7 +184,7 @@ def emit(ops):
 def main():
     ops = build()
     n = selftest(ops)
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fr_mul_ptx.inc")
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{FIELD}_mul_ptx.inc")
     with open(out, "w") as f:
         f.write(emit(ops))
     print(f"self-test ok on {n} operand pairs; {len(ops)} PTX instructions -> {out}")

@@ -1,0 +1,426 @@
+// msm.cu — multi-scalar multiplication over bn256 G1: the commitments of the columns this backend
+// produces.
+//
+// Replaces halo2_proofs v0.3.0 [UPSTREAM] arithmetic.rs best_multiexp as reached through
+// `ParamsKZG::commit_lagrange` / `commit` in keygen and create_proof (call sites main.rs:76-101,
+// benches/aes128.rs:88-107, benches/key_schedule.rs:105-124): out = sum_i scalars[i] * bases[i].
+// The blinding term (blind * W) stays with the caller: pass it as one more (scalar, base) pair or
+// add it afterwards.
+//
+// Bucket method with signed c-bit digits (2^(c-1) buckets per window):
+//   k_msm_digits   per scalar: leave Montgomery form, recode into W signed digits, histogram
+//   k_msm_scan     per window: bucket offsets and the task table (a bucket with cnt points is cut
+//                  into ceil(cnt / SEG) tasks so that skewed scalars — byte-valued advice columns,
+//                  0/1 selectors — spread over the machine instead of piling on a few threads)
+//   k_msm_scatter  point indices grouped by bucket (counting sort, order inside a bucket free)
+//   k_msm_tasks    one thread per task: <= SEG mixed additions (XYZZ += affine, 10 multiplies)
+//   k_msm_buckets  one thread per bucket: sum of its tasks' partial sums
+//   k_msm_chunks   per window, per chunk of buckets: sum_b (b - lo) B_b by running sums, + lo * S
+//   k_msm_windows  per window: sum of the chunk results
+//   k_msm_final    Horner over the windows (c doublings each), to affine
+// Bound by the Fq multiply rate (same IMAD.WIDE ceiling as Fr); bases are gathered from L2/HBM.
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+#include "fq.cuh"
+
+namespace h2 {
+
+constexpr int MSM_SEG = 32;     // points per task
+constexpr int MSM_NCH = 256;    // bucket chunks per window in the reduction
+
+struct MsmArgs {
+    uint64_t n;
+    int c, W;
+    uint32_t NB;               // 2^(c-1) buckets per window (index 1..NB; 0 = zero digit)
+    uint32_t max_tasks;        // per window
+    const fr_t *scalars;       // [n]
+    const g1a_t *bases;        // [n]
+    uint32_t *dig;             // [W][n] |digit| | sign << 31
+    uint32_t *hist;            // [W][NB + 1]
+    uint32_t *offs;            // [W][NB + 2] exclusive offsets of buckets into sorted
+    uint32_t *toffs;           // [W][NB + 2] exclusive offsets of buckets into the task list
+    uint32_t *cursor;          // [W][NB + 1]
+    uint32_t *sorted;          // [W][n] index | sign << 31
+    g1x_t *partial;            // [W][max_tasks]
+    g1x_t *buckets;            // [W][NB + 1]
+    g1x_t *chunks;             // [W][MSM_NCH]
+    g1x_t *wsum;               // [W]
+    g1a_t *out;                // result
+};
+
+__device__ __forceinline__ fr_t mfr_ld(const fr_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ fq_t mfq_ld(const fq_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fq_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ void mfq_st(fq_t *p, const fq_t &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+__device__ __forceinline__ g1x_t g1x_ld(const g1x_t *p) {
+    g1x_t r;
+    r.x = mfq_ld(&p->x); r.y = mfq_ld(&p->y); r.zz = mfq_ld(&p->zz); r.zzz = mfq_ld(&p->zzz);
+    return r;
+}
+__device__ __forceinline__ void g1x_st(g1x_t *p, const g1x_t &a) {
+    mfq_st(&p->x, a.x); mfq_st(&p->y, a.y); mfq_st(&p->zz, a.zz); mfq_st(&p->zzz, a.zzz);
+}
+
+__global__ void __launch_bounds__(256) k_msm_digits(const MsmArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const fr_t s = fr_to_canonical(mfr_ld(a.scalars + i));
+    const uint32_t full = 1u << a.c, mask = full - 1;
+    uint32_t carry = 0;
+    for (int w = 0; w < a.W; ++w) {
+        const int bit = w * a.c, lo = bit >> 5, sh = bit & 31;
+        uint32_t d = 0;
+        if (lo < 8) {
+            d = s.v[lo] >> sh;
+            if (sh + a.c > 32 && lo + 1 < 8) d |= s.v[lo + 1] << (32 - sh);
+            d &= mask;
+        }
+        d += carry;
+        uint32_t code;
+        if (d > a.NB) {  // negative digit d - 2^c, carry into the next window
+            code = (full - d) | 0x80000000u;
+            carry = 1;
+        } else {
+            code = d;
+            carry = 0;
+        }
+        const uint32_t mag = code & 0x7fffffffu;
+        a.dig[(uint64_t)w * a.n + i] = mag ? code : 0u;
+        if (mag) atomicAdd(a.hist + (uint64_t)w * (a.NB + 1) + mag, 1u);
+    }
+}
+
+// per window: exclusive scans of the bucket counts and of ceil(count / SEG)
+__global__ void __launch_bounds__(1024) k_msm_scan(const MsmArgs a) {
+    __shared__ uint32_t s_cnt[1024], s_tsk[1024];
+    const int w = blockIdx.x, t = threadIdx.x;
+    const uint32_t entries = a.NB + 1;
+    const uint32_t per = (entries + 1023) / 1024;
+    const uint32_t lo = min(entries, t * per), hi = min(entries, lo + per);
+    const uint32_t *h = a.hist + (uint64_t)w * entries;
+    uint32_t c = 0, k = 0;
+    for (uint32_t b = lo; b < hi; ++b) {
+        c += h[b];
+        k += (h[b] + MSM_SEG - 1) / MSM_SEG;
+    }
+    s_cnt[t] = c;
+    s_tsk[t] = k;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
+        uint32_t vc = 0, vk = 0;
+        if (t >= d) { vc = s_cnt[t - d]; vk = s_tsk[t - d]; }
+        __syncthreads();
+        s_cnt[t] += vc;
+        s_tsk[t] += vk;
+        __syncthreads();
+    }
+    uint32_t rc = s_cnt[t] - c, rk = s_tsk[t] - k;  // exclusive prefixes of this thread's range
+    uint32_t *o = a.offs + (uint64_t)w * (a.NB + 2), *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    for (uint32_t b = lo; b < hi; ++b) {
+        o[b] = rc;
+        to[b] = rk;
+        rc += h[b];
+        rk += (h[b] + MSM_SEG - 1) / MSM_SEG;
+    }
+    if (t == 1023) {
+        o[entries] = s_cnt[1023];
+        to[entries] = s_tsk[1023];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_msm_scatter(const MsmArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = blockIdx.y;
+    if (i >= a.n) return;
+    const uint32_t code = a.dig[(uint64_t)w * a.n + i];
+    const uint32_t mag = code & 0x7fffffffu;
+    if (!mag) return;
+    const uint32_t pos = a.offs[(uint64_t)w * (a.NB + 2) + mag] +
+                         atomicAdd(a.cursor + (uint64_t)w * (a.NB + 1) + mag, 1u);
+    a.sorted[(uint64_t)w * a.n + pos] = (uint32_t)i | (code & 0x80000000u);
+}
+
+// one thread per task: the sum of <= SEG points of one bucket
+__global__ void __launch_bounds__(128) k_msm_tasks(const MsmArgs a) {
+    const int w = blockIdx.y;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    if (t >= to[a.NB + 1]) return;
+    // bucket b with to[b] <= t < to[b + 1]
+    uint32_t lo = 0, hi = a.NB + 1;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (to[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t *o = a.offs + (uint64_t)w * (a.NB + 2);
+    const uint32_t start = o[b] + (t - to[b]) * MSM_SEG, end = min(o[b + 1], start + MSM_SEG);
+    const uint32_t *srt = a.sorted + (uint64_t)w * a.n;
+    g1x_t acc = g1x_identity();
+#pragma unroll 1
+    for (uint32_t pos = start; pos < end; ++pos) {
+        const uint32_t e = srt[pos];
+        const g1a_t *bp = a.bases + (e & 0x7fffffffu);
+        g1a_t q;
+        q.x = mfq_ld(&bp->x);
+        q.y = mfq_ld(&bp->y);
+        g1x_madd(acc, q, (e >> 31) != 0);
+    }
+    g1x_st(a.partial + (uint64_t)w * a.max_tasks + t, acc);
+}
+
+// one thread per bucket: sum of its tasks
+__global__ void __launch_bounds__(128) k_msm_buckets(const MsmArgs a) {
+    const int w = blockIdx.y;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > a.NB) return;
+    const uint32_t *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    g1x_t acc = g1x_identity();
+#pragma unroll 1
+    for (uint32_t t = to[b]; t < to[b + 1]; ++t) {
+        const g1x_t p = g1x_ld(a.partial + (uint64_t)w * a.max_tasks + t);
+        g1x_add(acc, p);
+    }
+    g1x_st(a.buckets + (uint64_t)w * (a.NB + 1) + b, acc);
+}
+
+// per (window, chunk of buckets (lo, hi]): sum_b b * B_b = sum_b (b - lo) B_b + lo * sum_b B_b
+__global__ void __launch_bounds__(64) k_msm_chunks(const MsmArgs a) {
+    const int w = blockIdx.y;
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= MSM_NCH) return;
+    const uint32_t cb = (a.NB + MSM_NCH - 1) / MSM_NCH;
+    const uint32_t lo = min(a.NB, ch * cb), hi = min(a.NB, lo + cb);
+    const g1x_t *B = a.buckets + (uint64_t)w * (a.NB + 1);
+    g1x_t run = g1x_identity(), acc = g1x_identity();
+#pragma unroll 1
+    for (uint32_t b = hi; b > lo; --b) {
+        const g1x_t p = g1x_ld(B + b);
+        g1x_add(run, p);
+        g1x_add(acc, run);
+    }
+    // acc += lo * run (double-and-add, lo < 2^15)
+    if (lo && !g1x_is_identity(run)) {
+        g1x_t m = g1x_identity();
+#pragma unroll 1
+        for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
+            g1x_double(m);
+            if ((lo >> bit) & 1u) g1x_add(m, run);
+        }
+        g1x_add(acc, m);
+    }
+    g1x_st(a.chunks + (uint64_t)w * MSM_NCH + ch, acc);
+}
+
+// per window: sum of the chunk results (32 lanes x MSM_NCH/32 chunks, then lane 0 adds 32)
+__global__ void __launch_bounds__(32) k_msm_windows(const MsmArgs a) {
+    __shared__ g1x_t s_part[32];
+    const int w = blockIdx.x, lane = threadIdx.x;
+    const g1x_t *C = a.chunks + (uint64_t)w * MSM_NCH;
+    g1x_t acc = g1x_identity();
+#pragma unroll 1
+    for (int j = 0; j < MSM_NCH / 32; ++j) {
+        const g1x_t p = g1x_ld(C + lane * (MSM_NCH / 32) + j);
+        g1x_add(acc, p);
+    }
+    s_part[lane] = acc;
+    __syncwarp();
+    if (lane == 0) {
+        g1x_t tot = s_part[0];
+#pragma unroll 1
+        for (int j = 1; j < 32; ++j) g1x_add(tot, s_part[j]);
+        g1x_st(a.wsum + w, tot);
+    }
+}
+
+// Horner over the windows, then to affine
+__global__ void k_msm_final(const MsmArgs a) {
+    if (threadIdx.x || blockIdx.x) return;
+    g1x_t tot = g1x_identity();
+#pragma unroll 1
+    for (int w = a.W - 1; w >= 0; --w) {
+#pragma unroll 1
+        for (int i = 0; i < a.c; ++i) g1x_double(tot);
+        const g1x_t p = g1x_ld(a.wsum + w);
+        g1x_add(tot, p);
+    }
+    const g1a_t r = g1x_to_affine(tot);
+    mfq_st(&a.out->x, r.x);
+    mfq_st(&a.out->y, r.y);
+}
+
+}  // namespace h2
+
+using namespace h2;
+
+struct h2aes_msm {
+    h2aes_ctx *ctx = nullptr;
+    uint64_t n = 0;
+    int c = 0, W = 0;
+    uint32_t NB = 0, max_tasks = 0;
+    const g1a_t *bases = nullptr;  // caller-owned
+    uint32_t *d_u32 = nullptr;     // dig, hist, offs, toffs, cursor, sorted in one allocation
+    g1x_t *d_pts = nullptr;        // partial, buckets, chunks, wsum
+    g1a_t *d_out = nullptr;        // [out_cap]
+    int out_cap = 0;
+    size_t hist_off = 0, offs_off = 0, toffs_off = 0, cursor_off = 0, sorted_off = 0, zero_words = 0;
+};
+
+namespace {
+int32_t mfail(h2aes_ctx *ctx, int32_t code, const char *what) {
+    if (ctx) ctx->last_error = what;
+    return code;
+}
+int32_t mcuda(h2aes_ctx *ctx, cudaError_t e, const char *what) {
+    if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? H2AES_ERR_NOMEM : H2AES_ERR_CUDA;
+}
+#define MCU(ctx, call)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return mcuda(ctx, e__, #call);  \
+    } while (0)
+unsigned cdivu(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+}  // namespace
+
+extern "C" {
+
+int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out) {
+    if (!ctx || !out) return H2AES_ERR_ARG;
+    *out = nullptr;
+    if (!bases_dev || n == 0 || n > (1ull << 26)) return mfail(ctx, H2AES_ERR_ARG, "msm: bases null or n out of range");
+    MCU(ctx, cudaSetDevice(ctx->device));
+    h2aes_msm *m = new (std::nothrow) h2aes_msm;
+    if (!m) return H2AES_ERR_NOMEM;
+    m->ctx = ctx;
+    m->n = n;
+    m->bases = reinterpret_cast<const g1a_t *>(bases_dev);
+    int lg = 0;
+    while ((1ull << (lg + 1)) <= n) ++lg;
+    m->c = std::max(4, std::min(16, lg - 4));
+    m->W = 254 / m->c + 1;
+    m->NB = 1u << (m->c - 1);
+    m->max_tasks = (uint32_t)(n / MSM_SEG) + m->NB + 1;
+    const size_t W = (size_t)m->W, nb1 = m->NB + 1, nb2 = m->NB + 2;
+    // layout: [hist | cursor] (zeroed per call) | offs | toffs | dig | sorted
+    m->hist_off = 0;
+    m->cursor_off = W * nb1;
+    m->zero_words = 2 * W * nb1;
+    m->offs_off = m->zero_words;
+    m->toffs_off = m->offs_off + W * nb2;
+    const size_t dig_off = m->toffs_off + W * nb2;
+    m->sorted_off = dig_off + W * n;
+    const size_t words = m->sorted_off + W * n;
+    const size_t pts = W * ((size_t)m->max_tasks + nb1 + MSM_NCH + 1);
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&m->d_u32, words * 4)) ||
+        (e = cudaMalloc((void **)&m->d_pts, pts * sizeof(g1x_t)))) {
+        h2aes_msm_destroy(m);
+        return mcuda(ctx, e, "msm: cudaMalloc");
+    }
+    *out = m;
+    return H2AES_OK;
+}
+
+int32_t h2aes_msm_destroy(h2aes_msm *m) {
+    if (!m) return H2AES_ERR_ARG;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->d_u32);
+    cudaFree(m->d_pts);
+    cudaFree(m->d_out);
+    delete m;
+    return H2AES_OK;
+}
+
+int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, uint64_t *out_dev) {
+    if (!m) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = m->ctx;
+    if (!scalars_dev || !out_dev || ncols < 0) return mfail(ctx, H2AES_ERR_ARG, "msm: null pointer");
+    MCU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t W = (size_t)m->W, nb1 = m->NB + 1;
+    MsmArgs a;
+    a.n = m->n; a.c = m->c; a.W = m->W; a.NB = m->NB; a.max_tasks = m->max_tasks;
+    a.bases = m->bases;
+    a.hist = m->d_u32 + m->hist_off;
+    a.cursor = m->d_u32 + m->cursor_off;
+    a.offs = m->d_u32 + m->offs_off;
+    a.toffs = m->d_u32 + m->toffs_off;
+    a.dig = m->d_u32 + m->toffs_off + W * (m->NB + 2);
+    a.sorted = m->d_u32 + m->sorted_off;
+    a.partial = m->d_pts;
+    a.buckets = a.partial + W * m->max_tasks;
+    a.chunks = a.buckets + W * nb1;
+    a.wsum = a.chunks + W * MSM_NCH;
+    for (int col = 0; col < ncols; ++col) {
+        a.scalars = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)col * m->n;
+        a.out = reinterpret_cast<g1a_t *>(out_dev) + col;
+        MCU(ctx, cudaMemsetAsync(m->d_u32, 0, m->zero_words * 4, s));
+        prof_begin(ctx, "k_msm_digits");
+        k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_scan");
+        k_msm_scan<<<m->W, 1024, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_scatter");
+        k_msm_scatter<<<dim3(cdivu(m->n, 256), m->W), 256, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_tasks");
+        k_msm_tasks<<<dim3(cdivu(m->max_tasks, 128), m->W), 128, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_buckets");
+        k_msm_buckets<<<dim3(cdivu(nb1, 128), m->W), 128, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_chunks");
+        k_msm_chunks<<<dim3(cdivu(MSM_NCH, 64), m->W), 64, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_windows");
+        k_msm_windows<<<m->W, 32, 0, s>>>(a);
+        prof_end(ctx);
+        prof_begin(ctx, "k_msm_final");
+        k_msm_final<<<1, 32, 0, s>>>(a);
+        prof_end(ctx);
+        ctx->launches += 8;
+    }
+    MCU(ctx, cudaGetLastError());
+    return H2AES_OK;
+}
+
+int32_t h2aes_msm_host(h2aes_msm *m, const uint64_t *scalars, int32_t ncols, uint64_t *out) {
+    if (!m) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = m->ctx;
+    if (!scalars || !out || ncols < 0) return mfail(ctx, H2AES_ERR_ARG, "msm: null pointer");
+    MCU(ctx, cudaSetDevice(ctx->device));
+    uint64_t *d_s = nullptr, *d_o = nullptr;
+    const size_t sb = (size_t)ncols * m->n * 32, ob = (size_t)ncols * 64;
+    MCU(ctx, cudaMalloc((void **)&d_s, sb + 32));
+    cudaError_t e = cudaMalloc((void **)&d_o, ob + 64);
+    int32_t rc = H2AES_OK;
+    if (!e) e = cudaMemcpyAsync(d_s, scalars, sb, cudaMemcpyHostToDevice, ctx->stream);
+    if (!e) rc = h2aes_msm_dev(m, d_s, ncols, d_o);
+    if (!e && !rc) e = cudaMemcpyAsync(out, d_o, ob, cudaMemcpyDeviceToHost, ctx->stream);
+    if (!e) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_s);
+    cudaFree(d_o);
+    if (e) return mcuda(ctx, e, "msm (host)");
+    return rc;
+}
+
+}  // extern "C"

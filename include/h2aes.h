@@ -319,6 +319,25 @@ int32_t h2aes_gate_perm_quotient_dev(h2aes_circuit *c, h2aes_domain *d, const ui
  * 1 / ((zeta * extended_omega^i)^n - 1).  In place on [ncols][2^extended_k][4]. */
 int32_t h2aes_divide_by_vanishing_dev(h2aes_domain *d, uint64_t *ext_dev, int32_t ncols);
 
+/* ---- commitments: multi-scalar multiplication over bn256 G1 — SURVEY 8(f) item 2 -------------
+ * replaces: halo2_proofs v0.3.0 arithmetic.rs best_multiexp as reached through
+ * ParamsKZG::commit_lagrange / commit in keygen and create_proof (call sites main.rs:76-101,
+ * benches/aes128.rs:88-107, benches/key_schedule.rs:105-124): out = sum_i scalars[i] * bases[i].
+ *   bases    n points as halo2curves `G1Affine`: x then y, 4 u64 Montgomery limbs of Fq each
+ *            (64 bytes per point, identity = all zero); device memory, caller-owned, must outlive
+ *            the handle (e.g. params.g_lagrange uploaded once)
+ *   scalars  [ncols][n][4]: columns of Fr exactly as every other entry point produces them
+ *   out      [ncols][2][4]: one G1Affine per column
+ * The blinding term of a halo2 commitment (blind * params.w) is the caller's: append it as one more
+ * (scalar, base) pair or add it to the result. */
+typedef struct h2aes_msm h2aes_msm;
+int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out);
+int32_t h2aes_msm_destroy(h2aes_msm *m);
+/* scalars and out in device memory; asynchronous on the context's stream. */
+int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, uint64_t *out_dev);
+/* scalars and out in host memory (the bases stay on the device). */
+int32_t h2aes_msm_host(h2aes_msm *m, const uint64_t *scalars, int32_t ncols, uint64_t *out);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-sharded single circuit (one process per GPU, shard g of G owns rows
  * [g*2^k/G, (g+1)*2^k/G) of every column).  The only cross-GPU data are the per-lookup bin

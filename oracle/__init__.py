@@ -91,6 +91,11 @@ def lib():
         L.orc_domain_transform.argtypes = [C.c_int, C.c_int, C.c_int, u64p, u64p]
         L.orc_domain_query.argtypes = [C.c_int, C.c_int, u64p]
         L.orc_lookup_quotient.argtypes = [C.c_void_p, C.c_int, C.c_int] + [u64p] * 5
+        L.orc_g1_msm.argtypes = [u64p, u64p, C.c_uint64, u64p]
+        L.orc_g1_test_bases.argtypes = [u64p, C.c_uint64, u64p]
+        L.orc_g1_mul_generator.argtypes = [u64p, u64p]
+        L.orc_g1_on_curve.argtypes = [u64p]
+        L.orc_g1_add_affine.argtypes = [u64p, u64p, u64p]
         L.orc_gate_perm_quotient.argtypes = [C.c_void_p] + [u64p] * 4
         L.orc_divide_by_vanishing.argtypes = [C.c_int, C.c_int, u64p]
         L.orc_poly_eval.argtypes = [u64p, C.c_uint64, u64p, u64p]
@@ -203,6 +208,46 @@ def poly_eval(coeffs: np.ndarray, x) -> np.ndarray:
     xx = np.ascontiguousarray(x, np.uint64)
     out = np.zeros(4, np.uint64)
     lib().orc_poly_eval(_u64(coeffs), coeffs.shape[0], _u64(xx), _u64(out))
+    return out
+
+
+# [UPSTREAM] bn256 G1 + best_multiexp restated (oracle/g1.hpp); points are [2, 4] uint64 (x, y)
+Q_MOD = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+
+
+def g1_msm(scalars: np.ndarray, bases: np.ndarray) -> np.ndarray:
+    scalars = np.ascontiguousarray(scalars, np.uint64)
+    bases = np.ascontiguousarray(bases, np.uint64)
+    n = scalars.shape[0]
+    assert scalars.shape == (n, 4) and bases.shape == (n, 2, 4)
+    out = np.zeros((2, 4), np.uint64)
+    lib().orc_g1_msm(_u64(scalars), _u64(bases), n, _u64(out))
+    return out
+
+
+def g1_test_bases(n: int, d) -> np.ndarray:
+    """bases[i] = (1 + i*d) * G: an SRS stand-in whose discrete logarithms are known"""
+    dd = np.ascontiguousarray(d, np.uint64)
+    out = np.zeros((n, 2, 4), np.uint64)
+    lib().orc_g1_test_bases(_u64(dd), n, _u64(out))
+    return out
+
+
+def g1_mul_generator(k) -> np.ndarray:
+    kk = np.ascontiguousarray(k, np.uint64)
+    out = np.zeros((2, 4), np.uint64)
+    lib().orc_g1_mul_generator(_u64(kk), _u64(out))
+    return out
+
+
+def g1_on_curve(p) -> bool:
+    return bool(lib().orc_g1_on_curve(_u64(np.ascontiguousarray(p, np.uint64))))
+
+
+def g1_add(a, b) -> np.ndarray:
+    out = np.zeros((2, 4), np.uint64)
+    lib().orc_g1_add_affine(_u64(np.ascontiguousarray(a, np.uint64)), _u64(np.ascontiguousarray(b, np.uint64)),
+                            _u64(out))
     return out
 
 

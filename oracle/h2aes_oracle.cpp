@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "fr.hpp"
+#include "g1.hpp"
 
 namespace orc {
 
@@ -1395,6 +1396,52 @@ void orc_poly_eval(const uint64_t *coeffs, uint64_t len, const uint64_t *x_, uin
     Fr acc = FR_ZERO;
     for (uint64_t i = len; i-- > 0;) acc = fr_add(fr_mul(acc, x), fr_load(coeffs + 4 * i));
     memcpy(out, acc.l, 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// [UPSTREAM] commitments: halo2curves bn256 G1 + halo2_proofs arithmetic.rs best_multiexp
+// (SURVEY 8(f) item 2).  Points travel as G1Affine (x, y: 4 + 4 u64 Montgomery limbs of Fq,
+// identity = all zero).
+// ---------------------------------------------------------------------------------------------
+// out = sum_i scalars[i] * bases[i]
+void orc_g1_msm(const uint64_t *scalars, const uint64_t *bases, uint64_t n, uint64_t out[8]) {
+    const G1Affine r = g1_to_affine(g1_msm((const Fr *)scalars, (const G1Affine *)bases, n));
+    memcpy(out, &r, 64);
+}
+// Test SRS with known discrete logarithms: bases[i] = (1 + i*d) * G, G = (1, 2): one addition of
+// D = d*G per point, then one batch inversion back to affine.  d is an Fr in Montgomery form.
+void orc_g1_test_bases(const uint64_t *d_, uint64_t n, uint64_t *bases) {
+    uint64_t dc[4];
+    fr_to_canonical(fr_load(d_), dc);
+    const G1 g = g1_from_affine(g1_generator());
+    const G1 dpt = g1_mul_canonical(g, dc);
+    std::vector<G1> pts(n);
+    G1 cur = g;
+    for (uint64_t i = 0; i < n; ++i) { pts[i] = cur; cur = g1_add(cur, dpt); }
+    // Montgomery-trick batch inversion of the z coordinates
+    std::vector<Fq> pre(n);
+    Fq acc = FQ_ONE;
+    for (uint64_t i = 0; i < n; ++i) { pre[i] = acc; acc = fq_mul(acc, pts[i].z); }
+    Fq inv = fq_inv(acc);
+    G1Affine *out = (G1Affine *)bases;
+    for (uint64_t i = n; i-- > 0;) {
+        const Fq zi = fq_mul(inv, pre[i]);
+        inv = fq_mul(inv, pts[i].z);
+        const Fq zi2 = fq_mul(zi, zi);
+        out[i] = G1Affine{fq_mul(pts[i].x, zi2), fq_mul(fq_mul(pts[i].y, zi2), zi)};
+    }
+}
+// k * G for an Fr scalar in Montgomery form (affine out); and the curve equation
+void orc_g1_mul_generator(const uint64_t *k_, uint64_t out[8]) {
+    uint64_t kc[4];
+    fr_to_canonical(fr_load(k_), kc);
+    const G1Affine r = g1_to_affine(g1_mul_canonical(g1_from_affine(g1_generator()), kc));
+    memcpy(out, &r, 64);
+}
+int orc_g1_on_curve(const uint64_t *p) { return g1a_on_curve(*(const G1Affine *)p) ? 1 : 0; }
+void orc_g1_add_affine(const uint64_t *a, const uint64_t *b, uint64_t out[8]) {
+    const G1Affine r = g1_to_affine(g1_add(g1_from_affine(*(const G1Affine *)a), g1_from_affine(*(const G1Affine *)b)));
+    memcpy(out, &r, 64);
 }
 
 // ---- small Fr helpers so Python tests can do field arithmetic through the same code ----------

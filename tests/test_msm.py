@@ -1,0 +1,221 @@
+"""Commitments: multi-scalar multiplication over bn256 G1, halo2's
+best_multiexp [UPSTREAM halo2_proofs v0.3.0 arithmetic.rs, halo2curves 0.6.1 bn256].
+
+CPU part: the oracle's Fq / Jacobian group law / bucket-method restatement against a
+first-principles affine group law on python integers and against the discrete-log anchor
+(bases[i] = (1 + i d) G, so sum a_i bases[i] = (sum a_i (1 + i d)) G).  GPU part (`-m gpu`): the CUDA
+MSM through the C ABI, bit-exact (affine coordinates as Montgomery limbs) against the oracle and
+against the anchor.  Parity unpinned: no reference test holds a commitment."""
+import numpy as np
+import pytest
+
+from conftest import R_MOD, SEED, splitmix_bytes
+
+Q = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+RQ = (1 << 256) % Q
+D_STEP = 0x1D2C3B4A5968778695A4B3C2D1E0F  # d of the test bases
+
+
+def fq_int(limbs):
+    v = sum(int(limbs[i]) << (64 * i) for i in range(4))
+    return v * pow(RQ, -1, Q) % Q
+
+
+def pt(p):
+    x, y = fq_int(p[0]), fq_int(p[1])
+    return None if (x, y) == (0, 0) else (x, y)
+
+
+def ec_add(P, Qp):
+    if P is None:
+        return Qp
+    if Qp is None:
+        return P
+    (x1, y1), (x2, y2) = P, Qp
+    if x1 == x2:
+        if (y1 + y2) % Q == 0:
+            return None
+        lam = 3 * x1 * x1 * pow(2 * y1, -1, Q) % Q
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, Q) % Q
+    x3 = (lam * lam - x1 - x2) % Q
+    return x3, (lam * (x1 - x3) - y1) % Q
+
+
+def ec_mul(k, P):
+    R = None
+    for b in bin(k)[2:] if k else "":
+        R = ec_add(R, R)
+        if b == "1":
+            R = ec_add(R, P)
+    return R
+
+
+G = (1, 2)
+
+
+def rand_scalars(orc, seed, n):
+    a = splitmix_bytes(seed, n * 32).view(np.uint64).reshape(n, 4).copy()
+    a[:, 3] %= np.uint64(0x30644E72E131A029)  # Montgomery limbs of some element < r
+    return a
+
+
+def scalar_values(orc, s):
+    rinv = pow((1 << 256) % R_MOD, -1, R_MOD)
+    return [orc.limbs_to_int(x) * rinv % R_MOD for x in s]
+
+
+def anchor(orc, s):
+    """(sum a_i (1 + i d)) * G by one scalar multiplication"""
+    tot = sum(a * (1 + i * D_STEP) for i, a in enumerate(scalar_values(orc, s))) % R_MOD
+    return ec_mul(tot, G)
+
+
+# ---- CPU --------------------------------------------------------------------------------------
+def test_oracle_group_law_against_python_integers(orc):
+    k = int.from_bytes(splitmix_bytes(SEED + 40, 32).tobytes(), "little") % R_MOD
+    g = orc.g1_mul_generator(orc.fr_from_int(k))
+    assert pt(g) == ec_mul(k, G) and orc.g1_on_curve(g)
+    assert pt(orc.g1_mul_generator(orc.fr_from_int(0))) is None
+    assert pt(orc.g1_mul_generator(orc.fr_from_int(R_MOD - 1))) == (1, Q - 2)  # -G
+    B = orc.g1_test_bases(64, orc.fr_from_int(D_STEP))
+    for i in (0, 1, 5, 63):
+        assert pt(B[i]) == ec_mul((1 + i * D_STEP) % R_MOD, G)
+    assert pt(orc.g1_add(B[3], B[3])) == ec_mul(2 * (1 + 3 * D_STEP) % R_MOD, G)  # doubling
+    neg = B[3].copy()
+    neg[1] = orc.int_to_limbs((Q - fq_int(B[3][1])) * RQ % Q)
+    assert pt(orc.g1_add(B[3], neg)) is None  # P + (-P)
+
+
+def test_oracle_msm_against_the_anchor(orc):
+    n = 3000
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    s = rand_scalars(orc, SEED + 41, n)
+    s[7] = 0
+    s[8] = orc.fr_from_int(R_MOD - 1)
+    assert pt(orc.g1_msm(s, B)) == anchor(orc, s)
+    assert pt(orc.g1_msm(np.zeros((n, 4), np.uint64), B)) is None
+
+
+# ---- GPU --------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu(ffi):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from halo2_aes_b200.backend import Context
+    ctx = Context(0)
+    yield ctx
+    ctx.close()
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def _host(t):
+    from halo2_aes_b200.backend import to_host_u64
+    return to_host_u64(t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 33, 1000, 1 << 12, 1 << 14])
+def test_msm_equals_oracle_and_anchor(gpu, orc, ffi, n):
+    from halo2_aes_b200.backend import Msm
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    msm = Msm(gpu, _dev(B))
+    cols = np.stack([
+        rand_scalars(orc, SEED + 50 + n, n),                       # uniform field elements
+        np.zeros((n, 4), np.uint64),                                # all zero -> identity
+        np.tile(orc.fr_from_int(1), (n, 1)),                        # sum of the bases
+        np.tile(orc.fr_from_int(R_MOD - 1), (n, 1)),                # -(sum of the bases)
+        np.stack([orc.fr_from_int(int(b)) for b in splitmix_bytes(SEED + 51, n)]),  # bytes (advice-like)
+        np.stack([orc.fr_from_int(int(b) & 1) for b in splitmix_bytes(SEED + 52, n)]),  # 0/1 (selector-like)
+    ])
+    cols[0, 0] = orc.fr_from_int((1 << 253) + 12345)  # top window with a carry chain below it
+    if n > 2:
+        cols[0, 1] = orc.fr_from_int((1 << 128) - 1)
+    got = _host(msm.commit(_dev(cols)))
+    for ci in range(cols.shape[0]):
+        want = orc.g1_msm(cols[ci], B)
+        assert (got[ci] == want).all(), f"column {ci}: {pt(got[ci])} != {pt(want)}"
+        assert orc.g1_on_curve(got[ci])
+    assert pt(got[0]) == anchor(orc, cols[0])
+    assert pt(got[1]) is None
+    # host entry point
+    assert (msm.commit_host(cols[:2]) == got[:2]).all()
+    msm.close()
+
+
+@pytest.mark.gpu
+def test_msm_repeated_points_hit_the_doubling_case(gpu, orc, ffi):
+    """equal bases with equal scalars land in one bucket: acc == point -> the doubling branch"""
+    from halo2_aes_b200.backend import Msm
+    n = 256
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    B[1::2] = B[0::2]                       # pairs of identical points
+    s = rand_scalars(orc, SEED + 60, n)
+    s[1::2] = s[0::2]                       # with identical scalars
+    neg = B[10].copy()
+    neg[1] = orc.int_to_limbs((Q - fq_int(B[10][1])) * RQ % Q)
+    B[11] = neg                             # and one P, -P pair: cancellation
+    msm = Msm(gpu, _dev(B))
+    got = _host(msm.commit(_dev(s[None])))[0]
+    assert (got == orc.g1_msm(s, B)).all()
+    msm.close()
+
+
+@pytest.mark.gpu
+def test_commitment_of_witness_columns(gpu, orc, ffi):
+    """advice columns of the key-schedule circuit (k = 17) committed against 2^17 bases"""
+    from halo2_aes_b200.backend import Circuit, Msm
+    k = 17
+    key = splitmix_bytes(SEED + 61, 16).tobytes()
+    cir = Circuit(gpu, ffi.KIND_KEYSCHED, k, 1)
+    advice, _ = cir.witness(key, None)
+    B = orc.g1_test_bases(1 << k, orc.fr_from_int(D_STEP))
+    msm = Msm(gpu, _dev(B))
+    got = _host(msm.commit(advice))
+    ref = orc.Circuit(orc.KIND_KEYSCHED, k, 1).synthesize(key, None)
+    for col in range(advice.shape[0]):
+        assert (got[col] == orc.g1_msm(ref.advice()[col], B)).all(), col
+    msm.close()
+    cir.close()
+
+
+@pytest.mark.gpu
+def test_msm_bench_size_anchor_and_linearity(gpu, orc, ffi):
+    """n = 2^20 (the bench shape's column length): anchor on uniform scalars, and
+    commit(a) + commit(b) == commit(a + b) with the sum formed by the oracle's field addition"""
+    import ctypes as C
+    from halo2_aes_b200.backend import Msm
+    n = 1 << 20
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    msm = Msm(gpu, _dev(B))
+    # a, b supported on the first 4096 rows (their sum is formed row by row with the oracle's
+    # field addition); the anchor below uses all 2^20 rows
+    a, b = np.zeros((n, 4), np.uint64), np.zeros((n, 4), np.uint64)
+    a[:4096], b[:4096] = rand_scalars(orc, SEED + 70, 4096), rand_scalars(orc, SEED + 71, 4096)
+    s = np.zeros_like(a)
+    u64p = C.POINTER(C.c_uint64)
+    for i in range(4096):
+        orc.lib().orc_fr_add(a[i].ctypes.data_as(u64p), b[i].ctypes.data_as(u64p),
+                             s[i].ctypes.data_as(u64p))
+    got = _host(msm.commit(_dev(np.stack([a, b, s]))))
+    assert (orc.g1_add(got[0], got[1]) == got[2]).all()
+    full = rand_scalars(orc, SEED + 72, n)
+    got_full = _host(msm.commit(_dev(full[None])))[0]
+    assert pt(got_full) == anchor(orc, full)
+    msm.close()
+
+
+@pytest.mark.gpu
+def test_msm_error_behaviour(gpu, ffi):
+    import ctypes as C
+    lib = ffi.lib()
+    h = C.c_void_p()
+    assert lib.h2aes_msm_create(gpu._h, None, 16, C.byref(h)) == ffi.ERR_ARG
+    assert lib.h2aes_msm_create(None, None, 16, C.byref(h)) == ffi.ERR_ARG
+    assert lib.h2aes_msm_dev(None, None, 1, None) == ffi.ERR_ARG
+    assert lib.h2aes_msm_host(None, None, 1, None) == ffi.ERR_ARG
