@@ -15,9 +15,10 @@
 //   k_msm_scatter  point indices grouped by bucket (counting sort, order inside a bucket free)
 //   k_msm_tasks    one thread per task: <= SEG mixed additions (XYZZ += affine, 10 multiplies)
 //   k_msm_buckets  one thread per bucket: sum of its tasks' partial sums
+//   k_msm_heavy    one CTA per bucket with more than MSM_HEAVY tasks (strided sums + tree)
 //   k_msm_chunks   per window, per chunk of buckets: sum_b (b - lo) B_b by running sums, + lo * S
 //   k_msm_windows  per window: sum of the chunk results
-//   k_msm_final    Horner over the windows (c doublings each), to affine
+//   k_msm_final    per column of a batch: Horner over the windows (c doublings each), to affine
 // Bound by the Fq multiply rate (same IMAD.WIDE ceiling as Fr); bases are gathered from L2/HBM.
 #include <algorithm>
 #include <new>
@@ -30,7 +31,9 @@
 namespace h2 {
 
 constexpr int MSM_SEG = 32;     // points per task
-constexpr int MSM_NCH = 256;    // bucket chunks per window in the reduction
+constexpr int MSM_NCH = 1024;   // bucket chunks per window in the reduction
+constexpr int MSM_HEAVY = 8;    // a bucket with more tasks than this is summed by a whole CTA
+constexpr int MSM_BATCH = 64;   // columns whose window sums wait for one k_msm_final launch
 
 struct MsmArgs {
     uint64_t n;
@@ -48,8 +51,12 @@ struct MsmArgs {
     g1x_t *partial;            // [W][max_tasks]
     g1x_t *buckets;            // [W][NB + 1]
     g1x_t *chunks;             // [W][MSM_NCH]
-    g1x_t *wsum;               // [W]
-    g1a_t *out;                // result
+    g1x_t *wsum;               // [MSM_BATCH][W] window sums of the columns of a batch
+    uint32_t *heavy;           // [W][max_heavy + 1]: count, then the heavy buckets of the window
+    uint32_t max_heavy;
+    g1a_t *out;                // results of the batch
+    int col;                   // column inside the batch
+    int ncols;                 // columns in the batch (k_msm_final)
 };
 
 __device__ __forceinline__ fr_t mfr_ld(const fr_t *p) {
@@ -133,11 +140,14 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const MsmArgs a) {
     }
     uint32_t rc = s_cnt[t] - c, rk = s_tsk[t] - k;  // exclusive prefixes of this thread's range
     uint32_t *o = a.offs + (uint64_t)w * (a.NB + 2), *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    uint32_t *hv = a.heavy + (uint64_t)w * (a.max_heavy + 1);
     for (uint32_t b = lo; b < hi; ++b) {
         o[b] = rc;
         to[b] = rk;
         rc += h[b];
-        rk += (h[b] + MSM_SEG - 1) / MSM_SEG;
+        const uint32_t tasks = (h[b] + MSM_SEG - 1) / MSM_SEG;
+        rk += tasks;
+        if (tasks > MSM_HEAVY) hv[1 + atomicAdd(hv, 1u)] = b;  // at most n / (SEG*HEAVY) of them
     }
     if (t == 1023) {
         o[entries] = s_cnt[1023];
@@ -192,6 +202,7 @@ __global__ void __launch_bounds__(128) k_msm_buckets(const MsmArgs a) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > a.NB) return;
     const uint32_t *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    if (to[b + 1] - to[b] > MSM_HEAVY) return;  // k_msm_heavy
     g1x_t acc = g1x_identity();
 #pragma unroll 1
     for (uint32_t t = to[b]; t < to[b + 1]; ++t) {
@@ -199,6 +210,47 @@ __global__ void __launch_bounds__(128) k_msm_buckets(const MsmArgs a) {
         g1x_add(acc, p);
     }
     g1x_st(a.buckets + (uint64_t)w * (a.NB + 1) + b, acc);
+}
+
+// block-wide sum of one g1x per thread (tree in shared memory); the result is valid in thread 0
+template <int T>
+__device__ __forceinline__ g1x_t g1x_block_sum(g1x_t acc, g1x_t *s_pts) {
+    const int t = threadIdx.x;
+    s_pts[t] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int d = T / 2; d > 0; d >>= 1) {
+        if (t < d) {
+            acc = s_pts[t];
+            g1x_add(acc, s_pts[t + d]);
+            s_pts[t] = acc;
+        }
+        __syncthreads();
+    }
+    return s_pts[0];
+}
+
+// one CTA per heavy bucket (skewed scalars: a 0/1 selector column puts a third of the points in
+// bucket 1): threads stride over the bucket's task sums, then a shared-memory tree
+__global__ void __launch_bounds__(128) k_msm_heavy(const MsmArgs a) {
+    __shared__ g1x_t s_pts[128];
+    const int w = blockIdx.y;
+    const uint32_t *hv = a.heavy + (uint64_t)w * (a.max_heavy + 1);
+    const uint32_t *to = a.toffs + (uint64_t)w * (a.NB + 2);
+    const uint32_t n_heavy = hv[0];
+#pragma unroll 1
+    for (uint32_t hb = blockIdx.x; hb < n_heavy; hb += gridDim.x) {
+        const uint32_t b = hv[1 + hb];
+        g1x_t acc = g1x_identity();
+#pragma unroll 1
+        for (uint32_t t = to[b] + threadIdx.x; t < to[b + 1]; t += 128) {
+            const g1x_t p = g1x_ld(a.partial + (uint64_t)w * a.max_tasks + t);
+            g1x_add(acc, p);
+        }
+        const g1x_t tot = g1x_block_sum<128>(acc, s_pts);
+        if (threadIdx.x == 0) g1x_st(a.buckets + (uint64_t)w * (a.NB + 1) + b, tot);
+        __syncthreads();
+    }
 }
 
 // per (window, chunk of buckets (lo, hi]): sum_b b * B_b = sum_b (b - lo) B_b + lo * sum_b B_b
@@ -229,41 +281,37 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const MsmArgs a) {
     g1x_st(a.chunks + (uint64_t)w * MSM_NCH + ch, acc);
 }
 
-// per window: sum of the chunk results (32 lanes x MSM_NCH/32 chunks, then lane 0 adds 32)
-__global__ void __launch_bounds__(32) k_msm_windows(const MsmArgs a) {
-    __shared__ g1x_t s_part[32];
-    const int w = blockIdx.x, lane = threadIdx.x;
+// per window: sum of the chunk results
+__global__ void __launch_bounds__(128) k_msm_windows(const MsmArgs a) {
+    __shared__ g1x_t s_pts[128];
+    const int w = blockIdx.x;
     const g1x_t *C = a.chunks + (uint64_t)w * MSM_NCH;
     g1x_t acc = g1x_identity();
 #pragma unroll 1
-    for (int j = 0; j < MSM_NCH / 32; ++j) {
-        const g1x_t p = g1x_ld(C + lane * (MSM_NCH / 32) + j);
+    for (int j = threadIdx.x; j < MSM_NCH; j += 128) {
+        const g1x_t p = g1x_ld(C + j);
         g1x_add(acc, p);
     }
-    s_part[lane] = acc;
-    __syncwarp();
-    if (lane == 0) {
-        g1x_t tot = s_part[0];
-#pragma unroll 1
-        for (int j = 1; j < 32; ++j) g1x_add(tot, s_part[j]);
-        g1x_st(a.wsum + w, tot);
-    }
+    const g1x_t tot = g1x_block_sum<128>(acc, s_pts);
+    if (threadIdx.x == 0) g1x_st(a.wsum + (uint64_t)a.col * a.W + w, tot);
 }
 
-// Horner over the windows, then to affine
-__global__ void k_msm_final(const MsmArgs a) {
-    if (threadIdx.x || blockIdx.x) return;
+// one thread per column of the batch: Horner over the windows (c doublings each), then to affine.
+// ~2400 dependent multiplies; the columns of a batch run side by side.
+__global__ void __launch_bounds__(32) k_msm_final(const MsmArgs a) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.ncols) return;
     g1x_t tot = g1x_identity();
 #pragma unroll 1
     for (int w = a.W - 1; w >= 0; --w) {
 #pragma unroll 1
         for (int i = 0; i < a.c; ++i) g1x_double(tot);
-        const g1x_t p = g1x_ld(a.wsum + w);
+        const g1x_t p = g1x_ld(a.wsum + (uint64_t)col * a.W + w);
         g1x_add(tot, p);
     }
     const g1a_t r = g1x_to_affine(tot);
-    mfq_st(&a.out->x, r.x);
-    mfq_st(&a.out->y, r.y);
+    mfq_st(&a.out[col].x, r.x);
+    mfq_st(&a.out[col].y, r.y);
 }
 
 }  // namespace h2
@@ -280,7 +328,9 @@ struct h2aes_msm {
     g1x_t *d_pts = nullptr;        // partial, buckets, chunks, wsum
     g1a_t *d_out = nullptr;        // [out_cap]
     int out_cap = 0;
-    size_t hist_off = 0, offs_off = 0, toffs_off = 0, cursor_off = 0, sorted_off = 0, zero_words = 0;
+    size_t hist_off = 0, offs_off = 0, toffs_off = 0, cursor_off = 0, sorted_off = 0, zero_words = 0,
+           heavy_off = 0;
+    uint32_t max_heavy = 0;
 };
 
 namespace {
@@ -319,16 +369,18 @@ int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, 
     m->NB = 1u << (m->c - 1);
     m->max_tasks = (uint32_t)(n / MSM_SEG) + m->NB + 1;
     const size_t W = (size_t)m->W, nb1 = m->NB + 1, nb2 = m->NB + 2;
-    // layout: [hist | cursor] (zeroed per call) | offs | toffs | dig | sorted
+    m->max_heavy = (uint32_t)(n / ((uint64_t)MSM_SEG * MSM_HEAVY)) + 1;
+    // layout: [hist | cursor | heavy] (zeroed per column) | offs | toffs | dig | sorted
     m->hist_off = 0;
     m->cursor_off = W * nb1;
-    m->zero_words = 2 * W * nb1;
+    m->heavy_off = 2 * W * nb1;
+    m->zero_words = m->heavy_off + W * ((size_t)m->max_heavy + 1);
     m->offs_off = m->zero_words;
     m->toffs_off = m->offs_off + W * nb2;
     const size_t dig_off = m->toffs_off + W * nb2;
     m->sorted_off = dig_off + W * n;
     const size_t words = m->sorted_off + W * n;
-    const size_t pts = W * ((size_t)m->max_tasks + nb1 + MSM_NCH + 1);
+    const size_t pts = W * ((size_t)m->max_tasks + nb1 + MSM_NCH + MSM_BATCH);
     cudaError_t e;
     if ((e = cudaMalloc((void **)&m->d_u32, words * 4)) ||
         (e = cudaMalloc((void **)&m->d_pts, pts * sizeof(g1x_t)))) {
@@ -369,35 +421,46 @@ int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, 
     a.buckets = a.partial + W * m->max_tasks;
     a.chunks = a.buckets + W * nb1;
     a.wsum = a.chunks + W * MSM_NCH;
-    for (int col = 0; col < ncols; ++col) {
-        a.scalars = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)col * m->n;
-        a.out = reinterpret_cast<g1a_t *>(out_dev) + col;
-        MCU(ctx, cudaMemsetAsync(m->d_u32, 0, m->zero_words * 4, s));
-        prof_begin(ctx, "k_msm_digits");
-        k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_scan");
-        k_msm_scan<<<m->W, 1024, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_scatter");
-        k_msm_scatter<<<dim3(cdivu(m->n, 256), m->W), 256, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_tasks");
-        k_msm_tasks<<<dim3(cdivu(m->max_tasks, 128), m->W), 128, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_buckets");
-        k_msm_buckets<<<dim3(cdivu(nb1, 128), m->W), 128, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_chunks");
-        k_msm_chunks<<<dim3(cdivu(MSM_NCH, 64), m->W), 64, 0, s>>>(a);
-        prof_end(ctx);
-        prof_begin(ctx, "k_msm_windows");
-        k_msm_windows<<<m->W, 32, 0, s>>>(a);
-        prof_end(ctx);
+    a.heavy = m->d_u32 + m->heavy_off;
+    a.max_heavy = m->max_heavy;
+    for (int c0 = 0; c0 < ncols; c0 += MSM_BATCH) {
+        const int nb = std::min(MSM_BATCH, ncols - c0);
+        a.out = reinterpret_cast<g1a_t *>(out_dev) + c0;
+        a.ncols = nb;
+        for (int col = 0; col < nb; ++col) {
+            a.scalars = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)(c0 + col) * m->n;
+            a.col = col;
+            MCU(ctx, cudaMemsetAsync(m->d_u32, 0, m->zero_words * 4, s));
+            prof_begin(ctx, "k_msm_digits");
+            k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_scan");
+            k_msm_scan<<<m->W, 1024, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_scatter");
+            k_msm_scatter<<<dim3(cdivu(m->n, 256), m->W), 256, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_tasks");
+            k_msm_tasks<<<dim3(cdivu(m->max_tasks, 128), m->W), 128, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_buckets");
+            k_msm_buckets<<<dim3(cdivu(nb1, 128), m->W), 128, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_heavy");
+            k_msm_heavy<<<dim3(std::min(m->max_heavy, 296u), m->W), 128, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_chunks");
+            k_msm_chunks<<<dim3(cdivu(MSM_NCH, 64), m->W), 64, 0, s>>>(a);
+            prof_end(ctx);
+            prof_begin(ctx, "k_msm_windows");
+            k_msm_windows<<<m->W, 128, 0, s>>>(a);
+            prof_end(ctx);
+            ctx->launches += 8;
+        }
         prof_begin(ctx, "k_msm_final");
-        k_msm_final<<<1, 32, 0, s>>>(a);
+        k_msm_final<<<cdivu(nb, 32), 32, 0, s>>>(a);
         prof_end(ctx);
-        ctx->launches += 8;
+        ctx->launches += 1;
     }
     MCU(ctx, cudaGetLastError());
     return H2AES_OK;
