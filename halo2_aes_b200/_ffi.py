@@ -120,6 +120,7 @@ SIGNATURES = {
                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "h2aes_gate_perm_quotient_dev": (C.c_int32, [_vp, _vp, _u64p, _u64p, _u64p, _vp, _vp, _vp, _vp, _vp, _vp]),
     "h2aes_divide_by_vanishing_dev": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "h2aes_g1_synthetic_bases_dev": (C.c_int32, [_vp, _u64p, C.c_uint64, _vp]),
     "h2aes_msm_create": (C.c_int32, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "h2aes_msm_destroy": (C.c_int32, [_vp]),
     "h2aes_msm_dev": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),

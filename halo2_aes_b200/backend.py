@@ -387,6 +387,14 @@ class Domain:
             pass
 
 
+def synthetic_bases(ctx: Context, n: int, d) -> torch.Tensor:
+    """[n, 2, 4] G1Affine points (1 + i*d) * G on the device (h2aes_g1_synthetic_bases_dev)"""
+    out = torch.empty((n, 2, 4), dtype=torch.int64, device=ctx.device)
+    da, dp = _fr_arg(d)
+    check(lib().h2aes_g1_synthetic_bases_dev(ctx._h, dp, n, _ptr(out)), ctx._h)
+    return out
+
+
 class Msm:
     """best_multiexp over bn256 G1 on the GPU (h2aes_msm_*): commitments of Fr columns against a
     fixed set of bases (halo2curves G1Affine: int64 CUDA tensor [n, 2, 4], x then y)."""

@@ -85,10 +85,24 @@ __device__ __forceinline__ void g1x_st(g1x_t *p, const g1x_t &a) {
     mfq_st(&p->x, a.x); mfq_st(&p->y, a.y); mfq_st(&p->zz, a.zz); mfq_st(&p->zzz, a.zzz);
 }
 
+// Lanes of a warp that hit the same counter add once: columns of this backend repeat values over
+// long runs (the padding value of S', the constant stretches of Z), which would otherwise
+// serialise hundreds of thousands of atomics on one address.  Returns the lane's slot.
+__device__ __forceinline__ uint32_t warp_aggregated_inc(uint32_t *counters, uint32_t key, bool active) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, active ? key : 0xffffffffu);
+    if (!active) return 0;
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1));
+}
+
 __global__ void __launch_bounds__(256) k_msm_digits(const MsmArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const fr_t s = fr_to_canonical(mfr_ld(a.scalars + i));
+    const bool valid = i < a.n;  // no early return: whole warps take part in the aggregation
+    fr_t s = fr_zero();
+    if (valid) s = fr_to_canonical(mfr_ld(a.scalars + i));
     const uint32_t full = 1u << a.c, mask = full - 1;
     uint32_t carry = 0;
     for (int w = 0; w < a.W; ++w) {
@@ -109,8 +123,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(const MsmArgs a) {
             carry = 0;
         }
         const uint32_t mag = code & 0x7fffffffu;
-        a.dig[(uint64_t)w * a.n + i] = mag ? code : 0u;
-        if (mag) atomicAdd(a.hist + (uint64_t)w * (a.NB + 1) + mag, 1u);
+        if (valid) a.dig[(uint64_t)w * a.n + i] = mag ? code : 0u;
+        warp_aggregated_inc(a.hist + (uint64_t)w * (a.NB + 1), mag, valid && mag != 0);
     }
 }
 
@@ -158,12 +172,11 @@ __global__ void __launch_bounds__(1024) k_msm_scan(const MsmArgs a) {
 __global__ void __launch_bounds__(256) k_msm_scatter(const MsmArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int w = blockIdx.y;
-    if (i >= a.n) return;
-    const uint32_t code = a.dig[(uint64_t)w * a.n + i];
+    const uint32_t code = i < a.n ? a.dig[(uint64_t)w * a.n + i] : 0u;
     const uint32_t mag = code & 0x7fffffffu;
+    const uint32_t slot = warp_aggregated_inc(a.cursor + (uint64_t)w * (a.NB + 1), mag, mag != 0);
     if (!mag) return;
-    const uint32_t pos = a.offs[(uint64_t)w * (a.NB + 2) + mag] +
-                         atomicAdd(a.cursor + (uint64_t)w * (a.NB + 1) + mag, 1u);
+    const uint32_t pos = a.offs[(uint64_t)w * (a.NB + 2) + mag] + slot;
     a.sorted[(uint64_t)w * a.n + pos] = (uint32_t)i | (code & 0x80000000u);
 }
 
@@ -314,6 +327,42 @@ __global__ void __launch_bounds__(32) k_msm_final(const MsmArgs a) {
     mfq_st(&a.out[col].y, r.y);
 }
 
+// Synthetic bases with known discrete logarithms: out[i] = (1 + i*d) * G, G = (1, 2).  A thread
+// walks a contiguous range: one double-and-add for its first point, one mixed addition of D = d*G
+// per further point, one inversion per point on the way back to affine.
+__global__ void __launch_bounds__(128) k_msm_synthetic_bases(fr_t d, uint64_t n, uint64_t per,
+                                                             g1a_t *__restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i0 = t * per;
+    if (i0 >= n) return;
+    g1a_t g;
+    g.x = fq_one();
+    g.y = fq_dbl(fq_one());
+    auto mul_g = [&](const fr_t &k_mont) {  // k * G, scalar in Montgomery form
+        const fr_t k = fr_to_canonical(k_mont);
+        g1x_t acc = g1x_identity();
+#pragma unroll 1
+        for (int bit = 253; bit >= 0; --bit) {
+            g1x_double(acc);
+            if ((k.v[bit >> 5] >> (bit & 31)) & 1u) g1x_madd(acc, g, false);
+        }
+        return acc;
+    };
+    const g1a_t step = g1x_to_affine(mul_g(d));
+    fr_t idx = fr_zero();
+    idx.v[0] = (uint32_t)i0;
+    idx.v[1] = (uint32_t)(i0 >> 32);
+    idx = fr_mul(idx, fr_r2());  // i0 in Montgomery form
+    g1x_t cur = mul_g(fr_add(fr_one(), fr_mul(idx, d)));
+#pragma unroll 1
+    for (uint64_t i = i0; i < n && i < i0 + per; ++i) {
+        const g1a_t p = g1x_to_affine(cur);
+        mfq_st(&out[i].x, p.x);
+        mfq_st(&out[i].y, p.y);
+        g1x_madd(cur, step, false);
+    }
+}
+
 }  // namespace h2
 
 using namespace h2;
@@ -351,6 +400,26 @@ unsigned cdivu(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 }  // namespace
 
 extern "C" {
+
+int32_t h2aes_g1_synthetic_bases_dev(h2aes_ctx *ctx, const uint64_t *d, uint64_t n, uint64_t *bases_dev) {
+    if (!ctx) return H2AES_ERR_ARG;
+    if (!d || !bases_dev || n == 0) return mfail(ctx, H2AES_ERR_ARG, "synthetic bases: null pointer or n == 0");
+    MCU(ctx, cudaSetDevice(ctx->device));
+    fr_t dd;
+    for (int i = 0; i < 4; ++i) {
+        dd.v[2 * i] = (uint32_t)d[i];
+        dd.v[2 * i + 1] = (uint32_t)(d[i] >> 32);
+    }
+    const uint64_t threads = std::min<uint64_t>(n, (uint64_t)ctx->sm_count * 512);
+    const uint64_t per = (n + threads - 1) / threads;
+    prof_begin(ctx, "k_msm_synthetic_bases");
+    k_msm_synthetic_bases<<<cdivu((n + per - 1) / per, 128), 128, 0, ctx->stream>>>(
+        dd, n, per, reinterpret_cast<g1a_t *>(bases_dev));
+    prof_end(ctx);
+    ctx->launches += 1;
+    MCU(ctx, cudaGetLastError());
+    return H2AES_OK;
+}
 
 int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out) {
     if (!ctx || !out) return H2AES_ERR_ARG;

@@ -330,6 +330,10 @@ int32_t h2aes_divide_by_vanishing_dev(h2aes_domain *d, uint64_t *ext_dev, int32_
  *   out      [ncols][2][4]: one G1Affine per column
  * The blinding term of a halo2 commitment (blind * params.w) is the caller's: append it as one more
  * (scalar, base) pair or add it to the result. */
+/* Synthetic bases for tests and benchmarks (the stand-in for ParamsKZG::setup's unsafe SRS, whose
+ * points halo2 derives from a random scalar): bases_dev[i] = (1 + i*d) * G with G = (1, 2) and d
+ * an Fr in Montgomery form (host).  n points of 64 bytes, device memory. */
+int32_t h2aes_g1_synthetic_bases_dev(h2aes_ctx *ctx, const uint64_t *d, uint64_t n, uint64_t *bases_dev);
 typedef struct h2aes_msm h2aes_msm;
 int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out);
 int32_t h2aes_msm_destroy(h2aes_msm *m);

@@ -12,7 +12,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from halo2_aes_b200 import _ffi  # noqa: E402
-from halo2_aes_b200.backend import Circuit, Context, Domain  # noqa: E402
+from halo2_aes_b200.backend import Circuit, Context, Domain, Msm, synthetic_bases  # noqa: E402
 
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 FR_MUL_PEAK_G = 67.0  # measured ceiling of the Montgomery multiply on B200 (profiles/microbench)
@@ -37,6 +37,8 @@ def measure(ctx, K=20, N=5):
     perm = cir.lookup_permuted(theta, want_inputs=False)
     Z = cir.lookup_product(beta, gamma)
     cir.lookup_check()
+    sigma = cir.perm_sigma()
+    Zp = cir.perm_product(beta, gamma, advice)
     dom = Domain(ctx, K)
     en, ek = dom.extended_n, dom.extended_k
     stream = ctx.stream
@@ -50,8 +52,22 @@ def measure(ctx, K=20, N=5):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), r
 
-    sigma = cir.perm_sigma()
-    Zp = cir.perm_product(beta, gamma, advice)
+    # commitments of the witness-dependent columns (best_multiexp against synthetic bases)
+    ms_bases, bases = timed(lambda: synthetic_bases(ctx, 1 << K, fr(5)))
+    msm = Msm(ctx, bases)
+    msm.commit(advice[:1])  # warm-up
+    ctx.profile(True)
+    ms_c_adv, c_adv = timed(lambda: msm.commit(advice))
+    helper = torch.cat([perm["Ap"], perm["Sp"], Z, Zp])
+    ms_c_help, c_help = timed(lambda: msm.commit(helper))
+    kern_msm = ctx.profile_read()
+    ctx.profile(False)
+    assert bool(c_adv.any()) and bool(c_help.any())
+    n_help = int(helper.shape[0])
+    del helper
+    msm.close()
+    del bases
+
     cols = {"advice": advice, "table": fixed[:4].contiguous(), "sel": sel[:L].contiguous(),
             "Ap": perm["Ap"], "Sp": perm["Sp"], "Z": Z,
             "rc_qrc": torch.stack([fixed[4], sel[L]]), "sigma": sigma, "Zp": Zp}
@@ -81,6 +97,12 @@ def measure(ctx, K=20, N=5):
         "what": "prover-side steps after the witness path (SURVEY 8f items 3/4), one circuit, "
                 "not part of the headline metric",
         "shape": {"k": K, "N": N, "blocks": int(nb), "extended_k": ek, "columns": int(ncols)},
+        "commitments": {"bases": "synthetic: (1 + i d) G, built on the device", "bases_ms": ms_bases,
+                        "advice": {"columns": int(advice.shape[0]), "ms": ms_c_adv,
+                                   "ms_per_column": ms_c_adv / advice.shape[0]},
+                        "Ap_Sp_Z_Zperm": {"columns": n_help, "ms": ms_c_help,
+                                          "ms_per_column": ms_c_help / n_help},
+                        "kernels": {k_: {"launches": v[0], "ms": v[1]} for k_, v in kern_msm.items()}},
         "lagrange_to_coeff": {"ms": ms_l2c, "ms_per_column": ms_l2c / ncols, "fr_multiplies": mul_l2c,
                               "gmul_s": mul_l2c / ms_l2c / 1e6,
                               "frac_of_mul_peak": mul_l2c / ms_l2c / 1e6 / FR_MUL_PEAK_G},

@@ -211,6 +211,14 @@ def test_msm_bench_size_anchor_and_linearity(gpu, orc, ffi):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 7, 5000, 1 << 17])
+def test_synthetic_bases_equal_the_oracle(gpu, orc, ffi, n):
+    from halo2_aes_b200.backend import synthetic_bases
+    got = _host(synthetic_bases(gpu, n, orc.fr_from_int(D_STEP)))
+    assert (got == orc.g1_test_bases(n, orc.fr_from_int(D_STEP))).all()
+
+
+@pytest.mark.gpu
 def test_msm_error_behaviour(gpu, ffi):
     import ctypes as C
     lib = ffi.lib()
@@ -219,3 +227,4 @@ def test_msm_error_behaviour(gpu, ffi):
     assert lib.h2aes_msm_create(None, None, 16, C.byref(h)) == ffi.ERR_ARG
     assert lib.h2aes_msm_dev(None, None, 1, None) == ffi.ERR_ARG
     assert lib.h2aes_msm_host(None, None, 1, None) == ffi.ERR_ARG
+    assert lib.h2aes_g1_synthetic_bases_dev(gpu._h, None, 4, None) == ffi.ERR_ARG
