@@ -138,10 +138,34 @@ def cpu_baseline_sample(threads: int, target_s: float = 12.0):
     sec, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
     blocks = nb * threads * rounds
     return {"value": blocks / sec, "unit": UNIT, "cores": threads, "kind": "port",
-            "seconds": sec,
+            "seconds": sec, "prover_side": cpu_prover_side_sample(oracle, threads),
             "sample": f"{threads * rounds} independent k=17,N=1 circuits x 95 blocks (synthesize + "
                       f"5 lookups A,S,A',S',Z each), one circuit per thread, CPU restatement "
                       f"(oracle/), {blocks} blocks in {sec:.2f} s"}
+
+
+def cpu_prover_side_sample(oracle, threads: int):
+    """The oracle's restatements of the prover-side steps timed on the host
+    cores on ONE column of the bench shape's length, beside the GPU numbers of `prover_side`:
+    lagrange_to_coeff and coeff_to_extended of a 2^20 column (butterflies under OpenMP), one
+    2^20-point multi-scalar multiplication (bucket method, windows under OpenMP)."""
+    k = K_BENCH
+    n = 1 << k
+    col = splitmix_bytes(SEED + 300, n * 32).view(np.uint64).reshape(n, 4).copy()
+    col[:, 3] %= np.uint64(0x30644E72E131A029)
+    t0 = time.perf_counter()
+    coeff = oracle.domain_transform(oracle.LAGRANGE_TO_COEFF, k, col)
+    t1 = time.perf_counter()
+    oracle.domain_transform(oracle.COEFF_TO_EXTENDED, k, coeff)
+    t2 = time.perf_counter()
+    bases = oracle.g1_test_bases(n, oracle.fr_from_int(0x1D2C3B4A5968778695A4B3C2D1E0F))
+    t3 = time.perf_counter()
+    oracle.g1_msm(col, bases)
+    t4 = time.perf_counter()
+    return {"cores": threads, "kind": "port", "sample": f"one column of 2^{k} uniform field elements",
+            "lagrange_to_coeff_ms_per_column": 1e3 * (t1 - t0),
+            "coeff_to_extended_ms_per_column": 1e3 * (t2 - t1),
+            "msm_ms_per_column": 1e3 * (t4 - t3)}
 
 
 def run_reference(args):
