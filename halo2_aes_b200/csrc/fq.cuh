@@ -106,7 +106,10 @@ __device__ __forceinline__ fq_t fq_sub(const fq_t &a, const fq_t &b) {
 __device__ __forceinline__ fq_t fq_neg(const fq_t &a) { return fq_is_zero(a) ? a : fq_sub(fq_zero(), a); }
 __device__ __forceinline__ fq_t fq_dbl(const fq_t &a) { return fq_add(a, a); }
 
-static __device__ __noinline__ fq_t fq_mul(fq_t a, fq_t b) {
+#ifndef FQ_MUL_LINKAGE
+#define FQ_MUL_LINKAGE __noinline__
+#endif
+static __device__ FQ_MUL_LINKAGE fq_t fq_mul(fq_t a, fq_t b) {
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
 #include "fq_mul_ptx.inc"
     fq_reduce_once_dev(r0, r1, r2, r3, r4, r5, r6, r7);
