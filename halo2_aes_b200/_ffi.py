@@ -123,6 +123,7 @@ SIGNATURES = {
     "h2aes_g1_synthetic_bases_dev": (C.c_int32, [_vp, _u64p, C.c_uint64, _vp]),
     "h2aes_msm_create": (C.c_int32, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "h2aes_msm_destroy": (C.c_int32, [_vp]),
+    "h2aes_msm_enable_runs": (C.c_int32, [_vp]),
     "h2aes_msm_dev": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
     "h2aes_msm_host": (C.c_int32, [_vp, _vp, C.c_int32, _vp]),
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),

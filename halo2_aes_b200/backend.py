@@ -407,6 +407,11 @@ class Msm:
         check(lib().h2aes_msm_create(ctx._h, _ptr(bases), self.n, C.byref(h)), ctx._h)
         self._h = h
 
+    def enable_runs(self):
+        """h2aes_msm_enable_runs: commit run-structured columns through their differences"""
+        check(lib().h2aes_msm_enable_runs(self._h), self.ctx._h)
+        return self
+
     def commit(self, cols: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
         """cols [ncols, n, 4] (device) -> [ncols, 2, 4] affine points (device); asynchronous"""
         assert cols.is_cuda and cols.is_contiguous() and cols.dtype == torch.int64

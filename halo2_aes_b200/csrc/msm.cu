@@ -8,6 +8,8 @@
 // add it afterwards.
 //
 // Bucket method with signed c-bit digits (2^(c-1) buckets per window):
+//   k_msm_diff     (after h2aes_msm_enable_runs) s_i - s_{i+1}, to run the method on the column's
+//                  differences against the running sums of the bases when that leaves fewer terms
 //   k_msm_digits   per scalar: leave Montgomery form, recode into W signed digits, histogram
 //   k_msm_scan     per window: bucket offsets and the task table (a bucket with cnt points is cut
 //                  into ceil(cnt / SEG) tasks so that skewed scalars — byte-valued advice columns,
@@ -40,13 +42,24 @@ constexpr int MSM_NCH = 1024;   // bucket chunks per window in the reduction
 constexpr int MSM_HEAVY = 8;    // a bucket with more tasks than this is summed by a whole CTA
 constexpr int MSM_BATCH = 64;   // columns whose window sums wait for one k_msm_final launch
 
+// which (scalars, bases) pair a column's kernels read: the column itself against the bases, or its
+// differences s_i - s_{i+1} against the running sums of the bases (see k_msm_diff)
+struct MsmSel {
+    const fr_t *scalars;
+    const g1a_t *bases;
+};
+
 struct MsmArgs {
     uint64_t n;
     int c, W;
     uint32_t NB;               // 2^(c-1) buckets per window (index 1..NB; 0 = zero digit)
     uint32_t max_tasks;        // per window
-    const fr_t *scalars;       // [n]
+    const fr_t *scalars;       // [n] the column
     const g1a_t *bases;        // [n]
+    const g1a_t *prefix;       // [n] prefix[i] = bases[0] + ... + bases[i], or null
+    fr_t *diff;                // [n] scratch: s_i - s_{i+1}
+    MsmSel *sel;               // device: the pair in use for the current column
+    uint32_t *nnz;             // device: [0] non-zero differences, [1] non-zero scalars
     uint32_t *dig;             // [W][n] |digit| | sign << 31
     uint32_t *hist;            // [W][NB + 1]
     uint32_t *offs;            // [W][NB + 2] exclusive offsets of buckets into sorted
@@ -90,6 +103,105 @@ __device__ __forceinline__ void g1x_st(g1x_t *p, const g1x_t &a) {
     mfq_st(&p->x, a.x); mfq_st(&p->y, a.y); mfq_st(&p->zz, a.zz); mfq_st(&p->zzz, a.zzz);
 }
 
+// Abel summation: sum_i s_i G_i = sum_i (s_i - s_{i+1}) P_i with P_i = G_0 + ... + G_i and s_n = 0.
+// The columns of this backend are constant over long runs (A' is sorted over <= 66 561 distinct
+// values, S' pads with one value, Z only moves on non-constant rows), so most differences are
+// zero and drop out of the bucket method; uniform columns keep the direct form.
+__global__ void __launch_bounds__(256) k_msm_diff(const MsmArgs a) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool nz_d = false, nz_s = false;
+    if (i < a.n) {
+        const fr_t s = mfr_ld(a.scalars + i);
+        const fr_t nx = i + 1 < a.n ? mfr_ld(a.scalars + i + 1) : fr_zero();
+        const fr_t d = fr_sub(s, nx);
+        uint4 *q = reinterpret_cast<uint4 *>(a.diff + i);
+        q[0] = make_uint4(d.v[0], d.v[1], d.v[2], d.v[3]);
+        q[1] = make_uint4(d.v[4], d.v[5], d.v[6], d.v[7]);
+        nz_d = !fr_is_zero(d);
+        nz_s = !fr_is_zero(s);
+    }
+    const uint32_t bd = __ballot_sync(0xffffffffu, nz_d), bs = __ballot_sync(0xffffffffu, nz_s);
+    if ((threadIdx.x & 31) == 0) {
+        if (bd) atomicAdd(a.nnz, (uint32_t)__popc(bd));
+        if (bs) atomicAdd(a.nnz + 1, (uint32_t)__popc(bs));
+    }
+}
+// the differences pay off when they leave clearly fewer non-zero scalars than the column has
+__global__ void k_msm_select(const MsmArgs a) {
+    const bool runs = a.prefix != nullptr && (uint64_t)a.nnz[0] * 2 < a.nnz[1];
+    a.sel->scalars = runs ? a.diff : a.scalars;
+    a.sel->bases = runs ? a.prefix : a.bases;
+}
+
+// running sums of the bases, prefix[i] = G_0 + ... + G_i (affine), built once per set of bases:
+//   k_msm_prefix_local   sum of every block of PFX_B consecutive points
+//   k_msm_prefix_blocks  exclusive scan of the block sums (one CTA, three sequential sweeps)
+//   k_msm_prefix_final   per block: walk it again from the block's prefix, one inversion per point
+constexpr int PFX_B = 64;
+__global__ void __launch_bounds__(128)
+k_msm_prefix_local(const g1a_t *__restrict__ bases, uint64_t n, g1x_t *__restrict__ bsum) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i0 = t * PFX_B;
+    if (i0 >= n) return;
+    g1x_t acc = g1x_identity();
+#pragma unroll 1
+    for (uint64_t i = i0; i < n && i < i0 + PFX_B; ++i) {
+        g1a_t q;
+        q.x = mfq_ld(&bases[i].x);
+        q.y = mfq_ld(&bases[i].y);
+        g1x_madd(acc, q, false);
+    }
+    g1x_st(bsum + t, acc);
+}
+__global__ void __launch_bounds__(128)
+k_msm_prefix_blocks(uint64_t nblk, g1x_t *__restrict__ bsum, g1x_t *__restrict__ part) {
+    const uint64_t per = (nblk + 127) / 128;
+    const uint64_t lo = min(nblk, threadIdx.x * per), hi = min(nblk, lo + per);
+    g1x_t acc = g1x_identity();
+#pragma unroll 1
+    for (uint64_t b = lo; b < hi; ++b) {
+        const g1x_t p = g1x_ld(bsum + b);
+        g1x_add(acc, p);
+    }
+    g1x_st(part + threadIdx.x, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive scan of the 128 partial sums
+        g1x_t run = g1x_identity();
+#pragma unroll 1
+        for (int j = 0; j < 128; ++j) {
+            const g1x_t p = g1x_ld(part + j);
+            g1x_st(part + j, run);
+            g1x_add(run, p);
+        }
+    }
+    __syncthreads();
+    g1x_t run = g1x_ld(part + threadIdx.x);
+#pragma unroll 1
+    for (uint64_t b = lo; b < hi; ++b) {
+        const g1x_t p = g1x_ld(bsum + b);
+        g1x_st(bsum + b, run);  // block sums -> their exclusive prefixes
+        g1x_add(run, p);
+    }
+}
+__global__ void __launch_bounds__(128)
+k_msm_prefix_final(const g1a_t *__restrict__ bases, uint64_t n, const g1x_t *__restrict__ bpre,
+                   g1a_t *__restrict__ prefix) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i0 = t * PFX_B;
+    if (i0 >= n) return;
+    g1x_t acc = g1x_ld(bpre + t);
+#pragma unroll 1
+    for (uint64_t i = i0; i < n && i < i0 + PFX_B; ++i) {
+        g1a_t q;
+        q.x = mfq_ld(&bases[i].x);
+        q.y = mfq_ld(&bases[i].y);
+        g1x_madd(acc, q, false);
+        const g1a_t r = g1x_to_affine(acc);
+        mfq_st(&prefix[i].x, r.x);
+        mfq_st(&prefix[i].y, r.y);
+    }
+}
+
 // Lanes of a warp that hit the same counter add once: columns of this backend repeat values over
 // long runs (the padding value of S', the constant stretches of Z), which would otherwise
 // serialise hundreds of thousands of atomics on one address.  Returns the lane's slot.
@@ -107,7 +219,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const MsmArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.n;  // no early return: whole warps take part in the aggregation
     fr_t s = fr_zero();
-    if (valid) s = fr_to_canonical(mfr_ld(a.scalars + i));
+    if (valid) s = fr_to_canonical(mfr_ld(a.sel->scalars + i));
     const uint32_t full = 1u << a.c, mask = full - 1;
     uint32_t carry = 0;
     for (int w = 0; w < a.W; ++w) {
@@ -201,11 +313,12 @@ __global__ void __launch_bounds__(128) k_msm_tasks(const MsmArgs a) {
     const uint32_t *o = a.offs + (uint64_t)w * (a.NB + 2);
     const uint32_t start = o[b] + (t - to[b]) * MSM_SEG, end = min(o[b + 1], start + MSM_SEG);
     const uint32_t *srt = a.sorted + (uint64_t)w * a.n;
+    const g1a_t *__restrict__ bases = a.sel->bases;
     g1x_t acc = g1x_identity();
 #pragma unroll 1
     for (uint32_t pos = start; pos < end; ++pos) {
         const uint32_t e = srt[pos];
-        const g1a_t *bp = a.bases + (e & 0x7fffffffu);
+        const g1a_t *bp = bases + (e & 0x7fffffffu);
         g1a_t q;
         q.x = mfq_ld(&bp->x);
         q.y = mfq_ld(&bp->y);
@@ -300,17 +413,17 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const MsmArgs a) {
 }
 
 // per window: sum of the chunk results
-__global__ void __launch_bounds__(128) k_msm_windows(const MsmArgs a) {
-    __shared__ g1x_t s_pts[128];
+__global__ void __launch_bounds__(256) k_msm_windows(const MsmArgs a) {
+    __shared__ g1x_t s_pts[256];
     const int w = blockIdx.x;
     const g1x_t *C = a.chunks + (uint64_t)w * MSM_NCH;
     g1x_t acc = g1x_identity();
 #pragma unroll 1
-    for (int j = threadIdx.x; j < MSM_NCH; j += 128) {
+    for (int j = threadIdx.x; j < MSM_NCH; j += 256) {
         const g1x_t p = g1x_ld(C + j);
         g1x_add(acc, p);
     }
-    const g1x_t tot = g1x_block_sum<128>(acc, s_pts);
+    const g1x_t tot = g1x_block_sum<256>(acc, s_pts);
     if (threadIdx.x == 0) g1x_st(a.wsum + (uint64_t)a.col * a.W + w, tot);
 }
 
@@ -380,8 +493,10 @@ struct h2aes_msm {
     const g1a_t *bases = nullptr;  // caller-owned
     uint32_t *d_u32 = nullptr;     // dig, hist, offs, toffs, cursor, sorted in one allocation
     g1x_t *d_pts = nullptr;        // partial, buckets, chunks, wsum
-    g1a_t *d_out = nullptr;        // [out_cap]
-    int out_cap = 0;
+    g1a_t *d_prefix = nullptr;     // [n] running sums of the bases (h2aes_msm_enable_runs)
+    fr_t *d_diff = nullptr;        // [n]
+    MsmSel *d_sel = nullptr;
+    uint32_t *d_nnz = nullptr;     // [2]
     size_t hist_off = 0, offs_off = 0, toffs_off = 0, cursor_off = 0, sorted_off = 0, zero_words = 0,
            heavy_off = 0;
     uint32_t max_heavy = 0;
@@ -457,11 +572,51 @@ int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, 
     const size_t pts = W * ((size_t)m->max_tasks + nb1 + MSM_NCH + MSM_BATCH);
     cudaError_t e;
     if ((e = cudaMalloc((void **)&m->d_u32, words * 4)) ||
-        (e = cudaMalloc((void **)&m->d_pts, pts * sizeof(g1x_t)))) {
+        (e = cudaMalloc((void **)&m->d_pts, pts * sizeof(g1x_t))) ||
+        (e = cudaMalloc((void **)&m->d_diff, n * sizeof(fr_t))) ||
+        (e = cudaMalloc((void **)&m->d_sel, sizeof(MsmSel))) ||
+        (e = cudaMalloc((void **)&m->d_nnz, 2 * sizeof(uint32_t)))) {
         h2aes_msm_destroy(m);
         return mcuda(ctx, e, "msm: cudaMalloc");
     }
     *out = m;
+    return H2AES_OK;
+}
+
+int32_t h2aes_msm_enable_runs(h2aes_msm *m) {
+    if (!m) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = m->ctx;
+    if (m->d_prefix) return H2AES_OK;
+    MCU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nblk = (m->n + PFX_B - 1) / PFX_B;
+    g1x_t *bsum = nullptr, *part = nullptr;
+    g1a_t *prefix = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&bsum, nblk * sizeof(g1x_t))) ||
+        (e = cudaMalloc((void **)&part, 128 * sizeof(g1x_t))) ||
+        (e = cudaMalloc((void **)&prefix, m->n * sizeof(g1a_t)))) {
+        cudaFree(bsum); cudaFree(part); cudaFree(prefix);
+        return mcuda(ctx, e, "msm: cudaMalloc(prefix)");
+    }
+    cudaStream_t s = ctx->stream;
+    prof_begin(ctx, "k_msm_prefix_local");
+    k_msm_prefix_local<<<cdivu(nblk, 128), 128, 0, s>>>(m->bases, m->n, bsum);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_prefix_blocks");
+    k_msm_prefix_blocks<<<1, 128, 0, s>>>(nblk, bsum, part);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_prefix_final");
+    k_msm_prefix_final<<<cdivu(nblk, 128), 128, 0, s>>>(m->bases, m->n, bsum, prefix);
+    prof_end(ctx);
+    ctx->launches += 3;
+    e = cudaStreamSynchronize(s);
+    cudaFree(bsum);
+    cudaFree(part);
+    if (e) {
+        cudaFree(prefix);
+        return mcuda(ctx, e, "msm: prefix sums of the bases");
+    }
+    m->d_prefix = prefix;
     return H2AES_OK;
 }
 
@@ -470,7 +625,10 @@ int32_t h2aes_msm_destroy(h2aes_msm *m) {
     cudaSetDevice(m->ctx->device);
     cudaFree(m->d_u32);
     cudaFree(m->d_pts);
-    cudaFree(m->d_out);
+    cudaFree(m->d_prefix);
+    cudaFree(m->d_diff);
+    cudaFree(m->d_sel);
+    cudaFree(m->d_nnz);
     delete m;
     return H2AES_OK;
 }
@@ -497,6 +655,10 @@ int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, 
     a.wsum = a.chunks + W * MSM_NCH;
     a.heavy = m->d_u32 + m->heavy_off;
     a.max_heavy = m->max_heavy;
+    a.prefix = m->d_prefix;
+    a.diff = m->d_diff;
+    a.sel = m->d_sel;
+    a.nnz = m->d_nnz;
     for (int c0 = 0; c0 < ncols; c0 += MSM_BATCH) {
         const int nb = std::min(MSM_BATCH, ncols - c0);
         a.out = reinterpret_cast<g1a_t *>(out_dev) + c0;
@@ -505,6 +667,15 @@ int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, 
             a.scalars = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)(c0 + col) * m->n;
             a.col = col;
             MCU(ctx, cudaMemsetAsync(m->d_u32, 0, m->zero_words * 4, s));
+            MCU(ctx, cudaMemsetAsync(m->d_nnz, 0, 2 * sizeof(uint32_t), s));
+            if (m->d_prefix) {
+                prof_begin(ctx, "k_msm_diff");
+                k_msm_diff<<<cdivu(m->n, 256), 256, 0, s>>>(a);
+                prof_end(ctx);
+                ctx->launches += 1;
+            }
+            k_msm_select<<<1, 1, 0, s>>>(a);
+            ctx->launches += 1;
             prof_begin(ctx, "k_msm_digits");
             k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
             prof_end(ctx);
@@ -527,7 +698,7 @@ int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, 
             k_msm_chunks<<<dim3(cdivu(MSM_NCH, 64), m->W), 64, 0, s>>>(a);
             prof_end(ctx);
             prof_begin(ctx, "k_msm_windows");
-            k_msm_windows<<<m->W, 128, 0, s>>>(a);
+            k_msm_windows<<<m->W, 256, 0, s>>>(a);
             prof_end(ctx);
             ctx->launches += 8;
         }

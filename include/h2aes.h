@@ -337,6 +337,12 @@ int32_t h2aes_g1_synthetic_bases_dev(h2aes_ctx *ctx, const uint64_t *d, uint64_t
 typedef struct h2aes_msm h2aes_msm;
 int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out);
 int32_t h2aes_msm_destroy(h2aes_msm *m);
+/* Optional, once per handle: builds the running sums P_i = bases[0] + ... + bases[i] (64 bytes per
+ * point more).  Afterwards every column is first differenced (s_i - s_{i+1}); when that leaves
+ * clearly fewer non-zero scalars than the column has — the permuted lookup columns, Z, Z_perm are
+ * constant over long runs — the bucket method runs on sum_i (s_i - s_{i+1}) P_i, the same group
+ * element by Abel summation, hence the same output bits.  Synchronizes the stream. */
+int32_t h2aes_msm_enable_runs(h2aes_msm *m);
 /* scalars and out in device memory; asynchronous on the context's stream. */
 int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, uint64_t *out_dev);
 /* scalars and out in host memory (the bases stay on the device). */

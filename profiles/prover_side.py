@@ -61,8 +61,14 @@ def measure(ctx, K=20, N=5):
     helper = torch.cat([perm["Ap"], perm["Sp"], Z, Zp])
     ms_c_help, c_help = timed(lambda: msm.commit(helper))
     kern_msm = ctx.profile_read()
+    # the same columns through their differences against the running sums of the bases
+    ms_prefix, _ = timed(lambda: msm.enable_runs())
+    msm.commit(helper[:1])
+    ctx.profile_read()
+    ms_c_runs, c_runs = timed(lambda: msm.commit(helper))
+    kern_runs = ctx.profile_read()
     ctx.profile(False)
-    assert bool(c_adv.any()) and bool(c_help.any())
+    assert bool(c_adv.any()) and bool(c_help.any()) and torch.equal(c_runs, c_help)
     n_help = int(helper.shape[0])
     del helper
     msm.close()
@@ -102,6 +108,10 @@ def measure(ctx, K=20, N=5):
                                    "ms_per_column": ms_c_adv / advice.shape[0]},
                         "Ap_Sp_Z_Zperm": {"columns": n_help, "ms": ms_c_help,
                                           "ms_per_column": ms_c_help / n_help},
+                        "Ap_Sp_Z_Zperm_through_differences": {
+                            "columns": n_help, "ms": ms_c_runs, "ms_per_column": ms_c_runs / n_help,
+                            "running_sums_of_the_bases_ms_once": ms_prefix,
+                            "kernels": {k_: {"launches": v[0], "ms": v[1]} for k_, v in kern_runs.items()}},
                         "kernels": {k_: {"launches": v[0], "ms": v[1]} for k_, v in kern_msm.items()}},
         "lagrange_to_coeff": {"ms": ms_l2c, "ms_per_column": ms_l2c / ncols, "fr_multiplies": mul_l2c,
                               "gmul_s": mul_l2c / ms_l2c / 1e6,

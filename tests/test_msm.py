@@ -167,6 +167,60 @@ def test_msm_repeated_points_hit_the_doubling_case(gpu, orc, ffi):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 65, 1000, (1 << 14) + 3])
+def test_run_structured_columns_through_differences(gpu, orc, ffi, n):
+    """h2aes_msm_enable_runs: the same commitments, bit for bit, through sum (s_i - s_{i+1}) P_i"""
+    from halo2_aes_b200.backend import Msm
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    vals = rand_scalars(orc, SEED + 80 + n, 8)
+    rng = np.random.default_rng(n)
+    cols = np.stack([
+        vals[np.sort(rng.integers(0, 8, n))],            # sorted over 8 values (A'-like)
+        vals[np.repeat(rng.integers(0, 8, (n + 15) // 16), 16)[:n]],  # constant stretches (Z-like)
+        np.tile(vals[3], (n, 1)),                        # one run: a single term s * P_{n-1}
+        rand_scalars(orc, SEED + 81 + n, n),             # uniform: keeps the direct form
+        np.zeros((n, 4), np.uint64),
+    ])
+    plain = Msm(gpu, _dev(B))
+    want = _host(plain.commit(_dev(cols)))
+    runs = Msm(gpu, _dev(B)).enable_runs()
+    got = _host(runs.commit(_dev(cols)))
+    assert (got == want).all()
+    for ci in range(cols.shape[0]):
+        assert (got[ci] == orc.g1_msm(cols[ci], B)).all(), ci
+    plain.close()
+    runs.close()
+
+
+@pytest.mark.gpu
+def test_commitment_of_lookup_columns_with_runs(gpu, orc, ffi, challenges):
+    """A', S', Z and Z_perm of a k=17 AES circuit: direct form == difference form == oracle"""
+    import torch
+    from halo2_aes_b200.backend import Circuit, Msm
+    k = 17
+    theta, beta, gamma = challenges
+    key = splitmix_bytes(SEED + 62, 16).tobytes()
+    pts = splitmix_bytes(SEED + 63, 60 * 16).reshape(60, 16)
+    cir = Circuit(gpu, ffi.KIND_AES, k, 1)
+    advice, _ = cir.witness(key, torch.from_numpy(pts).cuda())
+    perm = cir.lookup_permuted(theta, first=1, count=2, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma, first=1, count=2)
+    Zp = cir.perm_product(beta, gamma, advice)
+    cir.lookup_check()
+    cols = torch.cat([perm["Ap"], perm["Sp"], Z, Zp[:1]])
+    B = orc.g1_test_bases(1 << k, orc.fr_from_int(D_STEP))
+    plain, runs = Msm(gpu, _dev(B)), Msm(gpu, _dev(B)).enable_runs()
+    want, got = _host(plain.commit(cols)), _host(runs.commit(cols))
+    assert (got == want).all()
+    h = _host(cols)
+    for ci in (0, 2, 4, 6):
+        assert (got[ci] == orc.g1_msm(h[ci], B)).all(), ci
+    plain.close()
+    runs.close()
+    cir.close()
+
+
+@pytest.mark.gpu
 def test_commitment_of_witness_columns(gpu, orc, ffi):
     """advice columns of the key-schedule circuit (k = 17) committed against 2^17 bases"""
     from halo2_aes_b200.backend import Circuit, Msm
@@ -227,4 +281,5 @@ def test_msm_error_behaviour(gpu, ffi):
     assert lib.h2aes_msm_create(None, None, 16, C.byref(h)) == ffi.ERR_ARG
     assert lib.h2aes_msm_dev(None, None, 1, None) == ffi.ERR_ARG
     assert lib.h2aes_msm_host(None, None, 1, None) == ffi.ERR_ARG
+    assert lib.h2aes_msm_enable_runs(None) == ffi.ERR_ARG
     assert lib.h2aes_g1_synthetic_bases_dev(gpu._h, None, 4, None) == ffi.ERR_ARG
