@@ -193,3 +193,46 @@ def test_permutation_argument_invariants(orc, challenges):
     for s in range(1, Z.shape[0]):
         assert (Z[s, 0] == Z[s - 1, n - 6]).all()
     assert not Z[:, n - 5:].any()
+
+
+def test_prover_side_restatements_against_first_principles_vectors(orc):
+    """tests/golden/prover_side_vectors.json (pure python integers, make_prover_side_golden.py):
+    the oracle's evaluation domain, G1 group law and bucket-method MSM reproduce them exactly."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "prover_side_vectors.json")) as f:
+        g = json.load(f)
+    R, Q = int(g["r"], 16), int(g["q"], 16)
+    assert R == orc.R_MOD and Q == orc.Q_MOD
+    dom = g["domain"]
+    k = dom["k"]
+    dq = orc.domain_query(k, dom["j"])
+    assert dq["extended_k"] == dom["extended_k"]
+    assert orc.fr_to_int(dq["omega"]) == int(dom["omega"], 16)
+    assert orc.fr_to_int(dq["extended_omega"]) == int(dom["extended_omega"], 16)
+    assert orc.fr_to_int(dq["g_coset"]) == int(g["zeta"], 16)
+    _, delta = orc.domain_constants(k)
+    assert orc.fr_to_int(delta) == int(g["delta"], 16)
+
+    def col(name):
+        return np.stack([orc.fr_from_int(int(v, 16)) for v in dom[name]])
+
+    a = col("values")
+    assert (orc.domain_transform(orc.FFT, k, a) == col("best_fft")).all()
+    coeff = orc.domain_transform(orc.LAGRANGE_TO_COEFF, k, a)
+    assert (coeff == col("lagrange_to_coeff")).all()
+    assert (orc.domain_transform(orc.COEFF_TO_EXTENDED, k, coeff, dom["j"])
+            == col("coeff_to_extended_of_those_coefficients")).all()
+
+    rq = (1 << 256) % Q
+
+    def point(xy):
+        return np.stack([orc.int_to_limbs(int(c, 16) * rq % Q) for c in xy])
+
+    g1 = g["g1"]
+    bases = orc.g1_test_bases(len(g1["bases"]), orc.fr_from_int(int(g1["d"], 16)))
+    assert (bases == np.stack([point(p) for p in g1["bases"]])).all()
+    scalars = np.stack([orc.fr_from_int(int(s_, 16)) for s_ in g1["scalars"]])
+    assert (orc.g1_msm(scalars, bases) == point(g1["msm"])).all()
+    assert (orc.g1_mul_generator(orc.fr_from_int(2)) == point(g1["two_g"])).all()
+    assert (orc.g1_mul_generator(orc.fr_from_int(R - 1)) == point(g1["minus_g"])).all()
