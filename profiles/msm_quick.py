@@ -7,14 +7,14 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle  # noqa: E402  (only to build a valid set of bases: test infrastructure)
-from halo2_aes_b200.backend import Context, Msm  # noqa: E402
+from halo2_aes_b200.backend import Context, Msm, synthetic_bases  # noqa: E402
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 n = 1 << k
 ctx = Context(0)
-B = oracle.g1_test_bases(n, oracle.fr_from_int(0x1D2C3B4A5968778695A4B3C2D1E0F))
-msm = Msm(ctx, torch.from_numpy(B.view(np.int64)).cuda())
+one_limbs = np.array([0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f],
+                     dtype=np.uint64)  # d = 1 in Montgomery form: bases (1 + i) * G
+msm = Msm(ctx, synthetic_bases(ctx, n, one_limbs))
 g = torch.Generator(device="cuda").manual_seed(1)
 rnd = torch.randint(0, 2**62, (4, n, 4), dtype=torch.int64, device="cuda", generator=g)
 rnd[..., 3] &= (1 << 60) - 1
