@@ -258,3 +258,54 @@ def test_permutation_columns_and_mapping_equal_keygen_replay(ffi, orc, kind, k, 
     got = np.zeros_like(want)
     assert L.h2aes_perm_mapping_host(kind, k, N, nb, got.ctypes.data_as(u32p)) == 0
     assert (got == want).all()
+
+
+def _random_shapes():
+    """seeded (k, N, n_blocks) triples: boundaries of the column sets and random fills"""
+    rng = np.random.default_rng(SEED + 99)
+    shapes = []
+    for k, N in ((17, 3), (18, 2), (18, 4)):
+        n = 1 << k
+        cap0, cap = (n - 1760) // 1360, n // 1360
+        total = cap0 + (N - 1) * cap
+        shapes += [(k, N, cap0), (k, N, cap0 + 1), (k, N, total),
+                   (k, N, int(rng.integers(1, total)))]
+    return shapes
+
+
+@pytest.mark.parametrize("k,N,nb", _random_shapes())
+def test_closed_form_layout_on_more_shapes(ffi, orc, k, N, nb):
+    """block positions, enabled selectors per row, copy constraints and the permutation cycle
+    mapping from the product's closed forms == the oracle's region-by-region replay, at the
+    column-set boundaries (set 0 full, first block of the next set, circuit at capacity) and at a
+    random fill, for k = 17, 18 and N = 2..4."""
+    L = ffi.lib()
+    pts = splitmix_bytes(SEED + 7 * nb + N, 16 * nb).reshape(nb, 16)
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(splitmix_bytes(SEED + nb, 16).tobytes(), pts)
+    sel = ref.selectors()
+    # selectors: every row of every set at a sample of rows, incl. the ends of the columns
+    rng = np.random.default_rng(nb)
+    rows = np.unique(np.concatenate([np.arange(0, 500), np.arange((1 << k) - 1500, 1 << k),
+                                     rng.integers(0, 1 << k, 1500)]))
+    for s in range(N):
+        ops = np.array([L.h2aes_row_op(ffi.KIND_AES, k, N, nb, s, int(r)) for r in rows])
+        for t in range(5):
+            assert ((ops == t + 1) == (sel[5 * s + t][rows] != 0)).all(), (s, t)
+    for li in range(5 * N):
+        out = C.c_uint64()
+        assert L.h2aes_active_rows(ffi.KIND_AES, k, N, nb, li, C.byref(out)) == 0
+        assert out.value == int(sel[li].sum()), li
+    # copies
+    want = ref.copies()
+    got = np.zeros((len(want), 4), np.uint64)
+    assert L.h2aes_copy_constraints_host(ffi.KIND_AES, k, N, nb, 0, len(want), _p(got, u64p)) == 0
+    assert (got == want).all()
+    # permutation mapping
+    wm = ref.permutation(np.ones(4, np.uint64), np.ones(4, np.uint64), want=("mapping",))["mapping"]
+    gm = np.zeros_like(wm)
+    assert L.h2aes_perm_mapping_host(ffi.KIND_AES, k, N, nb, gm.ctypes.data_as(u32p)) == 0
+    assert (gm == wm).all()
+    # one block past capacity is the reference's panic
+    lay = ffi.layout_query(ffi.KIND_AES, k, N)
+    s_, r_ = C.c_int32(), C.c_uint64()
+    assert L.h2aes_block_position(k, N, lay["capacity_blocks"], C.byref(s_), C.byref(r_)) == ffi.ERR_CAPACITY
