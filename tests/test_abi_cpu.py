@@ -4,6 +4,7 @@ agrees with the oracle's region-by-region replay.  No GPU compute is called here
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -309,3 +310,28 @@ def test_closed_form_layout_on_more_shapes(ffi, orc, k, N, nb):
     lay = ffi.layout_query(ffi.KIND_AES, k, N)
     s_, r_ = C.c_int32(), C.c_uint64()
     assert L.h2aes_block_position(k, N, lay["capacity_blocks"], C.byref(s_), C.byref(r_)) == ffi.ERR_CAPACITY
+
+
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_generated_ptx_multiply_is_in_sync_and_self_tests(field, tmp_path):
+    """csrc/gen_fr_mul.py builds the device Montgomery multiply once, runs it on a python model of
+    the PTX carry flag against big-integer arithmetic (20 k operand pairs incl. the extremes) and
+    only then emits it: the committed fr_mul_ptx.inc / fq_mul_ptx.inc must be that output."""
+    import importlib.util
+    import shutil
+    src = os.path.join(ROOT, "halo2_aes_b200", "csrc")
+    work = tmp_path / "gen"
+    work.mkdir()
+    shutil.copy(os.path.join(src, "gen_fr_mul.py"), work / "gen_fr_mul.py")
+    argv = sys.argv
+    try:
+        sys.argv = ["gen_fr_mul.py", field]
+        spec = importlib.util.spec_from_file_location(f"gen_{field}", work / "gen_fr_mul.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ops = mod.build()
+        assert mod.selftest(ops, iters=3000) > 3000
+        text = mod.emit(ops)
+    finally:
+        sys.argv = argv
+    assert text == open(os.path.join(src, f"{field}_mul_ptx.inc")).read()
