@@ -335,3 +335,22 @@ def test_generated_ptx_multiply_is_in_sync_and_self_tests(field, tmp_path):
     finally:
         sys.argv = argv
     assert text == open(os.path.join(src, f"{field}_mul_ptx.inc")).read()
+
+
+def test_generated_rust_ffi_block_is_in_sync_with_the_header(ffi):
+    """integration/rust/ffi.rs (the extern "C" block a maintainer of the reference would add) is
+    the generator's output for the current include/h2aes.h and declares every exported symbol."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "gen_rust_ffi", os.path.join(ROOT, "integration", "gen_rust_ffi.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    text = mod.generate()
+    assert text == open(os.path.join(ROOT, "integration", "rust", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (h2aes_\w+)\(", text))
+    assert declared == set(ffi.SIGNATURES)
+    # argument counts agree with the ctypes signatures
+    for name, (_, args) in ffi.SIGNATURES.items():
+        m = re.search(r"pub fn %s\((.*?)\) ->" % name, text)
+        n_args = 0 if not m.group(1).strip() else m.group(1).count(":")
+        assert n_args == len(args), name
