@@ -57,6 +57,37 @@ def allgather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
     return out.view((world,) + tuple(partial.shape))
 
 
+# ---------------------------------------------------------------------------------------------
+# prover-side steps of one circuit (commitments, domain transforms): the columns are
+# independent of one another, so they are dealt to the ranks in contiguous blocks and only the
+# 64-byte commitments travel
+# ---------------------------------------------------------------------------------------------
+def columns_of_rank(n_columns: int, rank: int, world: int) -> range:
+    """contiguous block of column indices owned by `rank` (sizes differ by at most one)"""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank / world")
+    base, extra = divmod(n_columns, world)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def allgather_commitments(mine: torch.Tensor, n_columns: int, group=None) -> torch.Tensor:
+    """[len(columns_of_rank), 2, 4] int64 commitments of this rank's columns -> [n_columns, 2, 4]
+    on every rank, in column order (ranks own contiguous blocks; padded to equal length for the
+    collective)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        assert mine.shape[0] == n_columns
+        return mine
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = (n_columns + world - 1) // world
+    assert mine.shape[0] == len(columns_of_rank(n_columns, rank, world))
+    pad = torch.zeros((per, 2, 4), dtype=mine.dtype, device=mine.device)
+    pad[: mine.shape[0]] = mine
+    out = torch.empty((world, per, 2, 4), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
+    return torch.cat([out[r, : len(columns_of_rank(n_columns, r, world))] for r in range(world)])
+
+
 class RowShardedCircuit:
     """One circuit spread over the ranks of `group` by rows."""
 

@@ -83,6 +83,17 @@ def _worker(rank, world, port, ret):
             for s in range(rank):
                 carry = fr_mul(carry, gathered[s, 0].numpy().view(np.uint64))
             assert (carry == Z[lo]).all(), "carry-in of the shard != Z at its first row"
+        # ---- prover-side columns dealt to the ranks; only the commitments travel --------------
+        ncols = 5
+        n_pts = 64
+        bases = oracle.g1_test_bases(n_pts, oracle.fr_from_int(12345))
+        cols = np.stack([np.stack([oracle.fr_from_int((7 * c + 3 * i + 1) ** 3) for i in range(n_pts)])
+                         for c in range(ncols)])
+        mine = sharded.columns_of_rank(ncols, rank, world)
+        got = np.stack([oracle.g1_msm(cols[c], bases) for c in mine]) if len(mine) else np.zeros((0, 2, 4), np.uint64)
+        allc = sharded.allgather_commitments(torch.from_numpy(got.view(np.int64).copy()), ncols)
+        want = np.stack([oracle.g1_msm(cols[c], bases) for c in range(ncols)])
+        assert (allc.numpy().view(np.uint64) == want).all()
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -108,3 +119,11 @@ def test_partition_helpers():
     assert seen == list(range(273))
     with pytest.raises(ValueError):
         sharded.split_into_circuits(5, 0)
+    # prover-side columns: contiguous blocks, sizes within one of each other, every column once
+    for ncols, world in ((97, 8), (5, 2), (3, 8), (0, 4), (145, 3)):
+        blocks = [sharded.columns_of_rank(ncols, r, world) for r in range(world)]
+        assert [c for b in blocks for c in b] == list(range(ncols))
+        sizes = [len(b) for b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharded.columns_of_rank(5, 2, 2)
