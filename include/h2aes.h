@@ -281,7 +281,7 @@ int32_t h2aes_domain_transform_host(h2aes_domain *d, int32_t op, const uint64_t 
  *   (1 - z) l0;  (z^2 - z) l_last;  (z(wX)(a'+beta)(s'+gamma) - z (A+beta)(S+gamma)) l_active_row;
  *   (a' - s') l0;  (a' - s')(a' - a'(X/w)) l_active_row
  * evaluated on the extended coset; A, S = theta-folds of the lookup's input expressions
- * (q*tag, q*x, ...: src/chips/*.rs configure) and of its table columns.
+ * (q*tag, q*x, ...: the configure functions under src/chips) and of its table columns.
  *   d           domain (j = 5, k = the circuit's); l0 / l_last / l_active_row are built on first use
  *               as keygen.rs does (blinding_factors = 5)
  *   advice_ext  [n_advice][2^extended_k][4]  extended cosets of the advice polynomials
