@@ -97,6 +97,37 @@ def test_oracle_msm_against_the_anchor(orc):
     assert pt(orc.g1_msm(np.zeros((n, 4), np.uint64), B)) is None
 
 
+def test_signed_digit_recoding_model_for_every_window_size():
+    """python model of k_msm_digits' integer logic (csrc/msm.cu): for every window size c the
+    library can pick (4..16) the W = 254 // c + 1 signed digits stay within +-2^(c-1), rebuild the
+    scalar, and leave no carry after the top window — on the extremes and on random scalars."""
+    import random
+    rng = random.Random(SEED)
+    edge = [0, 1, 2, R_MOD - 1, R_MOD - 2, (1 << 253), (1 << 253) - 1, (1 << 128) - 1, (1 << 128),
+            int("f" * 60, 16) % R_MOD, sum(1 << (16 * i + 15) for i in range(15))]
+    cases = edge + [rng.randrange(R_MOD) for _ in range(300)]
+    for c in range(4, 17):
+        W, NB, full = 254 // c + 1, 1 << (c - 1), 1 << c
+        for k in cases:
+            limbs = [(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+            carry, total = 0, 0
+            for w in range(W):
+                bit = w * c
+                lo, sh = bit >> 5, bit & 31
+                assert lo < 8
+                d = limbs[lo] >> sh
+                if sh + c > 32 and lo + 1 < 8:
+                    d |= (limbs[lo + 1] << (32 - sh)) & 0xFFFFFFFF
+                d = (d & (full - 1)) + carry
+                if d > NB:
+                    digit, carry = d - full, 1
+                else:
+                    digit, carry = d, 0
+                assert -NB <= digit <= NB
+                total += digit << bit
+            assert carry == 0 and total == k, (c, hex(k))
+
+
 # ---- GPU --------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gpu(ffi):
