@@ -28,12 +28,12 @@ cudaError_t launch_lookup_bins(h2aes_circuit *c);
 cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
                             uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end);
 cudaError_t launch_inv_tables(h2aes_circuit *c);
-cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z,
-                             uint64_t row_begin, uint64_t row_end);
-cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                            uint64_t *Z, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
+                          uint64_t *Z, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, uint64_t row_begin,
+                            uint64_t row_end);
 cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
-void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk);
 uint32_t lookup_bin_tiles();
 cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta);
 cudaError_t launch_perm_sigma(h2aes_circuit *c, uint64_t *sigma_dev);
@@ -426,13 +426,14 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
-                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,
+                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_glist,    c->d_gbase,    c->d_gcount,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
-                    c->d_nacp,     c->d_ibgz,     c->d_ibpz,     c->d_sgz,      c->d_pmap,     c->d_wlo,
+                    c->d_ftab,     c->d_pmap,     c->d_wlo,
                     c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
                     c->d_omega_tab,     c->d_pmask,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
-                    c->d_ztot,     c->d_zbagg,    c->d_zbexcl,   c->d_err,
+                    c->d_ztot,    c->d_zagg,     c->d_zinc,     c->d_zflag,    c->d_zctl,
+                    c->d_err,
                     c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -633,7 +634,8 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     h2aes_ctx *ctx = c->ctx;
     const size_t L = (size_t)c->sh.n_lookups();
     const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
-    grand_product_ws(c->sh.n(), &c->zm, &c->znblk);
+    c->zm = (c->sh.n() + 31) / 32 + 4;
+    c->ztiles = L * zscan_tiles(c->sh.n()) + 1;  // >= tiles of the permutation's n_sets * n rows
     DA(c->d_chal, 4);
     DA(c->d_val, VB);
     DA(c->d_canon, VB);
@@ -657,13 +659,35 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_nac, VB);
     DA(c->d_ibg, VB);
     DA(c->d_ibp, VB);
-    DA(c->d_nacp, VB);
-    DA(c->d_ibgz, VB);
-    DA(c->d_ibpz, VB);
-    DA(c->d_sgz, VB);
+    DA(c->d_ftab, 4 * VB);  // the four merged tables share one allocation (gathered by selector)
+    c->d_nacp = c->d_ftab + FSEL_NACP * VB;
+    c->d_ibgz = c->d_ftab + FSEL_IBGZ * VB;
+    c->d_ibpz = c->d_ftab + FSEL_IBPZ * VB;
+    c->d_sgz = c->d_ftab + FSEL_SGZ * VB;
     DA(c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n());
     DA(c->d_codek, L * c->sh.n());
-    DA(c->d_codep, L * c->sh.n());
+    if (!c->d_gbase) {
+        // list of the rows whose grand-product factor is not a table entry (k_permuted ->
+        // k_z_general).  Such a row is a table row (< 66561 of them), or lies outside the zero
+        // run of A' and is active or received a leftover table value other than the padding
+        // value: at most the lookup's active rows plus one row per table bin, twice (the zero
+        // run's own rows with such a leftover value).
+        uint32_t base[5 * MAX_SETS + 1];
+        const int ops = c->sh.ops_per_set();
+        base[0] = 0;
+        for (size_t l = 0; l < L; ++l) {
+            uint64_t cap = active_rows(c->sh, c->sh.capacity(), (int)l / ops, (uint32_t)(l % ops) + 1) +
+                           2 * (TABLE_ROWS + 1) + 64;
+            if (cap > c->sh.n()) cap = c->sh.n();
+            base[l + 1] = base[l] + (uint32_t)cap;
+        }
+        DA(c->d_glist, (size_t)base[L]);
+        DA(c->d_gcount, L);
+        DA(c->d_gbase, L + 1);
+        CU(ctx, cudaMemcpyAsync(c->d_gbase, base, (L + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));  // `base` is on the stack
+    }
     if (!c->code_valid) c->code_valid = new bool[L]();
     DA(c->d_cnt, LB);
     DA(c->d_offz, LB);
@@ -671,12 +695,20 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_loffz, LB);
     DA(c->d_lk, LB);
     DA(c->d_meta, L);
-    DA(c->d_ztot, L * c->zm);
     DA(c->d_zmask, L * c->zm);
+    DA(c->d_ztot, c->ztiles * ZT_T);
+    DA(c->d_zagg, c->ztiles);
+    DA(c->d_zinc, c->ztiles);
+    if (!c->d_zflag) {
+        DA(c->d_zflag, c->ztiles);
+        CU(ctx, cudaMemsetAsync(c->d_zflag, 0, c->ztiles * 4, ctx->stream));
+    }
+    if (!c->d_zctl) {
+        DA(c->d_zctl, 4);
+        CU(ctx, cudaMemsetAsync(c->d_zctl, 0, 16, ctx->stream));
+    }
     DA(c->d_znonconst, L);
     CU(ctx, cudaMemsetAsync(c->d_znonconst, 0, L * 8, ctx->stream));
-    DA(c->d_zbagg, L * c->znblk);
-    DA(c->d_zbexcl, L * c->znblk);
     DA(c->d_partial, L);
     DA(c->d_carry, L);
     c->lk_alloc = true;
@@ -689,10 +721,11 @@ static int32_t check_device_flags(h2aes_circuit *c) {
     CU(ctx, cudaMemcpyAsync(c->h_err, c->d_err, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                             ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (c->h_err[0] || c->h_err[1])
+    if (c->h_err[0] || c->h_err[1] || c->h_err[2])
         CU(ctx, cudaMemsetAsync(c->d_err, 0, 8 * sizeof(uint32_t), ctx->stream));
     if (c->h_err[0]) return fail(ctx, H2AES_ERR_ZERO_DENOM, "zero denominator in the grand product");
     if (c->h_err[1]) return fail(ctx, H2AES_ERR_LOOKUP, "lookup input not in table");
+    if (c->h_err[2]) return fail(ctx, H2AES_ERR_STATE, "internal: general-row list overflow");
     return H2AES_OK;
 }
 
@@ -786,8 +819,7 @@ int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const u
         l = e - 1;
     }
     if (count) {
-        CU(ctx, launch_z_factors(c, first, count, Z_dev, 0, c->sh.n()));
-        CU(ctx, launch_z_finish(c, first, count, nullptr, Z_dev, 0, c->sh.n()));
+        CU(ctx, launch_z_scan(c, first, count, nullptr, Z_dev, 0, c->sh.n()));
     }
     return H2AES_OK;
 }
@@ -1034,8 +1066,9 @@ int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const u
     if (rc) return rc;
     uint64_t rb, re;
     shard_rows(c, &rb, &re);
-    // per-row factors go to Z_dev, their total per lookup (the shard's partial product) to d_partial
-    CU(ctx, launch_z_factors(c, 0, c->sh.n_lookups(), Z_dev, rb, re));
+    // pass 1 of the scan: thread prefixes stay in the workspace, the product of the shard's
+    // factors per lookup (its partial product) goes to d_partial; Z_dev is written by pass 2
+    CU(ctx, launch_z_partial(c, Z_dev, rb, re));
     c->have_partial = true;
     c->partial_Z = Z_dev;
     *partial_dev = (uint64_t *)c->d_partial;
@@ -1054,7 +1087,7 @@ int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathere
     uint64_t rb, re;
     shard_rows(c, &rb, &re);
     CU(ctx, launch_shard_carry(c, gathered_dev));
-    CU(ctx, launch_z_finish(c, 0, c->sh.n_lookups(), c->d_carry, Z_dev, rb, re));
+    CU(ctx, launch_z_finish(c, c->d_carry, Z_dev, rb, re));
     c->have_partial = false;
     return H2AES_OK;
 }

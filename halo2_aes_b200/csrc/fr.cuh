@@ -398,6 +398,25 @@ FR_D fr_t fr_load_s(const uint4 *q) {  // shared / generic
     fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
     return r;
 }
+// one 256-bit load per element (LDG.E.ENL2.256 on sm_100a): half the LSU wavefronts of two
+// 128-bit loads when the lanes of a warp gather from 32 different lines.  _nc: read-only data.
+FR_D fr_t fr_ldg_256(const void *p) {
+    fr_t r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                   "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+FR_D fr_t fr_ldg_256_nc(const void *p) {
+    fr_t r;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+          "=r"(r.v[6]), "=r"(r.v[7])
+        : "l"(p));
+    return r;
+}
 // one 256-bit store per element (STG.E.ENL2.256 on sm_100a)
 FR_D void fr_store_256(uint64_t *p, const fr_t &a) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]),

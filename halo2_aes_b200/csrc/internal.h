@@ -54,6 +54,83 @@ struct LookupMeta {  // per lookup, produced by the bin-scan kernel
     uint32_t pad[2];
 };
 
+#if defined(__CUDACC__)
+// ---- device helpers shared by lookup.cu and gprod.cu ---------------------------------------
+__device__ __forceinline__ fr_t fr_from_tab(const uint4 *__restrict__ frtab, uint32_t b) {
+    uint4 lo = frtab[2 * b], hi = frtab[2 * b + 1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ fr_t fr_ld(const fr_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+    return r;
+}
+__device__ __forceinline__ void fr_st(fr_t *p, const fr_t &a) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+
+// bins (k of A', k' of S') of usable row i, and how S' relates to A'
+constexpr uint32_t CODE_FIRST = 0u, CODE_PAD = 1u, CODE_OTHER = 2u;  // stored in bits 30..31
+
+// factor code of a row for the grand product (bits 31..30 kind, 29..28 selector, 23..0 index):
+//   kind 0  factor exactly one (constant row)                       -> nothing to do
+//   kind 1  factor = one entry of a merged table: selector 0 nacp[bin of A], 1 ibgz[bin of A'],
+//           2 ibpz[bin of A'], 3 sgz[table entry of the row]
+//   kind 2  factor = nac[bin of A] * den(bin of A', class in the selector bits)
+//   kind 3  the same with S a table row: (A+beta)(S+gamma) * den
+constexpr uint32_t FK_ONE = 0u, FK_TABLE = 1u, FK_GENERAL = 2u, FK_TABLE_ROW = 3u;
+constexpr uint32_t FSEL_NACP = 0u, FSEL_IBGZ = 1u, FSEL_IBPZ = 2u, FSEL_SGZ = 3u;
+__device__ __forceinline__ uint32_t fcode_pack(uint32_t kind, uint32_t sel, uint32_t idx) {
+    return (kind << 30) | (sel << 28) | idx;
+}
+
+
+__device__ __forceinline__ fr_t fr_shfl_up(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_shfl_down(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_shfl_xor(const fr_t &a, int d) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+
+
+__device__ __forceinline__ fr_t fr_shfl_idx(const fr_t &a, int src) {
+    fr_t r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+#endif
+
+// ---- grand-product scan (gprod.cu): balanced tiles + decoupled look-back -----------------------
+// A tile is 32 x AES_ROWS consecutive rows.  Lane l of every warp works inside rows
+// [1360 l, 1360 l + 1360) of the tile and warp w on the ZT_R rows starting at ZT_R * w of that
+// range, so the 32 lanes of a warp sit at the SAME block-relative rows of 32 different AES blocks:
+// they see the same selector pattern and execute the same number of multiplies.
+constexpr int ZT_W = 16;                                  // warps per CTA
+constexpr int ZT_T = ZT_W * 32;                           // threads per CTA
+constexpr uint32_t ZT_LANE = (uint32_t)AES_ROWS;          // rows between two lanes of a warp
+constexpr uint32_t ZT_R = ZT_LANE / ZT_W;                 // consecutive rows per thread (85)
+constexpr uint32_t ZT_ROWS = 32u * ZT_LANE;               // rows per tile (43520)
+static_assert(ZT_R * ZT_W == ZT_LANE, "the warps of a CTA partition one AES block's rows");
+static_assert(ZT_R <= 96, "three 32-bit mask words per thread");
+H2_HD uint64_t zscan_tiles(uint64_t rows) { return (rows + ZT_ROWS - 1) / ZT_ROWS; }
+
 }  // namespace h2
 
 struct h2aes_prof_rec {
@@ -90,7 +167,9 @@ struct h2aes_circuit {
     uint32_t *d_trace = nullptr;   // n_sets * n words (a0 | a1<<8 | a2<<16 | op<<24)
     uint32_t *d_tracek = nullptr;  // n_sets * n words (op<<24 | bin of the row's tuple), per theta
     uint32_t *d_codek = nullptr;   // [L][n] factor code of every row (fcode_pack), written by k_permuted
-    uint32_t *d_codep = nullptr;   // [L][n] bin of S' where class == OTHER
+    uint4 *d_glist = nullptr;      // rows whose factor is not a table entry: (local row, code, bin of A, bin of S')
+    uint32_t *d_gbase = nullptr;   // [L+1] first list entry of every lookup (capacity bound, api.cu)
+    uint32_t *d_gcount = nullptr;  // [L] entries written by the last k_permuted
     bool *code_valid = nullptr;    // [L] host flags: codes of lookup l match the current bins
 
     // lookup workspace (allocated on first use)
@@ -122,6 +201,7 @@ struct h2aes_circuit {
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)
     h2::fr_t *d_ibg = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k]
     h2::fr_t *d_ibp = nullptr;       // [3][BIN_STRIDE] ib[k]*ig[k_pad]
+    h2::fr_t *d_ftab = nullptr;      // [4][3][BIN_STRIDE] the four merged tables below, by FSEL_*
     h2::fr_t *d_nacp = nullptr;      // [3][BIN_STRIDE] nac[k]*ibp[k_zero]
     h2::fr_t *d_ibgz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibg[k]
     h2::fr_t *d_ibpz = nullptr;      // [3][BIN_STRIDE] nac[k_zero]*ibp[k]
@@ -135,15 +215,18 @@ struct h2aes_circuit {
     h2::LookupMeta *d_meta = nullptr;  // [L]
     // grand-product scan workspace
     unsigned long long *d_znonconst = nullptr;  // [L] rows whose factor is not one (last product)
-    uint32_t *d_zmask = nullptr;      // [L][zm]   non-constant-row bit masks of the chunks
-    h2::fr_t *d_ztot = nullptr;       // [L][zm]   per-thread factor products / their prefixes
-    h2::fr_t *d_zbagg = nullptr;      // [L][znblk] block aggregates
-    h2::fr_t *d_zbexcl = nullptr;     // [L][znblk] exclusive prefixes of the block aggregates
+    uint32_t *d_zmask = nullptr;      // [L][zm] one bit per row: factor is not one
+    h2::fr_t *d_ztot = nullptr;      // [ztiles][ZT_T] thread totals in row order (k_z_totals -> k_z_scan)
+    h2::fr_t *d_zagg = nullptr;       // [ztiles] look-back: tile aggregates
+    h2::fr_t *d_zinc = nullptr;       // [ztiles] look-back: inclusive prefixes
+    uint32_t *d_zflag = nullptr;      // [ztiles] look-back: 2*epoch + {1: aggregate, 2: inclusive}
+    uint32_t *d_zctl = nullptr;       // [4] ticket, finished CTAs, epoch (device-resident: graph replay safe)
+    uint64_t ztiles = 0;              // tiles the look-back workspace holds
     uint32_t *d_err = nullptr;        // device error flags: [0] zero denominator, [1] not in table
     uint32_t *h_err = nullptr;        // pinned mirror of d_err
     h2::fr_t *d_partial = nullptr;    // [L] shard partial products
     h2::fr_t *d_carry = nullptr;      // [L] product of the partials of the shards before this one
-    uint64_t zm = 0, znblk = 0;
+    uint64_t zm = 0;
     uint64_t *partial_Z = nullptr;    // Z buffer holding the factors between phases 2a and 2b
 
     // permutation argument (allocated on first use)

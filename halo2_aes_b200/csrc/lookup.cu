@@ -21,26 +21,11 @@
 #include "internal.h"
 
 namespace h2 {
+cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const uint32_t *mask);
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ fr_t fr_from_tab(const uint4 *__restrict__ frtab, uint32_t b) {
-    uint4 lo = frtab[2 * b], hi = frtab[2 * b + 1];
-    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
-    return r;
-}
-__device__ __forceinline__ fr_t fr_ld(const fr_t *p) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 lo = q[0], hi = q[1];
-    fr_t r = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
-    return r;
-}
-__device__ __forceinline__ void fr_st(fr_t *p, const fr_t &a) {
-    uint4 *q = reinterpret_cast<uint4 *>(p);
-    q[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    q[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
-}
 __device__ __forceinline__ uint32_t fr_bitlen(const fr_t &c) {
     uint32_t bits = 0;
 #pragma unroll
@@ -551,8 +536,6 @@ k_run_index(Shape sh, const LookupMeta *__restrict__ meta, const uint32_t *__res
     lidx_all[(size_t)l * stride + t] = li;
 }
 
-// bins (k of A', k' of S') of usable row i, and how S' relates to A'
-constexpr uint32_t CODE_FIRST = 0u, CODE_PAD = 1u, CODE_OTHER = 2u;  // stored in bits 30..31
 struct RowBins {
     uint32_t k, kp, cls;
 };
@@ -587,18 +570,6 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
 // padding value — so that the grand product does not repeat the searches.  With Ap == null only
 // the codes are produced.
 // ---------------------------------------------------------------------------------------------
-// factor code of a row for the grand product (bits 31..30 kind, 29..28 selector, 23..0 index):
-//   kind 0  factor exactly one (constant row)                       -> nothing to do
-//   kind 1  factor = one entry of a merged table: selector 0 nacp[bin of A], 1 ibgz[bin of A'],
-//           2 ibpz[bin of A'], 3 sgz[table entry of the row]
-//   kind 2  factor = nac[bin of A] * den(bin of A', class in the selector bits)
-//   kind 3  the same with S a table row: (A+beta)(S+gamma) * den
-constexpr uint32_t FK_ONE = 0u, FK_TABLE = 1u, FK_GENERAL = 2u, FK_TABLE_ROW = 3u;
-constexpr uint32_t FSEL_NACP = 0u, FSEL_IBGZ = 1u, FSEL_IBPZ = 2u, FSEL_SGZ = 3u;
-__device__ __forceinline__ uint32_t fcode_pack(uint32_t kind, uint32_t sel, uint32_t idx) {
-    return (kind << 30) | (sel << 28) | idx;
-}
-
 __global__ void __launch_bounds__(256)
 k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            const uint32_t *__restrict__ tracek, const fr_t *__restrict__ val,
@@ -606,8 +577,9 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            const uint32_t *__restrict__ nzk_all, const uint32_t *__restrict__ loffz_all,
            const uint32_t *__restrict__ lk_all, const LookupMeta *__restrict__ meta,
            uint64_t *__restrict__ A, uint64_t *__restrict__ S, uint64_t *__restrict__ Ap,
-           uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint32_t *__restrict__ codep,
-           uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
+           uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint4 *__restrict__ glist,
+           const uint32_t *__restrict__ gbase, uint32_t *__restrict__ gcount,
+           uint32_t *__restrict__ err, uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
            const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, uint64_t row_begin,
            uint64_t row_end) {
     const int li = blockIdx.y;            // index inside this call
@@ -626,8 +598,9 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const fr_t *valv = val + (size_t)v * BIN_STRIDE;
     const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
     uint32_t *__restrict__ fc = fcode + (size_t)l * n;
-    uint32_t *__restrict__ cp = codep + (size_t)l * n;
     uint32_t *__restrict__ zmk = zmask + (size_t)l * zm;
+    uint4 *__restrict__ gl = glist + gbase[l];               // rows for k_z_general
+    const uint32_t gcap = gbase[l + 1] - gbase[l];
     const uint32_t *__restrict__ tk = tracek + (uint64_t)set * n;
     const uint32_t *__restrict__ jidx = jidx_all + (size_t)l * idx_stride;
     const uint32_t *__restrict__ lidx = lidx_all + (size_t)l * idx_stride;
@@ -639,7 +612,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
          lrow += stride) {
         const uint64_t row = row_begin + lrow;
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
-        uint32_t code = fcode_pack(FK_ONE, 0, 0);
+        uint32_t code = fcode_pack(FK_ONE, 0, 0), kin = 0, kp = 0;
         if (row >= usable) {
             if (A) fr_store_256(A + o, zero);
             if (S) fr_store_256(S + o, zero);
@@ -659,14 +632,15 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
                 fr_store_256(S + o, fr_ld(valv + e));
             }
             const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
-            if (rb.cls == CODE_OTHER) cp[row] = rb.kp;
+            kp = rb.kp;
             if (Ap) {
-                fr_store_256(Ap + o, fr_ld(dv + rb.k));
-                fr_store_256(Sp + o, fr_ld(dv + rb.kp));
+                fr_store_256(Ap + o, fr_ldg_256_nc(dv + rb.k));
+                fr_store_256(Sp + o, fr_ldg_256_nc(dv + rb.kp));
             }
             // classify the row's grand-product factor (see fcode_pack)
             const uint32_t t = tk[row];
             const bool active = (t >> 24) == op;
+            kin = active ? (t & 0xffffffu) : m.k_zero;  // bin of the row's own input value
             const bool in_zero_run = rb.k == m.k_zero && rb.cls == CODE_PAD;
             if (row < TABLE_ROWS) {
                 code = (!active && in_zero_run)
@@ -681,8 +655,26 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             }
         }
         fc[row] = code;
+        const int lane = threadIdx.x & 31;
         const uint32_t bal = __ballot_sync(0xffffffffu, (code >> 30) != FK_ONE);
-        if ((threadIdx.x & 31) == 0) zmk[lrow >> 5] = bal;
+        if (lane == 0) zmk[lrow >> 5] = bal;
+        // rows whose factor is not a table entry: everything k_z_general needs, appended to the
+        // lookup's list (one atomic per warp)
+        const bool gen = (code >> 30) >= FK_GENERAL;
+#ifdef PDBG_NOGEN
+        const uint32_t gbal = 0;
+#else
+        const uint32_t gbal = __ballot_sync(0xffffffffu, gen);
+#endif
+        if (gbal) {
+            uint32_t pos = 0;
+            if (lane == 0) pos = atomicAdd(gcount + l, (uint32_t)__popc(gbal));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(gbal & ((1u << lane) - 1u));
+            if (gen) {
+                if (pos < gcap) gl[pos] = make_uint4((uint32_t)lrow, code, kin, kp);
+                else atomicOr(err + 2, 1u);  // cannot happen: gcap bounds the count (api.cu)
+            }
+        }
     }
 }
 
@@ -697,25 +689,6 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
 constexpr int INV_T = 256;
 constexpr int INV_CH = 8;
 constexpr int INV_TILE = INV_T * INV_CH;
-
-__device__ __forceinline__ fr_t fr_shfl_up(const fr_t &a, int d) {
-    fr_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
-    return r;
-}
-__device__ __forceinline__ fr_t fr_shfl_down(const fr_t &a, int d) {
-    fr_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
-    return r;
-}
-__device__ __forceinline__ fr_t fr_shfl_xor(const fr_t &a, int d) {
-    fr_t r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], d);
-    return r;
-}
 
 __global__ void __launch_bounds__(INV_T)
 k_inv_tables(const fr_t *__restrict__ chal, const fr_t *__restrict__ dval,
@@ -824,327 +797,6 @@ k_inv_merge(const uint32_t *__restrict__ viewmeta, const uint32_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 2b: grand product Z as factor -> scan -> propagate (no spin-waits, no barriers on the
-// hot path; ~3.2 Montgomery multiplies per row):
-//   k_z_factors    per row f = num * den (one table x table multiply), stored in the Z buffer;
-//                  per thread (ZI consecutive rows) the product of its factors -> tot[]
-//   k_z_reduce / k_z_blocks / k_z_down   exclusive product scan of tot[] (n/ZI elements per
-//                  lookup) in three small kernels; the total is the shard's partial product
-//   k_z_propagate  per thread: running product from its exclusive prefix, overwriting the
-//                  factors in the Z buffer with Z itself
-// The kernel is bound by integer-multiply issue, not by HBM.
-// ---------------------------------------------------------------------------------------------
-#ifndef ZI_ROWS
-#define ZI_ROWS 32
-#endif
-constexpr int ZI = ZI_ROWS;  // consecutive rows per thread (<= 32: one mask word; row ranges are multiples)
-constexpr int ZF_T = 128;  // threads per CTA, factor / propagate kernels
-constexpr int ZS_T = 256;  // scan kernels: threads per CTA
-constexpr int ZS_E = 4;    //               elements per thread (latency-bound: keep chains short)
-constexpr int ZS_TILE = ZS_T * ZS_E;
-
-struct ZArgs {
-    Shape sh;
-    int first_lookup, count;
- const uint32_t *tracek;          // [sets][n]  op<<24 | bin of the row's input tuple
-    const uint32_t *fcode, *codep;   // [L][n]     factor code (k_permuted) ; bin of S' (class OTHER)
-    const fr_t *chal;
-    const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
-    const fr_t *nacp, *ibgz, *ibpz;                      // [3][BIN_STRIDE] one-operand-constant factors
-    const fr_t *sgz;                                     // [3][BIN_STRIDE] per table entry (see k_inv_merge)
-    const LookupMeta *meta;
-    uint32_t *chunkmask;  // [*][mstride] one bit per row of the chunk: factor is not one
-    uint64_t mstride;     //              (lookup l at l*mstride; the permutation sets at s*mstride)
-    unsigned long long *nonconst;  // [L] rows with a factor other than one (statistics)
-    fr_t *tot;        // [count][m]  thread totals, then their exclusive prefixes
-    fr_t *bagg;       // [count][nblk] block aggregates of tot
-    fr_t *bexcl;      // [count][nblk] exclusive prefixes of the block aggregates
-    fr_t *partial;    // [L] product of all factors of the row range
-    const fr_t *carry_in;  // [L] or null
-    uint64_t m, nblk;
-    uint64_t *Z;
-    uint64_t row_begin, row_end;
-};
-
-// k_z_fill: materialises the non-constant factors.  k_permuted already classified every row
-// (fcode) and wrote one bit per row (factor != 1) as a 32-bit word per chunk of ZI rows.  Most
-// rows are "constant": inactive in row order (A = 0, S = padding value) AND inside the zero run
-// of A' with the padding value as S' — numerator and denominator are the same two terms, so the
-// factor is EXACTLY ONE and the row costs no multiply and no store anywhere in the pipeline;
-// chunks without any other row are skipped after reading their mask.  Of the other rows almost
-// all have one constant operand and copy their factor from a merged table (k_inv_merge); only
-// rows that are both active and outside the zero run (or inside the table rows, where S
-// varies) multiply.  Factors are stored at the row's slot of the Z buffer.
-static_assert(ZI == 32, "one warp ballot = one chunk mask");
-#ifndef ZFILL_OCC
-#define ZFILL_OCC 6
-#endif
-__global__ void __launch_bounds__(256, ZFILL_OCC) k_z_fill(const ZArgs a) {
-    const Shape sh = a.sh;
-    const int li = blockIdx.y;
-    const int l = a.first_lookup + li;
-    const int ops = sh.ops_per_set();
-    const int set = l / ops;
-    const uint32_t op = (uint32_t)(l % ops) + 1;
-    const int v = view_of_op(op);
-    const uint64_t n = sh.n();
-    const uint64_t out_rows = a.row_end - a.row_begin;
-    const uint32_t k_zero = a.meta[l].k_zero;
-    const size_t vo = (size_t)v * BIN_STRIDE;
-    const fr_t *__restrict__ valv = a.val + vo, *__restrict__ dv = a.dval + vo,
-                             *__restrict__ ib = a.ib + vo, *__restrict__ ig = a.ig + vo,
-                             *__restrict__ nac = a.nac + vo, *__restrict__ ibg = a.ibg + vo,
-                             *__restrict__ ibp = a.ibp + vo;
-    const uint32_t *__restrict__ tkp = a.tracek + (uint64_t)set * n;
-    const uint32_t *__restrict__ fcp = a.fcode + (uint64_t)l * n;
-    const uint32_t *__restrict__ cpp = a.codep + (uint64_t)l * n;
-    uint64_t *__restrict__ zout = a.Z + (size_t)li * out_rows * 4;
-    const uint32_t *__restrict__ cmask = a.chunkmask + (size_t)li * a.mstride;
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    uint32_t n_nonconst = 0;
-    // warp w handles chunks w, w + warps, ... ; chunk c = rows [row_begin + 32c, +32)
-    for (uint64_t c = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.m;
-         c += warps) {
-        const uint32_t mask = cmask[c];
-        if (!mask) continue;  // every factor of the chunk is one
-        n_nonconst += __popc(mask);
-        const uint64_t row = a.row_begin + c * ZI + lane;
-        const uint32_t code = ((mask >> lane) & 1u) ? fcp[row] : 0u;
-        const uint32_t kind = code >> 30, sel = (code >> 28) & 3u, idx = code & 0xffffffu;
-        fr_t f;
-        if (kind == FK_TABLE) {
-            const fr_t *tab = sel == FSEL_NACP ? a.nacp : (sel == FSEL_IBGZ ? a.ibgz : (sel == FSEL_IBPZ ? a.ibpz : a.sgz));
-            f = fr_ld(tab + vo + idx);
-        }
-        if (__any_sync(0xffffffffu, kind >= FK_GENERAL)) {
-            if (kind >= FK_GENERAL) {
-                const uint32_t t = tkp[row];
-                const uint32_t kin = (t >> 24) == op ? (t & 0xffffffu) : k_zero;
-                const uint32_t cls = sel, k = idx;
-                fr_t den = fr_ld((cls == CODE_FIRST ? ibg : (cls == CODE_PAD ? ibp : ib)) + k);
-                fr_t num = fr_ld((kind == FK_TABLE_ROW ? dv : nac) + kin);
-                if (cls == CODE_OTHER) den = fr_mul(den, fr_ld(ig + cpp[row]));
-                if (kind == FK_TABLE_ROW) {  // S[i] is a table row: (A+beta)(S+gamma)
-                    const fr_t beta = fr_ld(a.chal + 1), gamma = fr_ld(a.chal + 2);
-                    const fr_t sg = fr_add(fr_ld(valv + entry_of_table_row(v, (uint32_t)row)), gamma);
-                    num = fr_mul(fr_add(num, beta), sg);
-                }
-                f = fr_mul(num, den);
-            }
-        }
-        if (kind != FK_ONE) fr_store_256(zout + (row - a.row_begin) * 4, f);
-    }
-    if (lane == 0 && n_nonconst) atomicAdd(a.nonconst + l, (unsigned long long)n_nonconst);
-}
-
-// Thread slot -> chunk for the chunk-per-thread kernels.  The rows a lookup is active on repeat
-// with the AES block (1360 rows = 42.5 chunks), so chunks 85 apart have the same number of
-// non-constant rows; the 32 lanes of a warp take chunks r, r+85, r+170, ... and run the same
-// number of multiply rounds (everything outside the zero run of A' is non-constant anyway).
-constexpr uint64_t Z_PERIOD = 85;  // chunks: 2 AES blocks = 2720 rows
-__device__ __forceinline__ bool z_chunk_of_slot(uint64_t slot, uint64_t m, uint64_t *e) {
-    const uint64_t per = (m + Z_PERIOD - 1) / Z_PERIOD;
-    *e = slot / per + Z_PERIOD * (slot % per);
-    return slot < Z_PERIOD * per && *e < m;
-}
-
-// k_z_chunks: one thread per chunk of ZI rows: product of the chunk's factors = c0^(constant
-// rows) * the non-constant factors (read back; their positions come from the chunk mask, so
-// several loads are in flight ahead of the multiply chain).
-#ifndef ZC_OCC
-#define ZC_OCC 4
-#endif
-__global__ void __launch_bounds__(128, ZC_OCC) k_z_chunks(const ZArgs a) {
-    uint64_t e;
-    if (!z_chunk_of_slot((uint64_t)blockIdx.x * blockDim.x + threadIdx.x, a.m, &e)) return;
-    const int li = blockIdx.y;
-    const uint64_t out_rows = a.row_end - a.row_begin;
-    const uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + e * ZI) * 4;
-    uint32_t mask = a.chunkmask[(size_t)li * a.mstride + e];
-    fr_t tot = fr_one();  // constant rows have factor one
-    auto next_q = [&]() -> int {
-        if (!mask) return -1;
-        const int q = __ffs(mask) - 1;
-        mask &= mask - 1;
-        return q;
-    };
-#ifndef ZC_DEPTH
-#define ZC_DEPTH 2
-#endif
-    constexpr int D = ZC_DEPTH;  // loads in flight
-    int q[D];
-    fr_t f[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        q[j] = next_q();
-        f[j] = fr_one();
-        if (q[j] >= 0) f[j] = fr_load(z + 4 * q[j]);
-    }
-#pragma unroll 1
-    while (q[0] >= 0) {
-        const fr_t cur = f[0];
-#pragma unroll
-        for (int j = 0; j + 1 < D; ++j) {
-            q[j] = q[j + 1];
-            f[j] = f[j + 1];
-        }
-        q[D - 1] = next_q();
-        if (q[D - 1] >= 0) f[D - 1] = fr_load(z + 4 * q[D - 1]);
-        tot = fr_mul_inline(tot, cur);  // the loop's only multiply: inlined (no call shuffling)
-    }
-    fr_st(a.tot + (size_t)li * a.m + e, tot);
-}
-
-// block aggregate of ZS_TILE consecutive thread totals
-__global__ void __launch_bounds__(ZS_T) k_z_reduce(const ZArgs a) {
-    __shared__ fr_t s_w[ZS_T / 32];
-    const int li = blockIdx.y;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const fr_t *__restrict__ x = a.tot + (size_t)li * a.m;
-    const uint64_t base = (uint64_t)blockIdx.x * ZS_TILE + (uint64_t)t * ZS_E;
-    fr_t p = fr_one();
-#pragma unroll 1
-    for (int j = 0; j < ZS_E; ++j)
-        if (base + j < a.m) p = fr_mul(p, fr_ld(x + base + j));
-#pragma unroll 1
-    for (int d = 16; d > 0; d >>= 1) p = fr_mul(p, fr_shfl_xor(p, d));
-    if (lane == 0) s_w[wid] = p;
-    __syncthreads();
-    if (t == 0) {
-        fr_t all = s_w[0];
-        for (int w = 1; w < ZS_T / 32; ++w) all = fr_mul(all, s_w[w]);
-        fr_st(a.bagg + (size_t)li * a.nblk + blockIdx.x, all);
-    }
-}
-
-// one warp per lookup: exclusive prefixes of the block aggregates, and the grand total
-__global__ void __launch_bounds__(32) k_z_blocks(const ZArgs a) {
-    const int li = blockIdx.x, lane = threadIdx.x;
-    const fr_t *__restrict__ g = a.bagg + (size_t)li * a.nblk;
-    fr_t *__restrict__ ex = a.bexcl + (size_t)li * a.nblk;
-    const uint64_t per = (a.nblk + 31) / 32;
-    const uint64_t lo = min(a.nblk, (uint64_t)lane * per), hi = min(a.nblk, lo + per);
-    fr_t acc = fr_one();
-    for (uint64_t b = lo; b < hi; ++b) acc = fr_mul(acc, fr_ld(g + b));
-    fr_t inc = acc;
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
-        const fr_t y = fr_shfl_up(inc, d);
-        if (lane >= d) inc = fr_mul(inc, y);
-    }
-    fr_t run = fr_shfl_up(inc, 1);
-    if (lane == 0) run = fr_one();
-    for (uint64_t b = lo; b < hi; ++b) {
-        fr_st(ex + b, run);
-        run = fr_mul(run, fr_ld(g + b));
-    }
-    if (lane == 31) fr_st(a.partial + a.first_lookup + li, inc);
-}
-
-// thread totals -> exclusive prefixes (times the block prefix, times the shard carry-in)
-__global__ void __launch_bounds__(ZS_T) k_z_down(const ZArgs a) {
-    __shared__ fr_t s_w[ZS_T / 32];
-    const int li = blockIdx.y;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    fr_t *__restrict__ x = a.tot + (size_t)li * a.m;
-    const uint64_t base = (uint64_t)blockIdx.x * ZS_TILE + (uint64_t)t * ZS_E;
-    fr_t p = fr_one();
-#pragma unroll 1
-    for (int j = 0; j < ZS_E; ++j)
-        if (base + j < a.m) p = fr_mul(p, fr_ld(x + base + j));
-    fr_t inc = p;
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
-        const fr_t y = fr_shfl_up(inc, d);
-        if (lane >= d) inc = fr_mul(inc, y);
-    }
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    fr_t run = fr_shfl_up(inc, 1);
-    if (lane == 0) run = fr_one();
-    for (int w = 0; w < wid; ++w) run = fr_mul(run, s_w[w]);
-    fr_t bp = fr_ld(a.bexcl + (size_t)li * a.nblk + blockIdx.x);
-    if (a.carry_in) bp = fr_mul(bp, fr_ld(a.carry_in + a.first_lookup + li));
-    run = fr_mul(run, bp);
-#pragma unroll 1
-    for (int j = 0; j < ZS_E; ++j) {
-        if (base + j >= a.m) break;
-        const fr_t xv = fr_ld(x + base + j);
-        fr_st(x + base + j, run);
-        run = fr_mul(run, xv);
-    }
-}
-
-// k_z_propagate: one thread per chunk: Z[row] = running product, which changes only after a
-// non-constant row (mask bit): ZI stores, popc(mask) multiplies.  The factors sit in the Z buffer
-// at the rows they belong to and are fetched ahead of the multiply chain.
-#ifndef ZP_OCC
-#define ZP_OCC 5
-#endif
-__global__ void __launch_bounds__(ZF_T, ZP_OCC) k_z_propagate(const ZArgs a) {
-    uint64_t e;
-    if (!z_chunk_of_slot((uint64_t)blockIdx.x * ZF_T + threadIdx.x, a.m, &e)) return;
-    const int li = blockIdx.y;
-    const uint32_t usable = (uint32_t)a.sh.usable();
-    const uint64_t out_rows = a.row_end - a.row_begin;
-    const uint64_t row0 = a.row_begin + e * ZI;
-    uint64_t *__restrict__ z = a.Z + ((size_t)li * out_rows + (row0 - a.row_begin)) * 4;
-    fr_t cur = fr_ld(a.tot + (size_t)li * a.m + e);
-    uint32_t mask = a.chunkmask[(size_t)li * a.mstride + e];
-    // Z has n-5 deterministic entries: rows 0..usable; the last 5 are blinding (zero)
-    const int nvalid = row0 + ZI <= (uint64_t)usable + 1 ? ZI
-                       : (row0 > usable ? 0 : (int)(usable + 1 - row0));
-    int done = 0;  // rows [0, done) of the chunk are written
-    auto next_q = [&]() -> int {
-        if (!mask) return -1;
-        const int q = __ffs(mask) - 1;
-        mask &= mask - 1;
-        return q;
-    };
-#ifndef ZP_DEPTH
-#define ZP_DEPTH 2
-#endif
-    constexpr int D = ZP_DEPTH;  // factor loads in flight ahead of the multiply chain
-    int qn[D];
-    fr_t fn[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        qn[j] = next_q();
-        fn[j] = fr_one();
-        if (qn[j] >= 0) fn[j] = fr_load(z + 4 * qn[j]);
-    }
-#pragma unroll 1
-    while (true) {
-        // rows up to and including the next non-constant row (or the chunk end) get `cur`
-        const int upto = qn[0] >= 0 ? qn[0] + 1 : ZI;
-        for (int q = done; q < upto; ++q)
-            fr_store_256(z + 4 * q, q < nvalid ? cur : fr_zero());
-        done = upto;
-        if (qn[0] < 0) break;
-        const fr_t f = fn[0];
-#pragma unroll
-        for (int j = 0; j + 1 < D; ++j) {
-            qn[j] = qn[j + 1];
-            fn[j] = fn[j + 1];
-        }
-        qn[D - 1] = next_q();
-        if (qn[D - 1] >= 0) fn[D - 1] = fr_load(z + 4 * qn[D - 1]);
-        cur = fr_mul_inline(cur, f);  // the loop's only multiply: inlined
-    }
-}
-
-// carry[l] = product of the partial products of the shards before `shard` (row-sharded circuit)
-__global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, int shard,
-                              fr_t *__restrict__ carry) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_lookups) return;
-    fr_t acc = fr_one();
-    for (int s = 0; s < shard; ++s) acc = fr_mul(acc, fr_ld(gathered + (size_t)s * n_lookups + l));
-    fr_st(carry + l, acc);
-}
-
-// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -1231,10 +883,13 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     const unsigned cap = (unsigned)ctx->sm_count * 8;
     if (gx > cap) gx = cap;
     dim3 g(gx, count);
+    cudaError_t e0 = cudaMemsetAsync(c->d_gcount + first, 0, (size_t)count * 4, ctx->stream);
+    if (e0) return e0;
     prof_begin(ctx, "k_permuted");
     k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
                                            c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S,
-                                           Ap, Sp, c->d_codek, c->d_codep, c->d_zmask, c->zm,
+                                           Ap, Sp, c->d_codek, c->d_glist, c->d_gbase,
+                                           c->d_gcount, c->d_err, c->d_zmask, c->zm,
                                            c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride, row_begin,
                                            row_end);
     prof_end(ctx);
@@ -1256,96 +911,6 @@ cudaError_t launch_inv_tables(h2aes_circuit *c) {
                                              c->d_val, c->d_chal, c->d_sgz);
     prof_end(ctx);
     ctx->launches += 2;
-    return cudaGetLastError();
-}
-
-static ZArgs z_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in, uint64_t *Z,
-                    uint64_t row_begin, uint64_t row_end) {
-    ZArgs a;
-    a.sh = c->sh;
-    a.first_lookup = first;
-    a.count = count;
-    a.tracek = c->d_tracek;
-    a.fcode = c->d_codek;
-    a.codep = c->d_codep;
-    a.chal = c->d_chal;
-    a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;
-    a.ibg = c->d_ibg; a.ibp = c->d_ibp;
-    a.nacp = c->d_nacp; a.ibgz = c->d_ibgz; a.ibpz = c->d_ibpz;
-    a.sgz = c->d_sgz;
-    a.meta = c->d_meta;
-    a.chunkmask = c->d_zmask + (size_t)first * c->zm;
-    a.mstride = c->zm;
-    a.nonconst = c->d_znonconst;
-    a.tot = c->d_ztot; a.bagg = c->d_zbagg; a.bexcl = c->d_zbexcl;
-    a.partial = c->d_partial;
-    a.carry_in = carry_in;
-    a.m = (row_end - row_begin + ZI - 1) / ZI;
-    a.nblk = (a.m + ZS_TILE - 1) / ZS_TILE;
-    a.Z = Z;
-    a.row_begin = row_begin;
-    a.row_end = row_end;
-    return a;
-}
-
-// factors into Z, thread totals, block aggregates, block prefixes, partial[first..first+count)
-cudaError_t launch_z_factors(h2aes_circuit *c, int first, int count, uint64_t *Z,
-                             uint64_t row_begin, uint64_t row_end) {
-    h2aes_ctx *ctx = c->ctx;
-    cudaStream_t s = ctx->stream;
-    const ZArgs a = z_args(c, first, count, nullptr, Z, row_begin, row_end);
-    cudaError_t e0 = cudaMemsetAsync(c->d_znonconst + first, 0, (size_t)count * 8, s);
-    if (e0) return e0;
-    {
-        unsigned gx = cdiv(a.m, 8);  // 8 warps (chunks) per CTA pass
-#ifndef ZFILL_CAP
-#define ZFILL_CAP 4
-#endif
-        // few, long-lived CTAs: the per-CTA prologue (challenges, table pointers) is ~100
-        // instructions and a chunk only ~150
-        const unsigned cap = (unsigned)ctx->sm_count * ZFILL_CAP;
-        if (gx > cap) gx = cap;
-        prof_begin(ctx, "k_z_fill");
-        k_z_fill<<<dim3(gx, count), 256, 0, s>>>(a);
-        prof_end(ctx);
-    }
-    prof_begin(ctx, "k_z_chunks");
-    k_z_chunks<<<dim3(cdiv(85 * ((a.m + 84) / 85), 128), count), 128, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_reduce");
-    k_z_reduce<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_blocks");
-    k_z_blocks<<<count, 32, 0, s>>>(a);
-    prof_end(ctx);
-    ctx->launches += 4;
-    return cudaGetLastError();
-}
-
-// exclusive prefixes of the thread totals (with the shard carry-in), then Z in place
-cudaError_t launch_z_finish(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                            uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
-    h2aes_ctx *ctx = c->ctx;
-    cudaStream_t s = ctx->stream;
-    const ZArgs a = z_args(c, first, count, carry_in, Z, row_begin, row_end);
-    prof_begin(ctx, "k_z_down");
-    k_z_down<<<dim3((unsigned)a.nblk, count), ZS_T, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_propagate");
-    k_z_propagate<<<dim3(cdiv(85 * ((a.m + 84) / 85), ZF_T), count), ZF_T, 0, s>>>(a);
-    prof_end(ctx);
-    ctx->launches += 2;
-    return cudaGetLastError();
-}
-
-cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev) {
-    h2aes_ctx *ctx = c->ctx;
-    const int L = c->sh.n_lookups();
-    prof_begin(ctx, "k_shard_carry");
-    k_shard_carry<<<cdiv(L, 64), 64, 0, ctx->stream>>>((const fr_t *)gathered_dev, L, c->shard,
-                                                       c->d_carry);
-    prof_end(ctx);
-    ctx->launches += 1;
     return cudaGetLastError();
 }
 
@@ -1374,6 +939,7 @@ cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint
 //   one field inversion per CTA), then the same chunk-total / scan / propagate kernels as the
 //   lookup grand product.
 // ---------------------------------------------------------------------------------------------
+constexpr int ZI = 32;  // rows per mask word of the permutation product
 constexpr uint32_t W_LO_BITS = 10, W_LO = 1u << W_LO_BITS;  // omega^j = w_hi[j >> 10] * w_lo[j & 1023]
 constexpr uint32_t PMAP_ROW_BITS = 24;                       // packed mapping: position << 24 | row
 
@@ -1571,15 +1137,6 @@ __global__ void __launch_bounds__(PI_T) k_p_invert(const PArgs a) {
     }
 }
 
-// carry[s] = product of the totals of the sets before s (Z of set s starts at Z[n-6] of set s-1)
-__global__ void k_p_carry(const fr_t *__restrict__ partial, int n_sets, fr_t *__restrict__ carry) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_sets) return;
-    fr_t acc = fr_one();
-    for (int j = 0; j < s; ++j) acc = fr_mul(acc, fr_ld(partial + j));
-    fr_st(carry + s, acc);
-}
-
 cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta) {
     h2aes_ctx *ctx = c->ctx;
     const uint32_t n_hi = (uint32_t)(c->sh.n() >> W_LO_BITS);
@@ -1637,39 +1194,15 @@ cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, ui
     prof_begin(ctx, "k_p_invert");
     k_p_invert<<<dim3(cdiv(p.m, PI_T), n_sets), PI_T, 0, s>>>(p);
     prof_end(ctx);
-    // chunk totals, scan, chaining of the sets, running products: the lookup machinery
-    ZArgs a = z_args(c, 0, n_sets, nullptr, Zp, 0, n);
-    a.chunkmask = c->d_pmask;  // the permutation's own masks ([n_sets][n/32])
-    prof_begin(ctx, "k_z_chunks");
-    k_z_chunks<<<dim3(cdiv(85 * ((a.m + 84) / 85), 128), n_sets), 128, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_reduce");
-    k_z_reduce<<<dim3((unsigned)a.nblk, n_sets), ZS_T, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_blocks");
-    k_z_blocks<<<n_sets, 32, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_p_carry");
-    k_p_carry<<<1, 64, 0, s>>>(c->d_partial, n_sets, c->d_carry);
-    prof_end(ctx);
-    a.carry_in = c->d_carry;
-    prof_begin(ctx, "k_z_down");
-    k_z_down<<<dim3((unsigned)a.nblk, n_sets), ZS_T, 0, s>>>(a);
-    prof_end(ctx);
-    prof_begin(ctx, "k_z_propagate");
-    k_z_propagate<<<dim3(cdiv(85 * ((a.m + 84) / 85), ZF_T), n_sets), ZF_T, 0, s>>>(a);
-    prof_end(ctx);
-    ctx->launches += 9;
+    // the n_sets columns are ONE running product (set s starts from the last usable value of set
+    // s-1): a single look-back scan over n_sets * n rows (gprod.cu)
+    cudaError_t e = launch_z_scan_buffer(c, n_sets, Zp, c->d_pmask);
+    if (e) return e;
+    ctx->launches += 3;
     return cudaGetLastError();
 }
 
 uint32_t lookup_bin_tiles() { return LB_TILES; }
 uint64_t run_index_stride(uint64_t n) { return (n >> RUN_SHIFT) + 2; }
-
-// workspace sizes of the grand-product scan for `rows` rows: thread totals, block aggregates
-void grand_product_ws(uint64_t rows, uint64_t *m, uint64_t *nblk) {
-    *m = (rows + ZI - 1) / ZI;
-    *nblk = (*m + ZS_TILE - 1) / ZS_TILE;
-}
 
 }  // namespace h2

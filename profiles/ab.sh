@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 for v in "$@"; do
   if [ $v = default ]; then unset H2AES_LIB; else export H2AES_LIB=$PWD/halo2_aes_b200/lib/variants/libh2aes_$v.so; fi
-  timeout 600 python bench.py --no-cpu --no-e2e --no-prover-side --steps 100 > gpurun_out/ab_$v.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
+  timeout 600 python bench.py --no-cpu --no-e2e --no-prover-side --no-perm ${AB_ARGS} --steps 100 > gpurun_out/ab_$v.json 2> gpurun_out/ab.err || tail -3 gpurun_out/ab.err
   python - <<PY
 import json
 d = json.load(open("gpurun_out/ab_$v.json"))
