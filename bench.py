@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 SEED = 0x68326165  # "h2ae"
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 K_BENCH, N_BENCH = 20, 5
+BLOCKS_BENCH = 3853  # capacity of the shape: 769 + 4 * 771 (src/aes128.rs:303-325)
 METRIC = "AES-128 block witnesses/sec (Fr advice + lookup columns A',S',Z)"
 UNIT = "blocks/s"
 
@@ -120,28 +121,50 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------
-def cpu_baseline_sample(threads: int, target_s: float = 12.0):
-    """The oracle port on the host cores: independent k=17,N=1 circuits of 95 blocks each (same
-    rows-per-block ratio as the benchmarked K=20 shape: 2^k/capacity = 1380 vs 1363), one
-    circuit per thread, with all lookups (A,S,A',S',Z) of each circuit."""
+def cpu_circuit(oracle, seed: int, threads: int, n_lookups: int = -1):
+    """ONE circuit of the benchmarked shape on the CPU oracle: K=20, N=5, 3853 blocks under one
+    key.  synthesize runs on one thread (the reference's synthesize is sequential,
+    src/main.rs:42-54); the 25 lookup arguments (A, S, A', S', Z each) are independent and run
+    under OpenMP on `threads` threads.  Returns (synthesize s, lookups s)."""
+    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
+    nb = BLOCKS_BENCH
+    key = splitmix_bytes(seed, 16)
+    pts = splitmix_bytes(seed + 1, 16 * nb).reshape(nb, 16)
+    ts, tl, _ = oracle.bench_circuit(oracle.KIND_AES, K_BENCH, N_BENCH, key, pts, th, be, ga,
+                                     threads=threads, n_lookups=n_lookups)
+    return ts, tl
+
+
+def cpu_one_thread(oracle):
+    """the single-thread figure.  Measured: synthesize of the whole circuit and the
+    five lookups of ONE column set (range, xor, sbox, mul2, mul3) on one thread; the lookups of the
+    other four sets are the same work on other columns, so their time is taken as 5x (stated)."""
+    ts, tl = cpu_circuit(oracle, SEED + 40, 1, n_lookups=5)
+    total = ts + tl * (N_BENCH * 5) / 5
+    return {"value": BLOCKS_BENCH / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "synthesize_s": ts, "lookups_of_one_column_set_s": tl,
+            "sample": f"one K={K_BENCH},N={N_BENCH} circuit of {BLOCKS_BENCH} blocks on ONE thread: "
+                      f"synthesize {ts:.2f} s measured, the 5 lookups of one column set {tl:.2f} s "
+                      f"measured and counted {N_BENCH}x for the {N_BENCH * 5} lookups"}
+
+
+def cpu_baseline_sample(threads: int, circuits: int = 2):
+    """The oracle port on the host cores, on the SAME workload as the GPU arm: `circuits` whole
+    K=20,N=5 circuits of 3853 blocks (bounded sample: ~10-20 s)."""
     import oracle
     oracle.build()
-    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
-    k, N, nb = 17, 1, 95
-    # one calibration circuit, then as many rounds of `threads` circuits as fit the target
-    keys = splitmix_bytes(SEED + 20, 16 * threads).reshape(threads, 16)
-    pts = splitmix_bytes(SEED + 21, 16 * nb * threads).reshape(threads, nb, 16)
-    sec1, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
-    rounds = max(1, min(8, int(target_s / max(sec1, 1e-3))))
-    keys = splitmix_bytes(SEED + 22, 16 * threads * rounds).reshape(-1, 16)
-    pts = splitmix_bytes(SEED + 23, 16 * nb * threads * rounds).reshape(threads * rounds, nb, 16)
-    sec, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
-    blocks = nb * threads * rounds
+    t0 = time.perf_counter()
+    parts = [cpu_circuit(oracle, SEED + 20 + 2 * i, threads) for i in range(circuits)]
+    sec = time.perf_counter() - t0
+    blocks = BLOCKS_BENCH * circuits
     return {"value": blocks / sec, "unit": UNIT, "cores": threads, "kind": "port",
-            "seconds": sec, "prover_side": cpu_prover_side_sample(oracle, threads),
-            "sample": f"{threads * rounds} independent k=17,N=1 circuits x 95 blocks (synthesize + "
-                      f"5 lookups A,S,A',S',Z each), one circuit per thread, CPU restatement "
-                      f"(oracle/), {blocks} blocks in {sec:.2f} s"}
+            "seconds": sec, "synthesize_s": sum(p[0] for p in parts), "lookups_s": sum(p[1] for p in parts),
+            "one_thread": cpu_one_thread(oracle),
+            "prover_side": cpu_prover_side_sample(oracle, threads),
+            "sample": f"{circuits} whole K={K_BENCH},N={N_BENCH} circuits of {BLOCKS_BENCH} blocks (the GPU "
+                      f"arm's unit): synthesize on one thread as in the reference, the 25 lookups "
+                      f"(A,S,A',S',Z) under OpenMP on {threads} threads; CPU restatement (oracle/), "
+                      f"{blocks} blocks in {sec:.2f} s"}
 
 
 def cpu_prover_side_sample(oracle, threads: int):
@@ -170,53 +193,51 @@ def cpu_prover_side_sample(oracle, threads: int):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port: the Rust crate cannot be
-    compiled here — no cargo, un-vendored halo2_proofs) on all host threads."""
+    compiled here — no cargo, un-vendored halo2_proofs) on all host threads, on the workload the
+    GPU arm runs: whole K=20, N=5 circuits of 3853 blocks.  One circuit per step (a bounded
+    sample of the GPU arm's step, which is `circuits_per_step_per_gpu` such circuits)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     oracle.build()
     threads = os.cpu_count() or 1
-    th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
-    k, N, nb = 17, 1, 95
-
-    def step(i):
-        keys = splitmix_bytes(SEED + 100 + i, 16 * threads).reshape(threads, 16)
-        pts = splitmix_bytes(SEED + 200 + i, 16 * nb * threads).reshape(threads, nb, 16)
-        sec, _ = oracle.bench_batch(oracle.KIND_AES, k, N, keys, pts, th, be, ga, threads=threads)
-        return sec
-
     for i in range(args.warmup):
-        step(i)
+        cpu_circuit(oracle, SEED + 100 + 2 * i, threads)
     t0 = time.perf_counter()
+    ts = tl = 0.0
     for i in range(args.steps):
-        step(args.warmup + i)
+        a, b = cpu_circuit(oracle, SEED + 100 + 2 * (args.warmup + i), threads)
+        ts += a
+        tl += b
     total = time.perf_counter() - t0
-    blocks = nb * threads * args.steps
-    value = blocks / total
-    sample = (f"each step = {threads} independent k=17,N=1 circuits x 95 blocks (synthesize + 5 "
-              f"lookups A,S,A',S',Z), one circuit per host thread; CPU restatement of the "
-              f"reference (oracle/), the Rust crate itself is unbuildable here")
+    value = BLOCKS_BENCH * args.steps / total
+    sample = (f"each step = ONE whole K={K_BENCH},N={N_BENCH} circuit of {BLOCKS_BENCH} blocks (1/{args.circuits} of "
+              f"the GPU arm's step): synthesize on one thread as in the reference ({ts / args.steps:.2f} s), the "
+              f"25 lookups A,S,A',S',Z under OpenMP on {threads} threads ({tl / args.steps:.2f} s); CPU "
+              f"restatement of the reference (oracle/), the Rust crate itself is unbuildable here")
     emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 -> bn256 Fr (4x u64 Montgomery)", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, args.circuits),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
+        "cpu_baseline_1t": cpu_one_thread(oracle),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, circuits_per_step):
     return {"workload": "BASELINE config 4 unit: independent K=20,N=5 circuits filled to capacity "
                         "(3853 AES-128 blocks under one key each): 16 advice columns + A',S',Z of "
                         "all 25 lookups; random keys/plaintexts (SplitMix64 seed 0x68326165), "
                         "seeded theta/beta/gamma",
-            "k": K_BENCH, "column_sets": N_BENCH, "blocks_per_circuit": 3853,
-            "circuits_per_step_per_gpu": 1, "partitioning": f"independent circuits x{n_gpus}",
-            "l2_policy": "outputs are 2.86 GiB per step (>> 126 MB L2) and never re-read"}
+            "k": K_BENCH, "column_sets": N_BENCH, "blocks_per_circuit": BLOCKS_BENCH,
+            "circuits_per_step_per_gpu": circuits_per_step,
+            "partitioning": f"independent circuits x{n_gpus}",
+            "l2_policy": "outputs are 2.86 GiB per circuit (>> 126 MB L2) and never re-read"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -287,14 +308,15 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     P = max(1, args.pipelines)
-    n_in = args.warmup + args.steps + 8
+    CPS = max(1, args.circuits)  # circuits per step: the timed region is steps * CPS circuits
+    n_in = 64
     pipes = [Pipe(local, rank, j, n_in) for j in range(P)]
     lay = pipes[0].cir.layout
     n, nb, L, nadv = lay["n_rows"], lay["capacity_blocks"], lay["n_lookups"], lay["n_advice"]
     th, be, ga = seeded_fr(SEED + 1), seeded_fr(SEED + 2), seeded_fr(SEED + 3)
 
-    def step(i, pipe, ev=None):
-        """one circuit: fresh key, theta nudged per step so the per-theta bin build always runs"""
+    def circuit(i, pipe, ev=None):
+        """one circuit: fresh key, theta nudged per circuit so the per-theta bin build always runs"""
         th_i = th.copy()
         th_i[0] ^= np.uint64(i + 1)
         s, cir = pipe.stream, pipe.cir
@@ -323,8 +345,14 @@ def run_b200(args):
             # every Z column closes at 1: the lookup argument is satisfied
             assert bool((pipe.Z[:, n - 6] == one).all()), "Z[n-6] != 1"
 
-    for i in range(max(args.warmup, P)):
-        step(i, pipes[i % P])
+    def step(s, ev=None):
+        """one step = CPS circuits dealt to the P pipelines (events around the first one)"""
+        for c in range(CPS):
+            i = s * CPS + c
+            circuit(i, pipes[i % P], ev if c == 0 else None)
+
+    for s in range(args.warmup):
+        step(s)
     torch.cuda.synchronize()
     check_closed()
 
@@ -341,8 +369,8 @@ def run_b200(args):
     t_start.record(pipes[0].stream)
     for pipe in pipes[1:]:
         pipe.stream.wait_event(t_start)
-    for i in range(args.steps):
-        step(args.warmup + i, pipes[i % P], evs[i])
+    for s in range(args.steps):
+        step(args.warmup + s, evs[s])
     for pipe in pipes[1:]:
         done = torch.cuda.Event()
         done.record(pipe.stream)
@@ -375,7 +403,7 @@ def run_b200(args):
     iso = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(NPROF)]
     pipes[0].ctx.profile(True)
     for j in range(NPROF):
-        step(args.warmup + args.steps + j, pipes[0], iso[j])
+        circuit((args.warmup + args.steps) * CPS + j, pipes[0], iso[j])
     prof = pipes[0].ctx.profile_read()
     pipes[0].ctx.profile(False)
     nc = int(pipes[0].cir.lookup_stats().sum())  # rows whose grand-product factor is not one
@@ -406,15 +434,15 @@ def run_b200(args):
     alg = {  # algorithmic bytes per launch; None: not a streaming kernel
         "k_advice": nadv * n * 32 + nb * 16,      # every advice cell written once (+ plaintexts)
         "k_permuted": 2 * L * n * 32,             # A', S'
-        "k_z_scan": L * n * 32 + 2 * nc * 4 + 2 * L * n // 8,  # Z written; codes of the non-constant
-                                                              # rows and the masks read in both passes
+        "k_z_write": L * n * 32 + nc * 4 + L * n // 8,   # Z written; codes of the non-constant rows
+                                                          # and the masks read
+        "k_z_totals": nc * 4 + L * n // 8 + L * (n // 40) * 32,
         "k_lookup_hist": 2 * (nadv // 3) * n * 4, # trace words read, bin words written
     }
     # Fr-arithmetic kernels: Montgomery multiplies per launch where the count is exact, against the
     # multiply throughput measured on this chip (profiles/microbench/RESULTS.md: 67 Gmul/s)
     MUL_PEAK_G = 67.0
-    muls = {"k_z_scan": 2 * nc}  # one multiply per non-constant row in each pass (lower bound:
-    # rows whose factor is not a table entry add one or two, the block scans ~6 per thread)
+    muls = {"k_z_totals": nc, "k_z_write": nc}  # one multiply per non-constant row in each
     kernels = []
     for name, (cnt, ms) in prof.items():
         per_launch = ms / cnt
@@ -474,8 +502,8 @@ def run_b200(args):
         cpu = None
         if not args.no_cpu and world == 1:
             cpu = cpu_baseline_sample(os.cpu_count() or 1)
-        blocks = nb * args.steps * world
-        cfg = workload_config(world)
+        blocks = nb * CPS * args.steps * world
+        cfg = workload_config(world, CPS)
         cfg["circuits_in_flight_per_gpu"] = P
         cfg["host_numa_node_rank0"] = numa
         out = {
@@ -486,8 +514,9 @@ def run_b200(args):
             "data": "synthetic", "config": cfg,
             "roofline": roofline, "kernels": kernels,
             "phase_ms": ph_ms, "phase_ms_isolated": ph_iso,
-            "step_algorithmic_bytes": step_bytes,
-            "step_effective_gbs": step_bytes / (ms_total / args.steps * 1e-3) / 1e9,
+            "circuit_algorithmic_bytes": step_bytes,
+            "ms_per_circuit": ms_total / args.steps / CPS,
+            "step_effective_gbs": step_bytes * CPS / (ms_total / args.steps * 1e-3) / 1e9,
             "witness_only_blocks_per_s": nb / (ph_iso["witness"] * 1e-3),
             "permutation_product": perm,
             "nonconstant_rows": nc, "nonconstant_row_fraction": nc / (L * n),
@@ -577,7 +606,9 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--circuits", type=int, default=10,
+                    help="circuits per step per GPU (one step = this many whole K=20,N=5 circuits)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)

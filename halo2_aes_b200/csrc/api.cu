@@ -635,7 +635,10 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     const size_t L = (size_t)c->sh.n_lookups();
     const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
     c->zm = (c->sh.n() + 31) / 32 + 4;
-    c->ztiles = L * zscan_tiles(c->sh.n()) + 1;  // >= tiles of the permutation's n_sets * n rows
+    // block totals of L columns of n rows (>= the permutation's n_sets * n rows as one column);
+    // k_z_prefix scans them in tiles of 1024
+    c->zblocks = L * (zscan_blocks(c->sh.n()) + 1);
+    c->ztiles = L * (zscan_blocks(c->sh.n()) / 1024 + 2);
     DA(c->d_chal, 4);
     DA(c->d_val, VB);
     DA(c->d_canon, VB);
@@ -696,7 +699,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_lk, LB);
     DA(c->d_meta, L);
     DA(c->d_zmask, L * c->zm);
-    DA(c->d_ztot, c->ztiles * ZT_T);
+    DA(c->d_ztot, c->zblocks);
     DA(c->d_zagg, c->ztiles);
     DA(c->d_zinc, c->ztiles);
     if (!c->d_zflag) {

@@ -9,23 +9,25 @@
 //
 // A factor is exactly one on most rows (k_permuted's chunk masks say where it is not) and one
 // entry of an L2-resident per-bin table on most of the others (gathered through the row's 4-byte
-// factor code).  Three kernels:
+// factor code).  Four kernels, none of which keeps a CTA waiting on another:
 //   k_z_general  the remaining rows (active AND outside the zero run of A', or inside the table
-//                rows): their factor is a product of two to four table entries.  The warps
-//                compact these rows into shared-memory queues and evaluate 32 of them at a time
-//                (every lane multiplies), storing the factor in the row's slot of the Z buffer;
-//   k_z_totals   per tile of 32 x 1360 rows, every thread multiplies the factors of its ZT_R
-//                consecutive rows; thread totals and the tile aggregate go to the workspace;
-//   k_z_scan     per tile: exclusive product scan of the 512 thread totals (warp shuffles of
-//                256-bit Montgomery products), decoupled look-back over the tile aggregates /
-//                inclusive prefixes (tickets are handed out tile-major; the aggregates are all
-//                there already, so nothing ever waits long), then every thread walks its rows
-//                again from its exclusive prefix and stores Z: one 256-bit store per row, one
-//                multiply per non-constant row.
-// Lanes of a warp are 1360 rows (one AES block) apart: they see the same selector pattern, hence
-// the same number of multiplies; the 16 warps of a CTA cover the 1360 block-relative rows.
+//                rows): product of two to four table entries, one thread per entry of the list
+//                k_permuted wrote; the factor goes to the row's slot of the Z buffer;
+//   k_z_totals   the column is cut into blocks of ZB_R consecutive rows; one thread multiplies
+//                the factors of one block -> tot[block];
+//   k_z_prefix   exclusive product scan of the block totals in one pass: per tile of 1024
+//                totals a block-wide scan (warp shuffles of 256-bit Montgomery products) and a
+//                decoupled look-back over the preceding tiles' aggregates / inclusive prefixes
+//                (tickets are handed out in tile order, so a tile only waits on running tiles);
+//   k_z_write    one thread per block again: walk the rows from the block's exclusive prefix,
+//                one multiply per non-constant row; the values leave through shared memory as
+//                whole 128-byte lines (one 256-bit store per row).
+// Work unit = warp.  The 32 lanes of a warp take blocks that are 1360 rows (one AES block) apart:
+// they sit at the SAME block-relative rows of 32 different AES blocks, see the same selector
+// pattern and execute the same number of multiplies.  Warps are dealt heaviest region first
+// (the table rows at the start of a column, then the end of the column, where A' is not zero).
 // Bound by integer-multiply issue (one bn256 Montgomery product = 128 IMAD.WIDE), not by HBM:
-// 2 multiplies per non-constant row, +1..3 for the rows of k_z_general.
+// 2 multiplies per non-constant row, +1..3 for the rows of k_z_general, ~2 per block for the scan.
 #include "internal.h"
 
 namespace h2 {
@@ -51,15 +53,17 @@ struct ZScanArgs {
     uint64_t row_begin, rows;      // rows of every column handled by this launch
     uint64_t col_mask;             // n-1: row & col_mask = row inside its column (ZSRC_BUFFER scans
                                    // several columns as one long column)
-    uint64_t n_tiles;
+    uint64_t n_tiles;              // row tiles of 32 x 1360 rows per column (work distribution)
+    uint64_t n_blocks;             // blocks of ZB_R rows per column = block totals per column
+    uint64_t n_ptiles;             // tiles of ZP_TILE block totals per column (k_z_prefix)
     const fr_t *carry_in;          // [L] or null: product of everything before row_begin
-    fr_t *partial;                 // [L] or null: product of all factors (times carry_in)
+    fr_t *partial;                 // [L] or null: product of all factors of the column
     unsigned long long *nonconst;  // [L] or null: statistics
-    // look-back workspace
-    fr_t *tot;                     // [count*n_tiles][ZT_T] thread totals in row order
-    fr_t *agg, *inc;               // [count*n_tiles]
-    uint32_t *flag;                // [count*n_tiles]
-    uint32_t *ctl;                 // ticket, finished, epoch
+    fr_t *tot;                     // [count][n_blocks] block totals, then their exclusive prefixes
+    // look-back workspace of k_z_prefix
+    fr_t *agg, *inc;               // [count*n_ptiles]
+    uint32_t *flag;                // [count*n_ptiles] 2*epoch + {1: aggregate, 2: inclusive prefix}
+    uint32_t *ctl;                 // ticket, finished CTAs, epoch
 };
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
@@ -175,35 +179,31 @@ __global__ void __launch_bounds__(ZG_T, ZG_OCC) k_z_general(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_z_totals / k_z_scan
+// k_z_totals / k_z_write: one thread per block of ZB_R rows, one warp per 32 blocks 1360 rows apart
 // ---------------------------------------------------------------------------------------------
-struct ZThread {
-    int li, l, rk;
-    uint64_t T, lr0, row0;
-    size_t slot;
-    uint32_t nr;
-    uint64_t *z;
+struct ZBlock {
+    int li, l;
+    uint64_t T, w;        // row tile and slice of the tile this warp works on
+    uint64_t b, lr0, row0;  // my block, its first local / absolute row
+    uint32_t nr;          // rows of my block inside the column
     LookupLane cx;
     uint32_t mb[3];
 };
+// warp task -> (column, row tile, slice); heaviest tiles first (see the file header)
 template <int SRC>
-__device__ __forceinline__ void z_thread_setup(const ZScanArgs &a, uint32_t ticket, ZThread &t) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // tile-major, every column advances together; the tiles with the most multiplies first (the
-    // table rows at the start of a column, then the end of the column, where A' is not zero), so
-    // that the lightly loaded tiles fill the machine behind them.  Any order is deadlock free:
-    // the look-back only needs the aggregates, which k_z_totals has published for every tile.
-    t.li = (int)(ticket % (uint32_t)a.count);
-    const uint64_t ord = ticket / (uint32_t)a.count;
+__device__ __forceinline__ bool z_block_setup(const ZScanArgs &a, uint64_t task, ZBlock &t) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t per_tile = (uint64_t)a.count * ZB_W;
+    if (task >= a.n_tiles * per_tile) return false;
+    const uint64_t ord = task / per_tile, rem = task - ord * per_tile;
     t.T = ord < 2 ? ord : a.n_tiles + 1 - ord;
-    t.slot = (size_t)t.li * a.n_tiles + t.T;
+    t.li = (int)(rem / ZB_W);
+    t.w = rem - (uint64_t)t.li * ZB_W;
     t.l = a.first_lookup + t.li;
-    // my rows: local rows [lr0, lr0 + nr) of column li
-    t.lr0 = t.T * ZT_ROWS + (uint64_t)lane * ZT_LANE + (uint64_t)wid * ZT_R;
-    t.nr = t.lr0 >= a.rows ? 0u : (uint32_t)min((uint64_t)ZT_R, a.rows - t.lr0);
+    t.b = (t.T * 32 + (uint64_t)lane) * ZB_W + t.w;
+    t.lr0 = t.b * ZB_R;
+    t.nr = t.lr0 >= a.rows ? 0u : (uint32_t)min((uint64_t)ZB_R, a.rows - t.lr0);
     t.row0 = a.row_begin + t.lr0;
-    t.rk = lane * ZT_W + wid;  // rank of my rows among the CTA's threads
-    t.z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
     t.cx.l = t.l;
     t.cx.ln = t.cx.sn = 0;
     t.cx.vo = 0;
@@ -213,26 +213,22 @@ __device__ __forceinline__ void z_thread_setup(const ZScanArgs &a, uint32_t tick
         t.cx.ln = (uint64_t)t.l * a.sh.n();
     }
     span_mask(a.mask + (size_t)t.li * a.mstride, (a.rows + 31) >> 5, t.lr0, t.nr, t.mb);
+    return true;
 }
 
-constexpr uint32_t ZS_BURST = 4;  // rows per thread staged between two cooperative stores (one line)
-constexpr size_t ZS_SMEM = (size_t)ZT_W * ZS_BURST * 32 * sizeof(fr_t);
+constexpr int ZB_T = 128;  // threads per CTA (4 independent warps)
 #ifndef ZTOT_OCC
-#define ZTOT_OCC 2
+#define ZTOT_OCC 8
 #endif
-#ifndef ZSCAN_OCC
-#define ZSCAN_OCC 2
+#ifndef ZWRITE_OCC
+#define ZWRITE_OCC 8
 #endif
 
-// thread totals in row order + the tile aggregate (flag state 1)
 template <int SRC>
-__global__ void __launch_bounds__(ZT_T, ZTOT_OCC) k_z_totals(const __grid_constant__ ZScanArgs a) {
-    __shared__ fr_t s_w[ZT_W];
-    __shared__ uint32_t s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_cnt = 0;
-    ZThread t;
-    z_thread_setup<SRC>(a, blockIdx.x, t);
+__global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_constant__ ZScanArgs a) {
+    ZBlock t;
+    if (!z_block_setup<SRC>(a, (uint64_t)blockIdx.x * (ZB_T / 32) + (threadIdx.x >> 5), t)) return;
+    const uint64_t *__restrict__ z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
     // software pipeline over the non-constant rows: code of row i+2, factor of row i+1, multiply i
     fr_t tot = fr_one();
     RowIter it(t.mb);
@@ -240,7 +236,7 @@ __global__ void __launch_bounds__(ZT_T, ZTOT_OCC) k_z_totals(const __grid_consta
     uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
     uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
     fr_t f1 = fr_one();
-    if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, t.z);
+    if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
 #pragma unroll 1
     while (q1 >= 0) {
         const fr_t f = f1;
@@ -248,52 +244,24 @@ __global__ void __launch_bounds__(ZT_T, ZTOT_OCC) k_z_totals(const __grid_consta
         c1 = c2;
         q2 = it.next();
         if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
-        if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, t.z);
+        if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
         tot = fr_mul_inline(tot, f);
     }
-    fr_st(a.tot + t.slot * ZT_T + t.rk, tot);
-    // tile aggregate: product of everything (order is irrelevant)
-    fr_t p = tot;
-#pragma unroll 1
-    for (int d = 16; d > 0; d >>= 1) p = fr_mul(p, fr_shfl_xor(p, d));
-    if (lane == 0) fr_st(&s_w[wid], p);
-    uint32_t c = __popc(t.mb[0]) + __popc(t.mb[1]) + __popc(t.mb[2]);
+    if (t.nr) fr_st(a.tot + (size_t)t.li * a.n_blocks + t.b, tot);
+    if (a.nonconst) {
+        uint32_t c = __popc(t.mb[0]) + __popc(t.mb[1]) + __popc(t.mb[2]);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    __syncthreads();
-    if (lane == 0 && c) atomicAdd(&s_cnt, c);
-    if (wid == 0) {
-        fr_t w = lane < ZT_W ? fr_ld(&s_w[lane]) : fr_one();
-#pragma unroll 1
-        for (int d = ZT_W / 2; d > 0; d >>= 1) w = fr_mul(w, fr_shfl_xor(w, d));
-        if (lane == 0) {
-            fr_st_cg(a.agg + t.slot, w);
-            __threadfence();
-            st_volatile_u32(a.flag + t.slot, 2u * ld_volatile_u32(a.ctl + 2) + 1u);
-        }
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(a.nonconst + t.l, (unsigned long long)c);
     }
-    __syncthreads();
-    if (a.nonconst && tid == 0 && s_cnt) atomicAdd(a.nonconst + t.l, (unsigned long long)s_cnt);
 }
 
-// partial[l] = product of the tile aggregates of lookup l (row-sharded circuit: the shard's
-// partial product, exchanged before k_z_scan)
-__global__ void __launch_bounds__(32) k_z_partial(const __grid_constant__ ZScanArgs a) {
-    const int li = blockIdx.x, lane = threadIdx.x;
-    fr_t p = fr_one();
-    for (uint64_t T = lane; T < a.n_tiles; T += 32)
-        p = fr_mul(p, fr_ld_cg(a.agg + (size_t)li * a.n_tiles + T));
-#pragma unroll 1
-    for (int d = 16; d > 0; d >>= 1) p = fr_mul(p, fr_shfl_xor(p, d));
-    if (lane == 0) fr_st(a.partial + a.first_lookup + li, p);
-}
-
-template <int SRC>
-__global__ void __launch_bounds__(ZT_T, ZSCAN_OCC) k_z_scan(const __grid_constant__ ZScanArgs a) {
-    __shared__ fr_t s_x[ZT_T];      // thread prefixes in row order
-    extern __shared__ uint4 s_dyn[];
-    fr_t *s_stage = reinterpret_cast<fr_t *>(s_dyn);  // [ZT_W][ZS_BURST][32] rows on their way out
-    __shared__ fr_t s_w[ZT_W];      // warp totals, then warp exclusive prefixes (times the tile prefix)
+// ---------------------------------------------------------------------------------------------
+// k_z_prefix: tot[] -> exclusive prefixes (times the carry-in), single pass, decoupled look-back
+// ---------------------------------------------------------------------------------------------
+constexpr int ZP_T = 256, ZP_E = 4, ZP_TILE = ZP_T * ZP_E;
+__global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScanArgs a) {
+    __shared__ fr_t s_w[ZP_T / 32];
     __shared__ uint32_t s_ticket, s_epoch;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -301,120 +269,91 @@ __global__ void __launch_bounds__(ZT_T, ZSCAN_OCC) k_z_scan(const __grid_constan
         s_epoch = ld_volatile_u32(a.ctl + 2);
     }
     __syncthreads();
+    // tickets in tile order, all columns advancing together: a tile only waits on running tiles
     const uint32_t ep2 = 2u * s_epoch;
-    ZThread t;
-    z_thread_setup<SRC>(a, s_ticket, t);
-    const uint32_t usable = (uint32_t)a.sh.usable();
-
-    // ---- exclusive scan of the tile's thread totals (rank order = thread order here) -----------
-    const fr_t mine = fr_ld(a.tot + t.slot * ZT_T + tid);
-    fr_t inc = mine;
+    const int li = (int)(s_ticket % (uint32_t)a.count);
+    const uint64_t T = s_ticket / (uint32_t)a.count;
+    const size_t slot = (size_t)li * a.n_ptiles + T;
+    const int l = a.first_lookup + li;
+    fr_t *__restrict__ x = a.tot + (size_t)li * a.n_blocks;
+    const uint64_t base = T * ZP_TILE + (uint64_t)tid * ZP_E;
+    fr_t v[ZP_E];
+    fr_t p = fr_one();
+#pragma unroll
+    for (int j = 0; j < ZP_E; ++j) {
+        v[j] = base + j < a.n_blocks ? fr_ld(x + base + j) : fr_one();
+        p = j == 0 ? v[0] : fr_mul(p, v[j]);
+    }
+    fr_t inc = p;
 #pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         const fr_t y = fr_shfl_up(inc, d);
         if (lane >= d) inc = fr_mul(inc, y);
     }
-    if (lane == 31) fr_st(&s_w[wid], inc);
+    if (lane == 31) s_w[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        const fr_t wt = lane < ZT_W ? fr_ld(&s_w[lane]) : fr_one();
+        constexpr int NW = ZP_T / 32;
+        const fr_t wt = lane < NW ? s_w[lane] : fr_one();
         fr_t winc = wt;
 #pragma unroll 1
-        for (int d = 1; d < ZT_W; d <<= 1) {
+        for (int d = 1; d < NW; d <<= 1) {
             const fr_t y = fr_shfl_up(winc, d);
             if (lane >= d) winc = fr_mul(winc, y);
         }
-        const fr_t aggv = fr_shfl_idx(winc, ZT_W - 1);
+        const fr_t aggv = fr_shfl_idx(winc, NW - 1);
         fr_t wex = fr_shfl_up(winc, 1);
         if (lane == 0) wex = fr_one();
-        // ---- decoupled look-back over the aggregates (state 1, all published by k_z_totals) and
-        //      the inclusive prefixes (state 2) of the tiles before this one ----------------------
+        // ---- decoupled look-back ----------------------------------------------------------------
         fr_t excl = fr_one();
-        if (t.T == 0) {
-            if (a.carry_in) excl = fr_ld(a.carry_in + t.l);
+        if (T == 0) {
+            if (a.carry_in) excl = fr_ld(a.carry_in + l);
         } else {
-            int64_t p = (int64_t)t.T - 1;
+            if (lane == 0) {
+                fr_st_cg(a.agg + slot, aggv);
+                __threadfence();
+                st_volatile_u32(a.flag + slot, ep2 + 1u);
+            }
+            int64_t pp = (int64_t)T - 1;
             while (true) {
-                const int64_t tt = p - lane;
+                const int64_t tt = pp - lane;
                 uint32_t st;
                 do {
-                    st = tt >= 0 ? ld_volatile_u32(a.flag + (size_t)t.li * a.n_tiles + tt) - ep2 : 2u;
+                    st = tt >= 0 ? ld_volatile_u32(a.flag + (size_t)li * a.n_ptiles + tt) - ep2 : 2u;
                 } while (__any_sync(0xffffffffu, st - 1u > 1u));
                 __threadfence();
                 const uint32_t have_inc = __ballot_sync(0xffffffffu, st == 2u);
                 const int j = have_inc ? __ffs(have_inc) - 1 : 31;  // nearest inclusive prefix
-                fr_t v = fr_one();  // (the "tile" before tile 0 holds the carry-in as its inclusive prefix)
+                fr_t u = fr_one();  // (the "tile" before tile 0 holds the carry-in)
                 if (lane <= j && tt >= 0)
-                    v = fr_ld_cg((st == 2u ? a.inc : a.agg) + (size_t)t.li * a.n_tiles + tt);
+                    u = fr_ld_cg((st == 2u ? a.inc : a.agg) + (size_t)li * a.n_ptiles + tt);
                 else if (lane <= j && tt == -1 && a.carry_in)
-                    v = fr_ld(a.carry_in + t.l);
+                    u = fr_ld(a.carry_in + l);
 #pragma unroll 1
-                for (int d = 16; d > 0; d >>= 1) v = fr_mul(v, fr_shfl_xor(v, d));
-                excl = fr_mul(excl, v);
+                for (int d = 16; d > 0; d >>= 1) u = fr_mul(u, fr_shfl_xor(u, d));
+                excl = fr_mul(excl, u);
                 if (have_inc) break;
-                p -= 32;
+                pp -= 32;
             }
         }
+        const fr_t incl = fr_mul(excl, aggv);
         if (lane == 0) {
-            fr_st_cg(a.inc + t.slot, fr_mul(excl, aggv));
+            fr_st_cg(a.inc + slot, incl);
             __threadfence();
-            st_volatile_u32(a.flag + t.slot, ep2 + 2u);
+            st_volatile_u32(a.flag + slot, ep2 + 2u);
+            if (a.partial && T + 1 == a.n_ptiles) fr_st(a.partial + l, incl);
         }
-        if (lane < ZT_W) fr_st(&s_w[lane], fr_mul(excl, wex));
+        if (lane < NW) s_w[lane] = fr_mul(excl, wex);
     }
     __syncthreads();
-    fr_t before = fr_shfl_up(inc, 1);
-    if (lane == 0) before = fr_one();
-    fr_st(&s_x[tid], fr_mul(fr_ld(&s_w[wid]), before));  // exclusive prefix of rank `tid`
-    __syncthreads();
-
-    // ---- Z[row] = running product; it changes only after a non-constant row ---------------------
-    // Z has n-5 deterministic entries (rows 0..usable); the last 5 are blinding rows (zero).
-    // A thread's rows are consecutive but the lanes of a warp are 1360 rows apart, so the values go
-    // through shared memory four rows at a time and leave as whole 128-byte lines: lane l stores
-    // row l%4 of the burst of lane 8i + l/4 (i = 0..3), 8 lines per store instruction instead of
-    // 32 sectors in 32 different lines.
-    fr_t cur = fr_ld(&s_x[t.rk]);
-    const fr_t zero = fr_zero();
-    fr_t *__restrict__ stage = s_stage + wid * (ZS_BURST * 32);
-    const uint64_t lrw0 = t.T * ZT_ROWS + (uint64_t)wid * ZT_R;          // lane 0's first local row
-    uint64_t *__restrict__ zw = a.Z + ((size_t)t.li * a.rows + lrw0) * 4;  // ... and its Z slot
-    const uint64_t *__restrict__ z = t.z;
-    // software pipeline over the non-constant rows: code of row i+2, factor of row i+1
-    RowIter it(t.mb);
-    int q1 = it.next(), q2 = it.next();
-    uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
-    uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
-    fr_t f1 = fr_one();
-    if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
-#pragma unroll 1
-    for (uint32_t r = 0; r < ZT_R; ++r) {
-        const uint32_t jj = r & (ZS_BURST - 1);
-        const bool ok = r < t.nr && (uint32_t)((t.row0 + r) & a.col_mask) <= usable;
-        fr_st(stage + jj * 32 + lane, ok ? cur : zero);
-        if ((int)r == q1) {  // (the factor was fetched before any lane overwrites its slot)
-            const fr_t f = f1;
-            q1 = q2;
-            c1 = c2;
-            q2 = it.next();
-            if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
-            if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
-            cur = fr_mul_inline(cur, f);
-        }
-        if (jj == ZS_BURST - 1 || r == ZT_R - 1) {
-            __syncwarp();
-            const uint32_t j2 = lane & (ZS_BURST - 1), rr = r - jj + j2;
+    fr_t run = fr_shfl_up(inc, 1);
+    if (lane == 0) run = fr_one();
+    run = fr_mul(run, s_w[wid]);
 #pragma unroll
-            for (int i = 0; i < ZS_BURST; ++i) {
-                const uint32_t tt = (32 / ZS_BURST) * i + (lane / ZS_BURST);
-                const uint64_t lrow = lrw0 + (uint64_t)tt * ZT_LANE + rr;
-                if (j2 <= jj && lrow < a.rows)
-                    fr_store_256(zw + ((size_t)tt * ZT_LANE + rr) * 4, fr_ld(stage + j2 * 32 + tt));
-            }
-            __syncwarp();
-        }
+    for (int j = 0; j < ZP_E; ++j) {
+        if (base + j < a.n_blocks) fr_st(x + base + j, run);
+        if (j + 1 < ZP_E) run = fr_mul(run, v[j]);
     }
-
     // the last CTA to finish rearms the control block for the next scan
     if (tid == 0) {
         __threadfence();
@@ -425,6 +364,76 @@ __global__ void __launch_bounds__(ZT_T, ZSCAN_OCC) k_z_scan(const __grid_constan
             a.ctl[2] = s_epoch + 1u;
             __threadfence();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_z_write: Z[row] = running product from the block's exclusive prefix
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t ZS_BURST = 4;  // rows per thread staged between two cooperative stores (one line)
+template <int SRC>
+__global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_constant__ ZScanArgs a) {
+    __shared__ uint4 s_stage[ZB_T / 32][ZS_BURST * 32 * 2];  // (uint4: the type it is accessed as)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ZBlock t;
+    if (!z_block_setup<SRC>(a, (uint64_t)blockIdx.x * (ZB_T / 32) + wid, t)) return;
+    const uint32_t usable = (uint32_t)a.sh.usable();
+    // Z has n-5 deterministic entries (rows 0..usable); the last 5 are blinding rows (zero).
+    // A thread's rows are consecutive but the lanes of a warp are 1360 rows apart, so the values go
+    // through shared memory four rows at a time and leave as whole 128-byte lines: lane l stores
+    // row l%4 of the burst of lane 8i + l/4 (i = 0..3), 8 lines per store instruction instead of
+    // 32 sectors in 32 different lines.
+    fr_t cur = fr_one();
+    if (t.nr) cur = fr_ld(a.tot + (size_t)t.li * a.n_blocks + t.b);
+    const fr_t zero = fr_zero();
+    uint4 *stage = s_stage[wid];
+    const uint64_t lrw0 = (t.T * 32 * ZB_W + t.w) * ZB_R;                  // lane 0's first local row
+    uint64_t *zw = a.Z + ((size_t)t.li * a.rows + lrw0) * 4;  // ... and its Z slot
+    const uint64_t *z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
+    // software pipeline over the non-constant rows: code of row i+2, factor of row i+1
+    RowIter it(t.mb);
+    int q1 = it.next(), q2 = it.next();
+    uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
+    uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
+    fr_t f1 = fr_one();
+    if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+#pragma unroll 1
+    for (uint32_t r = 0; r < ZB_R; ++r) {
+        const uint32_t jj = r & (ZS_BURST - 1);
+        const bool ok = r < t.nr && (uint32_t)((t.row0 + r) & a.col_mask) <= usable;
+#ifdef ZWRITE_DIRECT
+        if (r < t.nr) fr_store_256(a.Z + ((size_t)t.li * a.rows + t.lr0 + r) * 4, ok ? cur : zero);
+#else
+        {
+            const fr_t o = ok ? cur : zero;
+            stage[2 * (jj * 32 + lane)] = make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]);
+            stage[2 * (jj * 32 + lane) + 1] = make_uint4(o.v[4], o.v[5], o.v[6], o.v[7]);
+        }
+#endif
+        if ((int)r == q1) {  // (the factor was fetched before any lane overwrites its slot)
+            const fr_t f = f1;
+            q1 = q2;
+            c1 = c2;
+            q2 = it.next();
+            if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
+            if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+            cur = fr_mul_inline(cur, f);
+        }
+#ifndef ZWRITE_DIRECT
+        if (jj == ZS_BURST - 1 || r == ZB_R - 1) {
+            __syncwarp();
+            const uint32_t j2 = lane & (ZS_BURST - 1), rr = r - jj + j2;
+#pragma unroll
+            for (int i = 0; i < (int)ZS_BURST; ++i) {
+                const uint32_t tt = (32 / ZS_BURST) * i + (lane / ZS_BURST);
+                const uint64_t lrow = lrw0 + (uint64_t)tt * ZT_LANE + rr;
+                if (j2 <= jj && lrow < a.rows)
+                    store_256(zw + ((size_t)tt * ZT_LANE + rr) * 4, stage[2 * (j2 * 32 + tt)],
+                              stage[2 * (j2 * 32 + tt) + 1]);
+            }
+            __syncwarp();
+        }
+#endif
     }
 }
 
@@ -442,19 +451,6 @@ __global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, 
 // launchers
 // ---------------------------------------------------------------------------------------------
 static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
-
-// k_z_scan stages its stores in 64 KB of dynamic shared memory (two CTAs per SM)
-static cudaError_t scan_smem_optin() {
-    static bool done = false;
-    if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_z_scan<ZSRC_LOOKUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ZS_SMEM);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_z_scan<ZSRC_BUFFER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ZS_SMEM);
-    done = e == cudaSuccess;
-    return e;
-}
 
 static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
                              uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
@@ -477,6 +473,8 @@ static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t 
     a.rows = row_end - row_begin;
     a.col_mask = c->sh.n() - 1;
     a.n_tiles = zscan_tiles(a.rows);
+    a.n_blocks = zscan_blocks(a.rows);
+    a.n_ptiles = (a.n_blocks + ZP_TILE - 1) / ZP_TILE;
     a.carry_in = carry_in;
     a.partial = c->d_partial;
     a.nonconst = c->d_znonconst;
@@ -484,8 +482,11 @@ static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t 
     a.ctl = c->d_zctl;
     return a;
 }
+static inline unsigned block_grid(const ZScanArgs &a) {  // one warp per (column, row tile, slice)
+    return cdiv(a.n_tiles * (uint64_t)a.count * ZB_W, ZB_T / 32);
+}
 
-// factors of the rows that are not table entries, then thread totals + tile aggregates
+// factors of the rows that are not table entries, then the block totals
 static cudaError_t launch_totals(h2aes_circuit *c, const ZScanArgs &a) {
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
@@ -498,9 +499,17 @@ static cudaError_t launch_totals(h2aes_circuit *c, const ZScanArgs &a) {
     k_z_general<<<dim3(gx, a.count), ZG_T, 0, s>>>(a);
     prof_end(ctx);
     prof_begin(ctx, "k_z_totals");
-    k_z_totals<ZSRC_LOOKUP><<<(unsigned)(a.n_tiles * a.count), ZT_T, 0, s>>>(a);
+    k_z_totals<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, s>>>(a);
     prof_end(ctx);
     ctx->launches += 2;
+    return cudaGetLastError();
+}
+static cudaError_t launch_prefix(h2aes_circuit *c, const ZScanArgs &a) {
+    h2aes_ctx *ctx = c->ctx;
+    prof_begin(ctx, "k_z_prefix");
+    k_z_prefix<<<(unsigned)(a.n_ptiles * a.count), ZP_T, 0, ctx->stream>>>(a);
+    prof_end(ctx);
+    ctx->launches += 1;
     return cudaGetLastError();
 }
 
@@ -511,38 +520,45 @@ cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *ca
     const ZScanArgs a = lookup_args(c, first, count, carry_in, Z, row_begin, row_end);
     cudaError_t e = launch_totals(c, a);
     if (e) return e;
-    if (cudaError_t es = scan_smem_optin()) return es;
-    prof_begin(ctx, "k_z_scan");
-    k_z_scan<ZSRC_LOOKUP><<<(unsigned)(a.n_tiles * count), ZT_T, ZS_SMEM, ctx->stream>>>(a);
+    if ((e = launch_prefix(c, a))) return e;
+    prof_begin(ctx, "k_z_write");
+    k_z_write<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
 }
 
-// row-sharded circuit, first half: thread totals and tile aggregates of the shard's rows stay in
-// the workspace, partial[l] = product of the shard's factors
+// row-sharded circuit, first half: the block prefixes of the shard's rows (without the carry of
+// the shards before it) stay in the workspace, partial[l] = product of the shard's factors
 cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
-    h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
     const ZScanArgs a = lookup_args(c, 0, L, nullptr, Z, row_begin, row_end);
     cudaError_t e = launch_totals(c, a);
     if (e) return e;
-    prof_begin(ctx, "k_z_partial");
-    k_z_partial<<<L, 32, 0, ctx->stream>>>(a);
-    prof_end(ctx);
-    ctx->launches += 1;
-    return cudaGetLastError();
+    return launch_prefix(c, a);
 }
 
-// second half: Z from the stored totals, starting from the carry of the shards before this one
+// second half: fold the carry of the shards before this one into the prefixes, then write Z
+__global__ void __launch_bounds__(256) k_z_carry(const __grid_constant__ ZScanArgs a) {
+    const int li = blockIdx.y;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_blocks) return;
+    fr_t *p = a.tot + (size_t)li * a.n_blocks + i;
+    fr_st(p, fr_mul(fr_ld(p), fr_ld(a.carry_in + a.first_lookup + li)));
+}
 cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, uint64_t row_begin,
                             uint64_t row_end) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
     const ZScanArgs a = lookup_args(c, 0, L, carry_in, Z, row_begin, row_end);
-    if (cudaError_t es = scan_smem_optin()) return es;
-    prof_begin(ctx, "k_z_scan");
-    k_z_scan<ZSRC_LOOKUP><<<(unsigned)(a.n_tiles * L), ZT_T, ZS_SMEM, ctx->stream>>>(a);
+    if (carry_in) {
+        prof_begin(ctx, "k_z_carry");
+        k_z_carry<<<dim3(cdiv(a.n_blocks, 256), L), 256, 0, ctx->stream>>>(a);
+        prof_end(ctx);
+        ctx->launches += 1;
+    }
+    prof_begin(ctx, "k_z_write");
+    k_z_write<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -558,11 +574,12 @@ cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const 
     a.partial = nullptr;
     a.nonconst = nullptr;
     prof_begin(ctx, "k_z_totals");
-    k_z_totals<ZSRC_BUFFER><<<(unsigned)a.n_tiles, ZT_T, 0, ctx->stream>>>(a);
+    k_z_totals<ZSRC_BUFFER><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
-    if (cudaError_t es = scan_smem_optin()) return es;
-    prof_begin(ctx, "k_z_scan");
-    k_z_scan<ZSRC_BUFFER><<<(unsigned)a.n_tiles, ZT_T, ZS_SMEM, ctx->stream>>>(a);
+    cudaError_t e = launch_prefix(c, a);
+    if (e) return e;
+    prof_begin(ctx, "k_z_write");
+    k_z_write<ZSRC_BUFFER><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();

@@ -117,18 +117,21 @@ __device__ __forceinline__ fr_t fr_shfl_idx(const fr_t &a, int src) {
 }
 #endif
 
-// ---- grand-product scan (gprod.cu): balanced tiles + decoupled look-back -----------------------
-// A tile is 32 x AES_ROWS consecutive rows.  Lane l of every warp works inside rows
-// [1360 l, 1360 l + 1360) of the tile and warp w on the ZT_R rows starting at ZT_R * w of that
-// range, so the 32 lanes of a warp sit at the SAME block-relative rows of 32 different AES blocks:
-// they see the same selector pattern and execute the same number of multiplies.
-constexpr int ZT_W = 16;                                  // warps per CTA
-constexpr int ZT_T = ZT_W * 32;                           // threads per CTA
+// ---- grand-product scan (gprod.cu) ----------------------------------------------------------------
+// A column is cut into blocks of ZB_R consecutive rows (one thread each).  The 32 lanes of a warp
+// take blocks that are AES_ROWS rows apart, so they sit at the SAME block-relative rows of 32
+// different AES blocks: same selector pattern, same number of multiplies.  A row tile = 32 x
+// AES_ROWS rows = ZB_W warps' worth of blocks.
+#ifndef ZB_ROWS
+#define ZB_ROWS 40
+#endif
 constexpr uint32_t ZT_LANE = (uint32_t)AES_ROWS;          // rows between two lanes of a warp
-constexpr uint32_t ZT_R = ZT_LANE / ZT_W;                 // consecutive rows per thread (85)
-constexpr uint32_t ZT_ROWS = 32u * ZT_LANE;               // rows per tile (43520)
-static_assert(ZT_R * ZT_W == ZT_LANE, "the warps of a CTA partition one AES block's rows");
-static_assert(ZT_R <= 96, "three 32-bit mask words per thread");
+constexpr uint32_t ZB_R = ZB_ROWS;                        // consecutive rows per thread
+constexpr uint32_t ZB_W = ZT_LANE / ZB_R;                 // warps per row tile (34)
+constexpr uint32_t ZT_ROWS = 32u * ZT_LANE;               // rows per row tile (43520)
+static_assert(ZB_R * ZB_W == ZT_LANE, "the blocks of a lane partition one AES block's rows");
+static_assert(ZB_R <= 96, "three 32-bit mask words per thread");
+H2_HD uint64_t zscan_blocks(uint64_t rows) { return (rows + ZB_R - 1) / ZB_R; }
 H2_HD uint64_t zscan_tiles(uint64_t rows) { return (rows + ZT_ROWS - 1) / ZT_ROWS; }
 
 }  // namespace h2
@@ -216,12 +219,12 @@ struct h2aes_circuit {
     // grand-product scan workspace
     unsigned long long *d_znonconst = nullptr;  // [L] rows whose factor is not one (last product)
     uint32_t *d_zmask = nullptr;      // [L][zm] one bit per row: factor is not one
-    h2::fr_t *d_ztot = nullptr;      // [ztiles][ZT_T] thread totals in row order (k_z_totals -> k_z_scan)
-    h2::fr_t *d_zagg = nullptr;       // [ztiles] look-back: tile aggregates
-    h2::fr_t *d_zinc = nullptr;       // [ztiles] look-back: inclusive prefixes
-    uint32_t *d_zflag = nullptr;      // [ztiles] look-back: 2*epoch + {1: aggregate, 2: inclusive}
+    h2::fr_t *d_ztot = nullptr;       // [L][zblocks] block totals, then their exclusive prefixes
+    h2::fr_t *d_zagg = nullptr;       // [ztiles] look-back of k_z_prefix: tile aggregates
+    h2::fr_t *d_zinc = nullptr;       // [ztiles] inclusive prefixes
+    uint32_t *d_zflag = nullptr;      // [ztiles] 2*epoch + {1: aggregate, 2: inclusive}
     uint32_t *d_zctl = nullptr;       // [4] ticket, finished CTAs, epoch (device-resident: graph replay safe)
-    uint64_t ztiles = 0;              // tiles the look-back workspace holds
+    uint64_t ztiles = 0, zblocks = 0; // look-back tiles / block totals the workspace holds
     uint32_t *d_err = nullptr;        // device error flags: [0] zero denominator, [1] not in table
     uint32_t *h_err = nullptr;        // pinned mirror of d_err
     h2::fr_t *d_partial = nullptr;    // [L] shard partial products
