@@ -424,6 +424,24 @@ FR_D void fr_store_256(uint64_t *p, const fr_t &a) {
                  "r"(a.v[7])
                  : "memory");
 }
+// the same for the bulk output columns, which nothing on the GPU reads back soon: evict-first in
+// L2 (STG.E.EF), so that the streams of A', S', Z and advice cells do not flush the per-bin tables
+// and the factor codes the next kernels gather from
+#ifndef H2_STREAM_HINT
+#define H2_STREAM_HINT ".cs"
+#endif
+FR_D void fr_store_256_cs(uint64_t *p, const fr_t &a) {
+    asm volatile("st.global" H2_STREAM_HINT ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+                 "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]),
+                 "r"(a.v[6]), "r"(a.v[7])
+                 : "memory");
+}
+FR_D void store_256_cs(uint64_t *p, const uint4 &lo, const uint4 &hi) {
+    asm volatile("st.global" H2_STREAM_HINT ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+                 "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z),
+                 "r"(hi.w)
+                 : "memory");
+}
 FR_D void store_256(uint64_t *p, const uint4 &lo, const uint4 &hi) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x),
                  "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)

@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
                 const uint32_t tt = (32 / ZS_BURST) * i + (lane / ZS_BURST);
                 const uint64_t lrow = lrw0 + (uint64_t)tt * ZT_LANE + rr;
                 if (j2 <= jj && lrow < a.rows)
-                    store_256(zw + ((size_t)tt * ZT_LANE + rr) * 4, stage[2 * (j2 * 32 + tt)],
+                    store_256_cs(zw + ((size_t)tt * ZT_LANE + rr) * 4, stage[2 * (j2 * 32 + tt)],
                               stage[2 * (j2 * 32 + tt) + 1]);
             }
             __syncwarp();

@@ -21,6 +21,7 @@
 #include "internal.h"
 
 namespace h2 {
+size_t stream_pad_bytes(const void *func);
 cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const uint32_t *mask);
 
 // ---------------------------------------------------------------------------------------------
@@ -614,28 +615,28 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
         uint32_t code = fcode_pack(FK_ONE, 0, 0), kin = 0, kp = 0;
         if (row >= usable) {
-            if (A) fr_store_256(A + o, zero);
-            if (S) fr_store_256(S + o, zero);
+            if (A) fr_store_256_cs(A + o, zero);
+            if (S) fr_store_256_cs(S + o, zero);
             if (Ap) {
-                fr_store_256(Ap + o, zero);
-                fr_store_256(Sp + o, zero);
+                fr_store_256_cs(Ap + o, zero);
+                fr_store_256_cs(Sp + o, zero);
             }
         } else {
             if (A) {
                 const uint32_t w = trace[(uint64_t)set * n + row];
                 fr_t a = zero;
                 if ((w >> 24) == op) a = fr_ld(valv + entry_of_table_row(v, table_row_of_word(w)));
-                fr_store_256(A + o, a);
+                fr_store_256_cs(A + o, a);
             }
             if (S) {
                 const uint32_t e = row < TABLE_ROWS ? entry_of_table_row(v, (uint32_t)row) : 0u;
-                fr_store_256(S + o, fr_ld(valv + e));
+                fr_store_256_cs(S + o, fr_ld(valv + e));
             }
             const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
             kp = rb.kp;
             if (Ap) {
-                fr_store_256(Ap + o, fr_ldg_256_nc(dv + rb.k));
-                fr_store_256(Sp + o, fr_ldg_256_nc(dv + rb.kp));
+                fr_store_256_cs(Ap + o, fr_ldg_256_nc(dv + rb.k));
+                fr_store_256_cs(Sp + o, fr_ldg_256_nc(dv + rb.kp));
             }
             // classify the row's grand-product factor (see fcode_pack)
             const uint32_t t = tk[row];
@@ -885,8 +886,9 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     dim3 g(gx, count);
     cudaError_t e0 = cudaMemsetAsync(c->d_gcount + first, 0, (size_t)count * 4, ctx->stream);
     if (e0) return e0;
+    const size_t pad = stream_pad_bytes((const void *)k_permuted);
     prof_begin(ctx, "k_permuted");
-    k_permuted<<<g, 256, 0, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
+    k_permuted<<<g, 256, pad, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
                                            c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S,
                                            Ap, Sp, c->d_codek, c->d_glist, c->d_gbase,
                                            c->d_gcount, c->d_err, c->d_zmask, c->zm,

@@ -14,6 +14,8 @@
 //                    (3*sets+1) * 2^k * 32 bytes per circuit.
 //   k_fixed          table columns, round_constants and selector columns (input independent).
 //   k_copies         the copy-constraint list (closed form).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace h2 {
@@ -144,12 +146,12 @@ k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const uint32_t b = (word >> (8 * j)) & 255u;
-                store_256(o + (uint64_t)j * out_rows * 4, s_fr[2 * b], s_fr[2 * b + 1]);
+                store_256_cs(o + (uint64_t)j * out_rows * 4, s_fr[2 * b], s_fr[2 * b + 1]);
             }
         } else {
             const uint32_t b = row < (uint64_t)WORDS_ROWS ? ks_words_byte(s_rk, (uint32_t)row) : 0;
             uint64_t *o = advice + ((uint64_t)(3 * nsets) * out_rows + lrow) * 4;
-            store_256(o, s_fr[2 * b], s_fr[2 * b + 1]);
+            store_256_cs(o, s_fr[2 * b], s_fr[2 * b + 1]);
         }
     }
 }
@@ -226,6 +228,19 @@ __global__ void k_build_frtab(uint4 *__restrict__ frtab) {
 }
 
 // ---- launchers -----------------------------------------------------------------------------
+// H2AES_STREAM_PAD_KB (tuning): unused dynamic shared memory requested by the HBM-bound streaming
+// kernels, which caps how many of their CTAs an SM holds and leaves registers / warp slots for
+// the multiply-bound kernels of the next circuit in flight.
+size_t stream_pad_bytes(const void *func) {
+    static int kb = -1;
+    if (kb < 0) {
+        const char *s = getenv("H2AES_STREAM_PAD_KB");
+        kb = s ? atoi(s) : 0;
+    }
+    if (kb > 48) cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
+    return (size_t)kb * 1024;
+}
+
 static inline int grid_for(const h2aes_ctx *ctx, int ctas_per_sm) { return ctx->sm_count * ctas_per_sm; }
 
 cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
@@ -249,8 +264,9 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
                                                   c->d_states, cts_dev);
     prof_end(ctx);
     ctx->launches++;
+    const size_t pad = stream_pad_bytes((const void *)k_advice);
     prof_begin(ctx, "k_advice");
-    k_advice<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
+    k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
                                                         ctx->d_sbox, ctx->d_frtab, advice_dev,
                                                         c->d_trace, row_begin, row_end);
     prof_end(ctx);
