@@ -21,6 +21,7 @@ KIND_AES, KIND_KEYSCHED = 0, 1
 SBOX_REFERENCE, SBOX_FIPS197 = 0, 1
 OP_NONE, OP_RANGE, OP_XOR, OP_SBOX, OP_MUL2, OP_MUL3 = 0, 1, 2, 3, 4, 5
 DOMAIN_FFT, DOMAIN_LAGRANGE_TO_COEFF, DOMAIN_COEFF_TO_EXTENDED, DOMAIN_EXTENDED_TO_COEFF = 0, 1, 2, 3
+COMM_ID_BYTES = 128  # an ncclUniqueId
 CS_DEGREE = 5  # cs.degree() of both circuits (lookups: 2 + 2 + 1)
 
 
@@ -133,6 +134,10 @@ SIGNATURES = {
     "h2aes_lookup_permuted_shard_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
     "h2aes_lookup_partial_dev": (C.c_int32, [_vp, _u64p, _u64p, _vp, C.POINTER(_vp)]),
     "h2aes_lookup_product_shard_dev": (C.c_int32, [_vp, _vp, _vp]),
+    "h2aes_comm_unique_id": (C.c_int32, [_u8p]),
+    "h2aes_comm_init": (C.c_int32, [_vp, _u8p, C.c_int32, C.c_int32]),
+    "h2aes_comm_destroy": (C.c_int32, [_vp]),
+    "h2aes_lookup_columns_sharded_dev": (C.c_int32, [_vp, _u64p, _u64p, _u64p, _vp, _vp, _vp]),
     "h2aes_dbg_fr_mul": (C.c_int32, [_u64p, _u64p, _u64p]),
     "h2aes_dbg_fr_add": (C.c_int32, [_u64p, _u64p, _u64p]),
     "h2aes_dbg_fr_sub": (C.c_int32, [_u64p, _u64p, _u64p]),

@@ -64,6 +64,23 @@ class Context:
             out[name] = (int(n), float(ms))
         return out
 
+    # ---- NCCL inside the library (h2aes_comm_*) ------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """the 128-byte id rank 0 ships to every rank before comm_init"""
+        buf = (C.c_uint8 * _ffi.COMM_ID_BYTES)()
+        check(lib().h2aes_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """collective: every rank of the row-sharded circuit calls it with rank 0's id"""
+        assert len(unique_id) == _ffi.COMM_ID_BYTES
+        buf = (C.c_uint8 * _ffi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().h2aes_comm_init(self._h, buf, rank, world), self._h)
+
+    def comm_destroy(self):
+        check(lib().h2aes_comm_destroy(self._h), self._h)
+
     def close(self):
         if getattr(self, "_h", None):
             lib().h2aes_ctx_destroy(self._h)
@@ -298,6 +315,24 @@ class Circuit:
         assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == self.n_shards * L * 4
         check(lib().h2aes_lookup_product_shard_dev(self._h, _ptr(gathered), _ptr(Z)), self.ctx._h)
         return Z
+
+    def lookup_columns_sharded(self, theta, beta=None, gamma=None, want_permuted=True, out=None):
+        """h2aes_lookup_columns_sharded_dev: this shard's rows of A', S' and (with beta, gamma) Z of
+        ALL lookups, both exchanges done by the library over its NCCL communicator."""
+        L = self.layout["n_lookups"]
+        bufs = dict(out or {})
+        names = (["Ap", "Sp"] if want_permuted else []) + (["Z"] if beta is not None else [])
+        for nm in names:
+            if nm not in bufs:
+                bufs[nm] = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
+        th, thp = _fr_arg(theta)
+        be, bep = _fr_arg(beta) if beta is not None else (None, None)
+        ga, gap = _fr_arg(gamma) if gamma is not None else (None, None)
+        check(lib().h2aes_lookup_columns_sharded_dev(
+            self._h, thp, bep, gap, _ptr(bufs.get("Ap")) if want_permuted else None,
+            _ptr(bufs.get("Sp")) if want_permuted else None,
+            _ptr(bufs.get("Z")) if beta is not None else None), self.ctx._h)
+        return bufs
 
     def close(self):
         if getattr(self, "_h", None):

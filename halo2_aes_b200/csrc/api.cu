@@ -338,6 +338,7 @@ int32_t h2aes_ctx_create(int32_t device, int32_t sbox_mode, h2aes_ctx **out) {
 int32_t h2aes_ctx_destroy(h2aes_ctx *ctx) {
     if (!ctx) return H2AES_ERR_ARG;
     cudaSetDevice(ctx->device);
+    if (ctx->comm) h2aes_comm_destroy(ctx);
     for (auto &r : ctx->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -426,7 +427,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
                     c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
-                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_glist,    c->d_gbase,    c->d_gcount,
+                    c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_glist,    c->d_gbase,    c->d_gcount,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
                     c->d_ftab,     c->d_pmap,     c->d_wlo,
                     c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
@@ -434,7 +435,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
                     c->d_ztot,    c->d_zagg,     c->d_zinc,     c->d_zflag,    c->d_zctl,
                     c->d_err,
-                    c->d_partial,  c->d_carry,    c->d_stage,    c->d_pt,       c->d_ct};
+                    c->d_partial,  c->d_carry,    c->d_gathered,    c->d_stage,    c->d_pt,       c->d_ct};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_err) cudaFreeHost(c->h_err);
@@ -669,6 +670,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     c->d_sgz = c->d_ftab + FSEL_SGZ * VB;
     DA(c->d_tracek, (size_t)c->sh.n_sets() * c->sh.n());
     DA(c->d_codek, L * c->sh.n());
+    DA(c->d_codep, L * c->sh.n());
     if (!c->d_gbase) {
         // list of the rows whose grand-product factor is not a table entry (k_permuted ->
         // k_z_general).  Such a row is a table row (< 66561 of them), or lies outside the zero
@@ -698,7 +700,7 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_loffz, LB);
     DA(c->d_lk, LB);
     DA(c->d_meta, L);
-    DA(c->d_zmask, L * c->zm);
+    DA(c->d_zmask, 2 * L * c->zm);  // non-constant rows, then the rows of k_z_general
     DA(c->d_ztot, c->zblocks);
     DA(c->d_zagg, c->ztiles);
     DA(c->d_zinc, c->ztiles);

@@ -40,8 +40,9 @@ struct ZScanArgs {
     // ZSRC_LOOKUP: factors from the per-row codes written by k_permuted
     const uint32_t *tracek;        // [sets][n]  op<<24 | bin of the row's input tuple
     const uint32_t *fcode;         // [L][n]     factor code of every row (k_permuted)
-    const uint4 *glist;            // rows whose factor is not a table entry: (local row, code, bin
-    const uint32_t *gbase, *gcount;//   of A, bin of S'); lookup l at [gbase[l], +gcount[l])
+    const uint32_t *codep;         // [L][n]     bin of S' where it is neither A' nor the padding value
+    const uint32_t *glist;         // local rows whose factor is not a table entry (k_general_list);
+    const uint32_t *gbase, *gcount;//   lookup l at [gbase[l], +gcount[l])
     const fr_t *chal;              // theta, beta, gamma
     const fr_t *val, *dval, *ib, *ig, *nac, *ibg, *ibp;  // [3][BIN_STRIDE]
     const fr_t *ftab;              // [4][3][BIN_STRIDE] nacp, ibgz, ibpz, sgz (k_inv_merge)
@@ -169,12 +170,23 @@ constexpr int ZG_T = 128;
 #endif
 __global__ void __launch_bounds__(ZG_T, ZG_OCC) k_z_general(const __grid_constant__ ZScanArgs a) {
     const int li = blockIdx.y, l = a.first_lookup + li;
+    const int ops = a.sh.ops_per_set();
+    const uint32_t op = (uint32_t)(l % ops) + 1;
+    const uint64_t n = a.sh.n();
     const uint32_t cnt = min(a.gcount[l], a.gbase[l + 1] - a.gbase[l]);
-    const uint4 *__restrict__ gl = a.glist + a.gbase[l];
+    const uint32_t *__restrict__ gl = a.glist + a.gbase[l];
+    const uint32_t *__restrict__ fc = a.fcode + (uint64_t)l * n;
+    const uint32_t *__restrict__ cp = a.codep + (uint64_t)l * n;
+    const uint32_t *__restrict__ tk = a.tracek + (uint64_t)(l / ops) * n;
+    const uint32_t k_zero = a.meta[l].k_zero;
     uint64_t *__restrict__ zout = a.Z + (size_t)li * a.rows * 4;
     for (uint32_t i = blockIdx.x * ZG_T + threadIdx.x; i < cnt; i += gridDim.x * ZG_T) {
-        const uint4 e = __ldg(gl + i);  // (local row, code, bin of A, bin of S')
-        fr_store_256(zout + 4 * (size_t)e.x, general_factor(a, l, a.row_begin + e.x, e.y, e.z, e.w));
+        const uint32_t lrow = __ldg(gl + i);
+        const uint64_t row = a.row_begin + lrow;
+        const uint32_t code = __ldg(fc + row), t = __ldg(tk + row);
+        const uint32_t kin = (t >> 24) == op ? (t & 0xffffffu) : k_zero;  // bin of the row's input value
+        const uint32_t kp = ((code >> 28) & 3u) == CODE_OTHER ? __ldg(cp + row) : 0u;
+        fr_store_256(zout + 4 * (size_t)lrow, general_factor(a, l, row, code, kin, kp));
     }
 }
 
@@ -460,6 +472,7 @@ static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t 
     a.count = count;
     a.tracek = c->d_tracek;
     a.fcode = c->d_codek;
+    a.codep = c->d_codep;
     a.glist = c->d_glist; a.gbase = c->d_gbase; a.gcount = c->d_gcount;
     a.chal = c->d_chal;
     a.val = c->d_val; a.dval = c->d_dval; a.ib = c->d_ib; a.ig = c->d_ig; a.nac = c->d_nac;

@@ -153,6 +153,8 @@ struct h2aes_ctx {
     uint4 *d_frtab = nullptr;    // 256 entries x 32 bytes: byte -> Fr (Montgomery)
     uint64_t launches = 0;
     std::string last_error;
+    void *comm = nullptr;        // ncclComm_t of h2aes_comm_init (comm.cu)
+    int comm_rank = 0, comm_world = 1;
 };
 
 struct h2aes_circuit {
@@ -170,7 +172,8 @@ struct h2aes_circuit {
     uint32_t *d_trace = nullptr;   // n_sets * n words (a0 | a1<<8 | a2<<16 | op<<24)
     uint32_t *d_tracek = nullptr;  // n_sets * n words (op<<24 | bin of the row's tuple), per theta
     uint32_t *d_codek = nullptr;   // [L][n] factor code of every row (fcode_pack), written by k_permuted
-    uint4 *d_glist = nullptr;      // rows whose factor is not a table entry: (local row, code, bin of A, bin of S')
+    uint32_t *d_codep = nullptr;   // [L][n] bin of S' where class == OTHER
+    uint32_t *d_glist = nullptr;   // local rows whose factor is not a table entry (k_general_list)
     uint32_t *d_gbase = nullptr;   // [L+1] first list entry of every lookup (capacity bound, api.cu)
     uint32_t *d_gcount = nullptr;  // [L] entries written by the last k_permuted
     bool *code_valid = nullptr;    // [L] host flags: codes of lookup l match the current bins
@@ -218,7 +221,7 @@ struct h2aes_circuit {
     h2::LookupMeta *d_meta = nullptr;  // [L]
     // grand-product scan workspace
     unsigned long long *d_znonconst = nullptr;  // [L] rows whose factor is not one (last product)
-    uint32_t *d_zmask = nullptr;      // [L][zm] one bit per row: factor is not one
+    uint32_t *d_zmask = nullptr;      // [2][L][zm] one bit per row: factor is not one ; factor is not a table entry
     h2::fr_t *d_ztot = nullptr;       // [L][zblocks] block totals, then their exclusive prefixes
     h2::fr_t *d_zagg = nullptr;       // [ztiles] look-back of k_z_prefix: tile aggregates
     h2::fr_t *d_zinc = nullptr;       // [ztiles] inclusive prefixes
@@ -229,6 +232,7 @@ struct h2aes_circuit {
     uint32_t *h_err = nullptr;        // pinned mirror of d_err
     h2::fr_t *d_partial = nullptr;    // [L] shard partial products
     h2::fr_t *d_carry = nullptr;      // [L] product of the partials of the shards before this one
+    uint64_t *d_gathered = nullptr;   // [64][L][4] every shard's partial products (comm.cu)
     uint64_t zm = 0;
     uint64_t *partial_Z = nullptr;    // Z buffer holding the factors between phases 2a and 2b
 

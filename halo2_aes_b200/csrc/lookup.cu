@@ -578,9 +578,8 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            const uint32_t *__restrict__ nzk_all, const uint32_t *__restrict__ loffz_all,
            const uint32_t *__restrict__ lk_all, const LookupMeta *__restrict__ meta,
            uint64_t *__restrict__ A, uint64_t *__restrict__ S, uint64_t *__restrict__ Ap,
-           uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint4 *__restrict__ glist,
-           const uint32_t *__restrict__ gbase, uint32_t *__restrict__ gcount,
-           uint32_t *__restrict__ err, uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
+           uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint32_t *__restrict__ codep,
+           uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
            const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, uint64_t row_begin,
            uint64_t row_end) {
     const int li = blockIdx.y;            // index inside this call
@@ -600,8 +599,8 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const fr_t *dv = dval + (size_t)v * BIN_STRIDE;
     uint32_t *__restrict__ fc = fcode + (size_t)l * n;
     uint32_t *__restrict__ zmk = zmask + (size_t)l * zm;
-    uint4 *__restrict__ gl = glist + gbase[l];               // rows for k_z_general
-    const uint32_t gcap = gbase[l + 1] - gbase[l];
+    uint32_t *__restrict__ gmk = zmask + ((size_t)sh.n_lookups() + l) * zm;  // rows for k_z_general
+    uint32_t *__restrict__ cp = codep + (size_t)l * n;
     const uint32_t *__restrict__ tk = tracek + (uint64_t)set * n;
     const uint32_t *__restrict__ jidx = jidx_all + (size_t)l * idx_stride;
     const uint32_t *__restrict__ lidx = lidx_all + (size_t)l * idx_stride;
@@ -613,7 +612,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
          lrow += stride) {
         const uint64_t row = row_begin + lrow;
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
-        uint32_t code = fcode_pack(FK_ONE, 0, 0), kin = 0, kp = 0;
+        uint32_t code = fcode_pack(FK_ONE, 0, 0);
         if (row >= usable) {
             if (A) fr_store_256_cs(A + o, zero);
             if (S) fr_store_256_cs(S + o, zero);
@@ -633,7 +632,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
                 fr_store_256_cs(S + o, fr_ld(valv + e));
             }
             const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
-            kp = rb.kp;
+            if (rb.cls == CODE_OTHER) cp[row] = rb.kp;  // (k_z_general reads it for these rows)
             if (Ap) {
                 fr_store_256_cs(Ap + o, fr_ldg_256_nc(dv + rb.k));
                 fr_store_256_cs(Sp + o, fr_ldg_256_nc(dv + rb.kp));
@@ -641,7 +640,6 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
             // classify the row's grand-product factor (see fcode_pack)
             const uint32_t t = tk[row];
             const bool active = (t >> 24) == op;
-            kin = active ? (t & 0xffffffu) : m.k_zero;  // bin of the row's own input value
             const bool in_zero_run = rb.k == m.k_zero && rb.cls == CODE_PAD;
             if (row < TABLE_ROWS) {
                 code = (!active && in_zero_run)
@@ -659,22 +657,43 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
         const int lane = threadIdx.x & 31;
         const uint32_t bal = __ballot_sync(0xffffffffu, (code >> 30) != FK_ONE);
         if (lane == 0) zmk[lrow >> 5] = bal;
-        // rows whose factor is not a table entry: everything k_z_general needs, appended to the
-        // lookup's list (one atomic per warp)
-        const bool gen = (code >> 30) >= FK_GENERAL;
-#ifdef PDBG_NOGEN
-        const uint32_t gbal = 0;
-#else
-        const uint32_t gbal = __ballot_sync(0xffffffffu, gen);
-#endif
-        if (gbal) {
-            uint32_t pos = 0;
-            if (lane == 0) pos = atomicAdd(gcount + l, (uint32_t)__popc(gbal));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(gbal & ((1u << lane) - 1u));
-            if (gen) {
-                if (pos < gcap) gl[pos] = make_uint4((uint32_t)lrow, code, kin, kp);
-                else atomicOr(err + 2, 1u);  // cannot happen: gcap bounds the count (api.cu)
-            }
+        // rows whose factor is not a table entry: one more mask, compacted into a list by
+        // k_general_list before k_z_general evaluates them densely
+        const uint32_t gbal = __ballot_sync(0xffffffffu, (code >> 30) >= FK_GENERAL);
+        if (lane == 0) gmk[lrow >> 5] = gbal;
+    }
+}
+
+// rows flagged in the second mask -> dense list of local row indices per lookup (one atomic per
+// warp = per 1024 rows; the order of the entries is irrelevant)
+__global__ void __launch_bounds__(256)
+k_general_list(int first_lookup, int n_lookups, const uint32_t *__restrict__ zmask, uint64_t zm,
+               uint64_t words, uint32_t *__restrict__ glist, const uint32_t *__restrict__ gbase,
+               uint32_t *__restrict__ gcount, uint32_t *__restrict__ err) {
+    const int l = first_lookup + blockIdx.y;
+    const uint32_t *__restrict__ gmk = zmask + ((size_t)n_lookups + l) * zm;
+    uint32_t *__restrict__ gl = glist + gbase[l];
+    const uint32_t gcap = gbase[l + 1] - gbase[l];
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); w0 < words; w0 += stride) {
+        uint32_t m = w0 + lane < words ? gmk[w0 + lane] : 0u;
+        const uint32_t cnt = __popc(m);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        if (!total) continue;
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(gcount + l, total);
+        pos = __shfl_sync(0xffffffffu, pos, 0) + inc - cnt;
+        const uint32_t row0 = (uint32_t)((w0 + lane) << 5);
+        for (; m; m &= m - 1u, ++pos) {
+            if (pos < gcap) gl[pos] = row0 + (uint32_t)__ffs(m) - 1u;
+            else atomicOr(err + 2, 1u);  // cannot happen: gcap bounds the count (api.cu)
         }
     }
 }
@@ -890,12 +909,19 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     prof_begin(ctx, "k_permuted");
     k_permuted<<<g, 256, pad, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
                                            c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S,
-                                           Ap, Sp, c->d_codek, c->d_glist, c->d_gbase,
-                                           c->d_gcount, c->d_err, c->d_zmask, c->zm,
+                                           Ap, Sp, c->d_codek, c->d_codep, c->d_zmask, c->zm,
                                            c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride, row_begin,
                                            row_end);
     prof_end(ctx);
-    ctx->launches += 1;
+    const uint64_t words = (rows + 31) >> 5;
+    unsigned lx = cdiv(words, 256);
+    if (lx > 64) lx = 64;
+    prof_begin(ctx, "k_general_list");
+    k_general_list<<<dim3(lx, count), 256, 0, ctx->stream>>>(first, c->sh.n_lookups(), c->d_zmask, c->zm,
+                                                               words, c->d_glist, c->d_gbase,
+                                                               c->d_gcount, c->d_err);
+    prof_end(ctx);
+    ctx->launches += 2;
     return cudaGetLastError();
 }
 

@@ -88,12 +88,28 @@ def allgather_commitments(mine: torch.Tensor, n_columns: int, group=None) -> tor
     return torch.cat([out[r, : len(columns_of_rank(n_columns, r, world))] for r in range(world)])
 
 
-class RowShardedCircuit:
-    """One circuit spread over the ranks of `group` by rows."""
+def library_comm_init(ctx, group=None):
+    """Give `ctx` the library's own NCCL communicator (h2aes_comm_init) spanning `group`: rank 0
+    draws the unique id, torch.distributed (any backend) ships its 128 bytes."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group else 0, group=group)
+    ctx.comm_init(box[0], rank, world)
 
-    def __init__(self, ctx, kind: int, k: int, N: int, group=None):
+
+class RowShardedCircuit:
+    """One circuit spread over the ranks of `group` by rows.
+
+    library_comm=False: the two exchanges go through torch.distributed on the buffers the phase
+    entry points expose.  library_comm=True: one call, h2aes_lookup_columns_sharded_dev, with the
+    exchanges done inside the library over its own NCCL communicator (library_comm_init first)."""
+
+    def __init__(self, ctx, kind: int, k: int, N: int, group=None, library_comm: bool = False):
         from .backend import Circuit
         self.group = group
+        self.library_comm = library_comm
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.circuit = Circuit(ctx, kind, k, N)
@@ -112,8 +128,11 @@ class RowShardedCircuit:
     def fixed_columns(self, **kw):
         return self.circuit.fixed_columns(**kw)
 
-    def lookup_columns(self, theta, beta, gamma, want_inputs=False):
+    def lookup_columns(self, theta, beta, gamma, want_inputs=False, out=None):
         c = self.circuit
+        if self.library_comm:
+            assert not want_inputs, "A, S are local data: use Circuit.shard_permuted for them"
+            return c.lookup_columns_sharded(theta, beta, gamma, out=out)
         hist = c.shard_hist(theta)
         allreduce_histogram(hist, self.group)                 # exchange 1
         cols = c.shard_permuted(want_inputs=want_inputs)

@@ -375,6 +375,32 @@ int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathere
                                        uint64_t *Z_dev);
 
 /* ---------------------------------------------------------------------------------------------
+ * The same with the two exchanges done INSIDE the library over NCCL (the
+ * reference has no communication layer at all, this is what a multi-GPU prover built on it would
+ * bind).  libnccl.so.2 is resolved at run time (dlopen) on the first h2aes_comm_* call, so the
+ * library still loads on a box without NCCL; a missing library or a failing NCCL call returns
+ * H2AES_ERR_NCCL with the NCCL error text in h2aes_ctx_last_error.
+ *   rank 0:      h2aes_comm_unique_id(id)          -> ship the 128 bytes to every rank (any channel)
+ *   every rank:  h2aes_comm_init(ctx, id, rank, world)   (collective; binds the ctx's device)
+ *                h2aes_circuit_set_shard(c, rank, world); h2aes_witness_dev(...)
+ *                h2aes_lookup_columns_sharded_dev(c, theta, beta, gamma, Ap, Sp, Z)
+ * h2aes_lookup_columns_sharded_dev = hist -> ncclAllReduce(sum, all lookups in ONE call) ->
+ * permuted (this shard's rows of A', S') -> partial products -> ncclAllGather (one 32-byte Fr per
+ * lookup per shard, ONE call) -> Z of this shard's rows; everything is enqueued on the context's
+ * stream, nothing synchronizes.  beta/gamma NULL stops after A', S' (the prover's order: the
+ * challenges beta, gamma only exist after A', S' are committed); a later call with Ap_dev ==
+ * Sp_dev == NULL and beta/gamma given finishes Z from the same theta.
+ * ------------------------------------------------------------------------------------------- */
+#define H2AES_COMM_ID_BYTES 128
+int32_t h2aes_comm_unique_id(uint8_t *id /* H2AES_COMM_ID_BYTES */);
+int32_t h2aes_comm_init(h2aes_ctx *ctx, const uint8_t *id /* H2AES_COMM_ID_BYTES */, int32_t rank,
+                        int32_t world);
+int32_t h2aes_comm_destroy(h2aes_ctx *ctx);
+int32_t h2aes_lookup_columns_sharded_dev(h2aes_circuit *c, const uint64_t *theta,
+                                         const uint64_t *beta, const uint64_t *gamma,
+                                         uint64_t *Ap_dev, uint64_t *Sp_dev, uint64_t *Z_dev);
+
+/* ---------------------------------------------------------------------------------------------
  * Debug / test hooks: the same host+device source the kernels use, run on the host, so
  * CPU-only tests can check the field arithmetic and closed-form layout without a GPU.
  * ------------------------------------------------------------------------------------------- */
