@@ -277,7 +277,10 @@ PHASES = ("witness", "lookup_prep", "permuted", "product_prep", "product")
 
 def bind_to_gpu_numa(local):
     """Run this rank on the CPUs next to its GPU's PCIe root, so the pinned host buffers of the
-    end-to-end leg (first touch) live on that NUMA node.  Returns the node (None: left alone)."""
+    end-to-end leg (first touch) live on that NUMA node.  Returns {"node", "cpus", "why"}: on the
+    pool's boxes sysfs reports numa_node -1 for the GPUs (one NUMA domain exposed to the
+    container), in which case there is nothing to bind to and the reason is recorded."""
+    info = {"node": None, "cpus": None, "why": None}
     try:
         import torch
         p = torch.cuda.get_device_properties(local)
@@ -287,14 +290,24 @@ def bind_to_gpu_numa(local):
         cpus = set()
         for part in open(f"{base}/local_cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if node < 0 or not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+            if lo:
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        info["node"] = node
+        if node < 0:
+            info["why"] = f"sysfs numa_node of {bdf} is {node}: no NUMA locality exposed"
+        elif not cpus:
+            info["why"] = "local_cpulist does not intersect this process's affinity mask"
+        elif cpus == allowed:
+            info["why"] = "the GPU's local CPUs are already the whole affinity mask"
+            info["cpus"] = len(cpus)
+        else:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as e:
+        info["why"] = repr(e)
+    return info
 
 
 def run_b200(args):
@@ -497,6 +510,13 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(args, pipes[0].ctx, pipes[0].cir, pipes[0].stream, pipes[0].keys, th, be, ga,
                       rank, world)
+    e2e_committed = None
+    if rank == 0 and not args.no_e2e and not args.no_prover_side:
+        try:
+            e2e_committed = run_e2e_committed(pipes[0].ctx, pipes[0].cir, pipes[0].stream, pipes[0].keys,
+                                              th, be, ga)
+        except Exception as e:
+            e2e_committed = {"error": repr(e)}
 
     # ---- BASELINE config 4 as specified: 2^20 blocks = 273 circuits dealt round-robin -----------
     config4 = None
@@ -551,7 +571,8 @@ def run_b200(args):
             "nonconstant_rows": nc, "nonconstant_row_fraction": nc / (L * n),
             "prover_side": prover_side,
             "config4_stream": config4, "sharded": sharded_rec,
-            "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "e2e_committed": e2e_committed,
+            "cpu_baseline": cpu,
         }
         emit(out)
     if world > 1:
@@ -692,6 +713,90 @@ def run_sharded(args, local, rank, world, th, be, ga):
     return rec
 
 
+def host_d2h_ceiling(stream, rank, world):
+    """What the box's host side can absorb: every rank copies 1 GiB device -> pinned host 4 times
+    with plain cudaMemcpyAsync (one copy per buffer), all ranks at once; GB/s per rank (min) and
+    summed over the ranks.  The end-to-end leg copies 3.05 GB per circuit, so this is its bound."""
+    import torch
+    import torch.distributed as dist
+    nbytes = 1 << 30
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    with torch.cuda.stream(stream):
+        host.copy_(dev, non_blocking=True)
+    stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for _ in range(4):
+            host.copy_(dev, non_blocking=True)
+    stream.synchronize()
+    dt = time.perf_counter() - t0
+    mine = 4 * nbytes / dt / 1e9
+    lo, total = mine, mine
+    if world > 1:
+        t = torch.tensor([mine, -mine], dtype=torch.float64, device="cuda")
+        s = t[:1].clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, lo = float(s[0]), -float(t[1])
+    return {"gbs_per_rank_min": lo, "gbs_all_ranks": total, "ranks": world,
+            "how": "4 x 1 GiB cudaMemcpyAsync device->pinned host per rank, all ranks concurrently"}
+
+
+def run_e2e_committed(ctx, cir, stream, keys, th, be, ga):
+    """The device-resident alternative the (f) rows enable: plaintexts from pinned host memory,
+    witness -> A', S', Z on the device, every witness-dependent column committed on the device
+    (h2aes_msm_dev against synthetic bases), only the 64-byte commitments come
+    back.  Separate from `e2e` (which returns every column); bound by the commitments."""
+    import torch
+
+    from halo2_aes_b200.backend import Msm, synthetic_bases
+    lay = cir.layout
+    n, nb, L, nadv = lay["n_rows"], lay["capacity_blocks"], lay["n_lookups"], lay["n_advice"]
+    with torch.cuda.stream(stream):
+        bases = synthetic_bases(ctx, n, seeded_fr(SEED + 9))
+        msm = Msm(ctx, bases).enable_runs()
+        pts_h = torch.from_numpy(splitmix_bytes(SEED + 33, 16 * nb).reshape(nb, 16)).pin_memory()
+        pts_d = torch.empty((nb, 16), dtype=torch.uint8, device="cuda")
+        advice = torch.empty((nadv, n, 4), dtype=torch.int64, device="cuda")
+        bufs = {nm: torch.empty((L, n, 4), dtype=torch.int64, device="cuda") for nm in ("Ap", "Sp")}
+        Z = torch.empty((L, n, 4), dtype=torch.int64, device="cuda")
+        com_d = torch.empty((nadv + 3 * L, 2, 4), dtype=torch.int64, device="cuda")
+    com_h = torch.empty((nadv + 3 * L, 2, 4), dtype=torch.int64).pin_memory()
+
+    def step(i):
+        th_i = th.copy()
+        th_i[0] ^= np.uint64(i + 177)
+        with torch.cuda.stream(stream):
+            pts_d.copy_(pts_h, non_blocking=True)
+            cir.witness(keys[i % len(keys)].tobytes(), pts_d, out=advice, want_ciphertexts=False)
+            msm.commit(advice, out=com_d[:nadv])
+            cir.lookup_permuted(th_i, first=0, count=L, want_inputs=False, out=bufs)
+            msm.commit(bufs["Ap"], out=com_d[nadv:nadv + L])
+            msm.commit(bufs["Sp"], out=com_d[nadv + L:nadv + 2 * L])
+            cir.lookup_product(be, ga, first=0, count=L, out=Z)
+            msm.commit(Z, out=com_d[nadv + 2 * L:])
+            com_h.copy_(com_d, non_blocking=True)
+        stream.synchronize()
+
+    step(0)
+    steps = 2
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(1 + i)
+    dt = time.perf_counter() - t0
+    assert bool(com_h.any()), "no commitment came back"
+    msm.close()
+    return {"value": nb * steps / dt, "unit": UNIT, "steps": steps, "ms_per_circuit": 1e3 * dt / steps,
+            "h2d_bytes_per_step": nb * 16 + 16 + 3 * 32, "d2h_bytes_per_step": (nadv + 3 * L) * 64,
+            "columns_committed": nadv + 3 * L,
+            "api": "h2aes_witness_dev + h2aes_lookup_permuted_dev + h2aes_lookup_product_dev + "
+                   "h2aes_msm_dev (synthetic bases), commitments only copied back",
+            "note": "rank 0 only; bound by the G1 multi-scalar multiplications, not by PCIe"}
+
+
 def run_e2e(args, ctx, cir, stream, keys, th, be, ga, rank, world):
     """Same step through the reference-facing _host entry points: plaintexts start in pinned
     host memory, every produced column ends in pinned host memory."""
@@ -741,7 +846,10 @@ def run_e2e(args, ctx, cir, stream, keys, th, be, ga, rank, world):
     one = [-0x5369cbe3b0000005, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f]
     assert Zh[:, n - 6].tolist() == [one] * L, "e2e: Z[n-6] != 1"
     d2h = (nadv + 3 * L) * n * 32 + nb * 16
+    ceiling = host_d2h_ceiling(stream, rank, world)
     return {"value": nb * steps * world / dt, "unit": UNIT, "steps": steps,
+            "achieved_d2h_gbs_all_ranks": world * d2h * steps / dt / 1e9,
+            "host_d2h_ceiling": ceiling,
             "ms_per_step": 1e3 * dt / steps, "h2d_bytes_per_step": nb * 16 + 16 + 3 * 32,
             "d2h_bytes_per_step": d2h,
             "api": "h2aes_witness_host + h2aes_lookup_permuted_host + h2aes_lookup_product_host "

@@ -339,6 +339,11 @@ int32_t h2aes_ctx_destroy(h2aes_ctx *ctx) {
     if (!ctx) return H2AES_ERR_ARG;
     cudaSetDevice(ctx->device);
     if (ctx->comm) h2aes_comm_destroy(ctx);
+    if (ctx->side) {
+        cudaStreamDestroy(ctx->side);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_join);
+    }
     for (auto &r : ctx->prof) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -766,6 +771,11 @@ static int32_t set_beta_gamma(h2aes_circuit *c, const uint64_t *beta, const uint
     CU(ctx, launch_inv_tables(c));
     c->have_beta_gamma = true;
     return H2AES_OK;
+}
+
+// (comm.cu: the per-(beta,gamma) tables on a side stream while the permuted columns are expanded)
+int32_t h2aes_internal_set_beta_gamma(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma) {
+    return set_beta_gamma(c, beta, gamma);
 }
 
 int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32_t first,

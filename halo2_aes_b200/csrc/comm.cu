@@ -74,6 +74,9 @@ static_assert(H2AES_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "the id is an ncclUni
         if (r__ != ncclSuccess) return nccl_fail(ctx, api, r__, #call); \
     } while (0)
 
+extern "C" int32_t h2aes_internal_set_beta_gamma(h2aes_circuit *c, const uint64_t *beta,
+                                                 const uint64_t *gamma);
+
 extern "C" {
 
 int32_t h2aes_comm_unique_id(uint8_t *id) {
@@ -143,12 +146,33 @@ int32_t h2aes_lookup_columns_sharded_dev(h2aes_circuit *c, const uint64_t *theta
     NcclApi &api = nccl_api();
     const bool multi = c->n_shards > 1;
     const bool fresh = !c->have_bins || !c->have_theta || memcmp(c->theta, theta, 32) != 0;
+    bool forked = false;
     int32_t rc;
     if (Ap_dev || fresh) {
         // exchange 1: the permuted columns are a GLOBAL sort -> sum of the bin histograms
         uint32_t *hist = nullptr;
         uint64_t words = 0;
         if ((rc = h2aes_lookup_hist_dev(c, theta, &hist, &words))) return rc;
+        if (beta) {
+            // beta, gamma are known up front here: their per-bin inverse tables only need the bins
+            // (just enqueued), so they are built on a side stream while the histogram is reduced
+            // and the permuted columns are expanded — serial work that does not shrink with G
+            if (!ctx->side) {
+                if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+                    return bad(H2AES_ERR_CUDA, "side stream");
+            }
+            cudaStream_t main_stream = ctx->stream;
+            cudaEventRecord(ctx->ev_fork, main_stream);
+            cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+            ctx->stream = ctx->side;
+            rc = h2aes_internal_set_beta_gamma(c, beta, gamma);
+            ctx->stream = main_stream;
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev_join, ctx->side);
+            forked = true;
+        }
         if (multi)
             NC(ctx, api, api.AllReduce(hist, hist, words, ncclUint32, ncclSum, (ncclComm_t)ctx->comm,
                                        ctx->stream));
@@ -157,6 +181,7 @@ int32_t h2aes_lookup_columns_sharded_dev(h2aes_circuit *c, const uint64_t *theta
     if (!beta) return H2AES_OK;
     // exchange 2: one partial product per lookup per shard -> carry of the shards before this one
     uint64_t *partial = nullptr;
+    if (forked) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if ((rc = h2aes_lookup_partial_dev(c, beta, gamma, Z_dev, &partial))) return rc;
     const size_t L = (size_t)c->sh.n_lookups();
     if (!c->d_gathered) {

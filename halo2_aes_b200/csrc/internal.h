@@ -153,6 +153,8 @@ struct h2aes_ctx {
     uint4 *d_frtab = nullptr;    // 256 entries x 32 bytes: byte -> Fr (Montgomery)
     uint64_t launches = 0;
     std::string last_error;
+    cudaStream_t side = nullptr;  // second stream + fork/join events (comm.cu)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *comm = nullptr;        // ncclComm_t of h2aes_comm_init (comm.cu)
     int comm_rank = 0, comm_world = 1;
 };
