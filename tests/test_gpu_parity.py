@@ -141,13 +141,6 @@ def test_fips_sbox_switch(gpu, orc, ffi, challenges):
               lookups=[2], fips=True)
 
 
-def test_1024_blocks_reference_shape(gpu, orc, ffi, challenges):
-    """BASELINE config 3: 1024 blocks under one key in one circuit, K=20, N=2."""
-    pts = splitmix_bytes(SEED + 6, 16 * 1024).reshape(-1, 16)
-    _run_case(gpu, orc, ffi, ffi.KIND_AES, 20, 2, splitmix_bytes(SEED + 7, 16).tobytes(), pts,
-              challenges, lookups=[1, 2, 6, 8])
-
-
 def test_error_behaviour(gpu, ffi):
     import torch
     from halo2_aes_b200.backend import Circuit
@@ -271,10 +264,31 @@ def test_fr_mul_device_vs_bigint(gpu, orc, ffi):
         assert orc.limbs_to_int(out[i]) == a[i] * b[i] * rinv % R_MOD, i
 
 
+def _oracle_lookups(ref, idxs, theta, beta, gamma, want=("Ap", "Sp", "Z"), workers=8):
+    """oracle columns of several lookups at once (the C calls release the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return dict(zip(idxs, ex.map(lambda li: ref.lookup(li, theta, beta, gamma, want=want), idxs)))
+
+
+def _same_on_device(dev_col, ref_col) -> bool:
+    import torch
+    return torch.equal(dev_col, torch.from_numpy(ref_col.view(np.int64)).to(dev_col.device))
+
+
+def _compare_all_lookups(cir, ref, perm, Z, theta, beta, gamma, idxs, chunk=5):
+    for c0 in range(0, len(idxs), chunk):
+        part = list(idxs[c0:c0 + chunk])
+        got = _oracle_lookups(ref, part, theta, beta, gamma)
+        for li in part:
+            for nm, t in (("Ap", perm["Ap"]), ("Sp", perm["Sp"]), ("Z", Z)):
+                assert _same_on_device(t[li], got[li][nm]), (nm, li)
+
+
 def test_bench_shape_full_capacity(gpu, orc, ffi, challenges):
     """The benchmarked circuit itself (BASELINE config 4 unit: K=20, N=5, 3853 random blocks):
-    every advice column and one lookup of each kind against the oracle, all 25 grand products
-    through the size-independent closing property Z[n-6] == 1."""
+    every advice column and ALL 25 lookups (A', S', Z) column for column against the oracle
+    (compared on the device; the oracle columns are uploaded once)."""
     import torch
     from halo2_aes_b200.backend import Circuit
     theta, beta, gamma = challenges
@@ -288,20 +302,135 @@ def test_bench_shape_full_capacity(gpu, orc, ffi, challenges):
     ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
     assert (cts.cpu().numpy() == ref.ciphertexts()).all()
     for col in range(16):
-        assert (_host(advice[col]) == ref.advice(col)).all(), col
+        assert _same_on_device(advice[col], ref.advice(col)), col
     del advice
     perm = cir.lookup_permuted(theta, want_inputs=False)
     Z = cir.lookup_product(beta, gamma)
     cir.lookup_check()
     one = orc.fr_from_int(1)
     n = 1 << k
-    zend = _host(Z[:, n - 6])
-    assert (zend == one).all() and (_host(Z[:, 0]) == one).all()
-    for li in (0, 6, 12, 18, 24):   # range, xor, sbox, mul2, mul3 of sets 0..4
-        r = ref.lookup(li, theta, beta, gamma, want=("Ap", "Sp", "Z"))
-        assert (_host(perm["Ap"][li]) == r["Ap"]).all(), ("Ap", li)
-        assert (_host(perm["Sp"][li]) == r["Sp"]).all(), ("Sp", li)
-        assert (_host(Z[li]) == r["Z"]).all(), ("Z", li)
+    assert (_host(Z[:, n - 6]) == one).all() and (_host(Z[:, 0]) == one).all()
+    _compare_all_lookups(cir, ref, perm, Z, theta, beta, gamma, list(range(25)))
+    cir.close()
+
+
+def test_single_block_at_the_bench_shape(gpu, orc, ffi, golden, challenges):
+    """BASELINE config 1 at the shape benches/aes128.rs uses (K=20, N=5): ONE block (FIPS-197
+    App. C.1) + key schedule; every advice column, all 25 lookups (20 of them over empty sets)."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    theta, beta, gamma = challenges
+    v = golden["fips197"][0]
+    key = bytes.fromhex(v["key"])
+    pts = np.frombuffer(bytes.fromhex(v["pt"]), np.uint8).reshape(1, 16).copy()
+    cir = Circuit(gpu, ffi.KIND_AES, 20, 5)
+    advice, cts = cir.witness(key, torch.from_numpy(pts).cuda())
+    ref = orc.Circuit(orc.KIND_AES, 20, 5).synthesize(key, pts)
+    assert cts.cpu().numpy()[0].tobytes().hex() == v["ct"] == ref.ciphertexts()[0].tobytes().hex()
+    for col in range(16):
+        assert _same_on_device(advice[col], ref.advice(col)), col
+    perm = cir.lookup_permuted(theta, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma)
+    cir.lookup_check()
+    _compare_all_lookups(cir, ref, perm, Z, theta, beta, gamma, list(range(25)))
+    cir.close()
+
+
+@pytest.mark.parametrize("k,N", [(20, 2), (21, 1)])
+def test_1024_blocks_all_lookups(gpu, orc, ffi, challenges, k, N):
+    """BASELINE config 3 (1024 blocks under one key in one circuit), both shapes of SURVEY 8(d):
+    the reference-shaped K=20, N=2 (769 blocks in set 0, 255 in set 1) and K=21, N=1; every advice
+    column and ALL lookups column for column."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    theta, beta, gamma = challenges
+    pts = splitmix_bytes(SEED + 6, 16 * 1024).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 7, 16).tobytes()
+    cir = Circuit(gpu, ffi.KIND_AES, k, N)
+    advice, cts = cir.witness(key, torch.from_numpy(pts).cuda())
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
+    assert (cts.cpu().numpy() == ref.ciphertexts()).all()
+    for col in range(3 * N + 1):
+        assert _same_on_device(advice[col], ref.advice(col)), col
+    perm = cir.lookup_permuted(theta, want_inputs=False)
+    Z = cir.lookup_product(beta, gamma)
+    cir.lookup_check()
+    _compare_all_lookups(cir, ref, perm, Z, theta, beta, gamma, list(range(5 * N)))
+    cir.close()
+
+
+def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges):
+    """BASELINE config 5's shape, oracle-compared: a K=22, N=1 circuit at capacity (3082 blocks)
+    through the row-sharded entry points (4 shards run one after another on this GPU, the two
+    exchanges done by hand): every advice column and the xor and sbox lookups."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    theta, beta, gamma = challenges
+    k, N, G = 22, 1, 4
+    nb = ffi.layout_query(ffi.KIND_AES, k, N)["capacity_blocks"]
+    assert nb == 3082
+    pts = splitmix_bytes(SEED + 60, 16 * nb).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 61, 16).tobytes()
+    d_pts = torch.from_numpy(pts).cuda()
+    shards = [Circuit(gpu, ffi.KIND_AES, k, N) for _ in range(G)]
+    for g, c in enumerate(shards):
+        c.set_shard(g, G)
+    adv = torch.cat([c.witness(key, d_pts)[0] for c in shards], dim=1)
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
+    for col in range(4):
+        assert _same_on_device(adv[col], ref.advice(col)), col
+    del adv
+    hists = [c.shard_hist(theta) for c in shards]
+    total = torch.stack(hists).sum(dim=0, dtype=torch.int32)
+    for h in hists:
+        h.copy_(total)
+    perm = [c.shard_permuted(want_inputs=False) for c in shards]
+    zp = [c.shard_partial(beta, gamma) for c in shards]
+    gathered = torch.stack([p.clone() for _, p in zp]).contiguous()
+    Zs = [c.shard_product(gathered, z) for c, (z, _) in zip(shards, zp)]
+    for c in shards:
+        c.lookup_check()
+    got = _oracle_lookups(ref, [1, 2], theta, beta, gamma, workers=2)
+    for li in (1, 2):
+        for nm, parts in (("Ap", [p["Ap"] for p in perm]), ("Sp", [p["Sp"] for p in perm]), ("Z", Zs)):
+            col = torch.cat([t[li] for t in parts], dim=0)
+            assert _same_on_device(col, got[li][nm]), (nm, li)
+    for c in shards:
+        c.close()
+
+
+@pytest.mark.parametrize("case", ["small", "wide", "beta_zero", "gamma_cancels_pad"])
+def test_challenge_sweep(gpu, orc, ffi, case):
+    """theta / beta / gamma away from the seeded defaults: tiny challenges, full-width ones, and
+    the two ways a denominator of the grand product can vanish — (A'+beta) with A' = 0 (beta = 0)
+    and (S'+gamma) with S' = the padding value — which halo2's batch_invert turns into a zero and
+    this library reports as H2AES_ERR_ZERO_DENOM instead of producing a column."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    rng = np.random.default_rng(0xC0FFEE)
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    big = lambda: orc.fr_from_int(int.from_bytes(rng.bytes(40), "little") % R)
+    pts = splitmix_bytes(SEED + 95, 16 * 20).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 96, 16).tobytes()
+    if case == "small":
+        ch = (orc.fr_from_int(3), orc.fr_from_int(1), orc.fr_from_int(2))
+    elif case == "wide":
+        ch = (big(), big(), big())
+    elif case == "beta_zero":
+        ch = (big(), orc.fr_from_int(0), big())
+    else:  # the 2-column range lookup pads its table with (1, 0): value theta -> gamma = -theta
+        th = big()
+        ch = (th, big(), orc.fr_from_int(R - orc.fr_to_int(th)))
+    if case in ("small", "wide"):
+        _run_case(gpu, orc, ffi, ffi.KIND_AES, 17, 1, key, pts, ch)
+        return
+    cir = Circuit(gpu, ffi.KIND_AES, 17, 1)
+    cir.witness(key, torch.from_numpy(pts).cuda())
+    cir.lookup_permuted(ch[0], want_inputs=False)
+    cir.lookup_product(ch[1], ch[2], first=0, count=1)
+    with pytest.raises(ffi.H2AesError) as ei:
+        cir.lookup_check()
+    assert ei.value.code == ffi.ERR_ZERO_DENOM
     cir.close()
 
 

@@ -127,3 +127,32 @@ def test_partition_helpers():
         assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sharded.columns_of_rank(5, 2, 2)
+
+
+def test_config4_dealing_covers_every_block_once():
+    """BASELINE config 4 as bench.py's config4_stream runs it: 2^20 blocks = 272 circuits at the
+    K=20, N=5 capacity + one of 560 blocks; the round-robin deal gives every circuit to exactly
+    one rank."""
+    from halo2_aes_b200 import sharded
+    total, cap = 1 << 20, 3853
+    circuits = sharded.split_into_circuits(total, cap)
+    assert len(circuits) == 273 and circuits[-1] == (272 * cap, 560)
+    assert sum(c for _, c in circuits) == total
+    assert all(s == i * cap for i, (s, _) in enumerate(circuits))
+    for world in (1, 2, 4, 8):
+        seen = sorted(i for r in range(world) for i in sharded.circuits_of_rank(len(circuits), r, world))
+        assert seen == list(range(273))
+        sizes = [len(sharded.circuits_of_rank(273, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_comm_entry_points_reject_bad_arguments():
+    """h2aes_comm_* argument checking needs neither a GPU nor NCCL"""
+    import ctypes as C
+    from halo2_aes_b200 import _ffi
+    L = _ffi.lib()
+    assert L.h2aes_comm_unique_id(None) == _ffi.ERR_ARG
+    buf = (C.c_uint8 * _ffi.COMM_ID_BYTES)()
+    assert L.h2aes_comm_init(None, buf, 0, 1) == _ffi.ERR_ARG
+    assert L.h2aes_comm_destroy(None) == _ffi.ERR_ARG
+    assert L.h2aes_lookup_columns_sharded_dev(None, None, None, None, None, None, None) == _ffi.ERR_ARG
