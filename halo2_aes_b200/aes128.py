@@ -254,9 +254,10 @@ class B200Layouter:
         self.table_loaded = False
         self.key = None
         self.plaintexts: list[bytes] = []
-        self.circuit = None        # backend.Circuit after flush
+        self.circuit = None        # backend.Circuit after the first flush
         self.advice = None
         self.ciphertexts = None
+        self._flushed = 0          # plaintexts already on the GPU
         self._shape = None
 
     def namespace(self, _name=None):  # Layouter::namespace: same layouter
@@ -270,24 +271,31 @@ class B200Layouter:
             raise ValueError("one layouter serves one circuit shape")
 
     def flush(self):
-        """Produce every advice column on the GPU (h2aes_witness_dev)."""
+        """Produce every advice column on the GPU.  The first flush is schedule_key + the blocks
+        recorded so far (h2aes_witness_dev); `encrypt` calls made after a flush are appended by the
+        next one (h2aes_encrypt_append_dev), like the reference's per-call `encrypt`."""
         import torch
 
         from .backend import Circuit, Context
-        if self.circuit is not None:
-            return self
         if self.key is None:
             raise KeysNotScheduled(_ffi.ERR_NOT_SCHEDULED)
-        kind, N = self._shape
-        if self.ctx is None:
-            self.ctx = Context(torch.cuda.current_device())
-        self.circuit = Circuit(self.ctx, kind, self.k, N)
+        pending = self.plaintexts[self._flushed:]
         pts = None
-        if self.plaintexts:
+        if pending:
             pts = torch.from_numpy(
-                np.frombuffer(b"".join(self.plaintexts), np.uint8).reshape(-1, 16).copy()
-            ).to(self.ctx.device)
-        self.advice, self.ciphertexts = self.circuit.witness(self.key, pts)
+                np.frombuffer(b"".join(pending), np.uint8).reshape(-1, 16).copy()
+            ).to(self.ctx.device if self.ctx is not None else "cuda")
+        if self.circuit is None:
+            kind, N = self._shape
+            if self.ctx is None:
+                self.ctx = Context(torch.cuda.current_device())
+            self.circuit = Circuit(self.ctx, kind, self.k, N)
+            self.advice, self.ciphertexts = self.circuit.witness(self.key, pts)
+        elif pending:
+            first, cts = self.circuit.encrypt_append(pts, self.advice)
+            assert first == self._flushed
+            self.ciphertexts = cts if self.ciphertexts is None else torch.cat([self.ciphertexts, cts])
+        self._flushed = len(self.plaintexts)
         return self
 
     def cell_value(self, column: int, row: int) -> int:

@@ -144,6 +144,20 @@ class Circuit:
         self.n_blocks = B
         return advice, cts
 
+    def encrypt_append(self, plaintexts, advice, want_ciphertexts=True):
+        """h2aes_encrypt_append_dev: `encrypt` for every row of `plaintexts` [B,16] after the blocks
+        this circuit already holds; `advice` is the buffer `witness` returned.  Returns
+        (index of the first appended block, ciphertexts [B,16] or None)."""
+        B = plaintexts.shape[0]
+        assert plaintexts.is_cuda and plaintexts.dtype == torch.uint8 and plaintexts.is_contiguous()
+        cts = torch.empty((B, 16), dtype=torch.uint8, device=self.ctx.device) \
+            if (want_ciphertexts and B) else None
+        first = C.c_uint64()
+        check(lib().h2aes_encrypt_append_dev(self._h, _ptr(plaintexts) if B else None, B, _ptr(advice),
+                                             _ptr(cts), C.byref(first)), self.ctx._h)
+        self.n_blocks += B
+        return first.value, cts
+
     def witness_host(self, key, plaintexts: np.ndarray, advice_out: np.ndarray,
                      ciphertexts_out: np.ndarray | None = None):
         """Same through the _host entry point: numpy in, numpy out, copies done by the library."""

@@ -19,6 +19,9 @@ cudaError_t launch_build_frtab(h2aes_ctx *ctx);
 cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
                            uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev,
                            uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
+                                  uint64_t first_block, uint64_t n, uint64_t *advice_dev,
+                                  uint8_t *cts_dev);
 cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
                          uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end);
 cudaError_t launch_copies(h2aes_circuit *c, uint64_t n_copies, uint64_t *out);
@@ -517,8 +520,29 @@ int32_t h2aes_witness_dev(h2aes_circuit *c, const uint8_t *key, const uint8_t *p
     uint64_t rb, re;
     shard_rows(c, &rb, &re);
     CU(ctx, launch_witness(c, key, plaintexts_dev, n_blocks, advice_dev, ciphertexts_dev, rb, re));
+    memcpy(c->key, key, 16);
     c->n_blocks = n_blocks;
     c->have_witness = true;
+    c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
+    return H2AES_OK;
+}
+
+int32_t h2aes_encrypt_append_dev(h2aes_circuit *c, const uint8_t *plaintexts_dev, uint64_t n,
+                                 uint64_t *advice_dev, uint8_t *ciphertexts_dev,
+                                 uint64_t *first_block) {
+    if (!c) return H2AES_ERR_ARG;
+    h2aes_ctx *ctx = c->ctx;
+    if (!advice_dev || (n && !plaintexts_dev)) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (c->sh.kind != KIND_AES) return fail(ctx, H2AES_ERR_ARG, "the key-schedule circuit has no AES blocks");
+    if (c->n_shards != 1) return fail(ctx, H2AES_ERR_STATE, "encrypt_append: unsharded circuits only");
+    if (!c->have_witness) return fail(ctx, H2AES_ERR_NOT_SCHEDULED, "Keys should be scheduled");
+    if (n > c->sh.capacity() - c->n_blocks)
+        return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
+    if (first_block) *first_block = c->n_blocks;
+    if (!n) return H2AES_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_witness_append(c, c->key, plaintexts_dev, c->n_blocks, n, advice_dev, ciphertexts_dev));
+    c->n_blocks += n;
     c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
     return H2AES_OK;
 }

@@ -88,26 +88,28 @@ __device__ __forceinline__ void fr_st_cg(fr_t *p, const fr_t &a) {
 }
 
 // the (at most 96) mask bits of rows [lr0, lr0 + nr) of a column whose mask words start at `words`
+// (three scalars, not an array: an indexed array would live in local memory)
 __device__ __forceinline__ void span_mask(const uint32_t *__restrict__ words, uint64_t n_words,
-                                          uint64_t lr0, uint32_t nr, uint32_t b[3]) {
+                                          uint64_t lr0, uint32_t nr, uint32_t &b0, uint32_t &b1,
+                                          uint32_t &b2) {
     const uint64_t w0 = lr0 >> 5;
     const uint32_t sh = (uint32_t)lr0 & 31u;
-    uint32_t x[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = w0 + i < n_words ? __ldg(words + w0 + i) : 0u;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        b[i] = __funnelshift_r(x[i], x[i + 1], sh);
-        const uint32_t lo = 32u * i;
-        if (nr <= lo) b[i] = 0u;
-        else if (nr < lo + 32u) b[i] &= (1u << (nr - lo)) - 1u;
-    }
+    const uint32_t x0 = w0 < n_words ? __ldg(words + w0) : 0u;
+    const uint32_t x1 = w0 + 1 < n_words ? __ldg(words + w0 + 1) : 0u;
+    const uint32_t x2 = w0 + 2 < n_words ? __ldg(words + w0 + 2) : 0u;
+    const uint32_t x3 = w0 + 3 < n_words ? __ldg(words + w0 + 3) : 0u;
+    auto clip = [nr](uint32_t v, uint32_t lo) {
+        return nr <= lo ? 0u : (nr < lo + 32u ? v & ((1u << (nr - lo)) - 1u) : v);
+    };
+    b0 = clip(__funnelshift_r(x0, x1, sh), 0u);
+    b1 = clip(__funnelshift_r(x1, x2, sh), 32u);
+    b2 = clip(__funnelshift_r(x2, x3, sh), 64u);
 }
 
 // the set bits of a thread's (up to 96) mask bits in ascending order
 struct RowIter {
     uint32_t m0, m1, m2;
-    __device__ __forceinline__ RowIter(const uint32_t b[3]) : m0(b[0]), m1(b[1]), m2(b[2]) {}
+    __device__ __forceinline__ RowIter(uint32_t b0, uint32_t b1, uint32_t b2) : m0(b0), m1(b1), m2(b2) {}
     __device__ __forceinline__ int next() {
         if (m0) { const int q = __ffs(m0) - 1; m0 &= m0 - 1u; return q; }
         if (m1) { const int q = 31 + __ffs(m1); m1 &= m1 - 1u; return q; }
@@ -199,7 +201,7 @@ struct ZBlock {
     uint64_t b, lr0, row0;  // my block, its first local / absolute row
     uint32_t nr;          // rows of my block inside the column
     LookupLane cx;
-    uint32_t mb[3];
+    uint32_t mb0, mb1, mb2;
 };
 // warp task -> (column, row tile, slice); heaviest tiles first (see the file header)
 template <int SRC>
@@ -224,7 +226,7 @@ __device__ __forceinline__ bool z_block_setup(const ZScanArgs &a, uint64_t task,
         t.cx.vo = (uint32_t)view_of_op((uint32_t)(t.l % ops) + 1) * BIN_STRIDE;
         t.cx.ln = (uint64_t)t.l * a.sh.n();
     }
-    span_mask(a.mask + (size_t)t.li * a.mstride, (a.rows + 31) >> 5, t.lr0, t.nr, t.mb);
+    span_mask(a.mask + (size_t)t.li * a.mstride, (a.rows + 31) >> 5, t.lr0, t.nr, t.mb0, t.mb1, t.mb2);
     return true;
 }
 
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
     const uint64_t *__restrict__ z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
     // software pipeline over the non-constant rows: code of row i+2, factor of row i+1, multiply i
     fr_t tot = fr_one();
-    RowIter it(t.mb);
+    RowIter it(t.mb0, t.mb1, t.mb2);
     int q1 = it.next(), q2 = it.next();
     uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
     uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
     }
     if (t.nr) fr_st(a.tot + (size_t)t.li * a.n_blocks + t.b, tot);
     if (a.nonconst) {
-        uint32_t c = __popc(t.mb[0]) + __popc(t.mb[1]) + __popc(t.mb[2]);
+        uint32_t c = __popc(t.mb0) + __popc(t.mb1) + __popc(t.mb2);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(a.nonconst + t.l, (unsigned long long)c);
@@ -271,7 +273,13 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // k_z_prefix: tot[] -> exclusive prefixes (times the carry-in), single pass, decoupled look-back
 // ---------------------------------------------------------------------------------------------
-constexpr int ZP_T = 256, ZP_E = 4, ZP_TILE = ZP_T * ZP_E;
+#ifndef ZP_THREADS
+#define ZP_THREADS 128
+#endif
+#ifndef ZP_ELEMS
+#define ZP_ELEMS 8
+#endif
+constexpr int ZP_T = ZP_THREADS, ZP_E = ZP_ELEMS, ZP_TILE = ZP_T * ZP_E;
 __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScanArgs a) {
     __shared__ fr_t s_w[ZP_T / 32];
     __shared__ uint32_t s_ticket, s_epoch;
@@ -403,12 +411,39 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     uint64_t *zw = a.Z + ((size_t)t.li * a.rows + lrw0) * 4;  // ... and its Z slot
     const uint64_t *z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
     // software pipeline over the non-constant rows: code of row i+2, factor of row i+1
-    RowIter it(t.mb);
+    RowIter it(t.mb0, t.mb1, t.mb2);
     int q1 = it.next(), q2 = it.next();
     uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
     uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
     fr_t f1 = fr_one();
     if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+#ifdef ZWRITE_RUNS
+    {
+        uint64_t *zt = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
+        uint32_t done = 0;
+        auto put = [&](uint32_t r) {
+            const bool ok = (uint32_t)((t.row0 + r) & a.col_mask) <= usable;
+            fr_store_256_cs(zt + 4 * (size_t)r, ok ? cur : zero);
+        };
+#pragma unroll 1
+        while (q1 >= 0) {
+            const fr_t f = f1;
+            const uint32_t q = (uint32_t)q1;
+            q1 = q2;
+            c1 = c2;
+            q2 = it.next();
+            if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
+            if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+#pragma unroll 1
+            for (uint32_t r = done; r <= q; ++r) put(r);
+            done = q + 1u;
+            cur = fr_mul_inline(cur, f);
+        }
+#pragma unroll 1
+        for (uint32_t r = done; r < t.nr; ++r) put(r);
+        return;
+    }
+#endif
 #pragma unroll 1
     for (uint32_t r = 0; r < ZB_R; ++r) {
         const uint32_t jj = r & (ZS_BURST - 1);

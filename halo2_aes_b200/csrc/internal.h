@@ -163,6 +163,7 @@ struct h2aes_circuit {
     h2aes_ctx *ctx = nullptr;
     h2::Shape sh{};
     uint64_t n_blocks = 0;
+    uint8_t key[16] = {0};         // key of the last h2aes_witness_* call (h2aes_encrypt_append_dev)
     bool have_witness = false;
     int shard = 0, n_shards = 1;
 

@@ -13,11 +13,13 @@
 //   * every input value is the compression of one of <= 66561 table tuples, so the rows are
 //     counted per *bin* (distinct compressed value) from the 4-byte trace word of each row;
 //   * the bins are ordered once per theta per view (2-, 3-, 4-column tables) with a bucket sort
-//     on the canonical value (16 leading bits) + exact 256-bit ranking inside each bucket;
+//     on the canonical value (12 leading bits) + exact 256-bit ranking inside each bucket;
 //   * A'/S' are expanded from the run structure (binary search of the row in the run offsets);
-//   * Z uses per-bin inverse tables (Montgomery-trick batch inversion over the bins, not the
-//     rows) and a single-pass decoupled-look-back prefix product over 256-bit Montgomery
-//     multiplies (warp shuffles inside a tile).
+//     the same kernel classifies every row's grand-product factor (4-byte code, one mask bit per
+//     row for "factor is not one" and one for "factor is not a single table entry");
+//   * Z: per-bin inverse tables here (Montgomery-trick batch inversion over the bins, not the
+//     rows), the running product itself in gprod.cu (k_z_general / k_z_totals / k_z_prefix with
+//     a single-pass decoupled-look-back scan / k_z_write).
 #include "internal.h"
 
 namespace h2 {

@@ -274,6 +274,30 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
     return cudaGetLastError();
 }
 
+// `n` more blocks after the `first_block` already held: their round states, then the advice
+// columns again from the states of ALL blocks (the streaming kernel writes whole columns: one
+// pass, 0.11 ms at K=20, N=5 — cheaper than a second kernel that patches row ranges)
+cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
+                                  uint64_t first_block, uint64_t n, uint64_t *advice_dev,
+                                  uint8_t *cts_dev) {
+    h2aes_ctx *ctx = c->ctx;
+    Key16 k16;
+    for (int i = 0; i < 16; ++i) k16.b[i] = key[i];
+    const unsigned grid = (unsigned)((n + 7) / 8);
+    prof_begin(ctx, "k_block_states");
+    k_block_states<<<grid, 128, 0, ctx->stream>>>(ctx->d_sbox, k16, c->d_rk, pts_dev, n,
+                                                  c->d_states + first_block * ST_BYTES, cts_dev);
+    prof_end(ctx);
+    const size_t pad = stream_pad_bytes((const void *)k_advice);
+    prof_begin(ctx, "k_advice");
+    k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, first_block + n, c->d_rk, c->d_states,
+                                                          ctx->d_sbox, ctx->d_frtab, advice_dev,
+                                                          c->d_trace, 0, c->sh.n());
+    prof_end(ctx);
+    ctx->launches += 2;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
                          uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end) {
     h2aes_ctx *ctx = c->ctx;

@@ -177,6 +177,31 @@ int32_t h2aes_witness_dev(h2aes_circuit *c, const uint8_t *key, const uint8_t *p
 int32_t h2aes_witness_host(h2aes_circuit *c, const uint8_t *key, const uint8_t *plaintexts,
                            uint64_t n_blocks, uint64_t *advice, uint8_t *ciphertexts);
 
+/* replaces: repeated FixedAes128Config::encrypt calls (aes128.rs:154, `&mut self`: one block per
+ * call, position kept in `current`/`count`, aes128.rs:303-325).  Appends n more blocks after the
+ * ones this circuit already holds, under the key of the last h2aes_witness_* call (which may have
+ * had n_blocks == 0: that is schedule_key alone) — so a shim behind `encrypt` can flush
+ * incrementally instead of collecting every plaintext first.
+ *   H2AES_ERR_NOT_SCHEDULED  no key scheduled yet (the reference's expect, aes128.rs:170)
+ *   H2AES_ERR_CAPACITY       held + n exceeds the capacity (the reference's panic, :160-162);
+ *                            nothing is written
+ *   advice_dev               the SAME buffer as the h2aes_witness_dev call (it is completed in
+ *                            place; rows of blocks not yet appended stay zero)
+ *   ciphertexts_dev          n*16 bytes for the appended blocks, nullable
+ *   *first_block             out, nullable: index the first appended block received
+ * Unsharded circuits only.
+ *
+ * The chips' own per-cell methods — U8XorChip::xor (u8_xor_chip.rs:63), SboxChip::substitute
+ * (sbox_chip.rs:57), MulBy2/3Chip::mul (gf_mul_chip.rs:59), U8RangeCheckChip::range_check
+ * (u8_range_check_chip.rs:51) — are NOT exported as stand-alone calls: every row they assign
+ * inside schedule_key / encrypt is produced by the fused witness kernels, and a cell outside those
+ * regions would also need its selector, copy constraints and the lookups' active-row counts
+ * patched, which this backend derives in closed form from (kind, k, N, n_blocks).  A circuit that
+ * uses the chips on its own cells must keep the reference's CPU path for those regions. */
+int32_t h2aes_encrypt_append_dev(h2aes_circuit *c, const uint8_t *plaintexts_dev, uint64_t n,
+                                 uint64_t *advice_dev, uint8_t *ciphertexts_dev,
+                                 uint64_t *first_block);
+
 /* the 176 expanded key bytes (values of the 11x16 cells schedule_keys returns). Host out. */
 int32_t h2aes_round_keys(h2aes_circuit *c, uint8_t *out176);
 
@@ -247,7 +272,11 @@ int32_t h2aes_perm_product_dev(h2aes_circuit *c, const uint64_t *beta, const uin
  *       = j - 1; extended_k = smallest with 2^extended_k >= 2^k * (j - 1)  (k + 2 here)
  * Columns are [ncols][len][4] as everywhere else.  The extended domain is the coset
  * zeta * <extended_omega>, zeta = Fr::ZETA = 7^((r-1)/3) (g_coset), exactly as halo2 evaluates it.
- * Limits: 2 <= k, extended_k <= 22.
+ * Limits: 2 <= k, extended_k <= 22 — i.e. k <= 20 for these circuits (extended_k = k + 2): a
+ * transform is two passes of at most 2^11-point sub-transforms in shared memory.  A K=21/22
+ * circuit (BASELINE config 5) gets its witness, lookup and permutation columns from this library
+ * but NOT the domain transforms, the quotient terms below or anything that needs a domain:
+ * h2aes_domain_create returns H2AES_ERR_ARG ("domain: 2 <= k, extended_k <= 22") for it.
  * ------------------------------------------------------------------------------------------- */
 typedef struct h2aes_domain h2aes_domain;
 #define H2AES_DOMAIN_FFT 0               /* best_fft(a, omega, k): a'[i] = sum_t a[t] omega^(it)  */

@@ -223,3 +223,18 @@ def test_domain_error_behaviour(gpu, ffi):
     assert lib.h2aes_coeff_to_extended_dev(dom._h, None, 1, None) == ffi.ERR_ARG
     assert lib.h2aes_domain_transform_host(dom._h, 7, None, 1, None) == ffi.ERR_ARG
     dom.close()
+
+
+@pytest.mark.gpu
+def test_domain_limit_k22_is_reported(gpu, ffi):
+    """The documented limit (include/h2aes.h): extended_k <= 22, so the K=21/22 circuits of
+    BASELINE config 5 have no domain — h2aes_domain_create says so instead of mis-computing."""
+    import ctypes as C
+    L = ffi.lib()
+    for k in (21, 22):
+        h = C.c_void_p()
+        assert L.h2aes_domain_create(gpu._h, ffi.CS_DEGREE, k, C.byref(h)) == ffi.ERR_ARG
+        assert not h.value
+        assert b"extended_k <= 22" in L.h2aes_ctx_last_error(gpu._h)
+    ek, _ = ffi.domain_query(20)
+    assert ek == 22

@@ -399,6 +399,41 @@ def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges):
         c.close()
 
 
+def test_encrypt_append_equals_one_shot(gpu, orc, ffi):
+    """h2aes_encrypt_append_dev (the reference's per-call `encrypt`, aes128.rs:154): schedule_key
+    alone, then blocks appended in ragged batches across the column-set switch, gives the same
+    advice columns and ciphertexts as one h2aes_witness_dev call; overflow is the capacity error
+    and leaves the circuit untouched; append before schedule_key is KeysNotScheduled."""
+    import torch
+    from halo2_aes_b200.backend import Circuit
+    k, N = 17, 2
+    cap = ffi.layout_query(ffi.KIND_AES, k, N)["capacity_blocks"]
+    pts = splitmix_bytes(SEED + 97, 16 * cap).reshape(-1, 16)
+    key = splitmix_bytes(SEED + 98, 16).tobytes()
+    d_pts = torch.from_numpy(pts).cuda()
+    one = Circuit(gpu, ffi.KIND_AES, k, N)
+    adv_ref, cts_ref = one.witness(key, d_pts)
+    inc = Circuit(gpu, ffi.KIND_AES, k, N)
+    with pytest.raises(ffi.KeysNotScheduled):
+        inc.encrypt_append(d_pts[:1], adv_ref)
+    adv, _ = inc.witness(key, None)                      # schedule_key alone
+    got, at = [], 0
+    for nb in (1, 7, 90, 40, cap):                       # 95 blocks fill set 0, the rest set 1
+        nb = min(nb, cap - at)
+        first, cts = inc.encrypt_append(d_pts[at:at + nb].contiguous(), adv)
+        assert first == at
+        got.append(cts)
+        at += nb
+    assert at == cap
+    with pytest.raises(ffi.CapacityError):
+        inc.encrypt_append(d_pts[:1].contiguous(), adv)
+    assert torch.equal(adv, adv_ref) and torch.equal(torch.cat(got), cts_ref)
+    ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
+    assert (_host(adv) == ref.advice()).all()
+    one.close()
+    inc.close()
+
+
 @pytest.mark.parametrize("case", ["small", "wide", "beta_zero", "gamma_cancels_pad"])
 def test_challenge_sweep(gpu, orc, ffi, case):
     """theta / beta / gamma away from the seeded defaults: tiny challenges, full-width ones, and
