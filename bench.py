@@ -552,15 +552,14 @@ def run_b200(args):
         if not args.no_cpu and world == 1:
             cpu = cpu_baseline_sample(os.cpu_count() or 1)
         blocks = nb * CPS * args.steps * world
-        cfg = workload_config(world, CPS)
-        cfg["circuits_in_flight_per_gpu"] = P
-        cfg["host_numa_node_rank0"] = numa
+        cfg = workload_config(world, CPS)  # (exactly the reference arm's dict)
         out = {
             "metric": METRIC, "value": blocks / (ms_total * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 -> bn256 Fr (4x u64 Montgomery)",
             "data": "synthetic", "config": cfg,
+            "circuits_in_flight_per_gpu": P, "host_numa_rank0": numa,
             "roofline": roofline, "kernels": kernels,
             "phase_ms": ph_ms, "phase_ms_isolated": ph_iso,
             "circuit_algorithmic_bytes": step_bytes,

@@ -23,7 +23,7 @@ def val(r, name):
 
 kern = {}
 for r in rows[2:]:
-    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("h2::", "")
+    name = r[idx["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").replace("h2::", "")
     if name in kern:
         continue
     rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
