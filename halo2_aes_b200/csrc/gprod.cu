@@ -235,7 +235,10 @@ constexpr int ZB_T = 128;  // threads per CTA (4 independent warps)
 #define ZTOT_OCC 8
 #endif
 #ifndef ZWRITE_OCC
-#define ZWRITE_OCC 8
+#define ZWRITE_OCC 6
+#endif
+#ifndef ZWRITE_SHALLOW
+#define ZWRITE_DEEP 1  // codes three rows ahead, factors two: 4 % faster than two / one at 6 CTAs per SM
 #endif
 
 template <int SRC>
@@ -410,6 +413,17 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     const uint64_t lrw0 = (t.T * 32 * ZB_W + t.w) * ZB_R;                  // lane 0's first local row
     uint64_t *zw = a.Z + ((size_t)t.li * a.rows + lrw0) * 4;  // ... and its Z slot
     const uint64_t *z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
+#ifdef ZWRITE_DEEP
+    // software pipeline over the non-constant rows: code of row i+3, factor of row i+2
+    RowIter it(t.mb0, t.mb1, t.mb2);
+    int q1 = it.next(), q2 = it.next(), q3 = it.next();
+    uint32_t c1 = q1 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q1) : 0u;
+    uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
+    uint32_t c3 = q3 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q3) : 0u;
+    fr_t f1 = fr_one(), f2 = fr_one();
+    if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+    if (q2 >= 0) f2 = row_factor<SRC>(a, t.cx, c2, (uint32_t)q2, z);
+#else
     // software pipeline over the non-constant rows: code of row i+2, factor of row i+1
     RowIter it(t.mb0, t.mb1, t.mb2);
     int q1 = it.next(), q2 = it.next();
@@ -417,6 +431,7 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
     fr_t f1 = fr_one();
     if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+#endif
 #ifdef ZWRITE_RUNS
     {
         uint64_t *zt = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
@@ -459,11 +474,21 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
 #endif
         if ((int)r == q1) {  // (the factor was fetched before any lane overwrites its slot)
             const fr_t f = f1;
+#ifdef ZWRITE_DEEP
+            f1 = f2;
+            q1 = q2;
+            q2 = q3;
+            c2 = c3;
+            q3 = it.next();
+            if (q3 >= 0) c3 = row_code<SRC>(a, t.cx, t.row0 + q3);
+            if (q2 >= 0) f2 = row_factor<SRC>(a, t.cx, c2, (uint32_t)q2, z);
+#else
             q1 = q2;
             c1 = c2;
             q2 = it.next();
             if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
             if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
+#endif
             cur = fr_mul_inline(cur, f);
         }
 #ifndef ZWRITE_DIRECT
