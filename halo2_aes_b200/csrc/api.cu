@@ -433,7 +433,8 @@ int32_t h2aes_host_free(void *p) {
 static void circuit_free(h2aes_circuit *c) {
     void *ptrs[] = {c->d_rk,       c->d_key,      c->d_states,   c->d_trace,    c->d_chal,
                     c->d_val,      c->d_canon,    c->d_dval,     c->d_rank,     c->d_ts,
-                    c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,
+                    c->d_sorted,   c->d_slot,     c->d_head,     c->d_bhist,    c->d_bcur,     c->d_bkt,
+                    c->d_bkt_b,    c->d_splval,   c->d_splidx,
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_glist,    c->d_gbase,    c->d_gcount,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
@@ -684,6 +685,10 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     DA(c->d_sorted, VB);
     DA(c->d_slot, VB);
     DA(c->d_head, VB);
+    DA(c->d_bkt, VB);
+    DA(c->d_bkt_b, VB);
+    DA(c->d_splval, (size_t)N_VIEWS * N_BUCKETS);
+    DA(c->d_splidx, (size_t)N_VIEWS * N_BUCKETS);
     DA(c->d_bhist, (size_t)N_VIEWS * (N_BUCKETS + 1));
     DA(c->d_bcur, (size_t)N_VIEWS * N_BUCKETS);
     DA(c->d_viewmeta, (size_t)N_VIEWS * 8);

@@ -16,7 +16,7 @@ namespace h2 {
 constexpr int N_VIEWS = 3;
 constexpr uint32_t VIEW0_ENTRIES = 5 * 256 + 1;  // (tag,x) pairs + the zero row
 constexpr uint32_t VIEW_MAX_ENTRIES = (uint32_t)TABLE_ROWS;
-constexpr uint32_t BUCKET_BITS = 12;  // ~20 table values per bucket for a random theta
+constexpr uint32_t BUCKET_BITS = 12;  // room for the N_SPLIT + 1 buckets of lookup.cu
 constexpr uint32_t N_BUCKETS = 1u << BUCKET_BITS;
 constexpr uint32_t BIN_STRIDE = 66568;  // >= VIEW_MAX_ENTRIES + 2, multiple of 8
 
@@ -202,9 +202,13 @@ struct h2aes_circuit {
     uint32_t *d_sorted = nullptr;    // [3][BIN_STRIDE] entries in ascending value order
     uint32_t *d_slot = nullptr;      // [3][BIN_STRIDE] bucket-ordered entries
     uint32_t *d_head = nullptr;      // [3][BIN_STRIDE]
+    uint32_t *d_bkt = nullptr;       // [3][BIN_STRIDE] bucket of every entry
+    uint32_t *d_bkt_b = nullptr;     // [3][BIN_STRIDE] the same in bucket order
+    h2::fr_t *d_splval = nullptr;    // [3][N_BUCKETS] sorted sample of the canonical values (splitters)
+    uint32_t *d_splidx = nullptr;    // [3][N_BUCKETS] ... and their entry indices (ties)
     uint32_t *d_bhist = nullptr;     // [3][N_BUCKETS+1]
     uint32_t *d_bcur = nullptr;      // [3][N_BUCKETS]
-    uint32_t *d_viewmeta = nullptr;  // [3][8]: maxbits, n_bins, ...
+    uint32_t *d_viewmeta = nullptr;  // [3][8]: [1] = number of bins
     h2::fr_t *d_ib = nullptr;        // [3][BIN_STRIDE] 1/(dval+beta)
     h2::fr_t *d_ig = nullptr;        // [3][BIN_STRIDE] 1/(dval+gamma)
     h2::fr_t *d_nac = nullptr;       // [3][BIN_STRIDE] (dval+beta)*(pad+gamma)

@@ -13,7 +13,8 @@
 //   * every input value is the compression of one of <= 66561 table tuples, so the rows are
 //     counted per *bin* (distinct compressed value) from the 4-byte trace word of each row;
 //   * the bins are ordered once per theta per view (2-, 3-, 4-column tables) with a bucket sort
-//     on the canonical value (12 leading bits) + exact 256-bit ranking inside each bucket;
+//     (splitters from a sorted sample of the values themselves) + exact 256-bit ranking inside
+//     each bucket;
 //   * A'/S' are expanded from the run structure (binary search of the row in the run offsets);
 //     the same kernel classifies every row's grand-product factor (4-byte code, one mask bit per
 //     row for "factor is not one" and one for "factor is not a single table entry");
@@ -29,26 +30,6 @@ cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const 
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fr_bitlen(const fr_t &c) {
-    uint32_t bits = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (c.v[i]) bits = 32 * i + (32 - __clz(c.v[i]));
-    return bits;
-}
-__device__ __forceinline__ uint32_t bucket_of(const fr_t &c, uint32_t maxbits) {
-    const uint32_t shift = maxbits > BUCKET_BITS ? maxbits - BUCKET_BITS : 0;
-    const uint32_t w = shift >> 5, b = shift & 31;
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i == (int)w) lo = c.v[i];
-        if (i == (int)w + 1) hi = c.v[i];
-    }
-    const uint64_t x = ((uint64_t)hi << 32) | lo;
-    return (uint32_t)((x >> b) & (N_BUCKETS - 1));
-}
-
 // Exclusive scan of data[0..n) in place by ONE CTA (<= 1024 threads); returns the total to all.
 // Rounds of SCAN_E*blockDim consecutive elements, thread t on SCAN_E consecutive elements of the
 // round (64 contiguous bytes per thread); few rounds because every round costs a block barrier
@@ -105,7 +86,7 @@ __device__ uint32_t block_exclusive_scan_u32(uint32_t *data, uint32_t n) {
 // ---------------------------------------------------------------------------------------------
 // phase 1a: per-view bins (once per theta)
 // ---------------------------------------------------------------------------------------------
-// viewmeta[v*8 + 0] = max bit length of the canonical values, +1 = number of bins
+// viewmeta[v*8 + 1] = number of bins
 __global__ void __launch_bounds__(256)
 k_view_values(const uint8_t *__restrict__ sbox, const uint4 *__restrict__ frtab,
               const fr_t *__restrict__ chal, fr_t *__restrict__ val, fr_t *__restrict__ canon,
@@ -121,39 +102,6 @@ k_view_values(const uint8_t *__restrict__ sbox, const uint4 *__restrict__ frtab,
     fr_st(val + (size_t)v * BIN_STRIDE + e, acc);
     const fr_t c = fr_to_canonical(acc);
     fr_st(canon + (size_t)v * BIN_STRIDE + e, c);
-    atomicMax(viewmeta + v * 8, fr_bitlen(c));
-}
-
-__global__ void __launch_bounds__(256)
-k_bucket_hist(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
-              uint32_t *__restrict__ bhist) {
-    const int v = blockIdx.y;
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= view_entries(v)) return;
-    const uint32_t b = bucket_of(fr_ld(canon + (size_t)v * BIN_STRIDE + e), viewmeta[v * 8]);
-    atomicAdd(bhist + (size_t)v * (N_BUCKETS + 1) + b, 1u);
-}
-
-__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ bhist) {
-    const int v = blockIdx.x;
-    uint32_t *h = bhist + (size_t)v * (N_BUCKETS + 1);
-    uint32_t total = block_exclusive_scan_u32(h, N_BUCKETS);
-    if (threadIdx.x == 0) h[N_BUCKETS] = total;
-}
-
-__global__ void __launch_bounds__(256)
-k_bucket_scatter(const fr_t *__restrict__ canon, const uint32_t *__restrict__ viewmeta,
-                 const uint32_t *__restrict__ bhist, uint32_t *__restrict__ bcur,
-                 uint32_t *__restrict__ slot, fr_t *__restrict__ canon_b) {
-    const int v = blockIdx.y;
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= view_entries(v)) return;
-    const fr_t me = fr_ld(canon + (size_t)v * BIN_STRIDE + e);
-    const uint32_t b = bucket_of(me, viewmeta[v * 8]);
-    const uint32_t pos = bhist[(size_t)v * (N_BUCKETS + 1) + b] +
-                         atomicAdd(bcur + (size_t)v * N_BUCKETS + b, 1u);
-    slot[(size_t)v * BIN_STRIDE + pos] = e;
-    fr_st(canon_b + (size_t)v * BIN_STRIDE + pos, me);  // bucket mates contiguous for k_bucket_rank
 }
 
 // branch-free 256-bit compare of canonical values: *lt = (a < b) from one borrow chain, *eq from
@@ -177,31 +125,126 @@ __device__ __forceinline__ void fr_lt_eq(const fr_t &a, const fr_t &b, uint32_t 
     *lt = borrow & 1u;  // 0xffffffff when a - b borrowed
     *eq = ((d0 | d1 | d2 | d3 | d4 | d5 | d6 | d7) == 0u) ? 1u : 0u;
 }
+// sort key = (canonical value, entry index): all keys are distinct, so equal values — a tiny theta
+// makes thousands of table tuples compress to the same element — spread over the buckets too
+__device__ __forceinline__ bool key_less(const fr_t &a, uint32_t ia, const fr_t &b, uint32_t ib) {
+    uint32_t lt, eq;
+    fr_lt_eq(a, b, &lt, &eq);
+    return lt || (eq && ia < ib);
+}
+
+// Bucket boundaries from the data (sample sort): N_SPLIT entries taken at regular index intervals
+// and sorted (k_splitters) by their (value, index) keys.  Whatever the
+// distribution of the values — 256 consecutive integers per (tag, x) for a 3-column view, a few
+// huge clusters for a theta below 2^64, everything equal for theta = 0 — a bucket then holds about
+// entries / N_SPLIT keys, and the exact in-bucket ranking below stays linear overall.
+constexpr uint32_t N_SPLIT = 2048;  // buckets = N_SPLIT + 1 <= N_BUCKETS
+static_assert(N_SPLIT + 1 <= N_BUCKETS, "bucket arrays");
+// the samples, contiguous (so that k_splitters reads them coalesced)
+__global__ void __launch_bounds__(256)
+k_sample(const fr_t *__restrict__ canon, fr_t *__restrict__ smp) {
+    const int v = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N_SPLIT) return;
+    const uint32_t e = (uint32_t)(((uint64_t)i * view_entries(v)) / N_SPLIT);
+    fr_st(smp + (size_t)v * N_SPLIT + i, fr_ld(canon + (size_t)v * BIN_STRIDE + e));
+}
+// one warp per sample: its position among the N_SPLIT samples by counting (lane l compares with
+// samples l, l+32, ...; ties — the same entry sampled twice when a view has fewer entries than
+// samples — by sample number), then the key goes to that position.  4 M cheap compares spread over
+// the whole GPU instead of a sorting network on one SM.
+__global__ void __launch_bounds__(128)
+k_splitters(const fr_t *__restrict__ smp, fr_t *__restrict__ spl_val, uint32_t *__restrict__ spl_idx) {
+    const int v = blockIdx.y;
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // my sample
+    if (i >= N_SPLIT) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t np = view_entries(v);
+    const fr_t *sv = smp + (size_t)v * N_SPLIT;
+    const uint32_t ei = (uint32_t)(((uint64_t)i * np) / N_SPLIT);
+    const fr_t me = fr_ld(sv + i);
+    uint32_t less = 0;
+#pragma unroll 4
+    for (uint32_t j = lane; j < N_SPLIT; j += 32) {
+        const uint32_t ej = (uint32_t)(((uint64_t)j * np) / N_SPLIT);
+        uint32_t lt, eq;
+        fr_lt_eq(fr_ldg_256_nc(sv + j), me, &lt, &eq);
+        less += lt | (eq & ((ej < ei || (ej == ei && j < i)) ? 1u : 0u));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) less += __shfl_xor_sync(0xffffffffu, less, d);
+    if (lane == 0) {
+        fr_st(spl_val + (size_t)v * N_SPLIT + less, me);
+        spl_idx[(size_t)v * N_SPLIT + less] = ei;
+    }
+}
+
+// bucket of an entry = number of splitters <= its key; stored for the scatter and ranking kernels
+__global__ void __launch_bounds__(256)
+k_bucket_hist(const fr_t *__restrict__ canon, const fr_t *__restrict__ spl_val,
+              const uint32_t *__restrict__ spl_idx, uint32_t *__restrict__ bkt,
+              uint32_t *__restrict__ bhist) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const fr_t me = fr_ld(canon + (size_t)v * BIN_STRIDE + e);
+    const fr_t *sv = spl_val + (size_t)v * N_SPLIT;
+    const uint32_t *si = spl_idx + (size_t)v * N_SPLIT;
+    uint32_t lo = 0, hi = N_SPLIT;  // first splitter > me
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key_less(me, e, fr_ld(sv + mid), si[mid])) hi = mid; else lo = mid + 1;
+    }
+    bkt[(size_t)v * BIN_STRIDE + e] = lo;
+    atomicAdd(bhist + (size_t)v * (N_BUCKETS + 1) + lo, 1u);
+}
+
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ bhist) {
+    const int v = blockIdx.x;
+    uint32_t *h = bhist + (size_t)v * (N_BUCKETS + 1);
+    uint32_t total = block_exclusive_scan_u32(h, N_BUCKETS);
+    if (threadIdx.x == 0) h[N_BUCKETS] = total;
+}
+
+// entries (and their keys and buckets) in bucket order, so that bucket mates are contiguous
+__global__ void __launch_bounds__(256)
+k_bucket_scatter(const fr_t *__restrict__ canon, const uint32_t *__restrict__ bkt,
+                 const uint32_t *__restrict__ bhist, uint32_t *__restrict__ bcur,
+                 uint32_t *__restrict__ slot, fr_t *__restrict__ canon_b,
+                 uint32_t *__restrict__ bkt_b) {
+    const int v = blockIdx.y;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= view_entries(v)) return;
+    const fr_t me = fr_ld(canon + (size_t)v * BIN_STRIDE + e);
+    const uint32_t b = bkt[(size_t)v * BIN_STRIDE + e];
+    const uint32_t pos = bhist[(size_t)v * (N_BUCKETS + 1) + b] +
+                         atomicAdd(bcur + (size_t)v * N_BUCKETS + b, 1u);
+    slot[(size_t)v * BIN_STRIDE + pos] = e;
+    bkt_b[(size_t)v * BIN_STRIDE + pos] = b;
+    fr_st(canon_b + (size_t)v * BIN_STRIDE + pos, me);
+}
 
 // exact position of the entry at bucket slot p: bucket offset + number of bucket mates that order
-// before it (ties broken by entry index).  Buckets can be large: the 256 values tag*theta^2 +
-// x*theta + y, y = 0..255, of one x are consecutive integers and share their leading bits.  The
-// CTA stages the canonical values of every bucket its 256 slots touch in shared memory (window
-// of RANK_WIN entries; anything beyond falls back to global loads).
+// before it (ties broken by entry index).  The CTA stages the canonical values of every bucket its
+// 256 slots touch in shared memory (window of RANK_WIN entries; anything beyond falls back to
+// global loads — with splitters from the data a bucket holds ~32 entries, so that is rare).
 constexpr uint32_t RANK_WIN = 1280;
 __global__ void __launch_bounds__(256)
-k_bucket_rank(const fr_t *__restrict__ canon_b, const uint32_t *__restrict__ viewmeta,
+k_bucket_rank(const fr_t *__restrict__ canon_b, const uint32_t *__restrict__ bkt_b,
               const uint32_t *__restrict__ bhist, const uint32_t *__restrict__ slot,
               uint32_t *__restrict__ sorted) {
     __shared__ uint4 s_c[2 * RANK_WIN];
-    __shared__ uint32_t s_lo, s_hi;
     const int v = blockIdx.y;
     const uint32_t np = view_entries(v);
     const uint32_t p0 = blockIdx.x * blockDim.x;
     if (p0 >= np) return;
     const fr_t *__restrict__ cb = canon_b + (size_t)v * BIN_STRIDE;
     const uint32_t *__restrict__ sl = slot + (size_t)v * BIN_STRIDE;
+    const uint32_t *__restrict__ bb = bkt_b + (size_t)v * BIN_STRIDE;
     const uint32_t *__restrict__ bh = bhist + (size_t)v * (N_BUCKETS + 1);
-    const uint32_t maxbits = viewmeta[v * 8];
-    if (threadIdx.x == 0) s_lo = bh[bucket_of(fr_ld(cb + p0), maxbits)];
-    if (threadIdx.x == 32) s_hi = bh[bucket_of(fr_ld(cb + min(p0 + blockDim.x, np) - 1), maxbits) + 1];
-    __syncthreads();
-    const uint32_t w_lo = s_lo, w_n = min(s_hi - s_lo, RANK_WIN);
+    const uint32_t w_lo = bh[bb[p0]];
+    const uint32_t w_hi = bh[bb[min(p0 + blockDim.x, np) - 1] + 1];
+    const uint32_t w_n = min(w_hi - w_lo, RANK_WIN);
     for (uint32_t i = threadIdx.x; i < w_n; i += blockDim.x) {
         const uint4 *src = reinterpret_cast<const uint4 *>(cb + w_lo + i);
         s_c[2 * i] = src[0];
@@ -212,7 +255,7 @@ k_bucket_rank(const fr_t *__restrict__ canon_b, const uint32_t *__restrict__ vie
     if (p >= np) return;
     const fr_t me = fr_ld(cb + p);
     const uint32_t e = sl[p];
-    const uint32_t b = bucket_of(me, maxbits);
+    const uint32_t b = bb[p];
     const uint32_t lo = bh[b], hi = bh[b + 1];
     uint32_t rank = 0;
     for (uint32_t q = lo; q < hi; ++q) {
@@ -836,18 +879,25 @@ cudaError_t launch_view_bins(h2aes_circuit *c) {
     k_view_values<<<g, 256, 0, s>>>(ctx->d_sbox, ctx->d_frtab, c->d_chal, c->d_val, c->d_canon,
                                     c->d_viewmeta);
     prof_end(ctx);
+    fr_t *smp = c->d_splval + (size_t)N_VIEWS * N_SPLIT;  // (second half of the allocation)
+    prof_begin(ctx, "k_sample");
+    k_sample<<<dim3(N_SPLIT / 256, N_VIEWS), 256, 0, s>>>(c->d_canon, smp);
+    prof_end(ctx);
+    prof_begin(ctx, "k_splitters");
+    k_splitters<<<dim3(N_SPLIT / 4, N_VIEWS), 128, 0, s>>>(smp, c->d_splval, c->d_splidx);
+    prof_end(ctx);
     prof_begin(ctx, "k_bucket_hist");
-    k_bucket_hist<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist);
+    k_bucket_hist<<<g, 256, 0, s>>>(c->d_canon, c->d_splval, c->d_splidx, c->d_bkt, c->d_bhist);
     prof_end(ctx);
     prof_begin(ctx, "k_bucket_scan");
     k_bucket_scan<<<N_VIEWS, 1024, 0, s>>>(c->d_bhist);
     prof_end(ctx);
     prof_begin(ctx, "k_bucket_scatter");
-    k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_viewmeta, c->d_bhist, c->d_bcur, c->d_slot,
-                                       c->d_canon_b);
+    k_bucket_scatter<<<g, 256, 0, s>>>(c->d_canon, c->d_bkt, c->d_bhist, c->d_bcur, c->d_slot,
+                                       c->d_canon_b, c->d_bkt_b);
     prof_end(ctx);
     prof_begin(ctx, "k_bucket_rank");
-    k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon_b, c->d_viewmeta, c->d_bhist, c->d_slot, c->d_sorted);
+    k_bucket_rank<<<g, 256, 0, s>>>(c->d_canon_b, c->d_bkt_b, c->d_bhist, c->d_slot, c->d_sorted);
     prof_end(ctx);
     // (d_slot is free again after k_bucket_rank: reused for the per-tile head counts)
     prof_begin(ctx, "k_bin_heads");
@@ -857,7 +907,7 @@ cudaError_t launch_view_bins(h2aes_circuit *c) {
     k_bin_fill<<<g, 256, 0, s>>>(c->d_val, c->d_sorted, c->d_head, c->d_slot, c->sh.usable(),
                                  c->d_dval, c->d_rank, c->d_ts, c->d_viewmeta);
     prof_end(ctx);
-    ctx->launches += 7;
+    ctx->launches += 9;
     return cudaGetLastError();
 }
 
