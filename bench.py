@@ -665,10 +665,11 @@ def run_sharded(args, local, rank, world, th, be, ga):
         cir.circuit.lookup_check()
         t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[0].elapsed_time(e[2])],
                          dtype=torch.float64, device="cuda")
+        mine_lk = float(t[1])
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if it >= 2:
-            times.append(t.tolist())
+            times.append(t.tolist() + [mine_lk])
     # size-independent checks on the device: Z[0] = 1, Z[n-6] = 1, blinding rows zero,
     # (A'_i - S'_i)(A'_i - A'_{i-1}) = 0 on the shard's usable rows
     lo, hi = cir.row_range
@@ -691,7 +692,13 @@ def run_sharded(args, local, rank, world, th, be, ga):
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     assert int(flag) == 1, "sharded lookup columns violate an invariant"
-    w, lk, tot = (float(np.mean([t[j] for t in times])) for j in range(3))
+    w, lk, tot, my_lk = (float(np.mean([t[j] for t in times])) for j in range(4))
+    per_rank = [my_lk]
+    if world > 1:
+        g = torch.zeros(world, dtype=torch.float64, device="cuda")
+        g[rank] = my_lk
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        per_rank = g.tolist()
     hist_bytes = L * 66568 * 4
     rec = {"config": f"ONE K={k}, N={N} circuit at capacity ({nb} blocks) row-sharded over {world} GPU(s)",
            "n_gpus": world, "blocks": nb, "rows_per_gpu": rows, "witness_ms": w, "lookup_columns_ms": lk,
@@ -702,9 +709,13 @@ def run_sharded(args, local, rank, world, th, be, ga):
            "collectives": "ncclAllReduce (u32 sum, all 25 lookups in one call) + ncclAllGather (one Fr "
                           "per lookup per shard), issued by h2aes_lookup_columns_sharded_dev on the "
                           "compute stream" if world > 1 else "none (one shard)",
-           "bound": "replicated per-theta bin order + per-(beta,gamma) inverse tables (~0.4 ms on every "
-                    "rank, do not shrink with G) and the latency of the two collectives; the bulk "
-                    "columns never cross NVLink",
+           "lookup_columns_ms_per_rank": per_rank,
+           "bound": "load balance of the grand product: with contiguous row ownership the shards at the "
+                    "END of the columns hold the rows where A' is not zero, every one of which costs two "
+                    "multiplies, while the first shards mostly hold rows whose factor is one (see "
+                    "lookup_columns_ms_per_rank); then the per-theta bin order and the per-(beta,gamma) "
+                    "inverse tables, replicated on every rank (~0.25 ms), and the two collectives.  The "
+                    "bulk columns never cross NVLink",
            "checks": "Z[0]=1, Z[n-6]=1, blinding rows zero, permuted-pair constraint on every shard: ok"}
     del advice, out, pts
     cir.circuit.close()
