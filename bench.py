@@ -529,7 +529,10 @@ def run_b200(args):
         for p_ in pipes[1:]:
             p_.free()
         try:
-            sharded_rec = run_sharded(args, local, rank, world, th, be, ga)
+            sharded_rec = run_sharded(args, local, rank, world, th, be, ga, tiled=True)
+            if world > 1:
+                sharded_rec["contiguous_ownership"] = run_sharded(args, local, rank, world, th, be, ga,
+                                                                  tiled=False)
         except Exception as e:  # never lose the headline line to the extra measurement
             sharded_rec = {"error": repr(e)}
 
@@ -621,7 +624,7 @@ def run_config4(pipes, circuit_with_blocks, rank, world, n, one):
             "note": "2^20 blocks as 273 independent K=20,N=5 circuits, round-robin over the ranks"}
 
 
-def run_sharded(args, local, rank, world, th, be, ga):
+def run_sharded(args, local, rank, world, th, be, ga, tiled=True):
     """BASELINE config 5: ONE K=22, N=5 circuit filled to capacity (15418 blocks), row-sharded over
     the ranks; both exchanges (bin-histogram all-reduce, partial-product all-gather) are issued by
     the library over its own NCCL communicator inside the timed region.  With one rank it is the
@@ -636,10 +639,10 @@ def run_sharded(args, local, rank, world, th, be, ga):
     stream = torch.cuda.Stream(device=local)
     ctx.use_stream(stream)
     sharded.library_comm_init(ctx)
-    cir = sharded.RowShardedCircuit(ctx, _ffi.KIND_AES, k, N, library_comm=True)
+    cir = sharded.RowShardedCircuit(ctx, _ffi.KIND_AES, k, N, library_comm=True, tiled=tiled)
     lay = cir.circuit.layout
     n, nb, L, nadv = lay["n_rows"], lay["capacity_blocks"], lay["n_lookups"], lay["n_advice"]
-    rows = n // world
+    rows = cir.circuit.rows
     key = splitmix_bytes(SEED + 80, 16).tobytes()
     one = torch.tensor([-0x5369cbe3b0000005, 0x36fc76959f60cd29, 0x666ea36f7879462e,
                         0x0e0a77c19a07df2f], dtype=torch.int64, device="cuda")
@@ -671,22 +674,25 @@ def run_sharded(args, local, rank, world, th, be, ga):
         if it >= 2:
             times.append(t.tolist() + [mine_lk])
     # size-independent checks on the device: Z[0] = 1, Z[n-6] = 1, blinding rows zero,
-    # (A'_i - S'_i)(A'_i - A'_{i-1}) = 0 on the shard's usable rows
-    lo, hi = cir.row_range
+    # (A'_i - S'_i)(A'_i - A'_{i-1}) = 0 on the shard's usable rows (inside its row ranges)
+    grow = torch.from_numpy(cir.circuit.global_rows()).cuda()
     ok = True
     with torch.cuda.stream(stream):
         Z, Ap, Sp = out["Z"], out["Ap"], out["Sp"]
-        if rank == 0:
-            ok &= bool((Z[:, 0] == one).all())
-        if lo <= n - 6 < hi:
-            ok &= bool((Z[:, n - 6 - lo] == one).all())
-            ok &= not bool(Z[:, n - 5 - lo:].any())
-        u = min(hi, n - 6) - lo
+        at = lambda r: torch.nonzero(grow == r).flatten()
+        i0, iu = at(0), at(n - 6)
+        if i0.numel():
+            ok &= bool((Z[:, i0[0]] == one).all())
+        if iu.numel():
+            ok &= bool((Z[:, iu[0]] == one).all())
+        ok &= not bool(Z[:, grow > n - 6].any())
+        usable = grow < n - 6
+        inner = usable[1:] & (grow[1:] == grow[:-1] + 1)      # rows whose predecessor is local too
         for l0 in range(0, L, 5):  # (a column set at a time: bounded temporaries)
             a_, s_ = Ap[l0:l0 + 5], Sp[l0:l0 + 5]
-            same_s = (a_[:, 1:u] == s_[:, 1:u]).all(dim=-1)
-            same_prev = (a_[:, 1:u] == a_[:, :u - 1]).all(dim=-1)
-            ok &= bool((same_s | same_prev).all())
+            same_s = (a_[:, 1:] == s_[:, 1:]).all(dim=-1)
+            same_prev = (a_[:, 1:] == a_[:, :-1]).all(dim=-1)
+            ok &= bool((same_s | same_prev)[:, inner].all())
         flag = torch.tensor([1 if ok else 0], device="cuda")
     stream.synchronize()
     if world > 1:
@@ -700,7 +706,10 @@ def run_sharded(args, local, rank, world, th, be, ga):
         dist.all_reduce(g, op=dist.ReduceOp.SUM)
         per_rank = g.tolist()
     hist_bytes = L * 66568 * 4
+    own = ("ownership tiles of 43520 rows dealt round-robin (h2aes_circuit_set_shard_tiled)" if tiled
+           else "contiguous n/G rows per shard (h2aes_circuit_set_shard)")
     rec = {"config": f"ONE K={k}, N={N} circuit at capacity ({nb} blocks) row-sharded over {world} GPU(s)",
+           "row_ownership": own if world > 1 else "one shard",
            "n_gpus": world, "blocks": nb, "rows_per_gpu": rows, "witness_ms": w, "lookup_columns_ms": lk,
            "ms": tot, "value": nb / (tot * 1e-3), "unit": UNIT,
            "bytes_per_gpu": (nadv + 3 * L) * rows * 32,
@@ -710,12 +719,14 @@ def run_sharded(args, local, rank, world, th, be, ga):
                           "per lookup per shard), issued by h2aes_lookup_columns_sharded_dev on the "
                           "compute stream" if world > 1 else "none (one shard)",
            "lookup_columns_ms_per_rank": per_rank,
-           "bound": "load balance of the grand product: with contiguous row ownership the shards at the "
-                    "END of the columns hold the rows where A' is not zero, every one of which costs two "
-                    "multiplies, while the first shards mostly hold rows whose factor is one (see "
-                    "lookup_columns_ms_per_rank); then the per-theta bin order and the per-(beta,gamma) "
-                    "inverse tables, replicated on every rank (~0.25 ms), and the two collectives.  The "
-                    "bulk columns never cross NVLink",
+           "bound": ("the per-theta bin order and the per-(beta,gamma) inverse tables, replicated on every "
+                     "rank (~0.25 ms, do not shrink with G), ~25 kernel launches and the two collectives; "
+                     "the multiplies of the grand product are balanced by the dealt tiles" if tiled else
+                     "load balance of the grand product: with contiguous ownership the shards at the END "
+                     "of the columns hold the rows where A' is not zero, every one of which costs two "
+                     "multiplies (see lookup_columns_ms_per_rank); then the replicated per-theta / "
+                     "per-(beta,gamma) tables and the two collectives") + ".  The bulk columns never "
+                    "cross NVLink",
            "checks": "Z[0]=1, Z[n-6]=1, blinding rows zero, permuted-pair constraint on every shard: ok"}
     del advice, out, pts
     cir.circuit.close()

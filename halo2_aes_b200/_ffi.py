@@ -22,6 +22,7 @@ SBOX_REFERENCE, SBOX_FIPS197 = 0, 1
 OP_NONE, OP_RANGE, OP_XOR, OP_SBOX, OP_MUL2, OP_MUL3 = 0, 1, 2, 3, 4, 5
 DOMAIN_FFT, DOMAIN_LAGRANGE_TO_COEFF, DOMAIN_COEFF_TO_EXTENDED, DOMAIN_EXTENDED_TO_COEFF = 0, 1, 2, 3
 COMM_ID_BYTES = 128  # an ncclUniqueId
+SHARD_TILE_ROWS = 43520  # rows of an ownership tile of h2aes_circuit_set_shard_tiled
 CS_DEGREE = 5  # cs.degree() of both circuits (lookups: 2 + 2 + 1)
 
 
@@ -131,6 +132,8 @@ SIGNATURES = {
     "h2aes_lookup_stats": (C.c_int32, [_vp, _u64p]),
     "h2aes_lookup_check": (C.c_int32, [_vp]),
     "h2aes_circuit_set_shard": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
+    "h2aes_circuit_set_shard_tiled": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
+    "h2aes_circuit_shard_query": (C.c_int32, [_vp, _u64p, _u64p]),
     "h2aes_lookup_hist_dev": (C.c_int32, [_vp, _u64p, C.POINTER(_vp), _u64p]),
     "h2aes_lookup_permuted_shard_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp]),
     "h2aes_lookup_partial_dev": (C.c_int32, [_vp, _u64p, _u64p, _vp, C.POINTER(_vp)]),

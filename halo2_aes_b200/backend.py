@@ -102,7 +102,8 @@ class Circuit:
         self.layout = _ffi.layout_query(kind, k, N)
         self.n = self.layout["n_rows"]
         self.n_blocks = 0
-        self.shard, self.n_shards = 0, 1
+        self.shard, self.n_shards, self.tiled = 0, 1, False
+        self._rows, self._partial_words = self.n, self.layout["n_lookups"] * 4
         h = C.c_void_p()
         check(lib().h2aes_circuit_create(ctx._h, kind, k, N, C.byref(h)), ctx._h)
         self._h = h
@@ -111,7 +112,16 @@ class Circuit:
     @property
     def rows(self) -> int:
         """rows of every column held by this (shard of the) circuit"""
-        return self.n // self.n_shards
+        return self._rows
+
+    def global_rows(self) -> np.ndarray:
+        """global row index of every local row of this shard (host; tests and checks)"""
+        if self.n_shards == 1:
+            return np.arange(self.n, dtype=np.int64)
+        ts = _ffi.SHARD_TILE_ROWS if self.tiled else self.n // self.n_shards
+        lr = np.arange(self._rows, dtype=np.int64)
+        t = lr // ts
+        return (t * self.n_shards + self.shard) * ts + (lr - t * ts)
 
     def _cols(self, ncols: int, out=None):
         if out is None:
@@ -119,9 +129,15 @@ class Circuit:
         assert out.is_cuda and out.is_contiguous() and out.numel() == ncols * self.rows * 4
         return out
 
-    def set_shard(self, shard: int, n_shards: int):
-        check(lib().h2aes_circuit_set_shard(self._h, shard, n_shards), self.ctx._h)
-        self.shard, self.n_shards = shard, n_shards
+    def set_shard(self, shard: int, n_shards: int, tiled: bool = False):
+        """shard `shard` of `n_shards`: contiguous rows, or (tiled) ownership tiles of 43520 rows
+        dealt round-robin — the balanced split for the grand product"""
+        fn = lib().h2aes_circuit_set_shard_tiled if tiled else lib().h2aes_circuit_set_shard
+        check(fn(self._h, shard, n_shards), self.ctx._h)
+        self.shard, self.n_shards, self.tiled = shard, n_shards, bool(tiled) and n_shards > 1
+        rows, pw = C.c_uint64(), C.c_uint64()
+        check(lib().h2aes_circuit_shard_query(self._h, C.byref(rows), C.byref(pw)), self.ctx._h)
+        self._rows, self._partial_words = rows.value, pw.value
 
     # ---- witness ------------------------------------------------------------------------------
     def witness(self, key, plaintexts=None, out=None, want_ciphertexts=True):
@@ -314,19 +330,20 @@ class Circuit:
         return bufs
 
     def shard_partial(self, beta, gamma):
-        """phase 2a: returns (Z buffer holding the factors, partial products [L,4])"""
+        """phase 2a: returns (Z buffer holding the factors, partial products [L * segments, 4])"""
         be, bep = _fr_arg(beta)
         ga, gap = _fr_arg(gamma)
         L = self.layout["n_lookups"]
         Z = torch.empty((L, self.rows, 4), dtype=torch.int64, device=self.ctx.device)
         p = C.c_void_p()
         check(lib().h2aes_lookup_partial_dev(self._h, bep, gap, _ptr(Z), C.byref(p)), self.ctx._h)
-        return Z, _wrap_device_i64(p.value, L * 4, self.ctx.device).view(L, 4)
+        return Z, _wrap_device_i64(p.value, self._partial_words, self.ctx.device).view(-1, 4)
 
     def shard_product(self, gathered: torch.Tensor, Z: torch.Tensor):
         """phase 2b: finishes Z in place from every shard's partial products"""
         L = self.layout["n_lookups"]
-        assert gathered.is_cuda and gathered.is_contiguous() and gathered.numel() == self.n_shards * L * 4
+        assert gathered.is_cuda and gathered.is_contiguous()
+        assert gathered.numel() == self.n_shards * self._partial_words
         check(lib().h2aes_lookup_product_shard_dev(self._h, _ptr(gathered), _ptr(Z)), self.ctx._h)
         return Z
 

@@ -17,26 +17,24 @@
 namespace h2 {
 cudaError_t launch_build_frtab(h2aes_ctx *ctx);
 cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
-                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev,
-                           uint64_t row_begin, uint64_t row_end);
+                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev, const RowMap &rm);
 cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
                                   uint64_t first_block, uint64_t n, uint64_t *advice_dev,
                                   uint8_t *cts_dev);
 cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
-                         uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end);
+                         uint64_t *selectors_dev, const RowMap &rm);
 cudaError_t launch_copies(h2aes_circuit *c, uint64_t n_copies, uint64_t *out);
 cudaError_t launch_view_bins(h2aes_circuit *c);
-cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t row_end);
+cudaError_t launch_lookup_hist(h2aes_circuit *c, const RowMap &rm);
 cudaError_t launch_lookup_bins(h2aes_circuit *c);
 cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
-                            uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end);
+                            uint64_t *Ap, uint64_t *Sp, const RowMap &rm);
 cudaError_t launch_inv_tables(h2aes_circuit *c);
 cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                          uint64_t *Z, uint64_t row_begin, uint64_t row_end);
-cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, uint64_t row_begin, uint64_t row_end);
-cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, uint64_t row_begin,
-                            uint64_t row_end);
-cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev);
+                          uint64_t *Z, const RowMap &rm);
+cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, const RowMap &rm);
+cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, const RowMap &rm);
+cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev, uint32_t segs);
 uint32_t lookup_bin_tiles();
 cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta);
 cudaError_t launch_perm_sigma(h2aes_circuit *c, uint64_t *sigma_dev);
@@ -490,10 +488,27 @@ int32_t h2aes_circuit_destroy(h2aes_circuit *c) {
     return H2AES_OK;
 }
 
-static void shard_rows(const h2aes_circuit *c, uint64_t *begin, uint64_t *end) {
-    const uint64_t per = c->sh.n() / (uint64_t)c->n_shards;
-    *begin = per * (uint64_t)c->shard;
-    *end = *begin + per;
+// the rows this (shard of the) circuit holds: contiguous n/G rows, or ownership tiles of
+// H2AES_SHARD_TILE_ROWS rows dealt round-robin (h2aes_circuit_set_shard_tiled)
+static RowMap shard_map(const h2aes_circuit *c) {
+    return row_map_of(c->sh.n(), c->shard_ts, (uint32_t)c->n_shards, (uint32_t)c->shard);
+}
+
+int32_t h2aes_circuit_set_shard_tiled(h2aes_circuit *c, int32_t shard, int32_t n_shards) {
+    int32_t rc = h2aes_circuit_set_shard(c, shard, n_shards);
+    if (rc != H2AES_OK || n_shards == 1) return rc;
+    if (zscan_tiles(c->sh.n()) < (uint64_t)n_shards)
+        return fail(c->ctx, H2AES_ERR_ARG, "tiled shards: fewer ownership tiles than shards");
+    c->shard_ts = H2AES_SHARD_TILE_ROWS;
+    return rc;
+}
+
+int32_t h2aes_circuit_shard_query(h2aes_circuit *c, uint64_t *rows, uint64_t *partial_words) {
+    if (!c) return H2AES_ERR_ARG;
+    const RowMap rm = shard_map(c);
+    if (rows) *rows = rm.rows;
+    if (partial_words) *partial_words = (uint64_t)c->sh.n_lookups() * rm.segments() * 4;
+    return H2AES_OK;
 }
 
 int32_t h2aes_circuit_set_shard(h2aes_circuit *c, int32_t shard, int32_t n_shards) {
@@ -503,6 +518,7 @@ int32_t h2aes_circuit_set_shard(h2aes_circuit *c, int32_t shard, int32_t n_shard
         return fail(c->ctx, H2AES_ERR_ARG, "n_shards must be a power of two <= 64");
     c->shard = shard;
     c->n_shards = n_shards;
+    c->shard_ts = 0;
     c->have_witness = c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
     return H2AES_OK;
 }
@@ -518,9 +534,8 @@ int32_t h2aes_witness_dev(h2aes_circuit *c, const uint8_t *key, const uint8_t *p
     if (n_blocks > c->sh.capacity())
         return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
     CU(ctx, cudaSetDevice(ctx->device));
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
-    CU(ctx, launch_witness(c, key, plaintexts_dev, n_blocks, advice_dev, ciphertexts_dev, rb, re));
+    const RowMap rm = shard_map(c);
+    CU(ctx, launch_witness(c, key, plaintexts_dev, n_blocks, advice_dev, ciphertexts_dev, rm));
     memcpy(c->key, key, 16);
     c->n_blocks = n_blocks;
     c->have_witness = true;
@@ -580,9 +595,8 @@ int32_t h2aes_witness_host(h2aes_circuit *c, const uint8_t *key, const uint8_t *
         CU(ctx, dalloc(&c->d_ct, cap * 16));
         c->pt_cap = cap;
     }
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
-    const uint64_t bytes = (uint64_t)c->sh.n_advice() * (re - rb) * 32;
+    const RowMap rm = shard_map(c);
+    const uint64_t bytes = (uint64_t)c->sh.n_advice() * rm.rows * 32;
     int32_t rc = ensure_stage(c, bytes);
     if (rc) return rc;
     if (n_blocks)
@@ -617,9 +631,8 @@ int32_t h2aes_fixed_columns_dev(h2aes_circuit *c, uint64_t n_blocks, uint64_t *f
         return fail(ctx, H2AES_ERR_CAPACITY, "AES calls too many. doesn't fit in the rows");
     if (!fixed_dev && !selectors_dev) return H2AES_OK;
     CU(ctx, cudaSetDevice(ctx->device));
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
-    CU(ctx, launch_fixed(c, n_blocks, fixed_dev, selectors_dev, rb, re));
+    const RowMap rm = shard_map(c);
+    CU(ctx, launch_fixed(c, n_blocks, fixed_dev, selectors_dev, rm));
     return H2AES_OK;
 }
 
@@ -628,10 +641,9 @@ int32_t h2aes_fixed_columns_host(h2aes_circuit *c, uint64_t n_blocks, uint64_t *
     if (!c) return H2AES_ERR_ARG;
     h2aes_ctx *ctx = c->ctx;
     CU(ctx, cudaSetDevice(ctx->device));
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
-    const uint64_t fbytes = fixed ? (uint64_t)c->sh.n_fixed() * (re - rb) * 32 : 0;
-    const uint64_t sbytes = selectors ? (uint64_t)c->sh.n_selectors() * (re - rb) * 32 : 0;
+    const RowMap rm = shard_map(c);
+    const uint64_t fbytes = fixed ? (uint64_t)c->sh.n_fixed() * rm.rows * 32 : 0;
+    const uint64_t sbytes = selectors ? (uint64_t)c->sh.n_selectors() * rm.rows * 32 : 0;
     int32_t rc = ensure_stage(c, fbytes + sbytes + 32);
     if (rc) return rc;
     uint64_t *df = fixed ? (uint64_t *)c->d_stage : nullptr;
@@ -669,7 +681,8 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     // block totals of L columns of n rows (>= the permutation's n_sets * n rows as one column);
     // k_z_prefix scans them in tiles of 1024
     c->zblocks = L * (zscan_blocks(c->sh.n()) + 1);
-    c->ztiles = L * (zscan_blocks(c->sh.n()) / 1024 + 2);
+    c->ztiles = L * (zscan_blocks(c->sh.n()) / 1024 + 2 * zscan_tiles(c->sh.n()) + 4);  // (tiled shards: 2 per segment)
+    static_assert(H2AES_SHARD_TILE_ROWS == ZT_ROWS, "an ownership tile is a row tile of the scan");
     DA(c->d_chal, 4);
     DA(c->d_val, VB);
     DA(c->d_canon, VB);
@@ -748,8 +761,10 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     }
     DA(c->d_znonconst, L);
     CU(ctx, cudaMemsetAsync(c->d_znonconst, 0, L * 8, ctx->stream));
-    DA(c->d_partial, L);
-    DA(c->d_carry, L);
+    // one partial product / carry per (lookup, segment): a tiled shard holds up to
+    // ceil(tiles / G) ownership tiles of every column
+    DA(c->d_partial, L * (zscan_tiles(c->sh.n()) + 1));
+    DA(c->d_carry, L * (zscan_tiles(c->sh.n()) + 1));
     c->lk_alloc = true;
     return H2AES_OK;
 }
@@ -826,14 +841,14 @@ int32_t h2aes_lookup_permuted_dev(h2aes_circuit *c, const uint64_t *theta, int32
     if (changed || !c->have_bins) {
         if ((rc = upload_active(c))) return rc;
         CU(ctx, launch_view_bins(c));
-        CU(ctx, launch_lookup_hist(c, 0, c->sh.n()));
+        CU(ctx, launch_lookup_hist(c, shard_map(c)));
         CU(ctx, launch_lookup_bins(c));
         c->have_bins = true;
         c->have_beta_gamma = false;
         for (int l = 0; l < c->sh.n_lookups(); ++l) c->code_valid[l] = false;
     }
     if (count) {
-        CU(ctx, launch_permuted(c, first, count, A_dev, S_dev, Ap_dev, Sp_dev, 0, c->sh.n()));
+        CU(ctx, launch_permuted(c, first, count, A_dev, S_dev, Ap_dev, Sp_dev, shard_map(c)));
         for (int l = first; l < first + count; ++l) c->code_valid[l] = true;
     }
     return H2AES_OK;
@@ -858,12 +873,12 @@ int32_t h2aes_lookup_product_dev(h2aes_circuit *c, const uint64_t *beta, const u
         if (c->code_valid[l]) continue;
         int e = l;
         while (e < first + count && !c->code_valid[e]) ++e;
-        CU(ctx, launch_permuted(c, l, e - l, nullptr, nullptr, nullptr, nullptr, 0, c->sh.n()));
+        CU(ctx, launch_permuted(c, l, e - l, nullptr, nullptr, nullptr, nullptr, shard_map(c)));
         for (int x = l; x < e; ++x) c->code_valid[x] = true;
         l = e - 1;
     }
     if (count) {
-        CU(ctx, launch_z_scan(c, first, count, nullptr, Z_dev, 0, c->sh.n()));
+        CU(ctx, launch_z_scan(c, first, count, nullptr, Z_dev, shard_map(c)));
     }
     return H2AES_OK;
 }
@@ -1069,10 +1084,9 @@ int32_t h2aes_lookup_hist_dev(h2aes_circuit *c, const uint64_t *theta, uint32_t 
     if (rc) return rc;
     bool changed;
     if ((rc = set_theta(c, theta, &changed))) return rc;
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
+    const RowMap rm = shard_map(c);
     CU(ctx, launch_view_bins(c));
-    CU(ctx, launch_lookup_hist(c, rb, re));
+    CU(ctx, launch_lookup_hist(c, rm));
     c->have_hist = true;
     c->have_bins = c->have_beta_gamma = c->have_partial = false;
     *hist_dev = c->d_cnt;
@@ -1092,10 +1106,9 @@ int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint6
     if (rc) return rc;
     CU(ctx, launch_lookup_bins(c));
     c->have_bins = true;
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
+    const RowMap rm = shard_map(c);
     // with no outputs this still records the per-row codes the grand product reads
-    CU(ctx, launch_permuted(c, 0, c->sh.n_lookups(), A_dev, S_dev, Ap_dev, Sp_dev, rb, re));
+    CU(ctx, launch_permuted(c, 0, c->sh.n_lookups(), A_dev, S_dev, Ap_dev, Sp_dev, rm));
     return H2AES_OK;
 }
 
@@ -1108,11 +1121,10 @@ int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const u
     CU(ctx, cudaSetDevice(ctx->device));
     int32_t rc = set_beta_gamma(c, beta, gamma);
     if (rc) return rc;
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
+    const RowMap rm = shard_map(c);
     // pass 1 of the scan: thread prefixes stay in the workspace, the product of the shard's
     // factors per lookup (its partial product) goes to d_partial; Z_dev is written by pass 2
-    CU(ctx, launch_z_partial(c, Z_dev, rb, re));
+    CU(ctx, launch_z_partial(c, Z_dev, rm));
     c->have_partial = true;
     c->partial_Z = Z_dev;
     *partial_dev = (uint64_t *)c->d_partial;
@@ -1128,10 +1140,9 @@ int32_t h2aes_lookup_product_shard_dev(h2aes_circuit *c, const uint64_t *gathere
     if (Z_dev != c->partial_Z)
         return fail(ctx, H2AES_ERR_ARG, "Z_dev must be the buffer given to h2aes_lookup_partial_dev");
     CU(ctx, cudaSetDevice(ctx->device));
-    uint64_t rb, re;
-    shard_rows(c, &rb, &re);
-    CU(ctx, launch_shard_carry(c, gathered_dev));
-    CU(ctx, launch_z_finish(c, c->d_carry, Z_dev, rb, re));
+    const RowMap rm = shard_map(c);
+    CU(ctx, launch_shard_carry(c, gathered_dev, rm.segments()));
+    CU(ctx, launch_z_finish(c, c->d_carry, Z_dev, rm));
     c->have_partial = false;
     return H2AES_OK;
 }

@@ -183,15 +183,17 @@ int32_t h2aes_lookup_columns_sharded_dev(h2aes_circuit *c, const uint64_t *theta
     uint64_t *partial = nullptr;
     if (forked) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if ((rc = h2aes_lookup_partial_dev(c, beta, gamma, Z_dev, &partial))) return rc;
-    const size_t L = (size_t)c->sh.n_lookups();
+    uint64_t pwords = 0;  // one Fr per (lookup, segment of this shard)
+    h2aes_circuit_shard_query(c, nullptr, &pwords);
     if (!c->d_gathered) {
-        cudaError_t e = cudaMalloc((void **)&c->d_gathered, 64 * L * 32);
+        const size_t L = (size_t)c->sh.n_lookups();
+        cudaError_t e = cudaMalloc((void **)&c->d_gathered, L * (zscan_tiles(c->sh.n()) + 64) * 32);
         if (e != cudaSuccess) return bad(H2AES_ERR_NOMEM, "partial-product gather buffer");
     }
     if (multi)
-        NC(ctx, api, api.AllGather(partial, c->d_gathered, L * 4, ncclUint64, (ncclComm_t)ctx->comm,
+        NC(ctx, api, api.AllGather(partial, c->d_gathered, pwords, ncclUint64, (ncclComm_t)ctx->comm,
                                    ctx->stream));
-    else if (cudaMemcpyAsync(c->d_gathered, partial, L * 32, cudaMemcpyDeviceToDevice, ctx->stream) !=
+    else if (cudaMemcpyAsync(c->d_gathered, partial, pwords * 8, cudaMemcpyDeviceToDevice, ctx->stream) !=
              cudaSuccess)
         return bad(H2AES_ERR_CUDA, "partial-product copy");
     return h2aes_lookup_product_shard_dev(c, c->d_gathered, Z_dev);

@@ -51,16 +51,20 @@ struct ZScanArgs {
     const uint32_t *mask;          // one bit per row: factor is not one; column li at li*mstride words
     uint64_t mstride;
     uint64_t *Z;                   // [count][rows][4]; ZSRC_BUFFER: holds the factors on entry
-    uint64_t row_begin, rows;      // rows of every column handled by this launch
+    RowMap rm;                     // local row -> row of the column (a shard holds rm.rows rows)
+    uint64_t rows;                 // = rm.rows: local rows of every column handled by this launch
     uint64_t col_mask;             // n-1: row & col_mask = row inside its column (ZSRC_BUFFER scans
                                    // several columns as one long column)
-    uint64_t n_tiles;              // row tiles of 32 x 1360 rows per column (work distribution)
-    uint64_t n_blocks;             // blocks of ZB_R rows per column = block totals per column
-    uint64_t n_ptiles;             // tiles of ZP_TILE block totals per column (k_z_prefix)
-    const fr_t *carry_in;          // [L] or null: product of everything before row_begin
-    fr_t *partial;                 // [L] or null: product of all factors of the column
+    uint64_t n_tiles;              // row tiles of 32 x 1360 local rows per column (work distribution)
+    // The scan runs per "segment" = the local rows of one ownership tile of one column: rows that
+    // are consecutive in the column.  Unsharded / contiguous shards: one segment per column.
+    uint32_t segs;                 // segments (local ownership tiles) per column
+    uint64_t n_blocks;             // blocks of ZB_R rows per segment = block totals per segment
+    uint64_t n_ptiles;             // tiles of ZP_TILE block totals per segment (k_z_prefix)
+    const fr_t *carry_in;          // [L][segs] or null: product of everything before the segment
+    fr_t *partial;                 // [L][segs] or null: product of all factors of the segment
     unsigned long long *nonconst;  // [L] or null: statistics
-    fr_t *tot;                     // [count][n_blocks] block totals, then their exclusive prefixes
+    fr_t *tot;                     // [count][segs][n_blocks] block totals, then their exclusive prefixes
     // look-back workspace of k_z_prefix
     fr_t *agg, *inc;               // [count*n_ptiles]
     uint32_t *flag;                // [count*n_ptiles] 2*epoch + {1: aggregate, 2: inclusive prefix}
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(ZG_T, ZG_OCC) k_z_general(const __grid_constan
     uint64_t *__restrict__ zout = a.Z + (size_t)li * a.rows * 4;
     for (uint32_t i = blockIdx.x * ZG_T + threadIdx.x; i < cnt; i += gridDim.x * ZG_T) {
         const uint32_t lrow = __ldg(gl + i);
-        const uint64_t row = a.row_begin + lrow;
+        const uint64_t row = a.rm.global(lrow);
         const uint32_t code = __ldg(fc + row), t = __ldg(tk + row);
         const uint32_t kin = (t >> 24) == op ? (t & 0xffffffu) : k_zero;  // bin of the row's input value
         const uint32_t kp = ((code >> 28) & 3u) == CODE_OTHER ? __ldg(cp + row) : 0u;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(ZG_T, ZG_OCC) k_z_general(const __grid_constan
 struct ZBlock {
     int li, l;
     uint64_t T, w;        // row tile and slice of the tile this warp works on
-    uint64_t b, lr0, row0;  // my block, its first local / absolute row
+    uint64_t b, lr0, row0;  // my block (index into tot[]), its first local / absolute row
     uint32_t nr;          // rows of my block inside the column
     LookupLane cx;
     uint32_t mb0, mb1, mb2;
@@ -214,10 +218,13 @@ __device__ __forceinline__ bool z_block_setup(const ZScanArgs &a, uint64_t task,
     t.li = (int)(rem / ZB_W);
     t.w = rem - (uint64_t)t.li * ZB_W;
     t.l = a.first_lookup + t.li;
-    t.b = (t.T * 32 + (uint64_t)lane) * ZB_W + t.w;
-    t.lr0 = t.b * ZB_R;
+    t.lr0 = ((t.T * 32 + (uint64_t)lane) * ZB_W + t.w) * ZB_R;
     t.nr = t.lr0 >= a.rows ? 0u : (uint32_t)min((uint64_t)ZB_R, a.rows - t.lr0);
-    t.row0 = a.row_begin + t.lr0;
+    t.row0 = a.rm.global(t.lr0);  // (a block never straddles two ownership tiles)
+    // slot of my block's total: [column][segment][block of the segment]
+    const uint64_t seg = a.segs > 1 ? t.lr0 / a.rm.ts : 0;
+    t.b = seg < a.segs ? ((uint64_t)t.li * a.segs + seg) * a.n_blocks + (t.lr0 - seg * (a.segs > 1 ? a.rm.ts : 0)) / ZB_R
+                       : ~0ull;
     t.cx.l = t.l;
     t.cx.ln = t.cx.sn = 0;
     t.cx.vo = 0;
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
         if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
         tot = fr_mul_inline(tot, f);
     }
-    if (t.nr) fr_st(a.tot + (size_t)t.li * a.n_blocks + t.b, tot);
+    if (t.b != ~0ull && (t.nr || a.segs > 1)) fr_st(a.tot + t.b, tot);  // (padding blocks of a partial segment: one)
     if (a.nonconst) {
         uint32_t c = __popc(t.mb0) + __popc(t.mb1) + __popc(t.mb2);
 #pragma unroll
@@ -294,10 +301,11 @@ __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScan
     __syncthreads();
     // tickets in tile order, all columns advancing together: a tile only waits on running tiles
     const uint32_t ep2 = 2u * s_epoch;
-    const int li = (int)(s_ticket % (uint32_t)a.count);
-    const uint64_t T = s_ticket / (uint32_t)a.count;
+    const uint32_t nseg = (uint32_t)a.count * a.segs;           // independent scans
+    const int li = (int)(s_ticket % nseg);                      // (column, segment)
+    const uint64_t T = s_ticket / nseg;
     const size_t slot = (size_t)li * a.n_ptiles + T;
-    const int l = a.first_lookup + li;
+    const int l = a.first_lookup * (int)a.segs + li;            // index into carry_in / partial
     fr_t *__restrict__ x = a.tot + (size_t)li * a.n_blocks;
     const uint64_t base = T * ZP_TILE + (uint64_t)tid * ZP_E;
     fr_t v[ZP_E];
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     // row l%4 of the burst of lane 8i + l/4 (i = 0..3), 8 lines per store instruction instead of
     // 32 sectors in 32 different lines.
     fr_t cur = fr_one();
-    if (t.nr) cur = fr_ld(a.tot + (size_t)t.li * a.n_blocks + t.b);
+    if (t.nr) cur = fr_ld(a.tot + t.b);
     const fr_t zero = fr_zero();
     uint4 *stage = s_stage[wid];
     const uint64_t lrw0 = (t.T * 32 * ZB_W + t.w) * ZB_R;                  // lane 0's first local row
@@ -509,14 +517,21 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     }
 }
 
-// carry[l] = product of the partial products of the shards before `shard` (row-sharded circuit)
-__global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, int shard,
-                              fr_t *__restrict__ carry) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_lookups) return;
+// carry[l][t] = product of the partial products of every segment that precedes segment t of this
+// shard in the column: segment t' of shard g' is ownership tile t' * G + g' (row-sharded circuit).
+// gathered = [G][L][segs] (segments a shard does not hold: one).
+__global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, uint32_t segs,
+                              uint32_t G, uint32_t shard, fr_t *__restrict__ carry) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // (lookup, segment)
+    if (i >= (uint32_t)n_lookups * segs) return;
+    const uint32_t l = i / segs, t = i - l * segs;
+    const uint64_t mine = (uint64_t)t * G + shard;
     fr_t acc = fr_one();
-    for (int s = 0; s < shard; ++s) acc = fr_mul(acc, fr_ld(gathered + (size_t)s * n_lookups + l));
-    fr_st(carry + l, acc);
+    for (uint32_t tt = 0; tt <= t; ++tt)
+        for (uint32_t gg = 0; gg < G; ++gg)
+            if ((uint64_t)tt * G + gg < mine)
+                acc = fr_mul(acc, fr_ld(gathered + ((size_t)gg * n_lookups + l) * segs + tt));
+    fr_st(carry + i, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -525,7 +540,7 @@ __global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, 
 static inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
 static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                             uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
+                             uint64_t *Z, const RowMap &rm) {
     ZScanArgs a;
     a.sh = c->sh;
     a.first_lookup = first;
@@ -542,11 +557,12 @@ static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t 
     a.mask = c->d_zmask + (size_t)first * c->zm;
     a.mstride = c->zm;
     a.Z = Z;
-    a.row_begin = row_begin;
-    a.rows = row_end - row_begin;
+    a.rm = rm;
+    a.rows = rm.rows;
     a.col_mask = c->sh.n() - 1;
-    a.n_tiles = zscan_tiles(a.rows);
-    a.n_blocks = zscan_blocks(a.rows);
+    a.segs = rm.segments();
+    a.n_tiles = a.segs > 1 ? a.segs : zscan_tiles(a.rows);  // (tiled shards: ownership tile = row tile)
+    a.n_blocks = zscan_blocks(a.segs > 1 ? rm.ts : a.rows);
     a.n_ptiles = (a.n_blocks + ZP_TILE - 1) / ZP_TILE;
     a.carry_in = carry_in;
     a.partial = c->d_partial;
@@ -580,7 +596,7 @@ static cudaError_t launch_totals(h2aes_circuit *c, const ZScanArgs &a) {
 static cudaError_t launch_prefix(h2aes_circuit *c, const ZScanArgs &a) {
     h2aes_ctx *ctx = c->ctx;
     prof_begin(ctx, "k_z_prefix");
-    k_z_prefix<<<(unsigned)(a.n_ptiles * a.count), ZP_T, 0, ctx->stream>>>(a);
+    k_z_prefix<<<(unsigned)(a.n_ptiles * a.count * a.segs), ZP_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -588,9 +604,9 @@ static cudaError_t launch_prefix(h2aes_circuit *c, const ZScanArgs &a) {
 
 // Z of lookups [first, first+count) over rows [row_begin, row_end)
 cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *carry_in,
-                          uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
+                          uint64_t *Z, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
-    const ZScanArgs a = lookup_args(c, first, count, carry_in, Z, row_begin, row_end);
+    const ZScanArgs a = lookup_args(c, first, count, carry_in, Z, rm);
     cudaError_t e = launch_totals(c, a);
     if (e) return e;
     if ((e = launch_prefix(c, a))) return e;
@@ -603,30 +619,29 @@ cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *ca
 
 // row-sharded circuit, first half: the block prefixes of the shard's rows (without the carry of
 // the shards before it) stay in the workspace, partial[l] = product of the shard's factors
-cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, uint64_t row_begin, uint64_t row_end) {
+cudaError_t launch_z_partial(h2aes_circuit *c, uint64_t *Z, const RowMap &rm) {
     const int L = c->sh.n_lookups();
-    const ZScanArgs a = lookup_args(c, 0, L, nullptr, Z, row_begin, row_end);
+    const ZScanArgs a = lookup_args(c, 0, L, nullptr, Z, rm);
     cudaError_t e = launch_totals(c, a);
     if (e) return e;
     return launch_prefix(c, a);
 }
 
-// second half: fold the carry of the shards before this one into the prefixes, then write Z
+// second half: fold the carry of everything before a segment into its prefixes, then write Z
 __global__ void __launch_bounds__(256) k_z_carry(const __grid_constant__ ZScanArgs a) {
-    const int li = blockIdx.y;
+    const int li = blockIdx.y;  // (column, segment)
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_blocks) return;
     fr_t *p = a.tot + (size_t)li * a.n_blocks + i;
-    fr_st(p, fr_mul(fr_ld(p), fr_ld(a.carry_in + a.first_lookup + li)));
+    fr_st(p, fr_mul(fr_ld(p), fr_ld(a.carry_in + (size_t)a.first_lookup * a.segs + li)));
 }
-cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, uint64_t row_begin,
-                            uint64_t row_end) {
+cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
-    const ZScanArgs a = lookup_args(c, 0, L, carry_in, Z, row_begin, row_end);
+    const ZScanArgs a = lookup_args(c, 0, L, carry_in, Z, rm);
     if (carry_in) {
         prof_begin(ctx, "k_z_carry");
-        k_z_carry<<<dim3(cdiv(a.n_blocks, 256), L), 256, 0, ctx->stream>>>(a);
+        k_z_carry<<<dim3(cdiv(a.n_blocks, 256), L * a.segs), 256, 0, ctx->stream>>>(a);
         prof_end(ctx);
         ctx->launches += 1;
     }
@@ -641,7 +656,7 @@ cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z,
 // (the permutation argument: set s starts from the last usable value of set s-1)
 cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const uint32_t *mask) {
     h2aes_ctx *ctx = c->ctx;
-    ZScanArgs a = lookup_args(c, 0, 1, nullptr, Z, 0, (uint64_t)cols * c->sh.n());
+    ZScanArgs a = lookup_args(c, 0, 1, nullptr, Z, row_map_of((uint64_t)cols * c->sh.n(), 0, 1, 0));
     a.mask = mask;
     a.mstride = 0;
     a.partial = nullptr;
@@ -658,12 +673,12 @@ cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const 
     return cudaGetLastError();
 }
 
-cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev) {
+cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev, uint32_t segs) {
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
     prof_begin(ctx, "k_shard_carry");
-    k_shard_carry<<<cdiv(L, 64), 64, 0, ctx->stream>>>((const fr_t *)gathered_dev, L, c->shard,
-                                                       c->d_carry);
+    k_shard_carry<<<cdiv((uint64_t)L * segs, 64), 64, 0, ctx->stream>>>(
+        (const fr_t *)gathered_dev, L, segs, (uint32_t)c->n_shards, (uint32_t)c->shard, c->d_carry);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();

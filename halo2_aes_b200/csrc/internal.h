@@ -166,6 +166,7 @@ struct h2aes_circuit {
     uint8_t key[16] = {0};         // key of the last h2aes_witness_* call (h2aes_encrypt_append_dev)
     bool have_witness = false;
     int shard = 0, n_shards = 1;
+    uint64_t shard_ts = 0;         // 0: contiguous rows, else rows per ownership tile (dealt round-robin)
 
     // witness workspace
     uint8_t *d_rk = nullptr;       // 176

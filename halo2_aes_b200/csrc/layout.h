@@ -89,6 +89,39 @@ struct Shape {
     }
 };
 
+// Which rows of every column a (shard of a) circuit holds.  The rows are cut into ownership tiles
+// of `ts` consecutive rows dealt round-robin to the G shards; shard g keeps its tiles back to back
+// ("local rows").  ts = n / G is the contiguous split (one tile per shard), G = 1 the whole column.
+struct RowMap {
+    uint64_t n, ts, rows;  // rows of a column, rows per ownership tile, local rows of this shard
+    uint32_t G, g;
+    H2_HD uint64_t global(uint64_t lr) const {
+        if (G == 1) return lr;
+        const uint32_t t = (uint32_t)lr / (uint32_t)ts;  // (lr < 2^32: k <= 26)
+        return ((uint64_t)t * G + g) * ts + (lr - (uint64_t)t * ts);
+    }
+    // segments = ownership tiles per shard, the same on every shard (a shard holding one tile less
+    // pads with an empty one): what the exchange of the partial products is sized by
+    H2_HD uint32_t segments() const {
+        if (G == 1) return 1;
+        const uint64_t nt = (n + ts - 1) / ts;
+        return (uint32_t)((nt + G - 1) / G);
+    }
+};
+H2_HD RowMap row_map_of(uint64_t n, uint64_t ts, uint32_t G, uint32_t g) {
+    RowMap m;
+    m.n = n;
+    m.ts = ts ? ts : n / G;
+    m.G = G;
+    m.g = g;
+    const uint64_t nt = (n + m.ts - 1) / m.ts;       // ownership tiles of a column
+    const uint64_t mine = nt > g ? (nt - g + G - 1) / G : 0;  // ... held by shard g
+    uint64_t rows = mine * m.ts;
+    if (mine && (nt - 1) % G == g) rows -= nt * m.ts - n;  // the last tile of the column is partial
+    m.rows = rows;
+    return m;
+}
+
 // aes_callable + get_advices: block -> (set, first row).  false past capacity.
 H2_HD bool block_position(const Shape &sh, uint64_t block, int *set, uint64_t *row) {
     uint64_t c0 = sh.cap0(), c = sh.cap();

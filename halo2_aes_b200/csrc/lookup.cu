@@ -360,15 +360,15 @@ k_bin_fill(const fr_t *__restrict__ val, const uint32_t *__restrict__ sorted,
 // grand-product kernel reads instead of re-deriving the bin from the trace word.
 __global__ void __launch_bounds__(256)
 k_lookup_hist(Shape sh, const uint32_t *__restrict__ trace, const uint32_t *__restrict__ rank,
-              uint32_t *__restrict__ cnt, uint32_t *__restrict__ tracek, uint64_t row_begin,
-              uint64_t row_end) {
+              uint32_t *__restrict__ cnt, uint32_t *__restrict__ tracek, RowMap rm) {
     const uint64_t n = sh.n();
     const int set = blockIdx.y;
     const int ops = sh.ops_per_set();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t usable = sh.usable();
-    for (uint64_t row = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < row_end;
-         row += stride) {
+    for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < rm.rows;
+         lrow += stride) {
+        const uint64_t row = rm.global(lrow);
         const uint32_t w = trace[(uint64_t)set * n + row];
         const uint32_t op = w >> 24;
         uint32_t tk = 0;
@@ -625,8 +625,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
            uint64_t *__restrict__ A, uint64_t *__restrict__ S, uint64_t *__restrict__ Ap,
            uint64_t *__restrict__ Sp, uint32_t *__restrict__ fcode, uint32_t *__restrict__ codep,
            uint32_t *__restrict__ zmask, uint64_t zm, const uint32_t *__restrict__ jidx_all,
-           const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, uint64_t row_begin,
-           uint64_t row_end) {
+           const uint32_t *__restrict__ lidx_all, uint32_t idx_stride, RowMap rm) {
     const int li = blockIdx.y;            // index inside this call
     const int l = first_lookup + li;      // lookup index in the circuit
     const int ops = sh.ops_per_set();
@@ -634,7 +633,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const uint32_t op = (uint32_t)(l % ops) + 1;
     const int v = view_of_op(op);
     const uint64_t n = sh.n(), usable = sh.usable();
-    const uint64_t out_rows = row_end - row_begin;
+    const uint64_t out_rows = rm.rows;
     const LookupMeta m = meta[l];
     const uint32_t *offz = offz_all + (size_t)l * BIN_STRIDE;
     const uint32_t *nzk = nzk_all + (size_t)l * BIN_STRIDE;
@@ -655,7 +654,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     // ballot per iteration is the non-constant mask of one chunk of the grand product
     for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
          lrow += stride) {
-        const uint64_t row = row_begin + lrow;
+        const uint64_t row = rm.global(lrow);
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
         uint32_t code = fcode_pack(FK_ONE, 0, 0);
         if (row >= usable) {
@@ -911,7 +910,7 @@ cudaError_t launch_view_bins(h2aes_circuit *c) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t row_end) {
+cudaError_t launch_lookup_hist(h2aes_circuit *c, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
     cudaStream_t s = ctx->stream;
     const int L = c->sh.n_lookups();
@@ -919,8 +918,7 @@ cudaError_t launch_lookup_hist(h2aes_circuit *c, uint64_t row_begin, uint64_t ro
     if ((e = cudaMemsetAsync(c->d_cnt, 0, (size_t)L * BIN_STRIDE * 4, s))) return e;
     dim3 g(ctx->sm_count * 2, c->sh.n_sets());
     prof_begin(ctx, "k_lookup_hist");
-    k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, c->d_tracek, row_begin,
-                                    row_end);
+    k_lookup_hist<<<g, 256, 0, s>>>(c->sh, c->d_trace, c->d_rank, c->d_cnt, c->d_tracek, rm);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -948,9 +946,9 @@ cudaError_t launch_lookup_bins(h2aes_circuit *c) {
 }
 
 cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A, uint64_t *S,
-                            uint64_t *Ap, uint64_t *Sp, uint64_t row_begin, uint64_t row_end) {
+                            uint64_t *Ap, uint64_t *Sp, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
-    const uint64_t rows = row_end - row_begin;
+    const uint64_t rows = rm.rows;
     unsigned gx = cdiv(rows, 256);
     const unsigned cap = (unsigned)ctx->sm_count * 8;
     if (gx > cap) gx = cap;
@@ -962,8 +960,7 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     k_permuted<<<g, 256, pad, ctx->stream>>>(c->sh, first, c->d_trace, c->d_tracek, c->d_val, c->d_dval,
                                            c->d_offz, c->d_nzk, c->d_loffz, c->d_lk, c->d_meta, A, S,
                                            Ap, Sp, c->d_codek, c->d_codep, c->d_zmask, c->zm,
-                                           c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride, row_begin,
-                                           row_end);
+                                           c->d_jidx, c->d_lidx, (uint32_t)c->idx_stride, rm);
     prof_end(ctx);
     const uint64_t words = (rows + 31) >> 5;
     unsigned lx = cdiv(words, 256);

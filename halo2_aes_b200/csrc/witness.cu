@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256)
 k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
          const uint8_t *__restrict__ states, const uint8_t *__restrict__ sbox,
          const uint4 *__restrict__ frtab, uint64_t *__restrict__ advice,
-         uint32_t *__restrict__ trace, uint64_t row_begin, uint64_t row_end) {
+         uint32_t *__restrict__ trace, RowMap rm) {
     __shared__ uint4 s_fr[512];
     __shared__ uint8_t s_rk[176];
     __shared__ uint8_t s_sbox[256];
@@ -128,7 +128,7 @@ k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
     __syncthreads();
     const uint64_t n = sh.n();
     const int nsets = sh.n_sets();
-    const uint64_t out_rows = row_end - row_begin;
+    const uint64_t out_rows = rm.rows;
     const uint64_t chunks = (out_rows + 31) >> 5;
     const uint64_t total = chunks * (uint64_t)(nsets + 1);
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
@@ -138,7 +138,7 @@ k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
         const int set = (int)(item / chunks);
         const uint64_t lrow = (item - (uint64_t)set * chunks) * 32 + lane;
         if (lrow >= out_rows) continue;
-        const uint64_t row = row_begin + lrow;
+        const uint64_t row = rm.global(lrow);
         if (set < nsets) {
             const uint32_t word = advice_word(sh, n_blocks, set, row, s_sbox, s_rk, states);
             trace[(uint64_t)set * n + row] = word;
@@ -160,14 +160,14 @@ k_advice(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ rk,
 __global__ void __launch_bounds__(256)
 k_fixed(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ sbox,
         const uint4 *__restrict__ frtab, uint64_t *__restrict__ fixed,
-        uint64_t *__restrict__ selectors, uint64_t row_begin, uint64_t row_end) {
+        uint64_t *__restrict__ selectors, RowMap rm) {
     __shared__ uint4 s_fr[512];
     __shared__ uint8_t s_sbox[256];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) s_fr[i] = frtab[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = sbox[i];
     __syncthreads();
     const uint64_t usable = sh.usable();
-    const uint64_t out_rows = row_end - row_begin;
+    const uint64_t out_rows = rm.rows;
     const uint64_t chunks = (out_rows + 31) >> 5;
     const int ncols = sh.n_fixed() + sh.n_selectors();
     const uint64_t total = chunks * (uint64_t)ncols;
@@ -179,7 +179,7 @@ k_fixed(Shape sh, uint64_t n_blocks, const uint8_t *__restrict__ sbox,
         const int col = (int)(item / chunks);
         const uint64_t lrow = (item - (uint64_t)col * chunks) * 32 + lane;
         if (lrow >= out_rows) continue;
-        const uint64_t row = row_begin + lrow;
+        const uint64_t row = rm.global(lrow);
         uint32_t v;
         uint64_t *o;
         if (col < 5) {
@@ -252,8 +252,7 @@ cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
 }
 
 cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
-                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev,
-                           uint64_t row_begin, uint64_t row_end) {
+                           uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
     Key16 k16;
     for (int i = 0; i < 16; ++i) k16.b[i] = key[i];
@@ -268,7 +267,7 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
     prof_begin(ctx, "k_advice");
     k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
                                                         ctx->d_sbox, ctx->d_frtab, advice_dev,
-                                                        c->d_trace, row_begin, row_end);
+                                                        c->d_trace, rm);
     prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();
@@ -292,18 +291,18 @@ cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const ui
     prof_begin(ctx, "k_advice");
     k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, first_block + n, c->d_rk, c->d_states,
                                                           ctx->d_sbox, ctx->d_frtab, advice_dev,
-                                                          c->d_trace, 0, c->sh.n());
+                                                          c->d_trace, row_map_of(c->sh.n(), 0, 1, 0));
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();
 }
 
 cudaError_t launch_fixed(h2aes_circuit *c, uint64_t n_blocks, uint64_t *fixed_dev,
-                         uint64_t *selectors_dev, uint64_t row_begin, uint64_t row_end) {
+                         uint64_t *selectors_dev, const RowMap &rm) {
     h2aes_ctx *ctx = c->ctx;
     prof_begin(ctx, "k_fixed");
     k_fixed<<<grid_for(ctx, 8), 256, 0, ctx->stream>>>(c->sh, n_blocks, ctx->d_sbox, ctx->d_frtab,
-                                                       fixed_dev, selectors_dev, row_begin, row_end);
+                                                       fixed_dev, selectors_dev, rm);
     prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();

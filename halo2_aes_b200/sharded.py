@@ -106,17 +106,20 @@ class RowShardedCircuit:
     entry points expose.  library_comm=True: one call, h2aes_lookup_columns_sharded_dev, with the
     exchanges done inside the library over its own NCCL communicator (library_comm_init first)."""
 
-    def __init__(self, ctx, kind: int, k: int, N: int, group=None, library_comm: bool = False):
+    def __init__(self, ctx, kind: int, k: int, N: int, group=None, library_comm: bool = False,
+                 tiled: bool = False):
         from .backend import Circuit
         self.group = group
         self.library_comm = library_comm
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.circuit = Circuit(ctx, kind, k, N)
-        self.circuit.set_shard(self.rank, self.world)
+        self.circuit.set_shard(self.rank, self.world, tiled=tiled)
 
     @property
     def row_range(self):
+        """(first, end) row of a contiguous shard"""
+        assert not self.circuit.tiled, "a tiled shard holds several row ranges: Circuit.global_rows()"
         per = self.circuit.n // self.world
         return per * self.rank, per * (self.rank + 1)
 

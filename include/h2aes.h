@@ -386,6 +386,18 @@ int32_t h2aes_msm_host(h2aes_msm *m, const uint64_t *scalars, int32_t ncols, uin
  * Outputs hold only the shard's rows: [column][rows_per_shard][4].
  * ------------------------------------------------------------------------------------------- */
 int32_t h2aes_circuit_set_shard(h2aes_circuit *c, int32_t shard, int32_t n_shards);
+/* The same with a balanced ownership: the rows are cut into tiles of H2AES_SHARD_TILE_ROWS
+ * consecutive rows (32 AES blocks) dealt round-robin — shard g holds tiles g, g+G, g+2G, ... back
+ * to back.  With contiguous shards the end of every column (where A' is not zero and every row of
+ * Z costs two multiplies) falls on the last shards; dealt tiles give every shard the same mix.
+ * All outputs then hold the shard's local rows, [column][local_rows][4] (the shard holding the
+ * last tile of the column holds fewer rows: h2aes_circuit_shard_query), and one partial product
+ * per (lookup, tile of this shard) is exchanged instead of one per lookup. */
+#define H2AES_SHARD_TILE_ROWS 43520
+int32_t h2aes_circuit_set_shard_tiled(h2aes_circuit *c, int32_t shard, int32_t n_shards);
+/* rows of every column this (shard of the) circuit holds, and the number of u64 words of its
+ * partial products (h2aes_lookup_partial_dev; the all-gather's send count).  Either may be NULL. */
+int32_t h2aes_circuit_shard_query(h2aes_circuit *c, uint64_t *rows, uint64_t *partial_words);
 /* phase 1a: local histogram of table-bin hits; *hist_dev/ *hist_words give the buffer to
  * all-reduce (uint32 sum) across shards before phase 1b. */
 int32_t h2aes_lookup_hist_dev(h2aes_circuit *c, const uint64_t *theta, uint32_t **hist_dev,
@@ -395,7 +407,8 @@ int32_t h2aes_lookup_permuted_shard_dev(h2aes_circuit *c, uint64_t *A_dev, uint6
                                         uint64_t *Ap_dev, uint64_t *Sp_dev);
 /* phase 2a: per-row factors of this shard's rows are written to Z_dev ([n_lookups][rows][4],
  * intermediate data), and their product, one Fr per lookup, to *partial_dev ([n_lookups][4]);
- * all-gather the partials into [n_shards][n_lookups][4] before phase 2b. */
+ * all-gather the partials into [n_shards][n_lookups][4] before phase 2b (tiled shards:
+ * [n_shards][n_lookups][tiles per shard][4], see h2aes_circuit_shard_query). */
 int32_t h2aes_lookup_partial_dev(h2aes_circuit *c, const uint64_t *beta, const uint64_t *gamma,
                                  uint64_t *Z_dev, uint64_t **partial_dev);
 /* phase 2b: turns the factors in Z_dev (the same buffer as in phase 2a) into Z for this

@@ -201,8 +201,17 @@ def test_host_entry_points(gpu, orc, ffi, challenges):
     cir.close()
 
 
-@pytest.mark.parametrize("G", [2, 8])
-def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G):
+def _assemble(shards, parts):
+    """[cols, local rows, 4] per shard -> [cols, n, 4] in column order (host)"""
+    n = shards[0].n
+    out = np.zeros((parts[0].shape[0], n, 4), np.uint64)
+    for c, p in zip(shards, parts):
+        out[:, c.global_rows()] = _host(p)
+    return out
+
+
+@pytest.mark.parametrize("G,tiled", [(2, False), (8, False), (2, True), (4, True)])
+def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G, tiled):
     """BASELINE config 5 (one circuit row-sharded over G GPUs) with the G shards run one after
     another on this GPU and the two exchanges (histogram sum, partial-product gather) done by
     hand — the same entry points sharded.RowShardedCircuit drives over NCCL."""
@@ -215,7 +224,8 @@ def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G):
     d_pts = torch.from_numpy(pts).cuda()
     shards = [Circuit(gpu, ffi.KIND_AES, k, N) for _ in range(G)]
     for g, c in enumerate(shards):
-        c.set_shard(g, G)
+        c.set_shard(g, G, tiled=tiled)
+    assert sum(c.rows for c in shards) == 1 << k
     adv = [c.witness(key, d_pts)[0] for c in shards]
     fx = [c.fixed_columns() for c in shards]
     hists = [c.shard_hist(theta) for c in shards]
@@ -229,7 +239,7 @@ def test_row_sharded_circuit_emulated_on_one_gpu(gpu, orc, ffi, challenges, G):
     for c in shards:
         c.lookup_check()
     ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
-    cat = lambda ts: np.concatenate([_host(t) for t in ts], axis=1)
+    cat = lambda ts: _assemble(shards, ts)
     assert (cat(adv) == ref.advice()).all()
     assert (cat([f[0] for f in fx]) == ref.fixed()).all()
     assert (_sel_bits(orc, cat([f[1] for f in fx])) == ref.selectors()).all()
@@ -359,7 +369,8 @@ def test_1024_blocks_all_lookups(gpu, orc, ffi, challenges, k, N):
     cir.close()
 
 
-def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges, tiled):
     """BASELINE config 5's shape, oracle-compared: a K=22, N=1 circuit at capacity (3082 blocks)
     through the row-sharded entry points (4 shards run one after another on this GPU, the two
     exchanges done by hand): every advice column and the xor and sbox lookups."""
@@ -374,8 +385,16 @@ def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges):
     d_pts = torch.from_numpy(pts).cuda()
     shards = [Circuit(gpu, ffi.KIND_AES, k, N) for _ in range(G)]
     for g, c in enumerate(shards):
-        c.set_shard(g, G)
-    adv = torch.cat([c.witness(key, d_pts)[0] for c in shards], dim=1)
+        c.set_shard(g, G, tiled=tiled)
+    gidx = [torch.from_numpy(c.global_rows()).cuda() for c in shards]
+
+    def glue(parts):   # [cols, local rows, 4] per shard -> [cols, n, 4] on the device
+        out = torch.empty((parts[0].shape[0], 1 << k, 4), dtype=torch.int64, device="cuda")
+        for ix, p in zip(gidx, parts):
+            out[:, ix] = p
+        return out
+
+    adv = glue([c.witness(key, d_pts)[0] for c in shards])
     ref = orc.Circuit(orc.KIND_AES, k, N).synthesize(key, pts)
     for col in range(4):
         assert _same_on_device(adv[col], ref.advice(col)), col
@@ -393,7 +412,7 @@ def test_k22_row_sharded_against_the_oracle(gpu, orc, ffi, challenges):
     got = _oracle_lookups(ref, [1, 2], theta, beta, gamma, workers=2)
     for li in (1, 2):
         for nm, parts in (("Ap", [p["Ap"] for p in perm]), ("Sp", [p["Sp"] for p in perm]), ("Z", Zs)):
-            col = torch.cat([t[li] for t in parts], dim=0)
+            col = glue([t[li:li + 1] for t in parts])[0]
             assert _same_on_device(col, got[li][nm]), (nm, li)
     for c in shards:
         c.close()
