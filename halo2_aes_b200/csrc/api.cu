@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "internal.h"
+#include "permmap.h"
 
 namespace h2 {
 cudaError_t launch_build_frtab(h2aes_ctx *ctx);
@@ -38,6 +39,7 @@ cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev, u
 uint32_t lookup_bin_tiles();
 cudaError_t launch_perm_tables(h2aes_circuit *c, const fr_t &omega, const fr_t &delta);
 cudaError_t launch_perm_sigma(h2aes_circuit *c, uint64_t *sigma_dev);
+cudaError_t launch_perm_mapping(h2aes_circuit *c, uint64_t n_blocks, const PermTemplate *tmpl_dev);
 cudaError_t launch_perm_product(h2aes_circuit *c, const uint64_t *advice_dev, uint64_t *Zp);
 uint64_t run_index_stride(uint64_t n);
 cudaError_t launch_dbg_fr_mul(h2aes_ctx *ctx, const fr_t *a, const fr_t *b, uint64_t n, fr_t *out);
@@ -254,37 +256,6 @@ int32_t h2aes_perm_query(int32_t kind, int32_t k, int32_t N, int32_t *n_columns,
     return H2AES_OK;
 }
 
-// halo2 keygen `permutation::keygen::Assembly` [UPSTREAM, v0.3.0 without thread-safe-region]
-// replayed over the closed-form copy list: cell = position * n + row.  Sequential by nature
-// (each copy splices two cycles); runs once per (shape, n_blocks), never per proof.
-static int32_t build_perm_mapping(const Shape &sh, uint64_t n_blocks, std::vector<uint32_t> &mapping) {
-    const uint64_t n = sh.n();
-    const uint64_t cells = (uint64_t)perm_n_columns(sh) * n;
-    if (cells > 0xffffffffull) return H2AES_ERR_ARG;
-    std::vector<uint32_t> aux(cells), sizes(cells, 1u);
-    mapping.resize(cells);
-    for (uint64_t i = 0; i < cells; ++i) mapping[i] = aux[i] = (uint32_t)i;
-    const uint64_t total = COPIES_KEY_SCHEDULE + COPIES_PER_BLOCK * n_blocks;
-    for (uint64_t idx = 0; idx < total; ++idx) {
-        CopyPair cp;
-        if (!copy_pair(sh, idx, &cp)) return H2AES_ERR_CAPACITY;
-        // constrain_equal(left = the freshly assigned copy, right = the cell it was copied from)
-        const uint32_t left = (uint32_t)(perm_pos_of_advice(sh, (int)cp.dst.col) * n + cp.dst.row);
-        const uint32_t right = (uint32_t)(perm_pos_of_advice(sh, (int)cp.src.col) * n + cp.src.row);
-        uint32_t lc = aux[left], rc = aux[right];
-        if (lc == rc) continue;
-        if (sizes[lc] < sizes[rc]) std::swap(lc, rc);
-        sizes[lc] += sizes[rc];
-        uint32_t i = rc;
-        do {
-            aux[i] = lc;
-            i = mapping[i];
-        } while (i != rc);
-        std::swap(mapping[left], mapping[right]);
-    }
-    return H2AES_OK;
-}
-
 int32_t h2aes_perm_mapping_host(int32_t kind, int32_t k, int32_t N, uint64_t n_blocks,
                                 uint32_t *mapping_out) {
     if (!mapping_out || !shape_ok(kind, k, N)) return H2AES_ERR_ARG;
@@ -292,14 +263,19 @@ int32_t h2aes_perm_mapping_host(int32_t kind, int32_t k, int32_t N, uint64_t n_b
     if (!rows_ok(sh)) return H2AES_ERR_ROWS;
     if (kind == KIND_KEYSCHED && n_blocks) return H2AES_ERR_ARG;
     if (n_blocks > sh.capacity()) return H2AES_ERR_CAPACITY;
-    std::vector<uint32_t> m;
-    int32_t rc = build_perm_mapping(sh, n_blocks, m);
-    if (rc) return rc;
+    // closed form (permmap.h): (position, row) pairs like halo2's Vec<Vec<(usize,usize)>>
+    PermTemplate t;
+    perm_template_build(sh, &t);
     const uint64_t n = sh.n();
-    for (uint64_t i = 0; i < m.size(); ++i) {  // (position, row) pairs like halo2's Vec<Vec<(usize,usize)>>
-        mapping_out[2 * i] = (uint32_t)(m[i] / n);
-        mapping_out[2 * i + 1] = (uint32_t)(m[i] % n);
-    }
+    const uint32_t nc = (uint32_t)perm_n_columns(sh);
+    for (uint32_t p = 0; p < nc; ++p)
+        for (uint64_t row = 0; row < n; ++row) {
+            uint32_t op;
+            uint64_t orow;
+            perm_successor(sh, n_blocks, t, p, row, &op, &orow);
+            mapping_out[2 * (p * n + row)] = op;
+            mapping_out[2 * (p * n + row) + 1] = (uint32_t)orow;
+        }
     return H2AES_OK;
 }
 
@@ -436,7 +412,7 @@ static void circuit_free(h2aes_circuit *c) {
                     c->d_viewmeta, c->d_ib,       c->d_ig,       c->d_nac,      c->d_cnt,
                     c->d_ibg,      c->d_ibp,      c->d_tracek,   c->d_codek,    c->d_codep,    c->d_glist,    c->d_gbase,    c->d_gcount,
                     c->d_canon_b,  c->d_active,   c->d_lbsum,    c->d_jidx,     c->d_lidx,
-                    c->d_ftab,     c->d_pmap,     c->d_wlo,
+                    c->d_ftab,     c->d_pmap,     c->d_ptmpl,    c->d_wlo,
                     c->d_whi,      c->d_dpow,     c->d_bdp,      c->d_pnum,     c->d_ppre,
                     c->d_omega_tab,     c->d_pmask,     c->d_zmask,    c->d_znonconst,
                     c->d_offz,     c->d_nzk,      c->d_loffz,    c->d_lk,       c->d_meta,
@@ -1017,18 +993,20 @@ static int32_t ensure_perm_ws(h2aes_circuit *c) {
     return H2AES_OK;
 }
 
-// cycle structure of (shape, n_blocks) -> device, packed position << 24 | row
+// cycle structure of (shape, n_blocks) on the device, packed position << 24 | row: the two small
+// successor templates are built on the host (a few thousand cells) and every cell's successor is
+// evaluated in closed form by k_p_mapping (permmap.h)
 static int32_t ensure_perm_mapping(h2aes_circuit *c, uint64_t n_blocks) {
     h2aes_ctx *ctx = c->ctx;
     if (c->perm_blocks == n_blocks) return H2AES_OK;
-    std::vector<uint32_t> m;
-    int32_t rc = build_perm_mapping(c->sh, n_blocks, m);
-    if (rc) return fail(ctx, rc, "permutation mapping");
-    const uint64_t n = c->sh.n();
-    for (auto &x : m) x = (uint32_t)((x / n) << 24) | (uint32_t)(x % n);
-    CU(ctx, cudaMemcpyAsync(c->d_pmap, m.data(), m.size() * sizeof(uint32_t),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));  // `m` goes out of scope
+    if (!c->d_ptmpl) {
+        PermTemplate t;
+        perm_template_build(c->sh, &t);
+        DA(c->d_ptmpl, 1);
+        CU(ctx, cudaMemcpyAsync(c->d_ptmpl, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));  // `t` is on the stack
+    }
+    CU(ctx, launch_perm_mapping(c, n_blocks, c->d_ptmpl));
     c->perm_blocks = n_blocks;
     return H2AES_OK;
 }

@@ -9,6 +9,7 @@
 #include "../../include/h2aes.h"
 #include "fr.cuh"
 #include "layout.h"
+#include "permmap.h"
 
 namespace h2 {
 
@@ -248,6 +249,7 @@ struct h2aes_circuit {
     bool perm_alloc = false, perm_tables = false;
     uint64_t perm_blocks = ~0ull;     // n_blocks the mapping on the device was built for
     uint32_t *d_pmap = nullptr;       // [n_cols][n] packed mapping: position << 24 | row
+    h2::PermTemplate *d_ptmpl = nullptr;  // successor templates of one block / the key schedule
     h2::fr_t *d_wlo = nullptr;        // [1024] omega^t
     h2::fr_t *d_whi = nullptr;        // [n/1024] omega^(1024 b)
     h2::fr_t *d_dpow = nullptr;       // [n_cols] delta^p

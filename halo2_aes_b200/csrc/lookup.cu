@@ -1076,6 +1076,29 @@ k_p_sigma(const uint32_t *__restrict__ pmap, uint64_t cells, const fr_t *__restr
     }
 }
 
+// mapping of every cell in closed form (permmap.h), packed position << 24 | row
+__global__ void __launch_bounds__(256)
+k_p_mapping(Shape sh, uint64_t n_blocks, const PermTemplate *__restrict__ tmpl, int n_cols,
+            uint32_t *__restrict__ pmap) {
+    const uint64_t n = sh.n(), cells = (uint64_t)n_cols * n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        uint32_t op;
+        uint64_t orow;
+        perm_successor(sh, n_blocks, *tmpl, (uint32_t)(i / n), i % n, &op, &orow);
+        pmap[i] = (op << PMAP_ROW_BITS) | (uint32_t)orow;
+    }
+}
+cudaError_t launch_perm_mapping(h2aes_circuit *c, uint64_t n_blocks, const PermTemplate *tmpl_dev) {
+    h2aes_ctx *ctx = c->ctx;
+    prof_begin(ctx, "k_p_mapping");
+    k_p_mapping<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->sh, n_blocks, tmpl_dev,
+                                                            perm_n_columns(c->sh), c->d_pmap);
+    prof_end(ctx);
+    ctx->launches += 1;
+    return cudaGetLastError();
+}
+
 struct PArgs {
     Shape sh;
     int n_cols, n_sets;
