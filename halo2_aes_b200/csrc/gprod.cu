@@ -28,6 +28,9 @@
 // (the table rows at the start of a column, then the end of the column, where A' is not zero).
 // Bound by integer-multiply issue (one bn256 Montgomery product = 128 IMAD.WIDE), not by HBM:
 // 2 multiplies per non-constant row, +1..3 for the rows of k_z_general, ~2 per block for the scan.
+#include <algorithm>
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace h2 {
@@ -250,8 +253,12 @@ constexpr int ZB_T = 128;  // threads per CTA (4 independent warps)
 
 template <int SRC>
 __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_constant__ ZScanArgs a) {
+    // (persistent form: with a grid smaller than the task count every warp walks several tasks,
+    // heaviest first; see launch_totals)
+    for (uint64_t task = (uint64_t)blockIdx.x * (ZB_T / 32) + (threadIdx.x >> 5);;
+         task += (uint64_t)gridDim.x * (ZB_T / 32)) {
     ZBlock t;
-    if (!z_block_setup<SRC>(a, (uint64_t)blockIdx.x * (ZB_T / 32) + (threadIdx.x >> 5), t)) return;
+    if (!z_block_setup<SRC>(a, task, t)) return;
     const uint64_t *__restrict__ z = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
     // software pipeline over the non-constant rows: code of row i+2, factor of row i+1, multiply i
     fr_t tot = fr_one();
@@ -277,6 +284,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
         if ((threadIdx.x & 31) == 0 && c) atomicAdd(a.nonconst + t.l, (unsigned long long)c);
+    }
     }
 }
 
@@ -406,8 +414,9 @@ template <int SRC>
 __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_constant__ ZScanArgs a) {
     __shared__ uint4 s_stage[ZB_T / 32][ZS_BURST * 32 * 2];  // (uint4: the type it is accessed as)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint64_t task = (uint64_t)blockIdx.x * (ZB_T / 32) + wid;; task += (uint64_t)gridDim.x * (ZB_T / 32)) {
     ZBlock t;
-    if (!z_block_setup<SRC>(a, (uint64_t)blockIdx.x * (ZB_T / 32) + wid, t)) return;
+    if (!z_block_setup<SRC>(a, task, t)) return;
     const uint32_t usable = (uint32_t)a.sh.usable();
     // Z has n-5 deterministic entries (rows 0..usable); the last 5 are blinding rows (zero).
     // A thread's rows are consecutive but the lanes of a warp are 1360 rows apart, so the values go
@@ -439,33 +448,6 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
     uint32_t c2 = q2 >= 0 ? row_code<SRC>(a, t.cx, t.row0 + q2) : 0u;
     fr_t f1 = fr_one();
     if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
-#endif
-#ifdef ZWRITE_RUNS
-    {
-        uint64_t *zt = a.Z + ((size_t)t.li * a.rows + t.lr0) * 4;
-        uint32_t done = 0;
-        auto put = [&](uint32_t r) {
-            const bool ok = (uint32_t)((t.row0 + r) & a.col_mask) <= usable;
-            fr_store_256_cs(zt + 4 * (size_t)r, ok ? cur : zero);
-        };
-#pragma unroll 1
-        while (q1 >= 0) {
-            const fr_t f = f1;
-            const uint32_t q = (uint32_t)q1;
-            q1 = q2;
-            c1 = c2;
-            q2 = it.next();
-            if (q2 >= 0) c2 = row_code<SRC>(a, t.cx, t.row0 + q2);
-            if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
-#pragma unroll 1
-            for (uint32_t r = done; r <= q; ++r) put(r);
-            done = q + 1u;
-            cur = fr_mul_inline(cur, f);
-        }
-#pragma unroll 1
-        for (uint32_t r = done; r < t.nr; ++r) put(r);
-        return;
-    }
 #endif
 #pragma unroll 1
     for (uint32_t r = 0; r < ZB_R; ++r) {
@@ -514,6 +496,7 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
             __syncwarp();
         }
 #endif
+    }
     }
 }
 
@@ -571,8 +554,27 @@ static ZScanArgs lookup_args(h2aes_circuit *c, int first, int count, const fr_t 
     a.ctl = c->d_zctl;
     return a;
 }
-static inline unsigned block_grid(const ZScanArgs &a) {  // one warp per (column, row tile, slice)
-    return cdiv(a.n_tiles * (uint64_t)a.count * ZB_W, ZB_T / 32);
+// H2AES_Z_CTAS_PER_SM (tuning, default 0 = one warp per task): run the multiply-bound kernels as
+// persistent grids of that many CTAs per SM, leaving room for the HBM-bound kernels of the other
+// circuit in flight to be dispatched beside them.  Measured (profiles/persist.sh): the persistent
+// form is slower by itself (static striding over tasks of very different weight: k_z_totals 0.22
+// -> 0.29 ms, k_z_write 0.31 -> 0.38 ms) and the co-scheduled step does not win it back (1.48 ms
+// per circuit at best against 1.30 ms), so it is off.
+#ifndef Z_CTAS_PER_SM
+#define Z_CTAS_PER_SM 0
+#endif
+static int z_ctas_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("H2AES_Z_CTAS_PER_SM");
+        v = s ? atoi(s) : Z_CTAS_PER_SM;
+    }
+    return v;
+}
+static inline unsigned block_grid(const h2aes_ctx *ctx, const ZScanArgs &a) {
+    const unsigned full = cdiv(a.n_tiles * (uint64_t)a.count * ZB_W, ZB_T / 32);  // one warp per task
+    const unsigned cap = (unsigned)(ctx->sm_count * z_ctas_per_sm());
+    return cap && cap < full ? cap : full;
 }
 
 // factors of the rows that are not table entries, then the block totals
@@ -582,13 +584,14 @@ static cudaError_t launch_totals(h2aes_circuit *c, const ZScanArgs &a) {
     cudaError_t e0 = cudaMemsetAsync(c->d_znonconst + a.first_lookup, 0, (size_t)a.count * 8, s);
     if (e0) return e0;
     unsigned gx = cdiv(a.rows / 4, ZG_T);  // lists are a fraction of the rows; CTAs past the end exit
-    const unsigned cap = (unsigned)ctx->sm_count * 4;
+    const unsigned cap = z_ctas_per_sm() ? std::max(1u, (unsigned)(ctx->sm_count * z_ctas_per_sm()) / (unsigned)a.count)
+                                         : (unsigned)ctx->sm_count * 4;
     if (gx > cap) gx = cap;
     prof_begin(ctx, "k_z_general");
     k_z_general<<<dim3(gx, a.count), ZG_T, 0, s>>>(a);
     prof_end(ctx);
     prof_begin(ctx, "k_z_totals");
-    k_z_totals<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, s>>>(a);
+    k_z_totals<ZSRC_LOOKUP><<<block_grid(ctx, a), ZB_T, 0, s>>>(a);
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();
@@ -611,7 +614,7 @@ cudaError_t launch_z_scan(h2aes_circuit *c, int first, int count, const fr_t *ca
     if (e) return e;
     if ((e = launch_prefix(c, a))) return e;
     prof_begin(ctx, "k_z_write");
-    k_z_write<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
+    k_z_write<ZSRC_LOOKUP><<<block_grid(ctx, a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -646,7 +649,7 @@ cudaError_t launch_z_finish(h2aes_circuit *c, const fr_t *carry_in, uint64_t *Z,
         ctx->launches += 1;
     }
     prof_begin(ctx, "k_z_write");
-    k_z_write<ZSRC_LOOKUP><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
+    k_z_write<ZSRC_LOOKUP><<<block_grid(ctx, a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 1;
     return cudaGetLastError();
@@ -662,12 +665,12 @@ cudaError_t launch_z_scan_buffer(h2aes_circuit *c, int cols, uint64_t *Z, const 
     a.partial = nullptr;
     a.nonconst = nullptr;
     prof_begin(ctx, "k_z_totals");
-    k_z_totals<ZSRC_BUFFER><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
+    k_z_totals<ZSRC_BUFFER><<<block_grid(ctx, a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     cudaError_t e = launch_prefix(c, a);
     if (e) return e;
     prof_begin(ctx, "k_z_write");
-    k_z_write<ZSRC_BUFFER><<<block_grid(a), ZB_T, 0, ctx->stream>>>(a);
+    k_z_write<ZSRC_BUFFER><<<block_grid(ctx, a), ZB_T, 0, ctx->stream>>>(a);
     prof_end(ctx);
     ctx->launches += 2;
     return cudaGetLastError();

@@ -21,6 +21,9 @@
 //   * Z: per-bin inverse tables here (Montgomery-trick batch inversion over the bins, not the
 //     rows), the running product itself in gprod.cu (k_z_general / k_z_totals / k_z_prefix with
 //     a single-pass decoupled-look-back scan / k_z_write).
+#include <algorithm>
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace h2 {
@@ -950,7 +953,15 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     h2aes_ctx *ctx = c->ctx;
     const uint64_t rows = rm.rows;
     unsigned gx = cdiv(rows, 256);
-    const unsigned cap = (unsigned)ctx->sm_count * 8;
+    // H2AES_STREAM_CTAS_PER_SM: total resident CTAs per SM of the streaming kernels (all lookups
+    // together); with H2AES_STREAM_PAD_KB this keeps them to a share of every SM
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        const char *s = getenv("H2AES_STREAM_CTAS_PER_SM");
+        per_sm = s ? atoi(s) : 0;
+    }
+    unsigned cap = (unsigned)ctx->sm_count * 8;
+    if (per_sm) cap = std::max(1u, (unsigned)(ctx->sm_count * per_sm) / (unsigned)count);
     if (gx > cap) gx = cap;
     dim3 g(gx, count);
     cudaError_t e0 = cudaMemsetAsync(c->d_gcount + first, 0, (size_t)count * 4, ctx->stream);

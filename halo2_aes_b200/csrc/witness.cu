@@ -242,6 +242,15 @@ size_t stream_pad_bytes(const void *func) {
 }
 
 static inline int grid_for(const h2aes_ctx *ctx, int ctas_per_sm) { return ctx->sm_count * ctas_per_sm; }
+// resident CTAs per SM of the streaming kernels (H2AES_STREAM_CTAS_PER_SM, 0 = the default 8)
+static inline int stream_ctas(int dflt) {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("H2AES_STREAM_CTAS_PER_SM");
+        v = s ? atoi(s) : 0;
+    }
+    return v ? v : dflt;
+}
 
 cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
     prof_begin(ctx, "k_build_frtab");
@@ -265,7 +274,7 @@ cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *
     ctx->launches++;
     const size_t pad = stream_pad_bytes((const void *)k_advice);
     prof_begin(ctx, "k_advice");
-    k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
+    k_advice<<<grid_for(ctx, stream_ctas(8)), 256, pad, ctx->stream>>>(c->sh, n_blocks, c->d_rk, c->d_states,
                                                         ctx->d_sbox, ctx->d_frtab, advice_dev,
                                                         c->d_trace, rm);
     prof_end(ctx);
@@ -289,7 +298,7 @@ cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const ui
     prof_end(ctx);
     const size_t pad = stream_pad_bytes((const void *)k_advice);
     prof_begin(ctx, "k_advice");
-    k_advice<<<grid_for(ctx, 8), 256, pad, ctx->stream>>>(c->sh, first_block + n, c->d_rk, c->d_states,
+    k_advice<<<grid_for(ctx, stream_ctas(8)), 256, pad, ctx->stream>>>(c->sh, first_block + n, c->d_rk, c->d_states,
                                                           ctx->d_sbox, ctx->d_frtab, advice_dev,
                                                           c->d_trace, row_map_of(c->sh.n(), 0, 1, 0));
     prof_end(ctx);
