@@ -63,6 +63,9 @@ struct NttArgs {
     uint64_t out_len;                // output elements >= out_len are not stored (truncation)
     int K, ka, kb;                   // N = 2^K = n1 * n2, n1 = 2^ka (strided), n2 = 2^kb (contiguous)
     int lg;                          // log2 of the columns / rows a CTA holds
+    int nest;                        // k_ntt_rows as the last pass of a three-pass transform: the batch
+                                     // index is (column, outer row j1o < 2^nest) and output element e
+                                     // of the inner transform lands at j1o + (e << nest)
     int tw_shift;                    // omega_N^e = tw[e << tw_shift]
     uint64_t tw_mask;                // table entries - 1
     int inverse;                     // read the table backwards: omega_N^-e
@@ -177,7 +180,8 @@ __global__ void __launch_bounds__(NTT_T, NTT_OCC) k_ntt_rows(const NttArgs a) {
     const int ka = a.ka, kb = a.kb, lg = a.lg;
     const uint64_t r0 = (uint64_t)blockIdx.x << lg;
     const uint64_t *__restrict__ in = a.in + (uint64_t)blockIdx.y * a.in_stride * 4;
-    uint64_t *__restrict__ out = a.out + (uint64_t)blockIdx.y * a.out_stride * 4;
+    const uint64_t j1o = blockIdx.y & ((1u << a.nest) - 1);
+    uint64_t *__restrict__ out = a.out + (uint64_t)(blockIdx.y >> a.nest) * a.out_stride * 4;
     const uint32_t elems = 1u << (lg + kb);
     for (uint32_t idx = threadIdx.x; idx < elems; idx += NTT_T) {
         const uint32_t g = idx >> kb, i2 = idx & ((1u << kb) - 1);
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(NTT_T, NTT_OCC) k_ntt_rows(const NttArgs a) {
     ntt_tile_stages(s, lg, kb, a);
     for (uint32_t idx = threadIdx.x; idx < elems; idx += NTT_T) {
         const uint32_t g = idx & ((1u << lg) - 1), j2 = idx >> lg;
-        const uint64_t o = r0 + g + ((uint64_t)j2 << ka);
+        const uint64_t o = j1o + ((r0 + g + ((uint64_t)j2 << ka)) << a.nest);
         fr_t v = nfr_ld(s + (g << kb) + j2);
         if (a.mul3) v = fr_mul(v, nfr_ld(a.c + (uint32_t)(o % 3)));
         if (o < a.out_len) fr_store_256(out + 4 * o, v);
@@ -296,37 +300,66 @@ struct Plan {
 
 int32_t run_plan(h2aes_domain *d, const Plan &p, const uint64_t *in, uint64_t *out, int ncols) {
     h2aes_ctx *ctx = d->ctx;
-    const int K = p.K, ka = (K + 1) / 2, kb = K - ka;
+    const int K = p.K;
     const uint64_t N = 1ull << K;
+    // two passes while both factors fit a shared-memory tile; beyond that (K = 23, 24) a third:
+    // N = n1o * M, the M-point row transforms are themselves two passes (over all rows at once)
+    const int ko = K > 2 * NTT_TILE_LOG ? K - 2 * ((K + 2) / 3) : 0;  // outer strided factor 2^ko
+    const int Ki = K - ko;                                           // inner transforms: 2^Ki points
+    const int ka = (Ki + 1) / 2, kb = Ki - ka;
     NttArgs a;
-    a.K = K; a.ka = ka; a.kb = kb;
-    a.tw_shift = d->extended_k - K;
-    a.tw_mask = d->en - 1;
     a.inverse = p.inverse;
     a.tw = d->d_tw;
+    a.tw_mask = d->en - 1;
     a.ctw = d->d_ctw;
-    const int lga = std::min(NTT_TILE_LOG - ka, kb), lgb = std::min(NTT_TILE_LOG - kb, ka);
-    const size_t smem_a = (size_t)32 << (lga + ka), smem_b = (size_t)32 << (lgb + kb);
+    a.nest = 0;
+    auto smem_of = [](int lg, int k) { return (size_t)32 << (lg + k); };
     for (int c0 = 0; c0 < ncols; c0 += d->batch) {
         const int nb = std::min(d->batch, ncols - c0);
-        a.in = in + (uint64_t)c0 * p.in_stride * 4;
-        a.out = reinterpret_cast<uint64_t *>(d->d_scratch);
-        a.in_stride = p.in_stride; a.out_stride = N;
-        a.in_len = p.in_len; a.out_len = N;
+        const uint64_t *src = in + (uint64_t)c0 * p.in_stride * 4;
+        uint64_t src_stride = p.in_stride, src_len = p.in_len;
+        const fr_t *c_in = p.c_in;
+        uint64_t *scratch = reinterpret_cast<uint64_t *>(d->d_scratch);
+        unsigned rows_batch = (unsigned)nb;  // independent inner transforms
+        if (ko) {
+            // pass 0: the 2^ko-point transforms over the outermost (strided) index, twiddled by
+            // omega_N^(i_M * j1o); rows j1o of M contiguous elements remain
+            a.K = K; a.ka = ko; a.kb = Ki;
+            a.tw_shift = d->extended_k - K;
+            a.lg = std::min(NTT_TILE_LOG - ko, Ki);
+            a.in = src; a.out = scratch;
+            a.in_stride = src_stride; a.out_stride = N;
+            a.in_len = src_len; a.out_len = N;
+            a.mul3 = c_in != nullptr; a.c = c_in;
+            prof_begin(ctx, "k_ntt_cols");
+            k_ntt_cols<<<dim3((unsigned)(1u << (Ki - a.lg)), nb), NTT_T, smem_of(a.lg, ko), ctx->stream>>>(a);
+            prof_end(ctx);
+            ctx->launches += 1;
+            src = scratch; src_stride = 1ull << Ki; src_len = 1ull << Ki; c_in = nullptr;
+            rows_batch = (unsigned)nb << ko;
+        }
+        const int lga = std::min(NTT_TILE_LOG - ka, kb), lgb = std::min(NTT_TILE_LOG - kb, ka);
+        a.K = Ki; a.ka = ka; a.kb = kb;
+        a.tw_shift = d->extended_k - Ki;
+        a.in = src; a.out = scratch;
+        a.in_stride = src_stride; a.out_stride = 1ull << Ki;
+        a.in_len = src_len; a.out_len = 1ull << Ki;
         a.lg = lga;
-        a.mul3 = p.c_in != nullptr; a.c = p.c_in;
+        a.mul3 = c_in != nullptr; a.c = c_in;
         prof_begin(ctx, "k_ntt_cols");
-        k_ntt_cols<<<dim3((unsigned)(1u << (kb - lga)), nb), NTT_T, smem_a, ctx->stream>>>(a);
+        k_ntt_cols<<<dim3((unsigned)(1u << (kb - lga)), rows_batch), NTT_T, smem_of(lga, ka), ctx->stream>>>(a);
         prof_end(ctx);
-        a.in = reinterpret_cast<const uint64_t *>(d->d_scratch);
+        a.in = scratch;
         a.out = out + (uint64_t)c0 * p.out_stride * 4;
-        a.in_stride = N; a.out_stride = p.out_stride;
-        a.in_len = N; a.out_len = p.out_len;
+        a.in_stride = 1ull << Ki; a.out_stride = p.out_stride;
+        a.in_len = 1ull << Ki; a.out_len = p.out_len;
         a.lg = lgb;
+        a.nest = ko;
         a.mul3 = p.c_out != nullptr; a.c = p.c_out;
         prof_begin(ctx, "k_ntt_rows");
-        k_ntt_rows<<<dim3((unsigned)(1u << (ka - lgb)), nb), NTT_T, smem_b, ctx->stream>>>(a);
+        k_ntt_rows<<<dim3((unsigned)(1u << (ka - lgb)), rows_batch), NTT_T, smem_of(lgb, kb), ctx->stream>>>(a);
         prof_end(ctx);
+        a.nest = 0;
         ctx->launches += 2;
     }
     DCU(ctx, cudaGetLastError());
@@ -360,7 +393,7 @@ int32_t h2aes_domain_create(h2aes_ctx *ctx, int32_t j, int32_t k, h2aes_domain *
     uint64_t q;
     if (!domain_shape(j, k, &ek, &q)) return dfail(ctx, H2AES_ERR_ARG, "domain: bad j or k");
     // both sub-transforms must fit the shared-memory tile
-    if (k < 2 || (ek + 1) / 2 > NTT_TILE_LOG) return dfail(ctx, H2AES_ERR_ARG, "domain: 2 <= k, extended_k <= 22");
+    if (k < 2 || ek > 24) return dfail(ctx, H2AES_ERR_ARG, "domain: 2 <= k, extended_k <= 24");
     DCU(ctx, cudaSetDevice(ctx->device));
     h2aes_domain *d = new (std::nothrow) h2aes_domain;
     if (!d) return H2AES_ERR_NOMEM;

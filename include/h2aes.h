@@ -272,11 +272,11 @@ int32_t h2aes_perm_product_dev(h2aes_circuit *c, const uint64_t *beta, const uin
  *       = j - 1; extended_k = smallest with 2^extended_k >= 2^k * (j - 1)  (k + 2 here)
  * Columns are [ncols][len][4] as everywhere else.  The extended domain is the coset
  * zeta * <extended_omega>, zeta = Fr::ZETA = 7^((r-1)/3) (g_coset), exactly as halo2 evaluates it.
- * Limits: 2 <= k, extended_k <= 22 — i.e. k <= 20 for these circuits (extended_k = k + 2): a
- * transform is two passes of at most 2^11-point sub-transforms in shared memory.  A K=21/22
- * circuit (BASELINE config 5) gets its witness, lookup and permutation columns from this library
- * but NOT the domain transforms, the quotient terms below or anything that needs a domain:
- * h2aes_domain_create returns H2AES_ERR_ARG ("domain: 2 <= k, extended_k <= 22") for it.
+ * Limits: 2 <= k, extended_k <= 24 — i.e. k <= 22 for these circuits (extended_k = k + 2): a
+ * transform is two passes of at most 2^11-point sub-transforms in shared memory up to 2^22
+ * points, three passes for 2^23 and 2^24.  h2aes_domain_create returns H2AES_ERR_ARG
+ * ("domain: 2 <= k, extended_k <= 24") beyond that.  The quotient entry points below are tested
+ * up to k = 20 (a K=22 circuit's extended columns are 512 MiB each).
  * ------------------------------------------------------------------------------------------- */
 typedef struct h2aes_domain h2aes_domain;
 #define H2AES_DOMAIN_FFT 0               /* best_fft(a, omega, k): a'[i] = sum_t a[t] omega^(it)  */

@@ -216,7 +216,7 @@ def test_domain_error_behaviour(gpu, ffi):
     from halo2_aes_b200.backend import Domain
     h = C.c_void_p()
     lib = ffi.lib()
-    assert lib.h2aes_domain_create(gpu._h, 5, 21, C.byref(h)) == ffi.ERR_ARG  # extended_k = 23
+    assert lib.h2aes_domain_create(gpu._h, 5, 23, C.byref(h)) == ffi.ERR_ARG  # extended_k = 25
     assert lib.h2aes_domain_create(gpu._h, 1, 17, C.byref(h)) == ffi.ERR_ARG
     dom = Domain(gpu, 10)
     assert lib.h2aes_fft_dev(dom._h, None, 1, 0) == ffi.ERR_ARG
@@ -226,15 +226,34 @@ def test_domain_error_behaviour(gpu, ffi):
 
 
 @pytest.mark.gpu
-def test_domain_limit_k22_is_reported(gpu, ffi):
-    """The documented limit (include/h2aes.h): extended_k <= 22, so the K=21/22 circuits of
-    BASELINE config 5 have no domain — h2aes_domain_create says so instead of mis-computing."""
+@pytest.mark.parametrize("k", [21, 22])
+def test_three_pass_transforms_equal_the_oracle(gpu, orc, ffi, k):
+    """extended_k = 23, 24 (the K=21 / K=22 circuits of BASELINE config 5): a 2^extended_k-point
+    transform no longer fits two shared-memory passes and runs as three (N = 2^7..8 x 2^8 x 2^8);
+    one column through coeff_to_extended and extended_to_coeff against the oracle, the 2^k-point
+    transforms (two passes) beside it."""
+    from halo2_aes_b200.backend import Domain
+    dom = Domain(gpu, k)
+    assert dom.extended_k == k + 2
+    a = rand_fr_cols(SEED + 300 + k, 1, dom.n)
+    c = _host(dom.lagrange_to_coeff(_dev(a)))
+    assert (c[0] == orc.domain_transform(orc.LAGRANGE_TO_COEFF, k, a[0])).all(), "lagrange_to_coeff"
+    e_t = dom.coeff_to_extended(_dev(a))
+    e = _host(e_t)
+    assert (e[0] == orc.domain_transform(orc.COEFF_TO_EXTENDED, k, a[0])).all(), "coeff_to_extended"
+    q = _host(dom.extended_to_coeff(e_t))
+    ref_q = orc.domain_transform(orc.EXTENDED_TO_COEFF, k, e[0])
+    assert (q[0, :dom.quotient_len] == ref_q).all() and not q[0, dom.quotient_len:].any()
+    dom.close()
+
+
+@pytest.mark.gpu
+def test_domain_limit_is_reported(gpu, ffi):
+    """The documented limit (include/h2aes.h): extended_k <= 24, i.e. k <= 22 for these circuits."""
     import ctypes as C
     L = ffi.lib()
-    for k in (21, 22):
-        h = C.c_void_p()
-        assert L.h2aes_domain_create(gpu._h, ffi.CS_DEGREE, k, C.byref(h)) == ffi.ERR_ARG
-        assert not h.value
-        assert b"extended_k <= 22" in L.h2aes_ctx_last_error(gpu._h)
-    ek, _ = ffi.domain_query(20)
-    assert ek == 22
+    h = C.c_void_p()
+    assert L.h2aes_domain_create(gpu._h, ffi.CS_DEGREE, 23, C.byref(h)) == ffi.ERR_ARG
+    assert not h.value
+    assert b"extended_k <= 24" in L.h2aes_ctx_last_error(gpu._h)
+    assert ffi.domain_query(22)[0] == 24
