@@ -142,6 +142,7 @@ static __device__ __forceinline__ fr_t general_factor(const ZScanArgs &a, int l,
     const int v = view_of_op(op);
     const size_t vo = (size_t)v * BIN_STRIDE;
     const uint32_t kind = code >> 30, cls = (code >> 28) & 3u, k = code & 0xffffffu;
+    H2_ASSERT(kind >= FK_GENERAL && k < BIN_STRIDE && kin < BIN_STRIDE && kp < BIN_STRIDE && row < a.sh.n());
     fr_t den = fr_ldg_256_nc((cls == CODE_FIRST ? a.ibg : (cls == CODE_PAD ? a.ibp : a.ib)) + vo + k);
     fr_t num = fr_ldg_256_nc((kind == FK_TABLE_ROW ? a.dval : a.nac) + vo + kin);
     if (cls == CODE_OTHER) den = fr_mul(den, fr_ldg_256_nc(a.ig + vo + kp));
@@ -164,6 +165,8 @@ __device__ __forceinline__ uint32_t row_code(const ZScanArgs &a, const LookupLan
 template <int SRC>
 __device__ __forceinline__ fr_t row_factor(const ZScanArgs &a, const LookupLane &cx, uint32_t code,
                                            uint32_t q, const uint64_t *__restrict__ z) {
+    H2_ASSERT(q < ZB_R && (SRC != ZSRC_LOOKUP || (code >> 30) != FK_ONE));
+    H2_ASSERT(SRC != ZSRC_LOOKUP || (code >> 30) != FK_TABLE || (code & 0xffffffu) < BIN_STRIDE);
     if (SRC == ZSRC_LOOKUP && (code >> 30) == FK_TABLE)  // merged table, selector in bits 28..29
         return fr_ldg_256_nc(a.ftab + (size_t)((code >> 28) & 3u) * (N_VIEWS * BIN_STRIDE) + cx.vo +
                              (code & 0xffffffu));
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(ZG_T, ZG_OCC) k_z_general(const __grid_constan
     uint64_t *__restrict__ zout = a.Z + (size_t)li * a.rows * 4;
     for (uint32_t i = blockIdx.x * ZG_T + threadIdx.x; i < cnt; i += gridDim.x * ZG_T) {
         const uint32_t lrow = __ldg(gl + i);
+        H2_ASSERT(lrow < a.rows);
         const uint64_t row = a.rm.global(lrow);
         const uint32_t code = __ldg(fc + row), t = __ldg(tk + row);
         const uint32_t kin = (t >> 24) == op ? (t & 0xffffffu) : k_zero;  // bin of the row's input value
@@ -278,6 +282,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
         if (q1 >= 0) f1 = row_factor<SRC>(a, t.cx, c1, (uint32_t)q1, z);
         tot = fr_mul_inline(tot, f);
     }
+    H2_ASSERT(!(t.b != ~0ull && (t.nr || a.segs > 1)) || t.b < (uint64_t)a.count * a.segs * a.n_blocks);
     if (t.b != ~0ull && (t.nr || a.segs > 1)) fr_st(a.tot + t.b, tot);  // (padding blocks of a partial segment: one)
     if (a.nonconst) {
         uint32_t c = __popc(t.mb0) + __popc(t.mb1) + __popc(t.mb2);

@@ -55,6 +55,17 @@ struct LookupMeta {  // per lookup, produced by the bin-scan kernel
     uint32_t pad[2];
 };
 
+// Debug build (`make -C halo2_aes_b200/csrc debug`, -DH2AES_DEBUG): bounds assertions on every
+// data-dependent index of the lookup / grand-product kernels (bins, runs, list entries, block
+// totals).  compute-sanitizer is not available on the pool's boxes; the parity suite run against
+// the debug library (H2AES_LIB=.../libh2aes_debug.so pytest -m gpu) is the memcheck substitute.
+#if defined(H2AES_DEBUG)
+#include <cassert>
+#define H2_ASSERT(cond) assert(cond)
+#else
+#define H2_ASSERT(cond) ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 // ---- device helpers shared by lookup.cu and gprod.cu ---------------------------------------
 __device__ __forceinline__ fr_t fr_from_tab(const uint4 *__restrict__ frtab, uint32_t b) {

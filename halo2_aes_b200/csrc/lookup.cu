@@ -378,7 +378,9 @@ k_lookup_hist(Shape sh, const uint32_t *__restrict__ trace, const uint32_t *__re
         if (op && row < usable) {
             const int v = view_of_op(op);
             const uint32_t e = entry_of_table_row(v, table_row_of_word(w));
+            H2_ASSERT(e < view_entries(v));
             const uint32_t k = rank[(size_t)v * BIN_STRIDE + e];
+            H2_ASSERT(k < BIN_STRIDE);
             atomicAdd(cnt + (size_t)(set * ops + (int)op - 1) * BIN_STRIDE + k, 1u);
             tk = (op << 24) | k;
         }
@@ -598,6 +600,7 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
     RowBins rb;
     const uint32_t t = i >> RUN_SHIFT;
     const uint32_t j = search_le_in(offz, jidx[t], jidx[t + 1] + 1, i);
+    H2_ASSERT(j < m.n_nonempty && offz[j] <= i && i < offz[j + 1]);
     rb.k = nzk[j];
     if (offz[j] == i) {
         rb.kp = rb.k;  // first occurrence: S' = A'
@@ -607,7 +610,10 @@ __device__ __forceinline__ RowBins row_bins(uint32_t i, const LookupMeta &m,
         const uint32_t rho = i - (j + 1);
         const uint32_t jj = m.repeated - 1 - rho;
         const uint32_t tt = jj >> RUN_SHIFT;
-        rb.kp = lk[search_le_in(loffz, lidx[tt], lidx[tt + 1] + 1, jj)];
+        H2_ASSERT(rho < m.repeated);
+        const uint32_t le = search_le_in(loffz, lidx[tt], lidx[tt + 1] + 1, jj);
+        H2_ASSERT(le < m.n_left && loffz[le] <= jj && jj < loffz[le + 1]);
+        rb.kp = lk[le];
         rb.cls = rb.kp == m.k_pad ? CODE_PAD : CODE_OTHER;
     }
     return rb;
@@ -679,6 +685,7 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
                 fr_store_256_cs(S + o, fr_ld(valv + e));
             }
             const RowBins rb = row_bins((uint32_t)row, m, offz, nzk, loffz, lk, jidx, lidx);
+            H2_ASSERT(rb.k < BIN_STRIDE && rb.kp < BIN_STRIDE && row < n);
             if (rb.cls == CODE_OTHER) cp[row] = rb.kp;  // (k_z_general reads it for these rows)
             if (Ap) {
                 fr_store_256_cs(Ap + o, fr_ldg_256_nc(dv + rb.k));
@@ -739,6 +746,7 @@ k_general_list(int first_lookup, int n_lookups, const uint32_t *__restrict__ zma
         pos = __shfl_sync(0xffffffffu, pos, 0) + inc - cnt;
         const uint32_t row0 = (uint32_t)((w0 + lane) << 5);
         for (; m; m &= m - 1u, ++pos) {
+            H2_ASSERT(pos < gcap);
             if (pos < gcap) gl[pos] = row0 + (uint32_t)__ffs(m) - 1u;
             else atomicOr(err + 2, 1u);  // cannot happen: gcap bounds the count (api.cu)
         }
