@@ -101,6 +101,7 @@ SIGNATURES = {
     "h2aes_witness_dev": (C.c_int32, [_vp, _u8p, _vp, C.c_uint64, _vp, _vp]),
     "h2aes_witness_host": (C.c_int32, [_vp, _u8p, _vp, C.c_uint64, _vp, _vp]),
     "h2aes_encrypt_append_dev": (C.c_int32, [_vp, _vp, C.c_uint64, _vp, _vp, _u64p]),
+    "h2aes_chip_rows_dev": (C.c_int32, [_vp, C.c_int32, _vp, _vp, C.c_uint64, _vp, _vp]),
     "h2aes_round_keys": (C.c_int32, [_vp, _u8p]),
     "h2aes_fixed_columns_dev": (C.c_int32, [_vp, C.c_uint64, _vp, _vp]),
     "h2aes_fixed_columns_host": (C.c_int32, [_vp, C.c_uint64, _vp, _vp]),

@@ -11,9 +11,10 @@ key_schedule.rs:296-315).  What changes is what happens underneath: instead of o
 `B200Layouter` and the whole circuit is produced by the CUDA kernels behind the C ABI
 (include/h2aes.h) when the layouter is flushed.  AssignedCell values are read back lazily.
 
-The chips' per-cell assign methods (xor / substitute / mul / range_check) are not separate
-entry points here: they only ever run inside schedule_keys / encrypt / lcon, and those are what
-the witness kernel fuses.  Calling them on their own raises NotImplementedError.
+The chips' per-cell assign methods (xor / substitute / mul / range_check) run fused inside
+schedule_keys / encrypt / lcon in the witness kernel.  Called on their own they assign a one-row
+region whose cells come from h2aes_chip_rows_dev (a row kernel); such a region is not placed in
+one of the two circuit shapes (h2aes.h says why), it is returned as a `ChipRegion`.
 """
 from __future__ import annotations
 
@@ -147,11 +148,39 @@ class MulBy3Config(SboxConfig):
     pass
 
 
-def _fused(name):
-    def f(self, *a, **k):
-        raise NotImplementedError(
-            f"{name} is fused into the witness kernel; call schedule_key/encrypt instead")
-    return f
+def _byte_of(cell) -> int:
+    v = cell.value() if hasattr(cell, "value") else int(cell)
+    if not 0 <= v < 256:
+        raise ValueError("chip inputs are u8 cells")
+    return v
+
+
+@dataclass
+class ChipRegion:
+    """The one-row region a stand-alone chip call assigns: `cells` = the Montgomery limbs of the
+    chip's columns in that row ([3, 4] int64 on the GPU), `out` = the byte of the returned cell."""
+    tag: int
+    cells: object
+    out: int
+
+    def value(self) -> int:
+        return self.out
+
+
+def _chip_row(layouter, tag, x, y=None) -> ChipRegion:
+    import torch
+
+    from .backend import Context
+    xv, yv = _byte_of(x), (_byte_of(y) if y is not None else None)
+    if layouter.ctx is None:
+        layouter.ctx = Context(torch.cuda.current_device())
+    dev = layouter.ctx.device
+    xb = torch.tensor([xv], dtype=torch.uint8, device=dev)
+    yb = torch.tensor([yv], dtype=torch.uint8, device=dev) if y is not None else None
+    out, cells = layouter.ctx.chip_rows(tag, xb, yb)
+    region = ChipRegion(tag, cells[:, 0], int(out.item()))
+    layouter.chip_regions.append(region)
+    return region
 
 
 class U8RangeCheckChip:
@@ -165,7 +194,8 @@ class U8RangeCheckChip:
         lk = meta.lookup("Check u8 range", selector, TAG_U8, (x,), (tag_tab, x_tab))
         return U8RangeCheckConfig(x, selector, lk)
 
-    range_check = _fused("U8RangeCheckChip::range_check")
+    def range_check(self, layouter, x):  # u8_range_check_chip.rs:51-70
+        return _chip_row(layouter, TAG_U8, x)
 
 
 class U8XorChip:
@@ -180,7 +210,8 @@ class U8XorChip:
                          (tag_tab, x_tab, y_tab, z_tab))
         return U8XorConfig(x, y, z, selector, lk)
 
-    xor = _fused("U8XorChip::xor")
+    def xor(self, layouter, x, y):  # u8_xor_chip.rs:63-100
+        return _chip_row(layouter, TAG_XOR, x, y)
 
 
 class SboxChip:
@@ -195,7 +226,8 @@ class SboxChip:
                          (tag_tab, x_tab, y_tab))
         return SboxConfig(x, y, selector, lk)
 
-    substitute = _fused("SboxChip::substitute")
+    def substitute(self, layouter, x):  # sbox_chip.rs:57-83
+        return _chip_row(layouter, TAG_SBOX, x)
 
 
 class MulBy2Chip:
@@ -210,7 +242,8 @@ class MulBy2Chip:
                          (tag_tab, x_tab, y_tab))
         return MulBy2Config(x, y, selector, lk)
 
-    mul = _fused("MulBy2Chip::mul")
+    def mul(self, layouter, x):  # gf_mul_chip.rs:59-89
+        return _chip_row(layouter, TAG_GFMUL2, x)
 
 
 class MulBy3Chip:
@@ -225,7 +258,8 @@ class MulBy3Chip:
                          (tag_tab, x_tab, y_tab))
         return MulBy3Config(x, y, selector, lk)
 
-    mul = _fused("MulBy3Chip::mul")
+    def mul(self, layouter, x):
+        return _chip_row(layouter, TAG_GFMUL3, x)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -259,6 +293,7 @@ class B200Layouter:
         self.ciphertexts = None
         self._flushed = 0          # plaintexts already on the GPU
         self._shape = None
+        self.chip_regions = []     # one-row regions of stand-alone chip calls (ChipRegion)
 
     def namespace(self, _name=None):  # Layouter::namespace: same layouter
         return self

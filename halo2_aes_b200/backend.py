@@ -64,6 +64,21 @@ class Context:
             out[name] = (int(n), float(ms))
         return out
 
+    def chip_rows(self, tag: int, x, y=None, want_cells=True):
+        """h2aes_chip_rows_dev: n one-row regions of the chip with table tag `tag` (1 range, 2 xor,
+        3 sbox, 4 mul2, 5 mul3) on uint8 CUDA tensors x (and y for xor).  Returns (out bytes [n],
+        cells [3, n, 4] int64 or None)."""
+        n = x.numel()
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
+        if y is not None:
+            assert y.is_cuda and y.dtype == torch.uint8 and y.is_contiguous() and y.numel() == n
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        cells = torch.empty((3, n, 4), dtype=torch.int64, device=self.device) if want_cells else None
+        check(lib().h2aes_chip_rows_dev(self._h, tag, _ptr(x) if n else None,
+                                        _ptr(y) if (y is not None and n) else None, n,
+                                        _ptr(cells) if n else None, _ptr(out) if n else None), self._h)
+        return out, cells
+
     # ---- NCCL inside the library (h2aes_comm_*) ------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -19,6 +19,8 @@ namespace h2 {
 cudaError_t launch_build_frtab(h2aes_ctx *ctx);
 cudaError_t launch_witness(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
                            uint64_t n_blocks, uint64_t *advice_dev, uint8_t *cts_dev, const RowMap &rm);
+cudaError_t launch_chip_rows(h2aes_ctx *ctx, int tag, const uint8_t *x, const uint8_t *y, uint64_t n,
+                             uint64_t *cells, uint8_t *out);
 cudaError_t launch_witness_append(h2aes_circuit *c, const uint8_t *key, const uint8_t *pts_dev,
                                   uint64_t first_block, uint64_t n, uint64_t *advice_dev,
                                   uint8_t *cts_dev);
@@ -536,6 +538,17 @@ int32_t h2aes_encrypt_append_dev(h2aes_circuit *c, const uint8_t *plaintexts_dev
     CU(ctx, launch_witness_append(c, c->key, plaintexts_dev, c->n_blocks, n, advice_dev, ciphertexts_dev));
     c->n_blocks += n;
     c->have_bins = c->have_hist = c->have_beta_gamma = c->have_partial = false;
+    return H2AES_OK;
+}
+
+int32_t h2aes_chip_rows_dev(h2aes_ctx *ctx, int32_t tag, const uint8_t *x_dev, const uint8_t *y_dev,
+                            uint64_t n, uint64_t *cells_dev, uint8_t *out_dev) {
+    if (!ctx) return H2AES_ERR_ARG;
+    if (tag < 1 || tag > 5) return fail(ctx, H2AES_ERR_ARG, "chip tag: 1 range, 2 xor, 3 sbox, 4 mul2, 5 mul3");
+    if (n && (!x_dev || (tag == 2 && !y_dev))) return fail(ctx, H2AES_ERR_ARG, "null pointer");
+    if (!n) return H2AES_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, launch_chip_rows(ctx, tag, x_dev, y_dev, n, cells_dev, out_dev));
     return H2AES_OK;
 }
 

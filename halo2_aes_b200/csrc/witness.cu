@@ -227,6 +227,33 @@ __global__ void k_build_frtab(uint4 *__restrict__ frtab) {
     frtab[2 * b + 1] = make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]);
 }
 
+// n one-row chip regions (the chips' stand-alone assign methods): row i holds x[i] in the chip's
+// first column, then y[i] (xor) and the chip's output byte; the output is also returned as a byte
+__global__ void __launch_bounds__(256)
+k_chip_rows(int tag, const uint8_t *__restrict__ sbox, const uint4 *__restrict__ frtab,
+            const uint8_t *__restrict__ x, const uint8_t *__restrict__ y, uint64_t n,
+            uint64_t *__restrict__ cells, uint8_t *__restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t a = x[i], b = tag == 2 ? y[i] : (uint8_t)0;
+        const uint8_t o = tag == 1 ? a
+                        : tag == 2 ? (uint8_t)(a ^ b)
+                        : tag == 3 ? sbox[a]
+                        : tag == 4 ? gf_mul2(a) : gf_mul3(a);
+        if (out) out[i] = o;
+        if (!cells) continue;
+        // columns of the region: range (x), xor (x, y, z), sbox / mul (x, y = out); the rest zero
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int col = 0; col < 3; ++col) {
+            const bool used = col == 0 || (tag == 2) || (tag >= 3 && col == 1);
+            const uint8_t v = col == 0 ? a : (tag == 2 ? (col == 1 ? b : o) : o);
+            uint4 *dst = reinterpret_cast<uint4 *>(cells + ((size_t)col * n + i) * 4);
+            dst[0] = used ? __ldg(frtab + 2 * v) : z4;
+            dst[1] = used ? __ldg(frtab + 2 * v + 1) : z4;
+        }
+    }
+}
+
 // ---- launchers -----------------------------------------------------------------------------
 // H2AES_STREAM_PAD_KB (tuning): unused dynamic shared memory requested by the HBM-bound streaming
 // kernels, which caps how many of their CTAs an SM holds and leaves registers / warp slots for
@@ -255,6 +282,16 @@ static inline int stream_ctas(int dflt) {
 cudaError_t launch_build_frtab(h2aes_ctx *ctx) {
     prof_begin(ctx, "k_build_frtab");
     k_build_frtab<<<1, 256, 0, ctx->stream>>>(ctx->d_frtab);
+    prof_end(ctx);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_chip_rows(h2aes_ctx *ctx, int tag, const uint8_t *x, const uint8_t *y, uint64_t n,
+                             uint64_t *cells, uint8_t *out) {
+    prof_begin(ctx, "k_chip_rows");
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    k_chip_rows<<<grid, 256, 0, ctx->stream>>>(tag, ctx->d_sbox, ctx->d_frtab, x, y, n, cells, out);
     prof_end(ctx);
     ctx->launches++;
     return cudaGetLastError();

@@ -189,18 +189,26 @@ int32_t h2aes_witness_host(h2aes_circuit *c, const uint8_t *key, const uint8_t *
  *                            place; rows of blocks not yet appended stay zero)
  *   ciphertexts_dev          n*16 bytes for the appended blocks, nullable
  *   *first_block             out, nullable: index the first appended block received
- * Unsharded circuits only.
- *
- * The chips' own per-cell methods — U8XorChip::xor (u8_xor_chip.rs:63), SboxChip::substitute
- * (sbox_chip.rs:57), MulBy2/3Chip::mul (gf_mul_chip.rs:59), U8RangeCheckChip::range_check
- * (u8_range_check_chip.rs:51) — are NOT exported as stand-alone calls: every row they assign
- * inside schedule_key / encrypt is produced by the fused witness kernels, and a cell outside those
- * regions would also need its selector, copy constraints and the lookups' active-row counts
- * patched, which this backend derives in closed form from (kind, k, N, n_blocks).  A circuit that
- * uses the chips on its own cells must keep the reference's CPU path for those regions. */
+ * Unsharded circuits only. */
 int32_t h2aes_encrypt_append_dev(h2aes_circuit *c, const uint8_t *plaintexts_dev, uint64_t n,
                                  uint64_t *advice_dev, uint8_t *ciphertexts_dev,
                                  uint64_t *first_block);
+
+/* replaces: the chips' own per-cell assign methods called outside schedule_key / encrypt --
+ * U8RangeCheckChip::range_check (u8_range_check_chip.rs:51-70, tag 1), U8XorChip::xor
+ * (u8_xor_chip.rs:63-100, tag 2; value rule utils.rs:8-19), SboxChip::substitute
+ * (sbox_chip.rs:57-83, tag 3; the context's S-box, i.e. the reference's table with its
+ * S_BOX[255] by default), MulBy2Chip / MulBy3Chip::mul (gf_mul_chip.rs:59-89, tags 4 / 5).
+ * Each of those calls assigns a ONE-ROW region; this call produces n such rows at once:
+ *   x_dev, y_dev   n input bytes each (y_dev only for tag 2)
+ *   cells_dev      nullable; [3][n][4] u64: the region's cells of row i in the chip's columns
+ *                  (x | x, y, z | x, y=out), Montgomery limbs, unused columns zero
+ *   out_dev        nullable; n bytes: the value of the cell the method returns (range: x)
+ * The rows are NOT placed in a circuit: only the two circuit shapes of the reference have a
+ * layout here (their chip rows come from the fused witness kernels), so a circuit that places
+ * chip regions of its own supplies selectors and copy constraints for them itself. */
+int32_t h2aes_chip_rows_dev(h2aes_ctx *ctx, int32_t tag, const uint8_t *x_dev, const uint8_t *y_dev,
+                            uint64_t n, uint64_t *cells_dev, uint8_t *out_dev);
 
 /* the 176 expanded key bytes (values of the 11x16 cells schedule_keys returns). Host out. */
 int32_t h2aes_round_keys(h2aes_circuit *c, uint8_t *out176);

@@ -141,6 +141,72 @@ def test_fips_sbox_switch(gpu, orc, ffi, challenges):
               lookups=[2], fips=True)
 
 
+@pytest.mark.parametrize("fips", [False, True])
+def test_chip_rows_over_their_whole_domain(gpu, orc, ffi, fips):
+    """The chips' stand-alone assign methods (u8_xor_chip.rs:63-100, sbox_chip.rs:57-83,
+    gf_mul_chip.rs:59-89, u8_range_check_chip.rs:51-70) as one-row regions: every input of every
+    chip against the oracle's tables (constant.rs, incl. the reference's S_BOX[255]) and
+    xor_bytes (utils.rs:8-19, test :41-47), values and Montgomery cells."""
+    import torch
+    from halo2_aes_b200.backend import Context
+    ctx = Context(0, ffi.SBOX_FIPS197) if fips else gpu
+    sbox, m2, m3 = orc.tables(fips)
+    assert (sbox[255] == 0x16) == fips                                   # SURVEY F1
+    frtab = np.stack([orc.fr_from_int(v) for v in range(256)])
+    zero = np.zeros(4, np.uint64)
+    x = torch.arange(256, dtype=torch.uint8, device="cuda")
+    for tag, tab in ((1, np.arange(256, dtype=np.uint8)), (3, sbox), (4, m2), (5, m3)):
+        out, cells = ctx.chip_rows(tag, x)
+        assert (out.cpu().numpy() == tab).all(), tag
+        c = _host(cells)
+        assert (c[0] == frtab).all() and (c[2] == zero).all()
+        assert (c[1] == (frtab[tab] if tag != 1 else zero)).all()
+    xs = x.repeat_interleave(256).contiguous()
+    ys = x.repeat(256).contiguous()
+    out, cells = ctx.chip_rows(2, xs, ys)
+    want = (xs.cpu().numpy() ^ ys.cpu().numpy())
+    assert (out.cpu().numpy() == want).all()
+    c = _host(cells)
+    assert (c[0] == frtab[xs.cpu().numpy()]).all() and (c[1] == frtab[ys.cpu().numpy()]).all()
+    assert (c[2] == frtab[want]).all()
+    out, _ = ctx.chip_rows(2, xs[:2304:256][5:6].contiguous(), ys[12:13].contiguous())
+    assert int(out.item()) == 9                                          # utils.rs:41-47
+    for a, b in ((5, 12), (255, 255), (0, 0)):                           # the oracle's xor_bytes on Fr
+        o = np.zeros(4, np.uint64)
+        assert orc.lib().orc_xor_bytes(orc._u64(orc.fr_from_int(a)), orc._u64(orc.fr_from_int(b)),
+                                       orc._u64(o)) == 0
+        assert orc.fr_to_int(o) == a ^ b
+    with pytest.raises(ffi.H2AesError):
+        ctx.chip_rows(6, x)
+    assert ctx.chip_rows(2, x[:0], x[:0])[0].numel() == 0
+    if fips:
+        ctx.close()
+
+
+def test_chip_methods_of_the_host_mirror(gpu, orc, ffi):
+    """U8XorChip::xor etc. called the way a user's synthesize would, chained, on cells of a
+    flushed AES circuit: ct[0] ^ ct[1], then Sbox, mul2, mul3, range check."""
+    from halo2_aes_b200 import aes128 as m
+    sbox, m2, m3 = orc.tables(False)
+    cfg = m.FixedAes128Config.configure(m.ConstraintSystem(), 17, 1)
+    lay = m.B200Layouter(17, gpu)
+    cfg.schedule_key(lay, bytes(range(16)))
+    ct = cfg.encrypt(lay, bytes.fromhex("00112233445566778899aabbccddeeff"))
+    want_ct = bytes.fromhex("69c4e0d86a7b0430d8cdb78070b4c55a")                 # FIPS-197 C.1
+    z = m.U8XorChip.construct(cfg.configs[1][0]).xor(lay, ct[0], ct[1])
+    assert z.value() == want_ct[0] ^ want_ct[1]
+    s = m.SboxChip.construct(cfg.configs[2][0]).substitute(lay, z)
+    assert s.value() == sbox[z.value()]
+    d = m.MulBy2Chip.construct(cfg.configs[3][0]).mul(lay, s)
+    t3 = m.MulBy3Chip.construct(cfg.configs[4][0]).mul(lay, s)
+    assert d.value() == m2[s.value()] and t3.value() == m3[s.value()]
+    r = m.U8RangeCheckChip.construct(cfg.configs[0][0]).range_check(lay, d)
+    assert r.value() == d.value() and len(lay.chip_regions) == 5
+    assert (_host(z.cells)[2] == orc.fr_from_int(z.value())).all()
+    with pytest.raises(ValueError):
+        m.SboxChip.construct(cfg.configs[2][0]).substitute(lay, 256)
+
+
 def test_error_behaviour(gpu, ffi):
     import torch
     from halo2_aes_b200.backend import Circuit

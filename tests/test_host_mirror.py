@@ -105,8 +105,8 @@ def test_capacity_rule_and_panics(ffi):
     with pytest.raises(ffi.NotEnoughRows):
         m.FixedAes128Config.configure(m.ConstraintSystem(), 16, 1).schedule_key(
             m.B200Layouter(16), bytes(16))
-    with pytest.raises(NotImplementedError):
-        m.U8XorChip.construct(cfg.configs[1][0]).xor(lay, None, None)
+    with pytest.raises(ValueError):   # chip inputs are u8 cells (checked before any device call)
+        m.U8XorChip.construct(cfg.configs[1][0]).xor(lay, 256, 0)
 
 
 @pytest.mark.gpu
