@@ -7,7 +7,14 @@
 // The blinding term (blind * W) stays with the caller: pass it as one more (scalar, base) pair or
 // add it afterwards.
 //
-// Bucket method with signed c-bit digits (2^(c-1) buckets per window):
+// Bucket method with signed c-bit digits (2^(c-1) buckets per window).  The window size is chosen
+// PER COLUMN from what k_msm_stats finds in it: the columns of this backend are very unlike one
+// another (byte-valued advice: 8 bits, one window; A' through its differences: <= 66 561 terms;
+// Z: a few hundred thousand full-width terms), and a window size fit for 2^20 uniform scalars
+// leaves most of them paying for 16 x 32 768 buckets they do not use.  The columns of a call run
+// on several streams with a workspace each, so that the short, latency-bound reduction kernels of
+// one column overlap the wide accumulation kernels of the next.
+//   k_msm_stats    per column: non-zero scalars, non-zero differences, OR of the canonical words
 //   k_msm_diff     (after h2aes_msm_enable_runs) s_i - s_{i+1}, to run the method on the column's
 //                  differences against the running sums of the bases when that leaves fewer terms
 //   k_msm_digits   per scalar: leave Montgomery form, recode into W signed digits, histogram
@@ -38,28 +45,30 @@
 namespace h2 {
 
 constexpr int MSM_SEG = 32;     // points per task
-constexpr int MSM_NCH = 1024;   // bucket chunks per window in the reduction
+constexpr int MSM_NCH = 1024;   // bucket chunks per window in the reduction, at most
+constexpr int MSM_CHB = 32;     // buckets per chunk aimed at
+constexpr int MSM_CMIN = 6, MSM_CMAX = 16;  // window sizes the per-column choice ranges over
+constexpr int MSM_WMAX = 254 / MSM_CMIN + 1;
+constexpr int MSM_STATS = 10;   // words per column: nnz scalars, nnz differences, OR of 8 words
 constexpr int MSM_HEAVY = 8;    // a bucket with more tasks than this is summed by a whole CTA
 constexpr int MSM_BATCH = 64;   // columns whose window sums wait for one k_msm_final launch
-
-// which (scalars, bases) pair a column's kernels read: the column itself against the bases, or its
-// differences s_i - s_{i+1} against the running sums of the bases (see k_msm_diff)
-struct MsmSel {
-    const fr_t *scalars;
-    const g1a_t *bases;
-};
 
 struct MsmArgs {
     uint64_t n;
     int c, W;
     uint32_t NB;               // 2^(c-1) buckets per window (index 1..NB; 0 = zero digit)
     uint32_t max_tasks;        // per window
+    uint32_t nch;              // chunks of buckets per window (k_msm_chunks / k_msm_windows)
     const fr_t *scalars;       // [n] the column
     const g1a_t *bases;        // [n]
     const g1a_t *prefix;       // [n] prefix[i] = bases[0] + ... + bases[i], or null
     fr_t *diff;                // [n] scratch: s_i - s_{i+1}
-    MsmSel *sel;               // device: the pair in use for the current column
-    uint32_t *nnz;             // device: [0] non-zero differences, [1] non-zero scalars
+    // the pair the bucket method runs on: the column itself against the bases, or its differences
+    // against the running sums of the bases (see k_msm_diff)
+    const fr_t *src_scalars;
+    const g1a_t *src_bases;
+    uint32_t *stats;           // [ncols][MSM_STATS] (k_msm_stats)
+    const uint32_t *colcfg;    // [ncols] c | W << 8 of every column of the batch (k_msm_final)
     uint32_t *dig;             // [W][n] |digit| | sign << 31
     uint32_t *hist;            // [W][NB + 1]
     uint32_t *offs;            // [W][NB + 2] exclusive offsets of buckets into sorted
@@ -68,8 +77,8 @@ struct MsmArgs {
     uint32_t *sorted;          // [W][n] index | sign << 31
     g1x_t *partial;            // [W][max_tasks]
     g1x_t *buckets;            // [W][NB + 1]
-    g1x_t *chunks;             // [W][MSM_NCH]
-    g1x_t *wsum;               // [MSM_BATCH][W] window sums of the columns of a batch
+    g1x_t *chunks;             // [W][nch]
+    g1x_t *wsum;               // [MSM_BATCH][MSM_WMAX] window sums of the columns of a batch
     uint32_t *heavy;           // [W][max_heavy + 1]: count, then the heavy buckets of the window
     uint32_t max_heavy;
     g1a_t *out;                // results of the batch
@@ -109,28 +118,46 @@ __device__ __forceinline__ void g1x_st(g1x_t *p, const g1x_t &a) {
 // zero and drop out of the bucket method; uniform columns keep the direct form.
 __global__ void __launch_bounds__(256) k_msm_diff(const MsmArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const fr_t s = mfr_ld(a.scalars + i);
+    const fr_t nx = i + 1 < a.n ? mfr_ld(a.scalars + i + 1) : fr_zero();
+    const fr_t d = fr_sub(s, nx);
+    uint4 *q = reinterpret_cast<uint4 *>(a.diff + i);
+    q[0] = make_uint4(d.v[0], d.v[1], d.v[2], d.v[3]);
+    q[1] = make_uint4(d.v[4], d.v[5], d.v[6], d.v[7]);
+}
+// what the host picks a column's path and window size from (blockIdx.y = column of the batch;
+// a.scalars = the first column of the batch)
+__global__ void __launch_bounds__(256) k_msm_stats(const MsmArgs a) {
+    __shared__ uint32_t s_or[8], s_cnt[2];
+    if (threadIdx.x < 8) s_or[threadIdx.x] = 0u;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const fr_t *col = a.scalars + (uint64_t)blockIdx.y * a.n;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool nz_d = false, nz_s = false;
+    fr_t cs = fr_zero();
     if (i < a.n) {
-        const fr_t s = mfr_ld(a.scalars + i);
-        const fr_t nx = i + 1 < a.n ? mfr_ld(a.scalars + i + 1) : fr_zero();
-        const fr_t d = fr_sub(s, nx);
-        uint4 *q = reinterpret_cast<uint4 *>(a.diff + i);
-        q[0] = make_uint4(d.v[0], d.v[1], d.v[2], d.v[3]);
-        q[1] = make_uint4(d.v[4], d.v[5], d.v[6], d.v[7]);
-        nz_d = !fr_is_zero(d);
+        const fr_t s = mfr_ld(col + i);
+        const fr_t nx = i + 1 < a.n ? mfr_ld(col + i + 1) : fr_zero();
+        nz_d = !fr_is_zero(fr_sub(s, nx));
         nz_s = !fr_is_zero(s);
+        cs = fr_to_canonical(s);
     }
     const uint32_t bd = __ballot_sync(0xffffffffu, nz_d), bs = __ballot_sync(0xffffffffu, nz_s);
-    if ((threadIdx.x & 31) == 0) {
-        if (bd) atomicAdd(a.nnz, (uint32_t)__popc(bd));
-        if (bs) atomicAdd(a.nnz + 1, (uint32_t)__popc(bs));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t o = __reduce_or_sync(0xffffffffu, cs.v[k]);
+        if ((threadIdx.x & 31) == 0 && o) atomicOr(s_or + k, o);
     }
-}
-// the differences pay off when they leave clearly fewer non-zero scalars than the column has
-__global__ void k_msm_select(const MsmArgs a) {
-    const bool runs = a.prefix != nullptr && (uint64_t)a.nnz[0] * 2 < a.nnz[1];
-    a.sel->scalars = runs ? a.diff : a.scalars;
-    a.sel->bases = runs ? a.prefix : a.bases;
+    if ((threadIdx.x & 31) == 0) {
+        if (bs) atomicAdd(s_cnt, (uint32_t)__popc(bs));
+        if (bd) atomicAdd(s_cnt + 1, (uint32_t)__popc(bd));
+    }
+    __syncthreads();
+    uint32_t *st = a.stats + (size_t)blockIdx.y * MSM_STATS;
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(st + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x >= 2 && threadIdx.x < 10 && s_or[threadIdx.x - 2]) atomicOr(st + threadIdx.x, s_or[threadIdx.x - 2]);
 }
 
 // running sums of the bases, prefix[i] = G_0 + ... + G_i (affine), built once per set of bases:
@@ -219,7 +246,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const MsmArgs a) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.n;  // no early return: whole warps take part in the aggregation
     fr_t s = fr_zero();
-    if (valid) s = fr_to_canonical(mfr_ld(a.sel->scalars + i));
+    if (valid) s = fr_to_canonical(mfr_ld(a.src_scalars + i));
     const uint32_t full = 1u << a.c, mask = full - 1;
     uint32_t carry = 0;
     for (int w = 0; w < a.W; ++w) {
@@ -313,7 +340,7 @@ __global__ void __launch_bounds__(128) k_msm_tasks(const MsmArgs a) {
     const uint32_t *o = a.offs + (uint64_t)w * (a.NB + 2);
     const uint32_t start = o[b] + (t - to[b]) * MSM_SEG, end = min(o[b + 1], start + MSM_SEG);
     const uint32_t *srt = a.sorted + (uint64_t)w * a.n;
-    const g1a_t *__restrict__ bases = a.sel->bases;
+    const g1a_t *__restrict__ bases = a.src_bases;
     g1x_t acc = g1x_identity();
 #pragma unroll 1
     for (uint32_t pos = start; pos < end; ++pos) {
@@ -388,8 +415,8 @@ __global__ void __launch_bounds__(128) k_msm_heavy(const MsmArgs a) {
 __global__ void __launch_bounds__(64) k_msm_chunks(const MsmArgs a) {
     const int w = blockIdx.y;
     const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= MSM_NCH) return;
-    const uint32_t cb = (a.NB + MSM_NCH - 1) / MSM_NCH;
+    if (ch >= a.nch) return;
+    const uint32_t cb = (a.NB + a.nch - 1) / a.nch;
     const uint32_t lo = min(a.NB, ch * cb), hi = min(a.NB, lo + cb);
     const g1x_t *B = a.buckets + (uint64_t)w * (a.NB + 1);
     g1x_t run = g1x_identity(), acc = g1x_identity();
@@ -409,22 +436,22 @@ __global__ void __launch_bounds__(64) k_msm_chunks(const MsmArgs a) {
         }
         g1x_add(acc, m);
     }
-    g1x_st(a.chunks + (uint64_t)w * MSM_NCH + ch, acc);
+    g1x_st(a.chunks + (uint64_t)w * a.nch + ch, acc);
 }
 
 // per window: sum of the chunk results
 __global__ void __launch_bounds__(256) k_msm_windows(const MsmArgs a) {
     __shared__ g1x_t s_pts[256];
     const int w = blockIdx.x;
-    const g1x_t *C = a.chunks + (uint64_t)w * MSM_NCH;
+    const g1x_t *C = a.chunks + (uint64_t)w * a.nch;
     g1x_t acc = g1x_identity();
 #pragma unroll 1
-    for (int j = threadIdx.x; j < MSM_NCH; j += 256) {
+    for (uint32_t j = threadIdx.x; j < a.nch; j += 256) {
         const g1x_t p = g1x_ld(C + j);
         g1x_add(acc, p);
     }
     const g1x_t tot = g1x_block_sum<256>(acc, s_pts);
-    if (threadIdx.x == 0) g1x_st(a.wsum + (uint64_t)a.col * a.W + w, tot);
+    if (threadIdx.x == 0) g1x_st(a.wsum + (uint64_t)a.col * MSM_WMAX + w, tot);
 }
 
 // one thread per column of the batch: Horner over the windows (c doublings each), then to affine.
@@ -432,12 +459,13 @@ __global__ void __launch_bounds__(256) k_msm_windows(const MsmArgs a) {
 __global__ void __launch_bounds__(32) k_msm_final(const MsmArgs a) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= a.ncols) return;
+    const int c = (int)(a.colcfg[col] & 0xffu), W = (int)(a.colcfg[col] >> 8);
     g1x_t tot = g1x_identity();
 #pragma unroll 1
-    for (int w = a.W - 1; w >= 0; --w) {
+    for (int w = W - 1; w >= 0; --w) {
 #pragma unroll 1
-        for (int i = 0; i < a.c; ++i) g1x_double(tot);
-        const g1x_t p = g1x_ld(a.wsum + (uint64_t)col * a.W + w);
+        for (int i = 0; i < c; ++i) g1x_double(tot);
+        const g1x_t p = g1x_ld(a.wsum + (uint64_t)col * MSM_WMAX + w);
         g1x_add(tot, p);
     }
     const g1a_t r = g1x_to_affine(tot);
@@ -485,21 +513,39 @@ __global__ void __launch_bounds__(128) k_msm_synthetic_bases(fr_t d, uint64_t n,
 
 using namespace h2;
 
+constexpr int MSM_PIPES = 6;  // columns in flight (one stream + workspace each)
+
+struct MsmPipe {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint32_t *d_u32 = nullptr;  // hist | cursor | heavy | offs | toffs | dig | sorted of the column in flight
+    g1x_t *d_pts = nullptr;     // partial | buckets | chunks
+    fr_t *d_diff = nullptr;     // [n]
+};
+
+// window size and path of one column
+struct MsmPlan {
+    int c = 0, W = 0;
+    uint32_t NB = 0, nch = 0, max_tasks = 0;
+    bool runs = false;  // through the differences
+};
+
 struct h2aes_msm {
     h2aes_ctx *ctx = nullptr;
     uint64_t n = 0;
-    int c = 0, W = 0;
-    uint32_t NB = 0, max_tasks = 0;
+    int lg = 0;
+    int w_cap = 0;                 // windows a column may use (bounds dig / sorted)
+    double kappa = 8.0;            // cost of one bucket of the reduction in mixed additions
+    int fixed_c = 0;               // H2AES_MSM_C: one window size for every column (tuning / tests)
+    int n_pipes = 1;
     const g1a_t *bases = nullptr;  // caller-owned
-    uint32_t *d_u32 = nullptr;     // dig, hist, offs, toffs, cursor, sorted in one allocation
-    g1x_t *d_pts = nullptr;        // partial, buckets, chunks, wsum
     g1a_t *d_prefix = nullptr;     // [n] running sums of the bases (h2aes_msm_enable_runs)
-    fr_t *d_diff = nullptr;        // [n]
-    MsmSel *d_sel = nullptr;
-    uint32_t *d_nnz = nullptr;     // [2]
-    size_t hist_off = 0, offs_off = 0, toffs_off = 0, cursor_off = 0, sorted_off = 0, zero_words = 0,
-           heavy_off = 0;
+    MsmPipe pipe[MSM_PIPES];
+    g1x_t *d_wsum = nullptr;       // [MSM_BATCH][MSM_WMAX]
+    uint32_t *d_stats = nullptr;   // [MSM_BATCH][MSM_STATS]
+    uint32_t *d_colcfg = nullptr;  // [MSM_BATCH]
     uint32_t max_heavy = 0;
+    size_t words = 0, pts = 0;
 };
 
 namespace {
@@ -541,6 +587,40 @@ int32_t h2aes_g1_synthetic_bases_dev(h2aes_ctx *ctx, const uint64_t *d, uint64_t
     return H2AES_OK;
 }
 
+// windows / buckets / chunks of a column with `bits`-bit scalars under window size c
+static MsmPlan msm_plan_of(const h2aes_msm *m, int c, int bits) {
+    MsmPlan p;
+    p.c = c;
+    p.W = bits / c + 1;  // signed digits: the top window only ever receives the carry on top of < c-1 bits
+    p.NB = 1u << (c - 1);
+    p.nch = std::max(1u, std::min((uint32_t)MSM_NCH, p.NB / MSM_CHB));
+    p.max_tasks = (uint32_t)(m->n / MSM_SEG) + p.NB + 1;
+    return p;
+}
+static size_t msm_words_of(const h2aes_msm *m, const MsmPlan &p) {
+    const size_t W = (size_t)p.W;
+    return 2 * W * (p.NB + 1) + W * ((size_t)m->max_heavy + 1) + 2 * W * (p.NB + 2) + 2 * W * m->n;
+}
+static size_t msm_pts_of(const MsmPlan &p) {
+    return (size_t)p.W * ((size_t)p.max_tasks + p.NB + 1 + p.nch);
+}
+// cheapest window size for m non-zero `bits`-bit terms: W * (m + kappa * buckets)
+static MsmPlan msm_choose(const h2aes_msm *m, uint64_t terms, int bits) {
+    MsmPlan best;
+    double best_cost = 0;
+    for (int c = MSM_CMIN; c <= MSM_CMAX; ++c) {
+        if (m->fixed_c && c != m->fixed_c) continue;
+        const MsmPlan p = msm_plan_of(m, c, bits);
+        if (p.W > m->w_cap && !m->fixed_c) continue;
+        const double cost = (double)p.W * ((double)terms + m->kappa * (double)p.NB);
+        if (!best.c || cost < best_cost) {
+            best = p;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
 int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, h2aes_msm **out) {
     if (!ctx || !out) return H2AES_ERR_ARG;
     *out = nullptr;
@@ -553,29 +633,36 @@ int32_t h2aes_msm_create(h2aes_ctx *ctx, const uint64_t *bases_dev, uint64_t n, 
     m->bases = reinterpret_cast<const g1a_t *>(bases_dev);
     int lg = 0;
     while ((1ull << (lg + 1)) <= n) ++lg;
-    m->c = std::max(4, std::min(16, lg - 4));
-    m->W = 254 / m->c + 1;
-    m->NB = 1u << (m->c - 1);
-    m->max_tasks = (uint32_t)(n / MSM_SEG) + m->NB + 1;
-    const size_t W = (size_t)m->W, nb1 = m->NB + 1, nb2 = m->NB + 2;
+    m->lg = lg;
+    // a full-width column never wants fewer than ~lg - 10 bits per window; narrower scalars get
+    // smaller windows but then need few of them
+    const int c_lo = std::max(MSM_CMIN, std::min(MSM_CMAX, lg - 10));
+    m->w_cap = 254 / c_lo + 1;
+    if (const char *e = getenv("H2AES_MSM_KAPPA")) m->kappa = atof(e);
+    if (const char *e = getenv("H2AES_MSM_C")) m->fixed_c = std::max(MSM_CMIN, std::min(MSM_CMAX, atoi(e)));
+    m->n_pipes = n <= (1ull << 22) ? MSM_PIPES : 1;
+    if (const char *e = getenv("H2AES_MSM_PIPES")) m->n_pipes = std::max(1, std::min(MSM_PIPES, atoi(e)));
     m->max_heavy = (uint32_t)(n / ((uint64_t)MSM_SEG * MSM_HEAVY)) + 1;
-    // layout: [hist | cursor | heavy] (zeroed per column) | offs | toffs | dig | sorted
-    m->hist_off = 0;
-    m->cursor_off = W * nb1;
-    m->heavy_off = 2 * W * nb1;
-    m->zero_words = m->heavy_off + W * ((size_t)m->max_heavy + 1);
-    m->offs_off = m->zero_words;
-    m->toffs_off = m->offs_off + W * nb2;
-    const size_t dig_off = m->toffs_off + W * nb2;
-    m->sorted_off = dig_off + W * n;
-    const size_t words = m->sorted_off + W * n;
-    const size_t pts = W * ((size_t)m->max_tasks + nb1 + MSM_NCH + MSM_BATCH);
-    cudaError_t e;
-    if ((e = cudaMalloc((void **)&m->d_u32, words * 4)) ||
-        (e = cudaMalloc((void **)&m->d_pts, pts * sizeof(g1x_t))) ||
-        (e = cudaMalloc((void **)&m->d_diff, n * sizeof(fr_t))) ||
-        (e = cudaMalloc((void **)&m->d_sel, sizeof(MsmSel))) ||
-        (e = cudaMalloc((void **)&m->d_nnz, 2 * sizeof(uint32_t)))) {
+    for (int c = MSM_CMIN; c <= MSM_CMAX; ++c) {  // the largest workspace any choice can ask for
+        if (m->fixed_c && c != m->fixed_c) continue;
+        MsmPlan p = msm_plan_of(m, c, 254);
+        if (!m->fixed_c) p.W = std::min(p.W, m->w_cap);
+        m->words = std::max(m->words, msm_words_of(m, p));
+        m->pts = std::max(m->pts, msm_pts_of(p));
+    }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < m->n_pipes && !e; ++i) {
+        MsmPipe &p = m->pipe[i];
+        if ((e = cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking)) ||
+            (e = cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming)) ||
+            (e = cudaMalloc((void **)&p.d_u32, m->words * 4)) ||
+            (e = cudaMalloc((void **)&p.d_pts, m->pts * sizeof(g1x_t))) ||
+            (e = cudaMalloc((void **)&p.d_diff, n * sizeof(fr_t)))) break;
+    }
+    if (!e) e = cudaMalloc((void **)&m->d_wsum, (size_t)MSM_BATCH * MSM_WMAX * sizeof(g1x_t));
+    if (!e) e = cudaMalloc((void **)&m->d_stats, (size_t)MSM_BATCH * MSM_STATS * 4);
+    if (!e) e = cudaMalloc((void **)&m->d_colcfg, (size_t)MSM_BATCH * 4);
+    if (e) {
         h2aes_msm_destroy(m);
         return mcuda(ctx, e, "msm: cudaMalloc");
     }
@@ -623,14 +710,83 @@ int32_t h2aes_msm_enable_runs(h2aes_msm *m) {
 int32_t h2aes_msm_destroy(h2aes_msm *m) {
     if (!m) return H2AES_ERR_ARG;
     cudaSetDevice(m->ctx->device);
-    cudaFree(m->d_u32);
-    cudaFree(m->d_pts);
+    for (MsmPipe &p : m->pipe) {
+        if (p.stream) {
+            cudaStreamSynchronize(p.stream);
+            cudaStreamDestroy(p.stream);
+        }
+        if (p.done) cudaEventDestroy(p.done);
+        cudaFree(p.d_u32);
+        cudaFree(p.d_pts);
+        cudaFree(p.d_diff);
+    }
     cudaFree(m->d_prefix);
-    cudaFree(m->d_diff);
-    cudaFree(m->d_sel);
-    cudaFree(m->d_nnz);
+    cudaFree(m->d_wsum);
+    cudaFree(m->d_stats);
+    cudaFree(m->d_colcfg);
     delete m;
     return H2AES_OK;
+}
+
+// the kernels of one column on one pipe
+static cudaError_t msm_column(h2aes_msm *m, MsmPipe &pp, const MsmPlan &pl, MsmArgs a) {
+    h2aes_ctx *ctx = m->ctx;
+    cudaStream_t s = pp.stream;
+    const size_t W = (size_t)pl.W, nb1 = pl.NB + 1, nb2 = pl.NB + 2;
+    a.c = pl.c; a.W = pl.W; a.NB = pl.NB; a.nch = pl.nch; a.max_tasks = pl.max_tasks;
+    a.max_heavy = m->max_heavy;
+    // layout: [hist | cursor | heavy] (zeroed per column) | offs | toffs | dig | sorted
+    a.hist = pp.d_u32;
+    a.cursor = a.hist + W * nb1;
+    a.heavy = a.cursor + W * nb1;
+    const size_t zero_words = 2 * W * nb1 + W * ((size_t)m->max_heavy + 1);
+    a.offs = pp.d_u32 + zero_words;
+    a.toffs = a.offs + W * nb2;
+    a.dig = a.toffs + W * nb2;
+    a.sorted = a.dig + W * m->n;
+    a.partial = pp.d_pts;
+    a.buckets = a.partial + W * pl.max_tasks;
+    a.chunks = a.buckets + W * nb1;
+    a.diff = pp.d_diff;
+    a.src_scalars = pl.runs ? pp.d_diff : a.scalars;
+    a.src_bases = pl.runs ? m->d_prefix : m->bases;
+    cudaError_t e = cudaMemsetAsync(pp.d_u32, 0, zero_words * 4, s);
+    if (e) return e;
+    cudaStream_t keep = ctx->stream;
+    ctx->stream = s;  // (prof_begin / prof_end record on the stream the kernel is launched on)
+    if (pl.runs) {
+        prof_begin(ctx, "k_msm_diff");
+        k_msm_diff<<<cdivu(m->n, 256), 256, 0, s>>>(a);
+        prof_end(ctx);
+        ctx->launches += 1;
+    }
+    prof_begin(ctx, "k_msm_digits");
+    k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_scan");
+    k_msm_scan<<<pl.W, 1024, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_scatter");
+    k_msm_scatter<<<dim3(cdivu(m->n, 256), pl.W), 256, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_tasks");
+    k_msm_tasks<<<dim3(cdivu(pl.max_tasks, 128), pl.W), 128, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_buckets");
+    k_msm_buckets<<<dim3(cdivu(nb1, 128), pl.W), 128, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_heavy");
+    k_msm_heavy<<<dim3(std::min(m->max_heavy, 296u), pl.W), 128, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_chunks");
+    k_msm_chunks<<<dim3(cdivu(pl.nch, 64), pl.W), 64, 0, s>>>(a);
+    prof_end(ctx);
+    prof_begin(ctx, "k_msm_windows");
+    k_msm_windows<<<pl.W, 256, 0, s>>>(a);
+    prof_end(ctx);
+    ctx->launches += 8;
+    ctx->stream = keep;
+    return cudaGetLastError();
 }
 
 int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, uint64_t *out_dev) {
@@ -639,73 +795,63 @@ int32_t h2aes_msm_dev(h2aes_msm *m, const uint64_t *scalars_dev, int32_t ncols, 
     if (!scalars_dev || !out_dev || ncols < 0) return mfail(ctx, H2AES_ERR_ARG, "msm: null pointer");
     MCU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const size_t W = (size_t)m->W, nb1 = m->NB + 1;
     MsmArgs a;
-    a.n = m->n; a.c = m->c; a.W = m->W; a.NB = m->NB; a.max_tasks = m->max_tasks;
+    memset(&a, 0, sizeof a);
+    a.n = m->n;
     a.bases = m->bases;
-    a.hist = m->d_u32 + m->hist_off;
-    a.cursor = m->d_u32 + m->cursor_off;
-    a.offs = m->d_u32 + m->offs_off;
-    a.toffs = m->d_u32 + m->toffs_off;
-    a.dig = m->d_u32 + m->toffs_off + W * (m->NB + 2);
-    a.sorted = m->d_u32 + m->sorted_off;
-    a.partial = m->d_pts;
-    a.buckets = a.partial + W * m->max_tasks;
-    a.chunks = a.buckets + W * nb1;
-    a.wsum = a.chunks + W * MSM_NCH;
-    a.heavy = m->d_u32 + m->heavy_off;
-    a.max_heavy = m->max_heavy;
     a.prefix = m->d_prefix;
-    a.diff = m->d_diff;
-    a.sel = m->d_sel;
-    a.nnz = m->d_nnz;
+    a.wsum = m->d_wsum;
+    a.stats = m->d_stats;
+    a.colcfg = m->d_colcfg;
+    std::vector<uint32_t> stats((size_t)MSM_BATCH * MSM_STATS), cfg(MSM_BATCH);
     for (int c0 = 0; c0 < ncols; c0 += MSM_BATCH) {
         const int nb = std::min(MSM_BATCH, ncols - c0);
+        const fr_t *cols = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)c0 * m->n;
+        // what is in the columns (one launch for the batch), then the host picks path and window
+        a.scalars = cols;
+        MCU(ctx, cudaMemsetAsync(m->d_stats, 0, (size_t)nb * MSM_STATS * 4, s));
+        prof_begin(ctx, "k_msm_stats");
+        k_msm_stats<<<dim3(cdivu(m->n, 256), nb), 256, 0, s>>>(a);
+        prof_end(ctx);
+        ctx->launches += 1;
+        MCU(ctx, cudaMemcpyAsync(stats.data(), m->d_stats, (size_t)nb * MSM_STATS * 4, cudaMemcpyDeviceToHost, s));
+        MCU(ctx, cudaStreamSynchronize(s));  // (also: everything the pipes will read is complete)
         a.out = reinterpret_cast<g1a_t *>(out_dev) + c0;
         a.ncols = nb;
+        bool used[MSM_PIPES] = {};
         for (int col = 0; col < nb; ++col) {
-            a.scalars = reinterpret_cast<const fr_t *>(scalars_dev) + (uint64_t)(c0 + col) * m->n;
-            a.col = col;
-            MCU(ctx, cudaMemsetAsync(m->d_u32, 0, m->zero_words * 4, s));
-            MCU(ctx, cudaMemsetAsync(m->d_nnz, 0, 2 * sizeof(uint32_t), s));
-            if (m->d_prefix) {
-                prof_begin(ctx, "k_msm_diff");
-                k_msm_diff<<<cdivu(m->n, 256), 256, 0, s>>>(a);
-                prof_end(ctx);
-                ctx->launches += 1;
+            const uint32_t *st = stats.data() + (size_t)col * MSM_STATS;
+            const uint64_t nz_s = st[0], nz_d = st[1];
+            MsmPlan pl;
+            // the differences pay off when they leave clearly fewer non-zero scalars than the column has
+            if (m->d_prefix && nz_d * 2 < nz_s) {
+                pl = msm_choose(m, nz_d, 254);
+                pl.runs = true;
+            } else {
+                int bits = 0;
+                for (int k = 7; k >= 0 && !bits; --k)
+                    if (st[2 + k]) bits = 32 * k + 32 - __builtin_clz(st[2 + k]);
+                pl = msm_choose(m, nz_s, std::max(bits, 1));
             }
-            k_msm_select<<<1, 1, 0, s>>>(a);
-            ctx->launches += 1;
-            prof_begin(ctx, "k_msm_digits");
-            k_msm_digits<<<cdivu(m->n, 256), 256, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_scan");
-            k_msm_scan<<<m->W, 1024, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_scatter");
-            k_msm_scatter<<<dim3(cdivu(m->n, 256), m->W), 256, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_tasks");
-            k_msm_tasks<<<dim3(cdivu(m->max_tasks, 128), m->W), 128, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_buckets");
-            k_msm_buckets<<<dim3(cdivu(nb1, 128), m->W), 128, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_heavy");
-            k_msm_heavy<<<dim3(std::min(m->max_heavy, 296u), m->W), 128, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_chunks");
-            k_msm_chunks<<<dim3(cdivu(MSM_NCH, 64), m->W), 64, 0, s>>>(a);
-            prof_end(ctx);
-            prof_begin(ctx, "k_msm_windows");
-            k_msm_windows<<<m->W, 256, 0, s>>>(a);
-            prof_end(ctx);
-            ctx->launches += 8;
+            cfg[col] = (uint32_t)pl.c | ((uint32_t)pl.W << 8);
+            MsmPipe &pp = m->pipe[col % m->n_pipes];
+            used[col % m->n_pipes] = true;
+            a.scalars = cols + (uint64_t)col * m->n;
+            a.col = col;
+            MCU(ctx, msm_column(m, pp, pl, a));
         }
+        MCU(ctx, cudaMemcpyAsync(m->d_colcfg, cfg.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, s));
+        for (int i = 0; i < m->n_pipes; ++i)
+            if (used[i]) {
+                MCU(ctx, cudaEventRecord(m->pipe[i].done, m->pipe[i].stream));
+                MCU(ctx, cudaStreamWaitEvent(s, m->pipe[i].done, 0));
+            }
         prof_begin(ctx, "k_msm_final");
         k_msm_final<<<cdivu(nb, 32), 32, 0, s>>>(a);
         prof_end(ctx);
         ctx->launches += 1;
+        // (cfg / stats are reused by the next batch: its first step synchronizes the stream)
+        if (c0 + MSM_BATCH < ncols) MCU(ctx, cudaStreamSynchronize(s));
     }
     MCU(ctx, cudaGetLastError());
     return H2AES_OK;
