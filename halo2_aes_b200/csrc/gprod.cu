@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
 #ifndef ZP_ELEMS
 #define ZP_ELEMS 8
 #endif
+#ifndef ZP_STAGE
+#define ZP_STAGE 0
+#endif
 constexpr int ZP_T = ZP_THREADS, ZP_E = ZP_ELEMS, ZP_TILE = ZP_T * ZP_E;
 __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScanArgs a) {
     __shared__ fr_t s_w[ZP_T / 32];
@@ -321,12 +324,26 @@ __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScan
     const int l = a.first_lookup * (int)a.segs + li;            // index into carry_in / partial
     fr_t *__restrict__ x = a.tot + (size_t)li * a.n_blocks;
     const uint64_t base = T * ZP_TILE + (uint64_t)tid * ZP_E;
+    // ZP_STAGE: where a thread's elements wait for the output pass.  0: registers (164 of them:
+    // 3 CTAs per SM, the 650 tiles of the bench shape take two waves); 1: shared memory (32 KiB per
+    // CTA); 2: read again from global memory
+#if ZP_STAGE == 1
+    __shared__ uint4 s_v[ZP_E * 2][ZP_T];
+#endif
+#if ZP_STAGE == 0
     fr_t v[ZP_E];
+#endif
     fr_t p = fr_one();
 #pragma unroll
     for (int j = 0; j < ZP_E; ++j) {
-        v[j] = base + j < a.n_blocks ? fr_ld(x + base + j) : fr_one();
-        p = j == 0 ? v[0] : fr_mul(p, v[j]);
+        const fr_t vj = base + j < a.n_blocks ? fr_ld(x + base + j) : fr_one();
+#if ZP_STAGE == 0
+        v[j] = vj;
+#elif ZP_STAGE == 1
+        s_v[2 * j][tid] = make_uint4(vj.v[0], vj.v[1], vj.v[2], vj.v[3]);
+        s_v[2 * j + 1][tid] = make_uint4(vj.v[4], vj.v[5], vj.v[6], vj.v[7]);
+#endif
+        p = j == 0 ? vj : fr_mul(p, vj);
     }
     fr_t inc = p;
 #pragma unroll 1
@@ -395,8 +412,16 @@ __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScan
     run = fr_mul(run, s_w[wid]);
 #pragma unroll
     for (int j = 0; j < ZP_E; ++j) {
+#if ZP_STAGE == 0
+        const fr_t vj = v[j];
+#elif ZP_STAGE == 1
+        const uint4 lo = s_v[2 * j][tid], hi = s_v[2 * j + 1][tid];
+        const fr_t vj = {{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w}};
+#else
+        const fr_t vj = base + j < a.n_blocks ? fr_ld(x + base + j) : fr_one();
+#endif
         if (base + j < a.n_blocks) fr_st(x + base + j, run);
-        if (j + 1 < ZP_E) run = fr_mul(run, v[j]);
+        if (j + 1 < ZP_E) run = fr_mul(run, vj);
     }
     // the last CTA to finish rearms the control block for the next scan
     if (tid == 0) {
@@ -508,18 +533,24 @@ __global__ void __launch_bounds__(ZB_T, ZWRITE_OCC) k_z_write(const __grid_const
 // carry[l][t] = product of the partial products of every segment that precedes segment t of this
 // shard in the column: segment t' of shard g' is ownership tile t' * G + g' (row-sharded circuit).
 // gathered = [G][L][segs] (segments a shard does not hold: one).
-__global__ void k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, uint32_t segs,
-                              uint32_t G, uint32_t shard, fr_t *__restrict__ carry) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // (lookup, segment)
-    if (i >= (uint32_t)n_lookups * segs) return;
+__global__ void __launch_bounds__(128)
+k_shard_carry(const fr_t *__restrict__ gathered, int n_lookups, uint32_t segs, uint32_t G,
+              uint32_t shard, fr_t *__restrict__ carry) {
+    // one warp per (lookup, segment): the lanes split the preceding ownership tiles, then a
+    // shuffle tree (<= 4 + 5 dependent multiplies instead of one chain over up to segs * G tiles)
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (lookup, segment)
+    const int lane = threadIdx.x & 31;
+    if (i >= (uint32_t)n_lookups * segs) return;  // (whole warps)
     const uint32_t l = i / segs, t = i - l * segs;
-    const uint64_t mine = (uint64_t)t * G + shard;
+    const uint32_t mine = t * G + shard;          // ownership tiles of the column before mine
     fr_t acc = fr_one();
-    for (uint32_t tt = 0; tt <= t; ++tt)
-        for (uint32_t gg = 0; gg < G; ++gg)
-            if ((uint64_t)tt * G + gg < mine)
-                acc = fr_mul(acc, fr_ld(gathered + ((size_t)gg * n_lookups + l) * segs + tt));
-    fr_st(carry + i, acc);
+    for (uint32_t j = lane; j < mine; j += 32) {
+        const uint32_t tt = j / G, gg = j - tt * G;
+        acc = fr_mul(acc, fr_ld(gathered + ((size_t)gg * n_lookups + l) * segs + tt));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = fr_mul(acc, fr_shfl_xor(acc, d));
+    if (lane == 0) fr_st(carry + i, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -685,7 +716,7 @@ cudaError_t launch_shard_carry(h2aes_circuit *c, const uint64_t *gathered_dev, u
     h2aes_ctx *ctx = c->ctx;
     const int L = c->sh.n_lookups();
     prof_begin(ctx, "k_shard_carry");
-    k_shard_carry<<<cdiv((uint64_t)L * segs, 64), 64, 0, ctx->stream>>>(
+    k_shard_carry<<<cdiv((uint64_t)L * segs * 32, 128), 128, 0, ctx->stream>>>(
         (const fr_t *)gathered_dev, L, segs, (uint32_t)c->n_shards, (uint32_t)c->shard, c->d_carry);
     prof_end(ctx);
     ctx->launches += 1;

@@ -661,9 +661,12 @@ k_permuted(Shape sh, int first_lookup, const uint32_t *__restrict__ trace,
     const fr_t zero = fr_zero();
     // row ranges are multiples of 32 and a warp's 32 lanes sit on 32 consecutive rows, so one
     // ballot per iteration is the non-constant mask of one chunk of the grand product
-    for (uint64_t lrow = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; lrow < out_rows;
-         lrow += stride) {
-        const uint64_t row = rm.global(lrow);
+    // (ownership tiles and shards are multiples of the CTA's 256 rows: one local -> global
+    // translation per CTA iteration, in the uniform datapath, instead of a division per row)
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < out_rows; base += stride) {
+        const uint64_t lrow = base + threadIdx.x;
+        if (lrow >= out_rows) break;  // (never splits a warp: out_rows is a multiple of 32)
+        const uint64_t row = rm.global(base) + threadIdx.x;
         const size_t o = ((size_t)li * out_rows + lrow) * 4;
         uint32_t code = fcode_pack(FK_ONE, 0, 0);
         if (row >= usable) {
@@ -970,6 +973,14 @@ cudaError_t launch_permuted(h2aes_circuit *c, int first, int count, uint64_t *A,
     }
     unsigned cap = (unsigned)ctx->sm_count * 8;
     if (per_sm) cap = std::max(1u, (unsigned)(ctx->sm_count * per_sm) / (unsigned)count);
+    // H2AES_PERM_WAVES: all lookups together fill the machine this many times (0: every lookup
+    // gets a machine-filling grid of its own, i.e. `count` waves of short-lived CTAs)
+    static int waves = -1;
+    if (waves < 0) {
+        const char *s = getenv("H2AES_PERM_WAVES");
+        waves = s ? atoi(s) : 0;
+    }
+    if (waves) cap = std::max(1u, (unsigned)(ctx->sm_count * 8 * waves) / (unsigned)count);
     if (gx > cap) gx = cap;
     dim3 g(gx, count);
     cudaError_t e0 = cudaMemsetAsync(c->d_gcount + first, 0, (size_t)count * 4, ctx->stream);
