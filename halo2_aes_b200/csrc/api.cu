@@ -668,9 +668,9 @@ static int32_t ensure_lookup_ws(h2aes_circuit *c) {
     const size_t VB = (size_t)N_VIEWS * BIN_STRIDE, LB = L * BIN_STRIDE;
     c->zm = (c->sh.n() + 31) / 32 + 4;
     // block totals of L columns of n rows (>= the permutation's n_sets * n rows as one column);
-    // k_z_prefix scans them in tiles of 1024
+    // k_z_prefix scans them in tiles of ZP_TILE_TOTALS
     c->zblocks = L * (zscan_blocks(c->sh.n()) + 1);
-    c->ztiles = L * (zscan_blocks(c->sh.n()) / 1024 + 2 * zscan_tiles(c->sh.n()) + 4);  // (tiled shards: 2 per segment)
+    c->ztiles = L * (zscan_blocks(c->sh.n()) / ZP_TILE_TOTALS + 2 * zscan_tiles(c->sh.n()) + 4);  // (tiled shards: 2 per segment)
     static_assert(H2AES_SHARD_TILE_ROWS == ZT_ROWS, "an ownership tile is a row tile of the scan");
     DA(c->d_chal, 4);
     DA(c->d_val, VB);

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(ZB_T, ZTOT_OCC) k_z_totals(const __grid_consta
 #define ZP_STAGE 0
 #endif
 constexpr int ZP_T = ZP_THREADS, ZP_E = ZP_ELEMS, ZP_TILE = ZP_T * ZP_E;
+static_assert(ZP_TILE == ZP_TILE_TOTALS, "the look-back workspace (api.cu) is sized for tiles of ZP_TILE_TOTALS block totals");
 __global__ void __launch_bounds__(ZP_T) k_z_prefix(const __grid_constant__ ZScanArgs a) {
     __shared__ fr_t s_w[ZP_T / 32];
     __shared__ uint32_t s_ticket, s_epoch;

@@ -138,6 +138,9 @@ __device__ __forceinline__ fr_t fr_shfl_idx(const fr_t &a, int src) {
 #define ZB_ROWS 40
 #endif
 constexpr uint32_t ZT_LANE = (uint32_t)AES_ROWS;          // rows between two lanes of a warp
+// block totals per look-back tile of k_z_prefix (gprod.cu asserts its tile is this; api.cu sizes
+// the look-back workspace by it)
+constexpr int ZP_TILE_TOTALS = 1024;
 constexpr uint32_t ZB_R = ZB_ROWS;                        // consecutive rows per thread
 constexpr uint32_t ZB_W = ZT_LANE / ZB_R;                 // warps per row tile (34)
 constexpr uint32_t ZT_ROWS = 32u * ZT_LANE;               // rows per row tile (43520)
