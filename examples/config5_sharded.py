@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--sets", type=int, default=5)
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
+    if "RANK" not in os.environ:  # plain `python examples/config5_sharded.py`: one shard
+        os.environ.update(RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29519")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)

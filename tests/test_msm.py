@@ -151,6 +151,40 @@ def _host(t):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("c", [6, 7, 9, 11, 13, 16])
+def test_msm_every_window_size_on_the_device(gpu, orc, ffi, c, monkeypatch):
+    """The window size is chosen per column (k_msm_stats + msm_choose in csrc/msm.cu); H2AES_MSM_C
+    pins it, so every size the choice ranges over is checked against the oracle on columns of all
+    shapes (full width, short scalars that need fewer windows, bytes, 0/1, extremes), directly and
+    through the differences."""
+    from halo2_aes_b200.backend import Msm
+    monkeypatch.setenv("H2AES_MSM_C", str(c))
+    n = 3000
+    B = orc.g1_test_bases(n, orc.fr_from_int(D_STEP))
+    runs = rand_scalars(orc, SEED + 71, 40)
+    cols = np.stack([
+        rand_scalars(orc, SEED + 70 + c, n),
+        np.repeat(runs, n // 40, axis=0),                           # long runs: the difference path
+        np.stack([orc.fr_from_int(int(b)) for b in splitmix_bytes(SEED + 72, n)]),
+        np.stack([orc.fr_from_int(int(b) & 1) for b in splitmix_bytes(SEED + 73, n)]),
+        np.stack([orc.fr_from_int((int(b) << 9) | 0x1ff) for b in splitmix_bytes(SEED + 74, n)]),  # 17 bits
+        np.tile(orc.fr_from_int(R_MOD - 1), (n, 1)),
+        np.tile(orc.fr_from_int((1 << c) - 1), (n, 1)),             # a full digit in the lowest window
+        np.tile(orc.fr_from_int(1 << (c - 1)), (n, 1)),             # the largest positive digit
+    ])
+    cols[0, 0] = orc.fr_from_int((1 << 253) + 12345)
+    want = [orc.g1_msm(col, B) for col in cols]
+    for with_runs in (False, True):
+        msm = Msm(gpu, _dev(B))
+        if with_runs:
+            msm.enable_runs()
+        got = _host(msm.commit(_dev(cols)))
+        for ci in range(cols.shape[0]):
+            assert (got[ci] == want[ci]).all(), (c, with_runs, ci)
+        msm.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 33, 1000, 1 << 12, 1 << 14])
 def test_msm_equals_oracle_and_anchor(gpu, orc, ffi, n):
     from halo2_aes_b200.backend import Msm
