@@ -661,7 +661,7 @@ def run_sharded(args, local, rank, world, th, be, ga, tiled=True):
         pts = torch.from_numpy(splitmix_bytes(SEED + 81, 16 * nb).reshape(-1, 16)).cuda()
         advice = torch.empty((nadv, rows, 4), dtype=torch.int64, device="cuda")
         out = {nm: torch.empty((L, rows, 4), dtype=torch.int64, device="cuda") for nm in ("Ap", "Sp", "Z")}
-    iters, times = 5, []
+    iters, times = 9, []
     for it in range(iters + 2):
         stream.synchronize()
         if world > 1:
@@ -709,7 +709,10 @@ def run_sharded(args, local, rank, world, th, be, ga, tiled=True):
     if world > 1:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     assert int(flag) == 1, "sharded lookup columns violate an invariant"
-    w, lk, tot, my_lk = (float(np.mean([t[j] for t in times])) for j in range(4))
+    # median over the iterations (each already the max over ranks): a single NCCL hiccup of a few
+    # hundred microseconds would move the mean of these ~1 ms steps by tens of percent
+    w, lk, tot, my_lk = (float(np.median([t[j] for t in times])) for j in range(4))
+    tot_mean, tot_max = float(np.mean([t[2] for t in times])), float(np.max([t[2] for t in times]))
     per_rank = [my_lk]
     if world > 1:
         g = torch.zeros(world, dtype=torch.float64, device="cuda")
@@ -723,6 +726,8 @@ def run_sharded(args, local, rank, world, th, be, ga, tiled=True):
            "row_ownership": own if world > 1 else "one shard",
            "n_gpus": world, "blocks": nb, "rows_per_gpu": rows, "witness_ms": w, "lookup_columns_ms": lk,
            "ms": tot, "value": nb / (tot * 1e-3), "unit": UNIT,
+           "timing": {"iterations": iters, "statistic": "median of the per-iteration max over ranks",
+                      "ms_mean": tot_mean, "ms_max": tot_max},
            "bytes_per_gpu": (nadv + 3 * L) * rows * 32,
            "nvlink_bytes_per_gpu": {"histogram_allreduce": hist_bytes if world > 1 else 0,
                                     "partial_allgather": world * L * 32 if world > 1 else 0},
@@ -910,7 +915,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--circuits", type=int, default=10,
+    ap.add_argument("--circuits", type=int, default=12,
                     help="circuits per step per GPU (one step = this many whole K=20,N=5 circuits)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -925,7 +930,7 @@ def main():
                     help="tuning only: skip the Z[n-6] == 1 assertions (diagnostic library variants)")
     ap.add_argument("--no-prover-side", action="store_true",
                     help="skip the NTT / lookup-quotient measurement (SURVEY 8f items 3/4)")
-    ap.add_argument("--pipelines", type=int, default=2,
+    ap.add_argument("--pipelines", type=int, default=4,
                     help="independent circuits in flight per GPU (each on its own stream)")
     args = ap.parse_args()
     protect_stdout()

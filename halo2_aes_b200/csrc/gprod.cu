@@ -624,6 +624,12 @@ static cudaError_t launch_totals(h2aes_circuit *c, const ZScanArgs &a) {
     const unsigned cap = z_ctas_per_sm() ? std::max(1u, (unsigned)(ctx->sm_count * z_ctas_per_sm()) / (unsigned)a.count)
                                          : (unsigned)ctx->sm_count * 4;
     if (gx > cap) gx = cap;
+    static int zg = -1;  // H2AES_ZG_CTAS (tuning): CTAs per lookup of k_z_general
+    if (zg < 0) {
+        const char *e = getenv("H2AES_ZG_CTAS");
+        zg = e ? atoi(e) : 0;
+    }
+    if (zg) gx = std::min(gx, (unsigned)zg);
     prof_begin(ctx, "k_z_general");
     k_z_general<<<dim3(gx, a.count), ZG_T, 0, s>>>(a);
     prof_end(ctx);

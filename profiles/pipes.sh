@@ -1,7 +1,7 @@
 # circuits in flight per GPU: bash profiles/pipes.sh 1 2 3 4
 mkdir -p gpurun_out
 for p in "$@"; do
-  timeout 600 python bench.py --no-cpu --no-e2e --no-prover-side --no-perm --steps 10 --pipelines $p > gpurun_out/pipes_$p.json 2> gpurun_out/pipes.err || tail -3 gpurun_out/pipes.err
+  timeout 200 python bench.py --no-cpu --no-e2e --no-prover-side --no-perm --no-config4 --no-sharded --no-check --steps 20 --pipelines $p > gpurun_out/pipes_$p.json 2> gpurun_out/pipes.err || tail -3 gpurun_out/pipes.err
   python - <<PY
 import json
 d = json.load(open("gpurun_out/pipes_$p.json"))

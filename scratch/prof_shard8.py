@@ -42,10 +42,10 @@ for it in range(2):
     for h in hists:
         h.copy_(total)
     gpu.profile(True) if it == 1 else None
-    p0 = mark("permuted0", lambda: shards[0].shard_permuted())
+    p0 = mark("permuted0", lambda: shards[0].shard_permuted(want_inputs=False))
     zp0 = mark("partial0", lambda: shards[0].shard_partial(be, ga))
     gpu.profile(False) if it == 1 else None
-    zps = [zp0] + [(c.shard_permuted(), c.shard_partial(be, ga))[1] for c in shards[1:]]
+    zps = [zp0] + [(c.shard_permuted(want_inputs=False), c.shard_partial(be, ga))[1] for c in shards[1:]]
     gathered = torch.stack([p.clone() for _, p in zps]).contiguous()
     gpu.profile(True) if it == 1 else None
     Z0 = mark("product0", lambda: shards[0].shard_product(gathered, zp0[0]))
