@@ -1,5 +1,5 @@
 import sys, numpy as np, torch, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from halo2_aes_b200 import _ffi as ffi
 from halo2_aes_b200.backend import Circuit, Context
 from bench import splitmix_bytes, SEED, seeded_fr

@@ -1,7 +1,7 @@
 """Per-kernel times of ONE shard of a K=22,N=5 circuit row-sharded 8 ways (tiled), with the 8 shards
 emulated on one GPU and the exchanges done by hand: where the 1.1 ms of the 8-GPU run goes."""
 import sys, numpy as np, torch, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from halo2_aes_b200 import _ffi as ffi
 from halo2_aes_b200.backend import Circuit, Context
 from bench import splitmix_bytes, SEED, seeded_fr
