@@ -354,3 +354,29 @@ def test_generated_rust_ffi_block_is_in_sync_with_the_header(ffi):
         m = re.search(r"pub fn %s\((.*?)\) ->" % name, text)
         n_args = 0 if not m.group(1).strip() else m.group(1).count(":")
         assert n_args == len(args), name
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU:
+    one step of the K=20, N=5 circuit through the oracle, one JSON line with the keys the
+    contract names and the same `config` the GPU arm reports."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "blocks/s" and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    cfg = d["config"]
+    assert cfg["k"] == 20 and cfg["column_sets"] == 5 and cfg["blocks_per_circuit"] == 3853
+    assert "model" not in cfg
