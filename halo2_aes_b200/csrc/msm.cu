@@ -325,7 +325,10 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const MsmArgs a) {
 }
 
 // one thread per task: the sum of <= SEG points of one bucket
-__global__ void __launch_bounds__(128) k_msm_tasks(const MsmArgs a) {
+#ifndef MSM_TASKS_OCC
+#define MSM_TASKS_OCC 4
+#endif
+__global__ void __launch_bounds__(128, MSM_TASKS_OCC) k_msm_tasks(const MsmArgs a) {
     const int w = blockIdx.y;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t *to = a.toffs + (uint64_t)w * (a.NB + 2);
